@@ -1,0 +1,138 @@
+"""ctypes binding of the C-ABI product library ``libgsr.so`` (include/gsr_capi.h).
+
+The library is hand-written CUDA for sm_100a; there is NO CPU fallback.  If the
+shared object is missing this module raises at first use (loudly), it never
+routes to the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsr.so")
+
+RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("W", C.c_int), ("H", C.c_int),
+        ("background", C.c_void_p), ("means3D", C.c_void_p), ("dc", C.c_void_p),
+        ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
+        ("scales", C.c_void_p), ("scale_modifier", C.c_float), ("rotations", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+        ("campos", C.c_void_p), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+        ("prefiltered", C.c_int), ("debug", C.c_int),
+        ("out_color", C.c_void_p), ("radii", C.c_void_p),
+        ("geom_resize", RESIZE_FN), ("geom_user", C.c_void_p),
+        ("binning_resize", RESIZE_FN), ("binning_user", C.c_void_p),
+        ("image_resize", RESIZE_FN), ("image_user", C.c_void_p),
+        ("sample_resize", RESIZE_FN), ("sample_user", C.c_void_p),
+        ("stream", C.c_void_p),
+        ("num_rendered", C.POINTER(C.c_int)), ("num_buckets", C.POINTER(C.c_int)),
+    ]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int), ("R", C.c_int), ("B", C.c_int),
+        ("W", C.c_int), ("H", C.c_int),
+        ("background", C.c_void_p), ("means3D", C.c_void_p), ("dc", C.c_void_p),
+        ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
+        ("scales", C.c_void_p), ("scale_modifier", C.c_float), ("rotations", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+        ("campos", C.c_void_p), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+        ("radii", C.c_void_p),
+        ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p),
+        ("image_buffer", C.c_void_p), ("sample_buffer", C.c_void_p),
+        ("dL_dpix", C.c_void_p),
+        ("dL_dmean2D", C.c_void_p), ("dL_dconic", C.c_void_p), ("dL_dopacity", C.c_void_p),
+        ("dL_dcolor", C.c_void_p), ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p),
+        ("dL_ddc", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
+        ("dL_drot", C.c_void_p),
+        ("debug", C.c_int), ("stream", C.c_void_p),
+    ]
+
+
+class AdamGroup(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p),
+        ("exp_avg_sq", C.c_void_p), ("numel", C.c_int64), ("lr", C.c_double),
+        ("step", C.c_int64),
+    ]
+
+
+# every symbol include/gsr_capi.h declares (checked by tests/test_capi_symbols.py)
+EXPORTED_SYMBOLS = [
+    "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step",
+    "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_sort_temp_bytes",
+    "gsr_sort_u64", "gsr_launch_count", "gsr_version",
+]
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libgsr.so in-tree with nvcc for sm_100a (no GPU needed)."""
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    res = subprocess.run(["bash", script], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libgsr.so failed:\n" + res.stderr[-4000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load the product library; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "There is no CPU fallback for the rasterizer hot path.")
+    L = C.CDLL(LIB_PATH)
+    L.gsr_forward.argtypes = [C.POINTER(ForwardArgs)]
+    L.gsr_forward.restype = C.c_int
+    L.gsr_backward.argtypes = [C.POINTER(BackwardArgs)]
+    L.gsr_backward.restype = C.c_int
+    L.gsr_mark_visible.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsr_mark_visible.restype = C.c_int
+    L.gsr_knn_mean_dist2.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsr_knn_mean_dist2.restype = C.c_int
+    L.gsr_adam_step.argtypes = [C.POINTER(AdamGroup), C.c_int, C.c_double, C.c_double, C.c_double,
+                                C.c_float, C.c_void_p]
+    L.gsr_adam_step.restype = C.c_int
+    L.gsr_export_binning.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    L.gsr_export_binning.restype = C.c_int
+    L.gsr_export_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsr_export_image.restype = C.c_int
+    L.gsr_export_geometry.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsr_export_geometry.restype = C.c_int
+    L.gsr_sort_temp_bytes.argtypes = [C.c_int64]
+    L.gsr_sort_temp_bytes.restype = C.c_size_t
+    L.gsr_sort_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p]
+    L.gsr_sort_u64.restype = C.c_int
+    L.gsr_launch_count.argtypes = []
+    L.gsr_launch_count.restype = C.c_int64
+    L.gsr_version.argtypes = []
+    L.gsr_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    """Translate a non-zero C-ABI return code into RuntimeError (the reference's
+    shim throws std::runtime_error from CHECK_CUDA, auxiliary.h:196-207)."""
+    if rc != 0:
+        kind = "gsr error" if rc < 0 else "cudaError"
+        raise RuntimeError(f"{what} failed: {kind} {rc}")

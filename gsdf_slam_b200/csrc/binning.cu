@@ -1,0 +1,130 @@
+// Binning: turn the depth-sorted Gaussians into per-tile, depth-ordered lists.
+//
+// The reference builds one 64-bit key (tile<<32 | depth bits) per (Gaussian,
+// tile) overlap and radix-sorts all R of them on 32+log2(T) bits
+// (duplicateWithKeys + cub SortPairs + identifyTileRanges,
+// rasterizer_impl.cu:139-246, 476-500).  Here the same total order is produced
+// with far less traffic by splitting the LSD sort at bit 32:
+//   * the low 32 key bits (depth) are identical for every duplicate of a
+//     Gaussian, so those four digit passes run on the P un-duplicated Gaussians
+//     (preprocess emits (depth<<32 | idx); launch_sort_u64 orders them);
+//   * duplicates are then emitted in that order (emit_kernel) and only the tile
+//     digits (bits 32..32+log2 T) are sorted on the R duplicates — LSD radix sort
+//     is stable, so the result is exactly the order of sorting the full key,
+//     including ties (equal tile and depth keep ascending Gaussian index).
+// finalize_kernel then derives the tile ranges and writes the packed,
+// tile-contiguous splat records that the blend kernels stream with bulk copies.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+// One thread per depth-sorted Gaussian: re-run the opacity-aware tile test and
+// write (tile<<32 | idx) for every surviving tile, row-major like the reference
+// (rasterizer_impl.cu:177-200).
+__global__ void __launch_bounds__(256)
+emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ tiles_touched,
+            const uint32_t* __restrict__ dup_offsets, const float2* __restrict__ means2D,
+            const float4* __restrict__ conic_opacity, const int* __restrict__ radii, int grid_x,
+            int grid_y, uint64_t* __restrict__ items) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P) return;
+  const uint32_t g = (uint32_t)(sorted[j] & 0xffffffffu);
+  const uint32_t cnt = tiles_touched[g];
+  if (cnt == 0) return;
+  uint32_t off = dup_offsets[j];
+  const float2 xy = means2D[g];
+  const float4 co = conic_opacity[g];
+  uint2 rect_min, rect_max;
+  tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
+  const float thr = opacity_power_threshold(co.w);
+  for (int y = rect_min.y; y < (int)rect_max.y; ++y) {
+    for (int x = rect_min.x; x < (int)rect_max.x; ++x) {
+      if (tile_min_power(co, xy, x, y) <= thr) {
+        const uint64_t tile = (uint64_t)(y * grid_x + x);
+        items[off++] = (tile << 32) | g;
+      }
+    }
+  }
+}
+
+int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
+                const uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
+                const int* radii, int grid_x, int grid_y, uint64_t* items, cudaStream_t s) {
+  if (P <= 0) return 0;
+  emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, sorted, tiles_touched, dup_offsets, means2D,
+                                              conic_opacity, radii, grid_x, grid_y, items);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+// One thread per sorted duplicate: tile boundaries -> ranges (the job of the
+// reference's identifyTileRanges, rasterizer_impl.cu:217-246) and the packed
+// per-duplicate record {xy, conic, opacity, reject threshold, idx, rgb}.
+__global__ void __launch_bounds__(256)
+finalize_kernel(uint32_t R, const uint64_t* __restrict__ sorted, const float2* __restrict__ means2D,
+                const float4* __restrict__ conic_opacity, const float* __restrict__ colors,
+                uint2* __restrict__ ranges, float4* __restrict__ rec_a, float4* __restrict__ rec_b,
+                float4* __restrict__ rec_c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  const uint64_t it = sorted[i];
+  const uint32_t tile = (uint32_t)(it >> 32);
+  const uint32_t g = (uint32_t)(it & 0xffffffffu);
+  if (i == 0) {
+    ranges[tile].x = 0;
+  } else {
+    const uint32_t prev = (uint32_t)(sorted[i - 1] >> 32);
+    if (prev != tile) {
+      ranges[prev].y = i;
+      ranges[tile].x = i;
+    }
+  }
+  if (i == R - 1) ranges[tile].y = R;
+
+  const float2 xy = means2D[g];
+  const float4 co = conic_opacity[g];
+  // power below which opacity*exp(power) is certainly < 1/255 (1 % safety margin):
+  // lets the blend kernels skip the exp for far-away pixels without changing any result.
+  const float reject = -logf(255.0f * co.w) - 0.01f;
+  rec_a[i] = make_float4(xy.x, xy.y, co.x, co.y);
+  rec_b[i] = make_float4(co.z, co.w, reject, __uint_as_float(g));
+  rec_c[i] = make_float4(colors[3 * (size_t)g], colors[3 * (size_t)g + 1], colors[3 * (size_t)g + 2], 0.f);
+}
+
+int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
+                    const float4* conic_opacity, const float* colors, uint2* ranges, uint32_t T,
+                    float4* rec_a, float4* rec_b, float4* rec_c, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), s);
+  if (e != cudaSuccess) return (int)e;
+  if (R == 0) return 0;
+  finalize_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted, means2D, conic_opacity, colors, ranges,
+                                                  rec_a, rec_b, rec_c);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+// Debug/test export: rebuild the reference's 64-bit sorted keys (tile<<32 | depth bits)
+// and the sorted Gaussian-id list from the packed records.
+__global__ void export_binning_kernel(uint32_t R, const uint64_t* __restrict__ sorted,
+                                      const float* __restrict__ depths, uint64_t* keys,
+                                      uint32_t* point_list) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  const uint64_t it = sorted[i];
+  const uint32_t g = (uint32_t)(it & 0xffffffffu);
+  if (keys) keys[i] = (it & 0xffffffff00000000ull) | (uint64_t)__float_as_uint(depths[g]);
+  if (point_list) point_list[i] = g;
+}
+
+int launch_export_binning(uint32_t R, const uint64_t* sorted, const float* depths, uint64_t* keys,
+                          uint32_t* point_list, cudaStream_t s) {
+  if (R == 0) return 0;
+  export_binning_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted, depths, keys, point_list);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gsr

@@ -1,0 +1,290 @@
+// C ABI of the B200-native rasterizer hot path (see include/gsr_capi.h).
+// Host-side orchestration only: every entry point validates its arguments,
+// carves the caller-provided scratch buffers and enqueues the kernels of
+// preprocess.cu / radix_sort.cu / binning.cu / blend_fwd.cu / blend_bwd.cu /
+// preprocess_bwd.cu / adam.cu / knn.cu on the caller's stream.
+//
+// Forward pipeline (reference: Rasterizer::forward, rasterizer_impl.cu:366-538):
+//   preprocess -> onesweep sort of (depth|idx) over P -> chained scan of the exact
+//   tile counts in depth order -> [one 4-byte readback of R] -> emit (tile|idx)
+//   -> onesweep sort of the tile digits over R -> ranges + packed records ->
+//   blend.  One host synchronisation (the reference has two blocking copies plus,
+//   as shipped with debug=true, a device-wide sync after every kernel).
+#include "gsr_capi.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+long long g_launch_count = 0;
+
+}  // namespace gsr
+
+#include "gsr_params.cuh"
+
+namespace gsr {
+static inline int tile_bits(uint32_t T) {  // bits needed to hold tile ids 0..T-1
+  int b = 0;
+  while ((1ull << b) < (uint64_t)T) ++b;
+  return b < 1 ? 1 : b;
+}
+
+static uint32_t* pinned_word() {
+  static thread_local uint32_t* p = nullptr;
+  if (!p) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), 64, cudaHostAllocPortable) != cudaSuccess) {
+      p = nullptr;
+    }
+  }
+  return p;
+}
+}  // namespace gsr
+
+using namespace gsr;
+
+#define GSR_CUDA(x)                         \
+  do {                                      \
+    cudaError_t _e = (x);                   \
+    if (_e != cudaSuccess) return (int)_e;  \
+  } while (0)
+#define GSR_RC(x)            \
+  do {                       \
+    int _r = (x);            \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+extern "C" {
+
+const char* gsr_version(void) { return "gsdf_slam_b200 0.1 (sm_100a)"; }
+int64_t gsr_launch_count(void) { return (int64_t)gsr::g_launch_count; }
+
+int gsr_forward(const gsr_forward_args* a) {
+  if (!a || a->P < 0 || a->W <= 0 || a->H <= 0 || !a->out_color || !a->num_rendered) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+  *a->num_rendered = 0;
+  if (a->num_buckets) *a->num_buckets = 0;
+  const int P = a->P, W = a->W, H = a->H;
+  const size_t N = (size_t)W * H;
+  if (P == 0) {
+    // reference: zero image, empty buffers, nothing launched (src/rasterize_points.cu:74-90)
+    GSR_CUDA(cudaMemsetAsync(a->out_color, 0, 3 * N * sizeof(float), s));
+    return GSR_OK;
+  }
+  if (!a->means3D || !a->opacities || !a->radii || !a->viewmatrix || !a->projmatrix || !a->campos ||
+      !a->background || !a->geom_resize || !a->binning_resize || !a->image_resize)
+    return GSR_ERR_BAD_ARG;
+  if (!a->colors_precomp && !a->dc) return GSR_ERR_BAD_ARG;
+  if (!a->cov3D_precomp && (!a->scales || !a->rotations)) return GSR_ERR_BAD_ARG;
+
+  const int gx = (W + GSR_TILE_X - 1) / GSR_TILE_X, gy = (H + GSR_TILE_Y - 1) / GSR_TILE_Y;
+  const uint32_t T = (uint32_t)gx * gy;
+
+  char* geom_base = a->geom_resize(a->geom_user, geom_bytes((size_t)P));
+  char* img_base = a->image_resize(a->image_user, image_bytes(N, T));
+  if (!geom_base || !img_base) return GSR_ERR_ALLOC;
+  GeomView g = geom_view(geom_base, (size_t)P);
+  ImageView im = image_view(img_base, N, T);
+
+  GSR_CUDA(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
+
+  PreprocessParams pp;
+  std::memset(&pp, 0, sizeof(pp));
+  pp.P = P; pp.D = a->D; pp.M = a->M; pp.W = W; pp.H = H;
+  pp.means3D = a->means3D; pp.scales = a->cov3D_precomp ? nullptr : a->scales;
+  pp.rotations = a->cov3D_precomp ? nullptr : a->rotations;
+  pp.opacities = a->opacities; pp.dc = a->dc; pp.shs = (a->M > 0) ? a->shs : nullptr;
+  pp.cov3D_precomp = a->cov3D_precomp; pp.colors_precomp = a->colors_precomp;
+  pp.scale_modifier = a->scale_modifier;
+  pp.view = a->viewmatrix; pp.proj = a->projmatrix; pp.campos = a->campos;
+  pp.tan_fovx = a->tan_fovx; pp.tan_fovy = a->tan_fovy;
+  pp.focal_y = H / (2.0f * a->tan_fovy);
+  pp.focal_x = W / (2.0f * a->tan_fovx);
+  pp.grid_x = gx; pp.grid_y = gy;
+  pp.prefiltered = a->prefiltered;
+  const uintptr_t al = (uintptr_t)a->means3D | (uintptr_t)pp.scales | (uintptr_t)pp.rotations |
+                       (uintptr_t)a->dc;
+  pp.vec_ok = (al & 15) == 0;
+  pp.radii = a->radii; pp.depths = g.depths; pp.means2D = g.means2D;
+  pp.conic_opacity = g.conic_opacity; pp.rgb = g.rgb; pp.clamped = g.clamped;
+  pp.tiles_touched = g.tiles_touched; pp.sort_items = g.sort_a; pp.num_visible = &g.hdr->num_visible;
+  GSR_RC(launch_preprocess(pp, s));
+
+  // depth order of the Gaussians: 32 key bits, 4 passes, result back in sort_a
+  uint64_t* order = nullptr;
+  GSR_RC(launch_sort_u64(g.sort_a, g.sort_a, g.sort_b, P, 32, 64, g.sort_tmp, s, &order));
+  GSR_RC(launch_scan_gather(g.tiles_touched, order, P, g.dup_offsets, &g.hdr->num_dup, g.sort_tmp, s));
+
+  uint32_t* host_R = pinned_word();
+  if (!host_R) return GSR_ERR_ALLOC;
+  GSR_CUDA(cudaMemcpyAsync(host_R, &g.hdr->num_dup, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  GSR_CUDA(cudaStreamSynchronize(s));
+  const uint32_t R = *host_R;
+  *a->num_rendered = (int)R;
+
+  char* bin_base = a->binning_resize(a->binning_user, bin_bytes((size_t)R));
+  if (!bin_base) return GSR_ERR_ALLOC;
+  if (a->sample_resize) a->sample_resize(a->sample_user, 0);
+  BinView b = bin_view(bin_base, (size_t)R);
+
+  if (R > 0) {
+    const int tb = tile_bits(T);
+    const int npass = (tb + 7) / 8;
+    // choose the emit target so that the sorted list always ends in items_a
+    uint64_t* emit_dst = (npass & 1) ? b.items_b : b.items_a;
+    uint64_t* other = (npass & 1) ? b.items_a : b.items_b;
+    GSR_RC(launch_emit(P, order, g.tiles_touched, g.dup_offsets, g.means2D, g.conic_opacity,
+                       a->radii, gx, gy, emit_dst, s));
+    uint64_t* sorted = nullptr;
+    // odd: in=b, out=a, alt=b ; even: in=a, out=a, alt=b
+    GSR_RC(launch_sort_u64(emit_dst, b.items_a, (npass & 1) ? emit_dst : other, R, 32, 32 + tb,
+                           b.sort_tmp, s, &sorted));
+  }
+  const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
+  GSR_RC(launch_finalize(R, b.items_a, g.means2D, g.conic_opacity, colors, im.ranges, T, b.rec_a,
+                         b.rec_b, b.rec_c, s));
+  GSR_RC(launch_blend_fwd(W, H, im.ranges, b.rec_a, b.rec_b, b.rec_c, a->background, a->out_color,
+                          im.final_T, im.n_contrib, im.accum_c, im.max_contrib, s));
+  if (a->debug) {
+    GSR_CUDA(cudaStreamSynchronize(s));
+    GSR_CUDA(cudaGetLastError());
+  }
+  return GSR_OK;
+}
+
+int gsr_backward(const gsr_backward_args* a) {
+  if (!a || a->P < 0 || a->W <= 0 || a->H <= 0) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+  const int P = a->P, W = a->W, H = a->H;
+  if (P == 0) return GSR_OK;
+  if (!a->geom_buffer || !a->image_buffer || !a->dL_dpix || !a->radii || !a->means3D ||
+      !a->dL_dmean2D || !a->dL_dopacity || !a->dL_dcolor || !a->dL_dmean3D || !a->dL_ddc ||
+      !a->dL_dscale || !a->dL_drot)
+    return GSR_ERR_BAD_ARG;
+  if (a->R > 0 && !a->binning_buffer) return GSR_ERR_BAD_ARG;
+  if (a->M > 0 && a->shs && !a->dL_dsh) return GSR_ERR_BAD_ARG;
+  if (((uintptr_t)a->dL_drot & 15) || ((uintptr_t)a->rotations & 15) || ((uintptr_t)a->dL_dconic & 15))
+    return GSR_ERR_BAD_ARG;
+  const size_t N = (size_t)W * H;
+  const int gx = (W + GSR_TILE_X - 1) / GSR_TILE_X, gy = (H + GSR_TILE_Y - 1) / GSR_TILE_Y;
+  const uint32_t T = (uint32_t)gx * gy;
+  GeomView g = geom_view(a->geom_buffer, (size_t)P);
+  ImageView im = image_view(a->image_buffer, N, T);
+
+  GSR_CUDA(cudaMemsetAsync(g.acc, 0, (size_t)P * 12 * sizeof(float), s));
+  if (a->R > 0) {
+    BinView b = bin_view(a->binning_buffer, (size_t)a->R);
+    GSR_RC(launch_blend_bwd(W, H, im.ranges, im.max_contrib, b.rec_a, b.rec_b, b.rec_c,
+                            a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, s));
+  }
+  PreBwdParams bp;
+  std::memset(&bp, 0, sizeof(bp));
+  bp.P = P; bp.D = a->D; bp.M = a->M;
+  bp.means3D = a->means3D; bp.radii = a->radii; bp.dc = a->dc;
+  bp.shs = (a->colors_precomp || a->M <= 0) ? nullptr : a->shs;
+  bp.clamped = g.clamped;
+  bp.scales = a->cov3D_precomp ? nullptr : a->scales;
+  bp.rotations = a->cov3D_precomp ? nullptr : a->rotations;
+  bp.cov3D_precomp = a->cov3D_precomp;
+  bp.scale_modifier = a->scale_modifier;
+  bp.view = a->viewmatrix; bp.proj = a->projmatrix; bp.campos = a->campos;
+  bp.focal_y = H / (2.0f * a->tan_fovy);
+  bp.focal_x = W / (2.0f * a->tan_fovx);
+  bp.tan_fovx = a->tan_fovx; bp.tan_fovy = a->tan_fovy;
+  bp.acc = g.acc;
+  bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
+  bp.dL_dcolor = a->dL_dcolor; bp.dL_dmean3D = a->dL_dmean3D; bp.dL_dcov3D = a->dL_dcov3D;
+  bp.dL_ddc = a->dL_ddc; bp.dL_dsh = a->dL_dsh; bp.dL_dscale = a->dL_dscale; bp.dL_drot = a->dL_drot;
+  GSR_RC(launch_preprocess_bwd(bp, s));
+  if (a->debug) {
+    GSR_CUDA(cudaStreamSynchronize(s));
+    GSR_CUDA(cudaGetLastError());
+  }
+  return GSR_OK;
+}
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return GSR_ERR_BAD_ARG;
+  return launch_mark_visible(P, means3D, viewmatrix, present, static_cast<cudaStream_t>(stream));
+}
+
+int gsr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* stream) {
+  if (P < 0 || (P > 0 && (!points || !mean_dist2))) return GSR_ERR_BAD_ARG;
+  if (P == 0) return GSR_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* tmp = nullptr;
+  GSR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tmp), knn_temp_bytes(P), s));
+  int rc = launch_knn(P, points, mean_dist2, tmp, s);
+  cudaError_t e = cudaFreeAsync(tmp, s);
+  if (rc) return rc;
+  return (int)e;
+}
+
+int gsr_adam_step(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
+                  float grad_scale, void* stream) {
+  if (n_groups < 0 || (n_groups > 0 && !groups)) return GSR_ERR_BAD_ARG;
+  return launch_adam(groups, n_groups, beta1, beta2, eps, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, int P, int R,
+                       uint64_t* keys_sorted, uint32_t* point_list, void* stream) {
+  if (R <= 0) return GSR_OK;
+  if (!geom_buffer || !binning_buffer) return GSR_ERR_BAD_ARG;
+  GeomView g = geom_view(const_cast<char*>(geom_buffer), (size_t)P);
+  BinView b = bin_view(const_cast<char*>(binning_buffer), (size_t)R);
+  return launch_export_binning((uint32_t)R, b.items_a, g.depths, keys_sorted, point_list,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int gsr_export_image(const char* image_buffer, int W, int H, float* final_T, uint32_t* n_contrib,
+                     uint32_t* ranges, uint32_t* max_contrib, void* stream) {
+  if (!image_buffer) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)W * H;
+  const size_t T = (size_t)((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y);
+  ImageView im = image_view(const_cast<char*>(image_buffer), N, T);
+  if (final_T) GSR_CUDA(cudaMemcpyAsync(final_T, im.final_T, N * 4, cudaMemcpyDeviceToDevice, s));
+  if (n_contrib) GSR_CUDA(cudaMemcpyAsync(n_contrib, im.n_contrib, N * 4, cudaMemcpyDeviceToDevice, s));
+  if (ranges) GSR_CUDA(cudaMemcpyAsync(ranges, im.ranges, T * 8, cudaMemcpyDeviceToDevice, s));
+  if (max_contrib) GSR_CUDA(cudaMemcpyAsync(max_contrib, im.max_contrib, T * 4, cudaMemcpyDeviceToDevice, s));
+  return GSR_OK;
+}
+
+int gsr_export_geometry(const char* geom_buffer, int P, float* depths, float* means2D,
+                        float* conic_opacity, float* rgb, uint32_t* tiles_touched, uint8_t* clamped,
+                        void* stream) {
+  if (P <= 0) return GSR_OK;
+  if (!geom_buffer) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GeomView g = geom_view(const_cast<char*>(geom_buffer), (size_t)P);
+  const size_t n = (size_t)P;
+  if (depths) GSR_CUDA(cudaMemcpyAsync(depths, g.depths, n * 4, cudaMemcpyDeviceToDevice, s));
+  if (means2D) GSR_CUDA(cudaMemcpyAsync(means2D, g.means2D, n * 8, cudaMemcpyDeviceToDevice, s));
+  if (conic_opacity) GSR_CUDA(cudaMemcpyAsync(conic_opacity, g.conic_opacity, n * 16, cudaMemcpyDeviceToDevice, s));
+  if (rgb) GSR_CUDA(cudaMemcpyAsync(rgb, g.rgb, n * 12, cudaMemcpyDeviceToDevice, s));
+  if (tiles_touched) GSR_CUDA(cudaMemcpyAsync(tiles_touched, g.tiles_touched, n * 4, cudaMemcpyDeviceToDevice, s));
+  if (clamped) GSR_CUDA(cudaMemcpyAsync(clamped, g.clamped, n, cudaMemcpyDeviceToDevice, s));
+  return GSR_OK;
+}
+
+size_t gsr_sort_temp_bytes(int64_t n) { return gsr::sort_temp_bytes(n); }
+
+int gsr_sort_u64(const uint64_t* items_in, uint64_t* items_out, uint64_t* items_alt, int64_t n,
+                 int begin_bit, int end_bit, char* tmp, void* stream) {
+  if (n < 0 || begin_bit < 0 || end_bit > 64 || end_bit < begin_bit) return GSR_ERR_BAD_ARG;
+  if (n == 0) return GSR_OK;
+  if (!items_in || !items_out || !tmp) return GSR_ERR_BAD_ARG;
+  const int npass = (end_bit - begin_bit + 7) / 8;
+  if (npass > 1 && (!items_alt || items_alt == items_out)) return GSR_ERR_BAD_ARG;
+  if (items_in == ((npass & 1) ? items_out : items_alt)) return GSR_ERR_BAD_ARG;
+  uint64_t* result = nullptr;
+  return launch_sort_u64(items_in, items_out, items_alt, n, begin_bit, end_bit, tmp,
+                         static_cast<cudaStream_t>(stream), &result);
+}
+
+}  // extern "C"

@@ -1,0 +1,255 @@
+// Shared definitions of the B200-native rasterizer: scratch-buffer layouts,
+// launch bookkeeping and the small fp32 maths helpers.
+//
+// Rounding contract: the per-Gaussian / per-pixel arithmetic must reproduce the
+// reference's results bit-for-bit where they drive discrete decisions (radii,
+// tile membership, n_contrib), so the expressions below keep the
+// reference's operation order (cited per function) and are compiled with the
+// same nvcc defaults (-fmad=true, no fast-math).  Kernel structure, memory
+// layout and scheduling are new.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cfloat>
+
+#define GSR_TILE_X 16
+#define GSR_TILE_Y 16
+#define GSR_TILE_PIX 256
+
+namespace gsr {
+
+extern long long g_launch_count;  // bumped by GSR_LAUNCHED()
+#define GSR_LAUNCHED() (++gsr::g_launch_count)
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ----------------------------------------------------------------------------
+// Scratch buffer layouts (opaque to callers; the reference's counterparts are
+// GeometryState / ImageState / BinningState, rasterizer_impl.h:36-84).
+// ----------------------------------------------------------------------------
+struct GeomHeader {          // lives at the start of the geometry buffer (256 B)
+  uint32_t num_dup;          // R: total (Gaussian,tile) duplicates
+  uint32_t num_visible;      // V
+  uint32_t pad[62];
+};
+
+struct GeomView {
+  GeomHeader* hdr;
+  float* depths;             // [P]
+  float2* means2D;           // [P]
+  float4* conic_opacity;     // [P]
+  float* rgb;                // [3P]
+  uint32_t* tiles_touched;   // [P] exact number of tiles passing the opacity-aware test
+  uint8_t* clamped;          // [P] bit c set <=> channel c was clamped
+  float* acc;                // [12P] backward accumulators (see blend_bwd.cu)
+  uint64_t* sort_a;          // [P] (depth_bits<<32 | idx) ping
+  uint64_t* sort_b;          // [P] pong
+  uint32_t* dup_offsets;     // [P] exclusive scan of tiles_touched in depth order
+  char* sort_tmp;            // onesweep temp for P items
+  size_t sort_tmp_bytes;
+};
+
+struct ImageView {
+  float* final_T;            // [N]
+  uint32_t* n_contrib;       // [N]
+  float* accum_c;            // [3N] blended colour WITHOUT background (planar)
+  uint2* ranges;             // [T]
+  uint32_t* max_contrib;     // [T]
+};
+
+struct BinView {
+  uint64_t* items_a;         // [R] (tile<<32 | idx) ping
+  uint64_t* items_b;         // [R] pong
+  float4* rec_a;             // [R] {x, y, conic.x, conic.y}
+  float4* rec_b;             // [R] {conic.z, opacity, reject_power, idx bits}
+  float4* rec_c;             // [R] {r, g, b, 0}
+  char* sort_tmp;
+  size_t sort_tmp_bytes;
+};
+
+size_t sort_temp_bytes(int64_t n);
+
+template <typename T>
+__host__ __device__ inline T* carve(char*& p, size_t count) {
+  uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127);
+  T* r = reinterpret_cast<T*>(a);
+  p = reinterpret_cast<char*>(r + count);
+  return r;
+}
+
+inline GeomView geom_view(char* base, size_t P) {
+  GeomView g;
+  char* p = base;
+  g.hdr = carve<GeomHeader>(p, 1);
+  g.depths = carve<float>(p, P);
+  g.means2D = carve<float2>(p, P);
+  g.conic_opacity = carve<float4>(p, P);
+  g.rgb = carve<float>(p, 3 * P);
+  g.tiles_touched = carve<uint32_t>(p, P);
+  g.clamped = carve<uint8_t>(p, P);
+  g.acc = carve<float>(p, 12 * P);
+  g.sort_a = carve<uint64_t>(p, P);
+  g.sort_b = carve<uint64_t>(p, P);
+  g.dup_offsets = carve<uint32_t>(p, P);
+  g.sort_tmp_bytes = sort_temp_bytes((int64_t)P);
+  g.sort_tmp = carve<char>(p, g.sort_tmp_bytes);
+  return g;
+}
+inline size_t geom_bytes(size_t P) {
+  GeomView g = geom_view(nullptr, P);
+  return reinterpret_cast<size_t>(g.sort_tmp) + g.sort_tmp_bytes + 128;
+}
+
+inline ImageView image_view(char* base, size_t N, size_t T) {
+  ImageView v;
+  char* p = base;
+  v.final_T = carve<float>(p, N);
+  v.n_contrib = carve<uint32_t>(p, N);
+  v.accum_c = carve<float>(p, 3 * N);
+  v.ranges = carve<uint2>(p, T);
+  v.max_contrib = carve<uint32_t>(p, T);
+  return v;
+}
+inline size_t image_bytes(size_t N, size_t T) {
+  ImageView v = image_view(nullptr, N, T);
+  return reinterpret_cast<size_t>(v.max_contrib) + T * 4 + 128;
+}
+
+inline BinView bin_view(char* base, size_t R) {
+  BinView b;
+  char* p = base;
+  size_t Rp = R + 8;  // slack so bulk copies may round up to 16 B multiples
+  b.items_a = carve<uint64_t>(p, Rp);
+  b.items_b = carve<uint64_t>(p, Rp);
+  b.rec_a = carve<float4>(p, Rp);
+  b.rec_b = carve<float4>(p, Rp);
+  b.rec_c = carve<float4>(p, Rp);
+  b.sort_tmp_bytes = sort_temp_bytes((int64_t)R);
+  b.sort_tmp = carve<char>(p, b.sort_tmp_bytes);
+  return b;
+}
+inline size_t bin_bytes(size_t R) {
+  BinView b = bin_view(nullptr, R);
+  return reinterpret_cast<size_t>(b.sort_tmp) + b.sort_tmp_bytes + 128;
+}
+
+// ----------------------------------------------------------------------------
+// fp32 helpers with the reference's operation order
+// ----------------------------------------------------------------------------
+
+// column-major 3x3 (m[c][r]), same storage convention the reference gets from glm
+struct M3 {
+  float m[3][3];
+  __device__ __forceinline__ float* operator[](int c) { return m[c]; }
+  __device__ __forceinline__ const float* operator[](int c) const { return m[c]; }
+};
+
+__device__ __forceinline__ M3 m3_make(float x1, float y1, float z1, float x2, float y2,
+                                      float z2, float x3, float y3, float z3) {
+  M3 r;
+  r[0][0] = x1; r[0][1] = y1; r[0][2] = z1;
+  r[1][0] = x2; r[1][1] = y2; r[1][2] = z2;
+  r[2][0] = x3; r[2][1] = y3; r[2][2] = z3;
+  return r;
+}
+__device__ __forceinline__ M3 m3_transpose(const M3& a) {
+  return m3_make(a[0][0], a[1][0], a[2][0], a[0][1], a[1][1], a[2][1], a[0][2], a[1][2],
+                 a[2][2]);
+}
+// (a*b)[c][r] = a[0][r]*b[c][0] + a[1][r]*b[c][1] + a[2][r]*b[c][2]   (left to right)
+__device__ __forceinline__ M3 m3_mul(const M3& a, const M3& b) {
+  M3 r;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      r[c][q] = a[0][q] * b[c][0] + a[1][q] * b[c][1] + a[2][q] * b[c][2];
+  return r;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) {
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+
+// view-space point: reference transformPoint4x3 (auxiliary.h:68-77)
+__device__ __forceinline__ float3 xform_4x3(const float3& p, const float* m) {
+  float3 t = {
+      m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+      m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+      m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+  };
+  return t;
+}
+// homogeneous point: reference transformPoint4x4 (auxiliary.h:79-88)
+__device__ __forceinline__ float4 xform_4x4(const float3& p, const float* m) {
+  float4 t = {m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+              m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+              m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+              m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]};
+  return t;
+}
+
+// NDC -> pixel centre; evaluated in double like the reference (auxiliary.h:33-36)
+__device__ __forceinline__ float ndc_to_pix(float v, int S) {
+  return ((v + 1.0) * S - 1.0) * 0.5;
+}
+
+// tile rectangle of a disc (reference getRect, auxiliary.h:38-51)
+__device__ __forceinline__ void tile_rect(const float2 p, int max_radius, int gx, int gy,
+                                          uint2& rect_min, uint2& rect_max) {
+  rect_min = {(unsigned)min(gx, max((int)0, (int)((p.x - max_radius) / GSR_TILE_X))),
+              (unsigned)min(gy, max((int)0, (int)((p.y - max_radius) / GSR_TILE_Y)))};
+  rect_max = {(unsigned)min(gx, max((int)0, (int)((p.x + max_radius + GSR_TILE_X - 1) / GSR_TILE_X))),
+              (unsigned)min(gy, max((int)0, (int)((p.y + max_radius + GSR_TILE_Y - 1) / GSR_TILE_Y)))};
+}
+
+// Opacity-aware tile test of the Taming-3DGS rasterizer: smallest value of the
+// Gaussian exponent 0.5*d^T*Conic*d over the pixel-centre rectangle of tile
+// (tx,ty) (reference max_contrib_power_rect_gaussian_float<15,15> and
+// evaluate_opacity_factor, rasterizer_impl.cu:59-118).  The tile is kept iff the
+// returned value <= logf(opacity * 255)  (rasterizer_impl.cu:169-170,193).
+__device__ __forceinline__ float tile_min_power(const float4 co, const float2 mean, int tx,
+                                                int ty) {
+  const float rminx = (float)(tx * GSR_TILE_X), rminy = (float)(ty * GSR_TILE_Y);
+  const float rmaxx = (float)((tx + 1) * GSR_TILE_X - 1), rmaxy = (float)((ty + 1) * GSR_TILE_Y - 1);
+  const float PW = 15.0f, PH = 15.0f;
+
+  const float x_min_diff = rminx - mean.x;
+  const float x_left = x_min_diff > 0.0f;
+  const float not_in_x_range = x_left + (mean.x > rmaxx);
+  const float y_min_diff = rminy - mean.y;
+  const float y_above = y_min_diff > 0.0f;
+  const float not_in_y_range = y_above + (mean.y > rmaxy);
+
+  float result = 0.0f;
+  if ((not_in_y_range + not_in_x_range) > 0.0f) {
+    const float px = x_left * rminx + (1.0f - x_left) * rmaxx;
+    const float py = y_above * rminy + (1.0f - y_above) * rmaxy;
+    const float dx = copysign(PW, x_min_diff);
+    const float dy = copysign(PH, y_min_diff);
+    const float diffx = mean.x - px;
+    const float diffy = mean.y - py;
+    const float rcp_dxdxcox = __frcp_rn(15 * 15 * co.x);
+    const float rcp_dydycoz = __frcp_rn(15 * 15 * co.z);
+    const float tx_ = not_in_y_range * __saturatef((dx * co.x * diffx + dx * co.y * diffy) * rcp_dxdxcox);
+    const float ty_ = not_in_x_range * __saturatef((dy * co.y * diffx + dy * co.z * diffy) * rcp_dydycoz);
+    const float mx = px + tx_ * dx, my = py + ty_ * dy;
+    const float ddx = mean.x - mx, ddy = mean.y - my;
+    result = 0.5f * (co.x * ddx * ddx + co.z * ddy * ddy) + co.y * ddx * ddy;
+  }
+  return result;
+}
+
+__device__ __forceinline__ float opacity_power_threshold(float opacity) {
+  const float opacity_threshold = 1.0f / 255.0f;
+  return logf(opacity / opacity_threshold);
+}
+
+// ---- launch helpers implemented across the .cu files ------------------------
+size_t scan_temp_bytes(int64_t n);
+int launch_scan_gather(const uint32_t* counts, const uint64_t* order_items, int64_t n,
+                       uint32_t* offsets, uint32_t* total_out, char* tmp, cudaStream_t s);
+int launch_sort_u64(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t n, int begin_bit,
+                    int end_bit, char* tmp, cudaStream_t s, uint64_t** result);
+
+}  // namespace gsr

@@ -1,0 +1,90 @@
+// Parameter blocks and launchers shared between the C-ABI orchestration
+// (gsr_capi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gsr_capi.h"
+
+namespace gsr {
+struct PreprocessParams {
+  int P, D, M, W, H;
+  const float* means3D;
+  const float* scales;
+  const float* rotations;
+  const float* opacities;
+  const float* dc;
+  const float* shs;
+  const float* cov3D_precomp;
+  const float* colors_precomp;
+  float scale_modifier;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  int grid_x, grid_y;
+  int prefiltered;
+  int vec_ok;
+  int* radii;
+  float* depths;
+  float2* means2D;
+  float4* conic_opacity;
+  float* rgb;
+  uint8_t* clamped;
+  uint32_t* tiles_touched;
+  uint64_t* sort_items;
+  uint32_t* num_visible;
+};
+struct PreBwdParams {
+  int P, D, M;
+  const float* means3D;
+  const int* radii;
+  const float* dc;
+  const float* shs;
+  const uint8_t* clamped;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D_precomp;
+  float scale_modifier;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  float focal_x, focal_y, tan_fovx, tan_fovy;
+  const float* acc;
+  float* dL_dmean2D;
+  float* dL_dconic;
+  float* dL_dopacity;
+  float* dL_dcolor;
+  float* dL_dmean3D;
+  float* dL_dcov3D;
+  float* dL_ddc;
+  float* dL_dsh;
+  float* dL_dscale;
+  float* dL_drot;
+};
+
+int launch_preprocess(const PreprocessParams& p, cudaStream_t s);
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
+                        cudaStream_t s);
+int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
+                const uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
+                const int* radii, int grid_x, int grid_y, uint64_t* items, cudaStream_t s);
+int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
+                    const float4* conic_opacity, const float* colors, uint2* ranges, uint32_t T,
+                    float4* rec_a, float4* rec_b, float4* rec_c, cudaStream_t s);
+int launch_export_binning(uint32_t R, const uint64_t* sorted, const float* depths, uint64_t* keys,
+                          uint32_t* point_list, cudaStream_t s);
+int launch_blend_fwd(int W, int H, const uint2* ranges, const float4* rec_a, const float4* rec_b,
+                     const float4* rec_c, const float* bg, float* out_color, float* final_T,
+                     uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s);
+int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* max_contrib,
+                     const float4* rec_a, const float4* rec_b, const float4* rec_c, const float* bg,
+                     const float* final_T, const uint32_t* n_contrib, const float* accum_c,
+                     const float* dL_dpix, float* acc, cudaStream_t s);
+int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s);
+int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
+                float grad_scale, cudaStream_t s);
+size_t knn_temp_bytes(int64_t P);
+int launch_knn(int P, const float* points, float* mean_dist2, char* tmp, cudaStream_t s);
+
+}  // namespace gsr

@@ -1,0 +1,364 @@
+// Backward per-Gaussian pass, one kernel: chains the 2D gradients produced by the
+// blend backward (dL/dmean2D, dL/dconic, dL/dopacity, dL/dcolor) to the 3D mean,
+// scale, rotation, SH coefficients and (optionally) the 3D covariance.
+// Replaces the reference's computeCov2DCUDA + BACKWARD::preprocessCUDA pair
+// (backward.cu:159-313, 402-461) and the shim's blanket zero-fill of ten gradient
+// tensors (src/rasterize_points.cu:157-166): every output row is written exactly
+// once here — zeros for Gaussians that were not rendered — and dL/dcov3D never
+// round-trips through HBM unless the caller asks for it.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gsr_common.cuh"
+#include "gsr_params.cuh"
+
+namespace gsr {
+
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__device__ const float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                   -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                   0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                   -0.5900435899266435f};
+
+struct V3 {
+  float x, y, z;
+};
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3& operator+=(V3& a, V3 b) {
+  a.x += b.x; a.y += b.y; a.z += b.z;
+  return a;
+}
+__device__ __forceinline__ float dotv(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+__device__ __forceinline__ void store3(float* p, size_t i, V3 v) {
+  p[3 * i + 0] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z;
+}
+
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.P) return;
+  const size_t i = (size_t)idx;
+  const int M = a.M;
+
+  if (!(a.radii[idx] > 0)) {
+    // not rendered: all gradients are zero
+    store3(a.dL_dmean2D, i, {0.f, 0.f, 0.f});
+    if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.dL_dopacity[i] = 0.f;
+    store3(a.dL_dcolor, i, {0.f, 0.f, 0.f});
+    store3(a.dL_dmean3D, i, {0.f, 0.f, 0.f});
+    if (a.dL_dcov3D)
+      for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * i + k] = 0.f;
+    store3(a.dL_ddc, i, {0.f, 0.f, 0.f});
+    if (a.dL_dsh)
+      for (int k = 0; k < 3 * M; ++k) a.dL_dsh[(size_t)3 * M * i + k] = 0.f;
+    store3(a.dL_dscale, i, {0.f, 0.f, 0.f});
+    reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+
+  // ---- accumulated 2D gradients ------------------------------------------------
+  const float4 acc0 = reinterpret_cast<const float4*>(a.acc)[3 * i + 0];
+  const float4 acc1 = reinterpret_cast<const float4*>(a.acc)[3 * i + 1];
+  const float4 acc2 = reinterpret_cast<const float4*>(a.acc)[3 * i + 2];
+  const float dmean2D_x = acc0.x, dmean2D_y = acc0.y;
+  const float3 dL_dconic = {acc0.z, acc0.w, acc1.x};  // (x, y, w) of the 2x2 conic gradient
+  const float dopacity = acc1.y;
+  V3 dL_dRGB = {acc1.z, acc1.w, acc2.x};
+
+  store3(a.dL_dmean2D, i, {dmean2D_x, dmean2D_y, 0.f});
+  if (a.dL_dconic)
+    reinterpret_cast<float4*>(a.dL_dconic)[i] = make_float4(dL_dconic.x, dL_dconic.y, 0.f, dL_dconic.z);
+  a.dL_dopacity[i] = dopacity;
+  store3(a.dL_dcolor, i, dL_dRGB);
+
+  const float3 mean = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
+
+  // ---- 3D covariance (recomputed rather than stored by the forward) -------------
+  float cov3D[6];
+  float3 scale = {0.f, 0.f, 0.f};
+  float4 q = {0.f, 0.f, 0.f, 0.f};
+  M3 R, Mm;
+  if (a.scales != nullptr) {
+    scale = {a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2]};
+    q = reinterpret_cast<const float4*>(a.rotations)[i];
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
+                2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
+                2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y));
+    M3 S = m3_make(1.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.0f);
+    S[0][0] = a.scale_modifier * scale.x;
+    S[1][1] = a.scale_modifier * scale.y;
+    S[2][2] = a.scale_modifier * scale.z;
+    Mm = m3_mul(S, R);
+    M3 Sigma = m3_mul(m3_transpose(Mm), Mm);
+    cov3D[0] = Sigma[0][0]; cov3D[1] = Sigma[0][1]; cov3D[2] = Sigma[0][2];
+    cov3D[3] = Sigma[1][1]; cov3D[4] = Sigma[1][2]; cov3D[5] = Sigma[2][2];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cov3D[k] = a.cov3D_precomp[6 * i + k];
+  }
+
+  // ---- conic -> cov2D -> cov3D / mean  (reference computeCov2DCUDA, backward.cu:159-313)
+  float3 t = xform_4x3(mean, a.view);
+  const float h_x = a.focal_x, h_y = a.focal_y;
+  const float limx = 1.3f * a.tan_fovx;
+  const float limy = 1.3f * a.tan_fovy;
+  const float txtz = t.x / t.z;
+  const float tytz = t.y / t.z;
+  t.x = min(limx, max(-limx, txtz)) * t.z;
+  t.y = min(limy, max(-limy, tytz)) * t.z;
+  const float x_grad_mul = txtz < -limx || txtz > limx ? 0 : 1;
+  const float y_grad_mul = tytz < -limy || tytz > limy ? 0 : 1;
+
+  M3 J = m3_make(h_x / t.z, 0.0f, -(h_x * t.x) / (t.z * t.z), 0.0f, h_y / t.z,
+                 -(h_y * t.y) / (t.z * t.z), 0, 0, 0);
+  const float* vm = a.view;
+  M3 Wm = m3_make(vm[0], vm[4], vm[8], vm[1], vm[5], vm[9], vm[2], vm[6], vm[10]);
+  M3 Vrk = m3_make(cov3D[0], cov3D[1], cov3D[2], cov3D[1], cov3D[3], cov3D[4], cov3D[2], cov3D[4],
+                   cov3D[5]);
+  M3 T = m3_mul(Wm, J);
+  M3 cov2D = m3_mul(m3_mul(m3_transpose(T), m3_transpose(Vrk)), T);
+
+  float aa = cov2D[0][0] += 0.3f;
+  float bb = cov2D[0][1];
+  float cc = cov2D[1][1] += 0.3f;
+
+  float denom = aa * cc - bb * bb;
+  float dL_da = 0, dL_db = 0, dL_dc = 0;
+  float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+
+  float dcov[6];
+  if (denom2inv != 0) {
+    dL_da = denom2inv * (-cc * cc * dL_dconic.x + 2 * bb * cc * dL_dconic.y + (denom - aa * cc) * dL_dconic.z);
+    dL_dc = denom2inv * (-aa * aa * dL_dconic.z + 2 * aa * bb * dL_dconic.y + (denom - aa * cc) * dL_dconic.x);
+    dL_db = denom2inv * 2 * (bb * cc * dL_dconic.x - (denom + 2 * bb * bb) * dL_dconic.y + aa * bb * dL_dconic.z);
+
+    dcov[0] = (T[0][0] * T[0][0] * dL_da + T[0][0] * T[1][0] * dL_db + T[1][0] * T[1][0] * dL_dc);
+    dcov[3] = (T[0][1] * T[0][1] * dL_da + T[0][1] * T[1][1] * dL_db + T[1][1] * T[1][1] * dL_dc);
+    dcov[5] = (T[0][2] * T[0][2] * dL_da + T[0][2] * T[1][2] * dL_db + T[1][2] * T[1][2] * dL_dc);
+    dcov[1] = 2 * T[0][0] * T[0][1] * dL_da + (T[0][0] * T[1][1] + T[0][1] * T[1][0]) * dL_db +
+              2 * T[1][0] * T[1][1] * dL_dc;
+    dcov[2] = 2 * T[0][0] * T[0][2] * dL_da + (T[0][0] * T[1][2] + T[0][2] * T[1][0]) * dL_db +
+              2 * T[1][0] * T[1][2] * dL_dc;
+    dcov[4] = 2 * T[0][2] * T[0][1] * dL_da + (T[0][1] * T[1][2] + T[0][2] * T[1][1]) * dL_db +
+              2 * T[1][1] * T[1][2] * dL_dc;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dcov[k] = 0;
+  }
+  if (a.dL_dcov3D) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * i + k] = dcov[k];
+  }
+
+  float dL_dT00 = 2 * (T[0][0] * Vrk[0][0] + T[0][1] * Vrk[0][1] + T[0][2] * Vrk[0][2]) * dL_da +
+                  (T[1][0] * Vrk[0][0] + T[1][1] * Vrk[0][1] + T[1][2] * Vrk[0][2]) * dL_db;
+  float dL_dT01 = 2 * (T[0][0] * Vrk[1][0] + T[0][1] * Vrk[1][1] + T[0][2] * Vrk[1][2]) * dL_da +
+                  (T[1][0] * Vrk[1][0] + T[1][1] * Vrk[1][1] + T[1][2] * Vrk[1][2]) * dL_db;
+  float dL_dT02 = 2 * (T[0][0] * Vrk[2][0] + T[0][1] * Vrk[2][1] + T[0][2] * Vrk[2][2]) * dL_da +
+                  (T[1][0] * Vrk[2][0] + T[1][1] * Vrk[2][1] + T[1][2] * Vrk[2][2]) * dL_db;
+  float dL_dT10 = 2 * (T[1][0] * Vrk[0][0] + T[1][1] * Vrk[0][1] + T[1][2] * Vrk[0][2]) * dL_dc +
+                  (T[0][0] * Vrk[0][0] + T[0][1] * Vrk[0][1] + T[0][2] * Vrk[0][2]) * dL_db;
+  float dL_dT11 = 2 * (T[1][0] * Vrk[1][0] + T[1][1] * Vrk[1][1] + T[1][2] * Vrk[1][2]) * dL_dc +
+                  (T[0][0] * Vrk[1][0] + T[0][1] * Vrk[1][1] + T[0][2] * Vrk[1][2]) * dL_db;
+  float dL_dT12 = 2 * (T[1][0] * Vrk[2][0] + T[1][1] * Vrk[2][1] + T[1][2] * Vrk[2][2]) * dL_dc +
+                  (T[0][0] * Vrk[2][0] + T[0][1] * Vrk[2][1] + T[0][2] * Vrk[2][2]) * dL_db;
+
+  float dL_dJ00 = Wm[0][0] * dL_dT00 + Wm[0][1] * dL_dT01 + Wm[0][2] * dL_dT02;
+  float dL_dJ02 = Wm[2][0] * dL_dT00 + Wm[2][1] * dL_dT01 + Wm[2][2] * dL_dT02;
+  float dL_dJ11 = Wm[1][0] * dL_dT10 + Wm[1][1] * dL_dT11 + Wm[1][2] * dL_dT12;
+  float dL_dJ12 = Wm[2][0] * dL_dT10 + Wm[2][1] * dL_dT11 + Wm[2][2] * dL_dT12;
+
+  float tz = 1.f / t.z;
+  float tz2 = tz * tz;
+  float tz3 = tz2 * tz;
+
+  float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+  float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+  float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 +
+                 (2 * h_y * t.y) * tz3 * dL_dJ12;
+
+  // transformVec4x3Transpose (auxiliary.h:101-110)
+  V3 dL_dmean_total = {vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz,
+                       vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz,
+                       vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz};
+
+  // ---- screen-space mean gradient -> 3D mean (reference preprocessCUDA, backward.cu:427-449)
+  {
+    const float* proj = a.proj;
+    const float3 m = mean;
+    float4 m_hom = xform_4x4(m, proj);
+    float m_w = 1.0f / (m_hom.w + 0.0000001f);
+    float mul1 = (proj[0] * m.x + proj[4] * m.y + proj[8] * m.z + proj[12]) * m_w * m_w;
+    float mul2 = (proj[1] * m.x + proj[5] * m.y + proj[9] * m.z + proj[13]) * m_w * m_w;
+    V3 dL_dmean;
+    dL_dmean.x = (proj[0] * m_w - proj[3] * mul1) * dmean2D_x + (proj[1] * m_w - proj[3] * mul2) * dmean2D_y;
+    dL_dmean.y = (proj[4] * m_w - proj[7] * mul1) * dmean2D_x + (proj[5] * m_w - proj[7] * mul2) * dmean2D_y;
+    dL_dmean.z = (proj[8] * m_w - proj[11] * mul1) * dmean2D_x + (proj[9] * m_w - proj[11] * mul2) * dmean2D_y;
+    dL_dmean_total += dL_dmean;
+  }
+
+  // ---- colour -> SH coefficients and view direction (backward.cu:27-154) --------
+  V3 out_ddc = {0.f, 0.f, 0.f};
+  if (a.shs != nullptr) {
+    // never index past the coefficients the caller provided
+    const int deg = min(a.D, M >= 15 ? 3 : (M >= 8 ? 2 : (M >= 3 ? 1 : 0)));
+    const V3 campos = {a.campos[0], a.campos[1], a.campos[2]};
+    const V3 dir_orig = {mean.x - campos.x, mean.y - campos.y, mean.z - campos.z};
+    const float len = sqrtf(dotv(dir_orig, dir_orig));
+    const V3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
+    const V3* sh = reinterpret_cast<const V3*>(a.shs) + i * M;
+    V3* dL_dsh = reinterpret_cast<V3*>(a.dL_dsh) + i * M;
+
+    const uint8_t cl = a.clamped[idx];
+    dL_dRGB.x *= (cl & 1) ? 0 : 1;
+    dL_dRGB.y *= (cl & 2) ? 0 : 1;
+    dL_dRGB.z *= (cl & 4) ? 0 : 1;
+
+    V3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+    const float x = dir.x, y = dir.y, z = dir.z;
+
+    float dRGBdsh0 = SH_C0;
+    out_ddc = dRGBdsh0 * dL_dRGB;
+    int written = 0;
+    if (deg > 0) {
+      float dRGBdsh1 = -SH_C1 * y;
+      float dRGBdsh2 = SH_C1 * z;
+      float dRGBdsh3 = -SH_C1 * x;
+      dL_dsh[0] = dRGBdsh1 * dL_dRGB;
+      dL_dsh[1] = dRGBdsh2 * dL_dRGB;
+      dL_dsh[2] = dRGBdsh3 * dL_dRGB;
+      written = 3;
+      dRGBdx = -SH_C1 * sh[2];
+      dRGBdy = -SH_C1 * sh[0];
+      dRGBdz = SH_C1 * sh[1];
+
+      if (deg > 1) {
+        float xx = x * x, yy = y * y, zz = z * z;
+        float xy = x * y, yz = y * z, xz = x * z;
+        float dRGBdsh4 = SH_C2[0] * xy;
+        float dRGBdsh5 = SH_C2[1] * yz;
+        float dRGBdsh6 = SH_C2[2] * (2.f * zz - xx - yy);
+        float dRGBdsh7 = SH_C2[3] * xz;
+        float dRGBdsh8 = SH_C2[4] * (xx - yy);
+        dL_dsh[3] = dRGBdsh4 * dL_dRGB;
+        dL_dsh[4] = dRGBdsh5 * dL_dRGB;
+        dL_dsh[5] = dRGBdsh6 * dL_dRGB;
+        dL_dsh[6] = dRGBdsh7 * dL_dRGB;
+        dL_dsh[7] = dRGBdsh8 * dL_dRGB;
+        written = 8;
+
+        dRGBdx += SH_C2[0] * y * sh[3] + SH_C2[2] * 2.f * -x * sh[5] + SH_C2[3] * z * sh[6] +
+                  SH_C2[4] * 2.f * x * sh[7];
+        dRGBdy += SH_C2[0] * x * sh[3] + SH_C2[1] * z * sh[4] + SH_C2[2] * 2.f * -y * sh[5] +
+                  SH_C2[4] * 2.f * -y * sh[7];
+        dRGBdz += SH_C2[1] * y * sh[4] + SH_C2[2] * 2.f * 2.f * z * sh[5] + SH_C2[3] * x * sh[6];
+
+        if (deg > 2) {
+          float dRGBdsh9 = SH_C3[0] * y * (3.f * xx - yy);
+          float dRGBdsh10 = SH_C3[1] * xy * z;
+          float dRGBdsh11 = SH_C3[2] * y * (4.f * zz - xx - yy);
+          float dRGBdsh12 = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+          float dRGBdsh13 = SH_C3[4] * x * (4.f * zz - xx - yy);
+          float dRGBdsh14 = SH_C3[5] * z * (xx - yy);
+          float dRGBdsh15 = SH_C3[6] * x * (xx - 3.f * yy);
+          dL_dsh[8] = dRGBdsh9 * dL_dRGB;
+          dL_dsh[9] = dRGBdsh10 * dL_dRGB;
+          dL_dsh[10] = dRGBdsh11 * dL_dRGB;
+          dL_dsh[11] = dRGBdsh12 * dL_dRGB;
+          dL_dsh[12] = dRGBdsh13 * dL_dRGB;
+          dL_dsh[13] = dRGBdsh14 * dL_dRGB;
+          dL_dsh[14] = dRGBdsh15 * dL_dRGB;
+          written = 15;
+
+          dRGBdx += (SH_C3[0] * sh[8] * 3.f * 2.f * xy + SH_C3[1] * sh[9] * yz +
+                     SH_C3[2] * sh[10] * -2.f * xy + SH_C3[3] * sh[11] * -3.f * 2.f * xz +
+                     SH_C3[4] * sh[12] * (-3.f * xx + 4.f * zz - yy) + SH_C3[5] * sh[13] * 2.f * xz +
+                     SH_C3[6] * sh[14] * 3.f * (xx - yy));
+          dRGBdy += (SH_C3[0] * sh[8] * 3.f * (xx - yy) + SH_C3[1] * sh[9] * xz +
+                     SH_C3[2] * sh[10] * (-3.f * yy + 4.f * zz - xx) +
+                     SH_C3[3] * sh[11] * -3.f * 2.f * yz + SH_C3[4] * sh[12] * -2.f * xy +
+                     SH_C3[5] * sh[13] * -2.f * yz + SH_C3[6] * sh[14] * -3.f * 2.f * xy);
+          dRGBdz += (SH_C3[1] * sh[9] * xy + SH_C3[2] * sh[10] * 4.f * 2.f * yz +
+                     SH_C3[3] * sh[11] * 3.f * (2.f * zz - xx - yy) +
+                     SH_C3[4] * sh[12] * 4.f * 2.f * xz + SH_C3[5] * sh[13] * (xx - yy));
+        }
+      }
+    }
+    for (int k = written; k < M; ++k) dL_dsh[k] = {0.f, 0.f, 0.f};
+
+    V3 dL_ddir = {dotv(dRGBdx, dL_dRGB), dotv(dRGBdy, dL_dRGB), dotv(dRGBdz, dL_dRGB)};
+    // dnormvdv (auxiliary.h:122-138)
+    {
+      const V3 v = dir_orig, dv = dL_ddir;
+      float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+      float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+      V3 r;
+      r.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+      r.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+      r.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+      dL_dmean_total += r;
+    }
+  } else if (a.dL_dsh) {
+    for (int k = 0; k < 3 * M; ++k) a.dL_dsh[(size_t)3 * M * i + k] = 0.f;
+  }
+  store3(a.dL_ddc, i, out_ddc);
+  store3(a.dL_dmean3D, i, dL_dmean_total);
+
+  // ---- cov3D -> scale, rotation (reference computeCov3D backward, backward.cu:317-397)
+  if (a.scales != nullptr) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    const V3 s = {a.scale_modifier * scale.x, a.scale_modifier * scale.y, a.scale_modifier * scale.z};
+    M3 dL_dSigma = m3_make(dcov[0], 0.5f * dcov[1], 0.5f * dcov[2], 0.5f * dcov[1], dcov[3],
+                           0.5f * dcov[4], 0.5f * dcov[2], 0.5f * dcov[4], dcov[5]);
+    M3 M2;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) M2[c][k] = Mm[c][k] * 2.0f;
+    M3 dL_dM = m3_mul(M2, dL_dSigma);
+    M3 Rt = m3_transpose(R);
+    M3 dL_dMt = m3_transpose(dL_dM);
+
+    V3 dscale;
+    dscale.x = dot3(Rt[0], dL_dMt[0]);
+    dscale.y = dot3(Rt[1], dL_dMt[1]);
+    dscale.z = dot3(Rt[2], dL_dMt[2]);
+    store3(a.dL_dscale, i, dscale);
+
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dL_dMt[0][k] *= s.x;
+      dL_dMt[1][k] *= s.y;
+      dL_dMt[2][k] *= s.z;
+    }
+    float4 dL_dq;
+    dL_dq.x = 2 * z * (dL_dMt[0][1] - dL_dMt[1][0]) + 2 * y * (dL_dMt[2][0] - dL_dMt[0][2]) +
+              2 * x * (dL_dMt[1][2] - dL_dMt[2][1]);
+    dL_dq.y = 2 * y * (dL_dMt[1][0] + dL_dMt[0][1]) + 2 * z * (dL_dMt[2][0] + dL_dMt[0][2]) +
+              2 * r * (dL_dMt[1][2] - dL_dMt[2][1]) - 4 * x * (dL_dMt[2][2] + dL_dMt[1][1]);
+    dL_dq.z = 2 * x * (dL_dMt[1][0] + dL_dMt[0][1]) + 2 * r * (dL_dMt[2][0] - dL_dMt[0][2]) +
+              2 * z * (dL_dMt[1][2] + dL_dMt[2][1]) - 4 * y * (dL_dMt[2][2] + dL_dMt[0][0]);
+    dL_dq.w = 2 * r * (dL_dMt[0][1] - dL_dMt[1][0]) + 2 * x * (dL_dMt[2][0] + dL_dMt[0][2]) +
+              2 * y * (dL_dMt[1][2] + dL_dMt[2][1]) - 4 * z * (dL_dMt[1][1] + dL_dMt[0][0]);
+    reinterpret_cast<float4*>(a.dL_drot)[i] = dL_dq;
+  } else {
+    store3(a.dL_dscale, i, {0.f, 0.f, 0.f});
+    reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s) {
+  if (p.P <= 0) return 0;
+  preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace gsr

@@ -1,0 +1,167 @@
+/*
+ * gsr_capi.h — C ABI of the B200-native Gaussian-splatting rasterizer hot path.
+ *
+ * This is the drop-in boundary for GSDF-SLAM's mapping hot path.  Each entry
+ * point below replaces one reference interface (file:line under /root/reference):
+ *
+ *   gsr_forward        <- CudaRasterizer::Rasterizer::forward   cuda_rasterizer/rasterizer.h:27-55
+ *                         (called by RasterizeGaussiansCUDA,     src/rasterize_points.cu:38-117)
+ *   gsr_backward       <- CudaRasterizer::Rasterizer::backward  cuda_rasterizer/rasterizer.h:57-94
+ *                         (called by RasterizeGaussiansBackwardCUDA, src/rasterize_points.cu:120-205)
+ *   gsr_mark_visible   <- CudaRasterizer::Rasterizer::markVisible cuda_rasterizer/rasterizer.h:22-26
+ *                         (called by markVisible,                src/rasterize_points.cu:207-226)
+ *   gsr_knn_mean_dist2 <- SimpleKNN::knn                          submodules/simple-knn/simple_knn.h:17
+ *                         (called by distCUDA2,                  submodules/simple-knn/spatial.cu:15-26)
+ *   gsr_adam_step      <- torch::optim::Adam::step on the 6 parameter groups
+ *                         (src/gaussian_model.cpp:319-352, stepped at src/gaussian_mapper.cpp:465)
+ *   gsr_export_*       <- test/debug decoders of the opaque scratch buffers (the
+ *                         reference's GeometryState/BinningState/ImageState::fromChunk,
+ *                         cuda_rasterizer/rasterizer_impl.cu:274-343)
+ *
+ * Conventions (same as the reference): every pointer is a DEVICE pointer to
+ * contiguous fp32/int32 data unless stated; viewmatrix/projmatrix are stored
+ * transposed (element m[4*col+row]); optional inputs are NULL when absent.
+ * Scratch memory is obtained through C callbacks — the C analogue of the
+ * reference's std::function<char*(size_t)> (rasterizer.h:28-31).
+ * All functions return 0 on success, a negative gsr error code or a positive
+ * cudaError_t otherwise; nothing throws across this ABI.  All work is enqueued
+ * on `stream` (a cudaStream_t); gsr_forward synchronises that stream once
+ * internally to size the per-duplicate buffers.
+ */
+#ifndef GSR_CAPI_H_
+#define GSR_CAPI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_OK 0
+#define GSR_ERR_BAD_ARG (-1)
+#define GSR_ERR_ALLOC (-2)
+#define GSR_ERR_NO_DEVICE (-3)
+
+/* Resizes the caller-owned scratch buffer to `bytes` and returns its device address. */
+typedef char* (*gsr_resize_fn)(void* user, size_t bytes);
+
+typedef struct gsr_forward_args {
+  int P;              /* number of Gaussians */
+  int D;              /* active SH degree (0..3) */
+  int M;              /* number of "rest" SH coefficients per Gaussian in `shs` (0 or 15) */
+  int W, H;           /* image size */
+  const float* background;     /* [3] */
+  const float* means3D;        /* [P,3] */
+  const float* dc;             /* [P,3]   SH band 0 */
+  const float* shs;            /* [P,M,3] or NULL */
+  const float* colors_precomp; /* [P,3] or NULL */
+  const float* opacities;      /* [P] */
+  const float* scales;         /* [P,3] or NULL (then cov3D_precomp) */
+  float scale_modifier;
+  const float* rotations;      /* [P,4] or NULL */
+  const float* cov3D_precomp;  /* [P,6] or NULL */
+  const float* viewmatrix;     /* [16] */
+  const float* projmatrix;     /* [16] */
+  const float* campos;         /* [3] */
+  float tan_fovx, tan_fovy;
+  int prefiltered;
+  int debug;                   /* !=0: synchronise + check after the call */
+  float* out_color;            /* [3,H,W] out */
+  int* radii;                  /* [P] out */
+  gsr_resize_fn geom_resize;    void* geom_user;
+  gsr_resize_fn binning_resize; void* binning_user;
+  gsr_resize_fn image_resize;   void* image_user;
+  gsr_resize_fn sample_resize;  void* sample_user;
+  void* stream;                /* cudaStream_t */
+  int* num_rendered;           /* host out: number of (Gaussian,tile) duplicates R */
+  int* num_buckets;            /* host out: kept for API parity (number of 32-splat buckets) */
+} gsr_forward_args;
+
+typedef struct gsr_backward_args {
+  int P, D, M, R, B, W, H;
+  const float* background;
+  const float* means3D;
+  const float* dc;
+  const float* shs;
+  const float* colors_precomp;
+  const float* opacities;      /* unused by the maths; kept for symmetry (may be NULL) */
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* campos;
+  float tan_fovx, tan_fovy;
+  const int* radii;
+  char* geom_buffer;           /* the four buffers filled by gsr_forward */
+  char* binning_buffer;
+  char* image_buffer;
+  char* sample_buffer;
+  const float* dL_dpix;        /* [3,H,W] */
+  /* outputs: fully written by the callee (no pre-zeroing needed) */
+  float* dL_dmean2D;           /* [P,3] */
+  float* dL_dconic;            /* [P,4] or NULL */
+  float* dL_dopacity;          /* [P] */
+  float* dL_dcolor;            /* [P,3] */
+  float* dL_dmean3D;           /* [P,3] */
+  float* dL_dcov3D;            /* [P,6] or NULL */
+  float* dL_ddc;               /* [P,3] */
+  float* dL_dsh;               /* [P,M,3] (may be NULL when M==0) */
+  float* dL_dscale;            /* [P,3] */
+  float* dL_drot;              /* [P,4] */
+  int debug;
+  void* stream;
+} gsr_backward_args;
+
+int gsr_forward(const gsr_forward_args* a);
+int gsr_backward(const gsr_backward_args* a);
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present, void* stream);
+
+/* mean of the squared distances to the 3 nearest neighbours; points [P,3]. */
+int gsr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* stream);
+
+/* One fused multi-tensor Adam step (torch::optim::Adam semantics, no amsgrad,
+ * no weight decay).  Bias corrections are computed in double on the host from
+ * `step` exactly like LibTorch does. */
+typedef struct gsr_adam_group {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+  double lr;
+  int64_t step;  /* step count AFTER this update (>=1) */
+} gsr_adam_group;
+int gsr_adam_step(const gsr_adam_group* groups, int n_groups, double beta1,
+                  double beta2, double eps, float grad_scale, void* stream);
+
+/* ---- test / debug exports (device -> device copies out of the opaque buffers) ---- */
+/* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits). */
+int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, int P,
+                       int R, uint64_t* keys_sorted, uint32_t* point_list, void* stream);
+int gsr_export_image(const char* image_buffer, int W, int H, float* final_T,
+                     uint32_t* n_contrib, uint32_t* ranges /*[T,2]*/,
+                     uint32_t* max_contrib /*[T]*/, void* stream);
+int gsr_export_geometry(const char* geom_buffer, int P, float* depths,
+                        float* means2D, float* conic_opacity, float* rgb,
+                        uint32_t* tiles_touched, uint8_t* clamped, void* stream);
+
+/* Stand-alone stable LSD onesweep radix sort of 64-bit items on bits
+ * [begin_bit, end_bit) (exposed for unit tests and benchmarks).
+ * `tmp` must hold gsr_sort_temp_bytes(n) bytes. Result ends in `items_out`. */
+size_t gsr_sort_temp_bytes(int64_t n);
+int gsr_sort_u64(const uint64_t* items_in, uint64_t* items_out, uint64_t* items_alt,
+                 int64_t n, int begin_bit, int end_bit, char* tmp, void* stream);
+
+/* Number of kernels this library has launched since load (bench bookkeeping). */
+int64_t gsr_launch_count(void);
+const char* gsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_CAPI_H_ */

@@ -1,0 +1,267 @@
+"""GPU parity tests proper: the product (hand-written sm_100a kernels, called through the
+C ABI) against the GPU oracle = the UNMODIFIED reference CUDA rasterizer compiled for the
+same B200 (oracle/_ref), on identical seeded inputs.
+
+Bars (BASELINE.json north_star): valid sorted keys / values, tile ranges, per-pixel
+contributor counts and radii BIT-EXACT; colour and final_T <= 1e-5 max-abs; every gradient
+tensor <= 1e-4 relative L2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import (product_exports, rel_l2, run_product_backward, run_product_forward,
+                  run_reference, scenes, to_dev, valid_prefix)
+
+pytestmark = pytest.mark.gpu
+
+COLOR_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _ref_available():
+    from oracle import ref_binding as rb
+    return rb.available()
+
+
+def _scene(name):
+    if name == "tiny_sh3":
+        return scenes.tiny(seed=7, P=3000, W=200, H=136, degree=3)
+    if name == "tiny_sh1":
+        return scenes.tiny(seed=8, P=2500, W=160, H=120, degree=1)
+    if name == "tiny_sh0_withrest":
+        return scenes.tiny(seed=9, P=2500, W=176, H=144, degree=0)
+    if name == "mid_frustum":
+        return scenes.frustum_scene(40_000, 640, 480, 517.3, 516.5, seed=11, degree=2, sh_coeffs=15,
+                                    name="mid")
+    if name == "cfg1_small":
+        return scenes.cfg1(P=30_000)
+    if name == "room_small":
+        return scenes.room_scene(60_000, 1200, 680, 600.0, 600.0, seed=2, name="room60k")
+    if name == "outdoor_small":
+        return scenes.outdoor_scene(50_000, 1241, 376, 718.856, 718.856, seed=4)
+    raise KeyError(name)
+
+
+SCENES = ["tiny_sh3", "tiny_sh1", "tiny_sh0_withrest", "mid_frustum", "cfg1_small", "room_small",
+          "outdoor_small"]
+
+
+def _compare_forward(scene, t, fwd, ref):
+    R, B, color, radii, *_ = fwd
+    ex = product_exports(scene, t, fwd)
+    # ---- per-Gaussian state
+    assert torch.equal(radii, ref["radii"]), "radii differ"
+    vis = ref["radii"] > 0
+    assert int(vis.sum()) > 0
+    for k in ("depths", "means2D", "conic_opacity"):
+        assert torch.equal(ex[k][vis], ref[k][vis]), f"{k} not bit-exact"
+    if scene.sh is not None:
+        assert torch.equal(ex["rgb"][vis], ref["rgb"][vis]), "SH colours not bit-exact"
+        cl = ref["clamped"][vis].to(torch.int32)
+        bits = cl[:, 0] + 2 * cl[:, 1] + 4 * cl[:, 2]
+        assert torch.equal(ex["clamped"][vis].to(torch.int32), bits), "clamp flags differ"
+    # ---- sorted duplicate list: reference valid prefix == product list, bit for bit
+    nv = valid_prefix(ref["keys"])
+    assert R == nv, f"duplicate count {R} != reference valid prefix {nv}"
+    assert torch.equal(ex["keys"], ref["keys"][:nv]), "sorted keys differ"
+    assert torch.equal(ex["ids"], ref["ids"][:nv]), "sorted Gaussian ids differ"
+    # exact per-Gaussian tile counts == number of valid keys the reference emitted for it
+    counts = torch.bincount(ref["ids"][:nv].long(), minlength=scene.P).to(torch.int32)
+    assert torch.equal(ex["tiles"], counts), "exact tile counts differ"
+    # ---- tile ranges, contributor counts
+    assert torch.equal(ex["ranges"], ref["ranges"]), "tile ranges differ"
+    assert torch.equal(ex["n_contrib"], ref["n_contrib"]), "n_contrib differs"
+    assert torch.equal(ex["max_contrib"], ref["max_contrib"]), "max_contrib differs"
+    # ---- image
+    dT = (ex["final_T"] - ref["final_T"]).abs().max().item()
+    dC = (color - ref["color"]).abs().max().item()
+    assert dT <= COLOR_TOL, f"final_T max-abs {dT}"
+    assert dC <= COLOR_TOL, f"colour max-abs {dC}"
+    return dict(R=R, dT=dT, dC=dC, bit_exact_color=bool(torch.equal(color, ref["color"])))
+
+
+def _compare_grads(mine, ref_g, skip=()):
+    worst = {}
+    for k, v in mine.items():
+        if k in skip:
+            continue
+        r = ref_g[k]
+        err = rel_l2(v.reshape(r.shape), r)
+        worst[k] = err
+        assert err <= GRAD_TOL, f"{k}: relative L2 {err:.3e} > {GRAD_TOL}"
+        assert torch.isfinite(v).all(), f"{k} has non-finite values"
+    return worst
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_forward_backward_vs_reference(name):
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libgsdf_ref.so not built")
+    scene = _scene(name)
+    t = to_dev(scene)
+    ref = run_reference(scene, t)
+    fwd = run_product_forward(scene, t)
+    torch.cuda.synchronize()
+    info = _compare_forward(scene, t, fwd, ref)
+    grads = run_product_backward(scene, t, fwd)
+    torch.cuda.synchronize()
+    worst = _compare_grads(grads, ref["grads"])
+    print(name, info, {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+def test_sh0_empty_rest_drops_colour_gradient():
+    """Reference quirk 14: a 0-element `sh` skips the whole SH backward (dL_ddc == 0)."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built")
+    scene = scenes.cfg1(P=20_000)
+    t = to_dev(scene)
+    assert t["sh"].numel() == 0
+    ref = run_reference(scene, t)
+    fwd = run_product_forward(scene, t)
+    _compare_forward(scene, t, fwd, ref)
+    g = run_product_backward(scene, t, fwd)
+    assert float(g["dL_ddc"].abs().max()) == 0.0
+    assert float(ref["grads"]["dL_ddc"].abs().max()) == 0.0
+    _compare_grads(g, ref["grads"])
+
+
+def test_colors_precomp_and_cov3d_precomp_paths():
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built")
+    scene = scenes.tiny(seed=21, P=4000, W=208, H=160, degree=0)
+    t = to_dev(scene)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    colors = torch.rand((scene.P, 3), device="cuda", generator=gen)
+    # cov3D from the reference's own forward (geometry buffer) -> feed back as precomputed input
+    ref0 = run_reference(scene, t, backward=False)
+    cov = ref0["cov3D"].clone()
+    vis = ref0["radii"] > 0
+    cov[~vis] = torch.tensor([1e-4, 0, 0, 1e-4, 0, 1e-4], device="cuda")
+    e = t["empty"]
+    for kw in (dict(colors_precomp=colors, sh=e), dict(cov3D_precomp=cov),
+               dict(colors_precomp=colors, cov3D_precomp=cov, sh=e)):
+        ref = run_reference(scene, t, **kw)
+        fwd = run_product_forward(scene, t, **kw)
+        saved_sh = scene.sh
+        if "colors_precomp" in kw:
+            scene.sh = None  # geometry rgb is not produced on this path
+        try:
+            _compare_forward(scene, t, fwd, ref)
+        finally:
+            scene.sh = saved_sh
+        g = run_product_backward(scene, t, fwd, **kw)
+        _compare_grads(g, ref["grads"])
+
+
+def test_depth_channel_via_colors_precomp():
+    """depth is rendered by passing per-Gaussian depth as a colour."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built")
+    scene = scenes.tiny(seed=22, P=3000, W=192, H=128, degree=0)
+    t = to_dev(scene)
+    z = t["means3D"][:, 2:3].clamp_min(0.0)
+    colors = torch.cat([z, z, z], 1).contiguous()
+    ref = run_reference(scene, t, colors_precomp=colors, sh=t["empty"], backward=False)
+    fwd = run_product_forward(scene, t, colors_precomp=colors, sh=t["empty"])
+    assert (fwd[2] - ref["color"]).abs().max().item() <= 1e-5 * max(1.0, float(z.max()))
+    ex = product_exports(scene, t, fwd)
+    assert torch.equal(ex["n_contrib"], ref["n_contrib"])
+
+
+def test_empty_and_all_culled():
+    import gsdf_slam_b200 as gs
+    dev = "cuda"
+    e = torch.empty(0, dtype=torch.float32, device=dev)
+    cam = scenes.make_camera(64, 48, 50.0, 50.0)
+    view = torch.from_numpy(cam.viewmatrix).to(dev)
+    proj = torch.from_numpy(cam.projmatrix).to(dev)
+    campos = torch.from_numpy(cam.campos).to(dev)
+    bg = torch.tensor([0.3, 0.2, 0.1], device=dev)
+    # P = 0: zero image, empty buffers (src/rasterize_points.cu:74-90)
+    out = gs.RasterizeGaussiansCUDA(bg, torch.zeros((0, 3), device=dev), e, torch.zeros((0, 1), device=dev),
+                                    torch.zeros((0, 3), device=dev), torch.zeros((0, 4), device=dev), 1.0,
+                                    e, view, proj, cam.tanfovx, cam.tanfovy, 48, 64,
+                                    torch.zeros((0, 1, 3), device=dev), torch.zeros((0, 15, 3), device=dev),
+                                    3, campos, False, False)
+    assert out[0] == 0 and float(out[2].abs().max()) == 0.0
+    # everything behind the camera: image == background, all radii 0, gradients all zero
+    P = 1000
+    g = torch.Generator(device=dev).manual_seed(0)
+    means = torch.randn((P, 3), device=dev, generator=g)
+    means[:, 2] = -means[:, 2].abs() - 0.5
+    sc = torch.full((P, 3), 0.05, device=dev)
+    rot = torch.zeros((P, 4), device=dev)
+    rot[:, 0] = 1
+    op = torch.full((P, 1), 0.5, device=dev)
+    dc = torch.zeros((P, 1, 3), device=dev)
+    sh = torch.zeros((P, 15, 3), device=dev)
+    fwd = gs.RasterizeGaussiansCUDA(bg, means, e, op, sc, rot, 1.0, e, view, proj, cam.tanfovx,
+                                    cam.tanfovy, 48, 64, dc, sh, 3, campos, False, True)
+    R, B, color, radii, geom, binning, img, sample = fwd
+    assert R == 0 and int(radii.abs().max()) == 0
+    assert torch.allclose(color, bg.view(3, 1, 1).expand(3, 48, 64))
+    dL = torch.ones((3, 48, 64), device=dev)
+    grads = gs.RasterizeGaussiansBackwardCUDA(bg, means, radii, e, sc, rot, 1.0, e, view, proj,
+                                              cam.tanfovx, cam.tanfovy, dL, dc, sh, 3, campos, geom, R,
+                                              binning, img, B, sample, True)
+    for gten in grads:
+        assert float(gten.abs().max()) == 0.0
+
+
+def test_single_huge_gaussian_covers_all_tiles():
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built")
+    scene = scenes.tiny(seed=31, P=64, W=200, H=136, degree=3)
+    scene.means3D[0] = [0.0, 0.0, 1.0]
+    scene.scales[0] = [3.0, 3.0, 0.01]
+    scene.rotations[0] = [1, 0, 0, 0]
+    scene.opacity[0] = 0.9
+    t = to_dev(scene)
+    ref = run_reference(scene, t)
+    fwd = run_product_forward(scene, t)
+    _compare_forward(scene, t, fwd, ref)
+    g = run_product_backward(scene, t, fwd)
+    _compare_grads(g, ref["grads"])
+
+
+def test_autograd_module_matches_functional():
+    import gsdf_slam_b200 as gs
+    scene = scenes.tiny(seed=41, P=2000, W=128, H=96, degree=3)
+    t = to_dev(scene)
+    rs = gs.GaussianRasterizationSettings(scene.cam.H, scene.cam.W, scene.cam.tanfovx, scene.cam.tanfovy,
+                                          t["bg"], 1.0, t["viewmatrix"], t["projmatrix"], 3, t["campos"],
+                                          False, False)
+    leaves = {k: t[k].clone().requires_grad_(True) for k in ("means3D", "opacity", "scales", "rotations", "dc", "sh")}
+    means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+    rast = gs.GaussianRasterizer(rs)
+    color, radii = rast(leaves["means3D"], means2D, leaves["opacity"], dc=leaves["dc"], shs=leaves["sh"],
+                        scales=leaves["scales"], rotations=leaves["rotations"])
+    (color * t["dL_dout"]).sum().backward()
+    fwd = run_product_forward(scene, t)
+    g = run_product_backward(scene, t, fwd)
+    assert torch.equal(color.detach(), fwd[2])
+    pairs = [("means3D", "dL_dmeans3D"), ("opacity", "dL_dopacity"), ("scales", "dL_dscales"),
+             ("rotations", "dL_drotations"), ("dc", "dL_ddc"), ("sh", "dL_dsh")]
+    for leaf, gname in pairs:
+        assert rel_l2(leaves[leaf].grad.reshape(g[gname].shape), g[gname]) <= 1e-5, leaf
+    assert rel_l2(means2D.grad, g["dL_dmeans2D"]) <= 1e-5
+    with pytest.raises(RuntimeError):
+        rast(leaves["means3D"], means2D, leaves["opacity"])  # neither SHs nor colours
+    with pytest.raises(RuntimeError):
+        gs.RasterizeGaussiansCUDA(t["bg"], t["means3D"].view(-1), t["empty"], t["opacity"], t["scales"],
+                                  t["rotations"], 1.0, t["empty"], t["viewmatrix"], t["projmatrix"], 1.0,
+                                  1.0, 96, 128, t["dc"], t["sh"], 3, t["campos"], False, False)
+
+
+def test_mark_visible():
+    import gsdf_slam_b200 as gs
+    scene = scenes.tiny(seed=51, P=5000)
+    t = to_dev(scene)
+    mine = gs.markVisible(t["means3D"], t["viewmatrix"], t["projmatrix"])
+    expect = (t["means3D"] @ t["viewmatrix"][:3, 2] + t["viewmatrix"][3, 2]) > 0.2
+    # fp32 dot order differs from the kernel's FMA chain only on razor-edge points
+    assert int((mine != expect).sum()) <= 2
+    if _ref_available():
+        from oracle import ref_binding as rb
+        assert torch.equal(mine, rb.ref_mark_visible(t["means3D"], t["viewmatrix"], t["projmatrix"]))
