@@ -68,7 +68,7 @@ class AdamGroup(C.Structure):
 EXPORTED_SYMBOLS = [
     "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step",
     "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_sort_temp_bytes",
-    "gsr_sort_u64", "gsr_launch_count", "gsr_version",
+    "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
 ]
 
 _lib = None
@@ -124,6 +124,10 @@ def lib() -> C.CDLL:
     L.gsr_sort_u64.restype = C.c_int
     L.gsr_launch_count.argtypes = []
     L.gsr_launch_count.restype = C.c_int64
+    L.gsr_profile_enable.argtypes = [C.c_int]
+    L.gsr_profile_enable.restype = None
+    L.gsr_profile_read.argtypes = [C.c_char_p, C.c_size_t]
+    L.gsr_profile_read.restype = C.c_int
     L.gsr_version.argtypes = []
     L.gsr_version.restype = C.c_char_p
     _lib = L

@@ -8,7 +8,7 @@
 // Arithmetic follows LibTorch's single-tensor Adam step kernel by kernel, so the
 // result is the one the reference's optimizer would produce:
 //   m  = m*b1 ; m = m + (1-b1)*g            (mul_, add_ with alpha -> one FMA)
-//   v  = v*b2 ; v = v + ((1-b2)*g)*g        (mul_, addcmul_       -> one FMA)
+//   v  = v*b2 ; v = v + (1-b2)*(g*g)        (mul_, addcmul_       -> one FMA)
 //   d  = sqrt(v) * (1/sqrt(bc2)) ; d = d + eps   (div by CPU scalar = mul by reciprocal; add_)
 //   p  = p + (-lr/bc1) * (m / d)            (addcdiv_             -> div + FMA)
 // Scalars are rounded to fp32 exactly where ATen rounds them.
@@ -51,7 +51,7 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
   const float m1 = __fmul_rn(m, a.beta1);
   const float m2 = __fmaf_rn(a.one_minus_beta1, g, m1);
   const float v1 = __fmul_rn(v, a.beta2);
-  const float v2 = __fmaf_rn(__fmul_rn(a.one_minus_beta2, g), g, v1);
+  const float v2 = __fmaf_rn(a.one_minus_beta2, __fmul_rn(g, g), v1);  // a + alpha * (b * c)
   const float d0 = __fmul_rn(__fsqrt_rn(v2), G.inv_sqrt_bc2);
   const float d = __fadd_rn(d0, a.eps);
   p = __fmaf_rn(G.neg_step_size, __fdiv_rn(m2, d), p);
@@ -130,7 +130,9 @@ int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double
     const double bc2 = 1.0 - std::pow(beta2, (double)g.step);
     const double step_size = g.lr / bc1;
     d.neg_step_size = (float)(-step_size);
-    d.inv_sqrt_bc2 = 1.0f / (float)std::sqrt(bc2);
+    // ATen's div by a CPU scalar multiplies by the reciprocal formed in double
+    // (measured on this image's torch 2.11: x / s == x * float(1.0 / s))
+    d.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
     d.first_block = blocks;
     const uintptr_t al = (uintptr_t)d.p | (uintptr_t)d.g | (uintptr_t)d.m | (uintptr_t)d.v;
     d.vec_ok = (al & 15) == 0;

@@ -28,34 +28,100 @@ __global__ void __launch_bounds__(256)
 emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ tiles_touched,
             const uint32_t* __restrict__ dup_offsets, const float2* __restrict__ means2D,
             const float4* __restrict__ conic_opacity, const int* __restrict__ radii, int grid_x,
-            int grid_y, uint64_t* __restrict__ items) {
+            int grid_y, uint64_t* __restrict__ items, uint32_t* __restrict__ large_count,
+            uint32_t* __restrict__ large_list) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= P) return;
-  const uint32_t g = (uint32_t)(sorted[j] & 0xffffffffu);
-  const uint32_t cnt = tiles_touched[g];
-  if (cnt == 0) return;
-  uint32_t off = dup_offsets[j];
-  const float2 xy = means2D[g];
-  const float4 co = conic_opacity[g];
-  uint2 rect_min, rect_max;
-  tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
-  const float thr = opacity_power_threshold(co.w);
-  for (int y = rect_min.y; y < (int)rect_max.y; ++y) {
-    for (int x = rect_min.x; x < (int)rect_max.x; ++x) {
-      if (tile_min_power(co, xy, x, y) <= thr) {
-        const uint64_t tile = (uint64_t)(y * grid_x + x);
-        items[off++] = (tile << 32) | g;
+  const int lane = threadIdx.x & 31;
+  uint32_t g = 0, cnt = 0, off = 0;
+  float2 xy = {0.f, 0.f};
+  float4 co = {0.f, 0.f, 0.f, 0.f};
+  uint2 rect_min = {0, 0}, rect_max = {0, 0};
+  float thr = 0.f;
+  if (j < P) {
+    g = (uint32_t)(sorted[j] & 0xffffffffu);
+    cnt = tiles_touched[g];
+  }
+  if (cnt != 0) {
+    off = dup_offsets[j];
+    xy = means2D[g];
+    co = conic_opacity[g];
+    tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
+    thr = opacity_power_threshold(co.w);
+  }
+  const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
+  const bool large = cnt != 0 && area > kSerialRectTiles;
+  if (cnt != 0 && !large) {
+    for (int y = rect_min.y; y < (int)rect_max.y; ++y) {
+      for (int x = rect_min.x; x < (int)rect_max.x; ++x) {
+        if (tile_min_power(co, xy, x, y) <= thr) {
+          const uint64_t tile = (uint64_t)(y * grid_x + x);
+          items[off++] = (tile << 32) | g;
+        }
       }
+    }
+  }
+  // Large rectangles are not walked here: in depth order the near (= huge) splats sit next
+  // to each other, so they would all land in the first few warps.  They are queued and
+  // spread over the whole GPU by emit_large_kernel.
+  (void)lane;
+  if (large) large_list[atomicAdd(large_count, 1u)] = (uint32_t)j;
+}
+
+// One warp per queued large-rectangle Gaussian (grid-stride over the queue): 32 tiles are
+// tested per step and the hits are written in row-major order.
+__global__ void __launch_bounds__(256)
+emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_list,
+                  const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ dup_offsets,
+                  const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+                  const int* __restrict__ radii, int grid_x, int grid_y,
+                  uint64_t* __restrict__ items) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t count = *large_count;
+  const unsigned lanemask_lt = (1u << lane) - 1u;
+  for (uint32_t k = warp_global; k < count; k += num_warps) {
+    const uint32_t j = large_list[k];
+    const uint32_t g = (uint32_t)(sorted[j] & 0xffffffffu);
+    uint32_t off = dup_offsets[j];
+    const float2 xy = means2D[g];
+    const float4 co = conic_opacity[g];
+    uint2 rect_min, rect_max;
+    tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
+    const float thr = opacity_power_threshold(co.w);
+    const int w = (int)(rect_max.x - rect_min.x), h = (int)(rect_max.y - rect_min.y);
+    const int area = w * h;
+    for (int t0 = 0; t0 < area; t0 += 32) {
+      const int t = t0 + lane;
+      bool pass = false;
+      int x = 0, y = 0;
+      if (t < area) {
+        y = (int)rect_min.y + t / w;
+        x = (int)rect_min.x + t - (t / w) * w;
+        pass = tile_min_power(co, xy, x, y) <= thr;
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, pass);
+      if (pass) {
+        const uint64_t tile = (uint64_t)(y * grid_x + x);
+        items[off + __popc(pm & lanemask_lt)] = (tile << 32) | g;
+      }
+      off += __popc(pm);
     }
   }
 }
 
 int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
                 const uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
-                const int* radii, int grid_x, int grid_y, uint64_t* items, cudaStream_t s) {
+                const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
+                uint32_t* large_list, cudaStream_t s) {
   if (P <= 0) return 0;
   emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, sorted, tiles_touched, dup_offsets, means2D,
-                                              conic_opacity, radii, grid_x, grid_y, items);
+                                              conic_opacity, radii, grid_x, grid_y, items,
+                                              large_count, large_list);
+  GSR_LAUNCHED();
+  // 148 SMs x 2 CTAs x 8 warps walk the queued large rectangles
+  emit_large_kernel<<<148 * 2, 256, 0, s>>>(large_count, large_list, sorted, dup_offsets, means2D,
+                                            conic_opacity, radii, grid_x, grid_y, items);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -1,68 +1,93 @@
-// Backward alpha-blend: gradients of the loss w.r.t. each splat's 2D mean, conic,
-// opacity and colour.  Replaces the reference's per-splat-bucket kernel
-// BACKWARD::PerGaussianRenderCUDA (backward.cu:463-653).
+// Backward alpha-blend: per-splat sums of the pixel gradients.  Replaces the reference's
+// per-splat-bucket kernel BACKWARD::PerGaussianRenderCUDA (backward.cu:463-653).
 //
-// Design (B200-first, not the reference's): one CTA per tile, one pixel per
-// thread, the tile's list is REPLAYED FRONT-TO-BACK exactly like the forward, so
-// T and the accumulated colour prefix are recomputed in registers and no
-// checkpoint stream is needed.  With the suffix colour written as
-// (prefix - final), the per-pair gradient terms are the same expressions the
-// reference evaluates (backward.cu:597-637).  A pair only costs the gradient
-// maths if some pixel of the warp's 8x4 block actually blends the splat; the nine
-// per-splat partial sums are then pre-reduced with warp shuffles, accumulated per
-// CTA in shared memory, and flushed with ONE global reduction per (splat, tile)
-// and component — the same atomic count as the reference, issued coalesced.
+// Design (B200-first, not the reference's): one 64-thread CTA per tile, four pixels per
+// thread (blend_common.cuh).  The tile's list is REPLAYED FRONT-TO-BACK exactly like the
+// forward, so T and the accumulated-colour prefix are recomputed in registers (bit-identical
+// to the forward) and no checkpoint stream exists.  For each (splat, pixel) pair that blends,
+// the same quantities as the reference (backward.cu:597-637) are formed — alpha, T,
+// dL/dalpha — but instead of nine per-pair gradient terms the kernel accumulates
+//     w = G * dL/dalpha   and its moments   w*dx, w*dy, w*dx^2, w*dx*dy, w*dy^2
+// plus the three colour sums: the gradients of the 2D mean, conic and opacity are linear
+// in those moments with per-splat coefficients, so that conversion happens ONCE per
+// Gaussian in preprocess_bwd.cu.  A thread first adds up its four pixels, the warp then
+// combines its 32 lanes with a 14-shuffle transposed reduction (only when some pixel of
+// the warp blends the splat), and nine lanes issue one global reduction each.
 // Splat records arrive through double-buffered TMA bulk copies.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "blend_common.cuh"
 #include "gsr_common.cuh"
 #include "tma.cuh"
 
 namespace gsr {
 
-constexpr int kBwdBatch = 256;
-constexpr int kAccStride = 9;
+// Sum nine per-lane values over the warp with 14 shuffles.  On return lane L with
+// (L & 3) == 0 holds the total of v[L >> 2] in `out8`; every lane holds the total of v[8]
+// in `out9`.
+__device__ __forceinline__ void warp_reduce9(const float (&v)[9], int lane, float& out8,
+                                             float& out9) {
+  const unsigned full = 0xffffffffu;
+  float w[4];
+  const bool u16 = (lane & 16) != 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = u16 ? v[k] : v[k + 4];
+    const float keep = u16 ? v[k + 4] : v[k];
+    w[k] = keep + __shfl_xor_sync(full, send, 16);
+  }
+  float x[2];
+  const bool u8 = (lane & 8) != 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = u8 ? w[k] : w[k + 2];
+    const float keep = u8 ? w[k + 2] : w[k];
+    x[k] = keep + __shfl_xor_sync(full, send, 8);
+  }
+  const bool u4 = (lane & 4) != 0;
+  float y = (u4 ? x[1] : x[0]) + __shfl_xor_sync(full, u4 ? x[0] : x[1], 4);
+  y += __shfl_xor_sync(full, y, 2);
+  y += __shfl_xor_sync(full, y, 1);
+  out8 = y;  // component index = 4*bit4 + 2*bit3 + bit2 = lane >> 2
+  float z = v[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(full, z, o);
+  out9 = z;
+}
 
-__global__ void __launch_bounds__(GSR_TILE_PIX)
+__global__ void __launch_bounds__(kBlendThreads)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ max_contrib,
                  const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
                  const float4* __restrict__ rec_c, int W, int H, const float* __restrict__ bg,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ accum_c, const float* __restrict__ dL_dpix,
                  float* __restrict__ acc /* [P][12] */) {
-  __shared__ __align__(128) float4 sA[2][kBwdBatch];
-  __shared__ __align__(128) float4 sB[2][kBwdBatch];
-  __shared__ __align__(128) float4 sC[2][kBwdBatch];
-  __shared__ float s_acc[kBwdBatch * kAccStride];
+  __shared__ __align__(128) float4 sA[2][kBlendBatch];
+  __shared__ __align__(128) float4 sB[2][kBlendBatch];
+  __shared__ __align__(128) float4 sC[2][kBlendBatch];
   __shared__ __align__(8) uint64_t s_full[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-  const uint32_t px = blockIdx.x * GSR_TILE_X + (warp & 1) * 8 + (lane & 7);
-  const uint32_t py = blockIdx.y * GSR_TILE_Y + (warp >> 1) * 4 + (lane >> 3);
-  const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-  const uint32_t pix_id = (uint32_t)W * py + px;
-  const float2 pixf = {(float)px, (float)py};
   const size_t N = (size_t)W * H;
 
   const uint2 range = ranges[tile_id];
   // nothing behind the deepest contributor of the tile receives gradient
   const int total = min((int)(range.y - range.x), (int)max_contrib[tile_id]);
-  const int rounds = (total + kBwdBatch - 1) / kBwdBatch;
+  const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
 
   if (tid == 0) {
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < kBwdBatch * kAccStride; i += GSR_TILE_PIX) s_acc[i] = 0.f;
   __syncthreads();
 
   auto issue = [&](int round) {
     const int buf = round & 1;
-    const int start = range.x + round * kBwdBatch;
-    const int cnt = min(kBwdBatch, total - round * kBwdBatch);
+    const int start = range.x + round * kBlendBatch;
+    const int cnt = min(kBlendBatch, total - round * kBlendBatch);
     const uint32_t bytes = (uint32_t)cnt * 16u;
     mbar_expect_tx(&s_full[buf], 3u * bytes);
     bulk_g2s(&sA[buf][0], rec_a + start, bytes, &s_full[buf]);
@@ -71,107 +96,123 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   };
   if (tid == 0 && rounds > 0) issue(0);
 
-  // per-pixel state
-  float T = 1.0f;
-  float T_final = 0.f;
-  uint32_t last = 0;
-  float ar[3] = {0.f, 0.f, 0.f};
-  float dL[3] = {0.f, 0.f, 0.f};
+  // per-pixel state of the four slots
+  float pxf[kSlots], pyf[kSlots], T[kSlots], T_final[kSlots], bg_dot[kSlots];
+  uint32_t last[kSlots];
+  float ar[kSlots][3], dL[kSlots][3];
   const float bgc[3] = {bg[0], bg[1], bg[2]};
-  if (inside) {
-    T_final = final_T[pix_id];
-    last = n_contrib[pix_id];
+  uint32_t my_last = 0;
+#pragma unroll
+  for (int q = 0; q < kSlots; ++q) {
+    const uint32_t px = slot_px(blockIdx.x, lane, q);
+    const uint32_t py = slot_py(blockIdx.y, warp, lane, q);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+    pxf[q] = (float)px;
+    pyf[q] = (float)py;
+    T[q] = 1.0f;
+    T_final[q] = 0.f;
+    last[q] = 0;
+    bg_dot[q] = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      ar[ch] = -accum_c[ch * N + pix_id];  // minus the colour still to be blended
-      dL[ch] = dL_dpix[ch * N + pix_id];
+      ar[q][ch] = 0.f;
+      dL[q][ch] = 0.f;
     }
-  }
-  float bg_dot_dpixel = 0.0f;
+    if (inside) {
+      T_final[q] = final_T[pix_id];
+      last[q] = n_contrib[pix_id];
 #pragma unroll
-  for (int ch = 0; ch < 3; ++ch) bg_dot_dpixel += bgc[ch] * dL[ch];
-  const float ddelx_dx = 0.5f * W;
-  const float ddely_dy = 0.5f * H;
+      for (int ch = 0; ch < 3; ++ch) {
+        ar[q][ch] = -accum_c[ch * N + pix_id];  // minus the colour still to be blended
+        dL[q][ch] = dL_dpix[ch * N + pix_id];
+        bg_dot[q] += bgc[ch] * dL[q][ch];
+      }
+    }
+    my_last = max(my_last, last[q]);
+  }
+  // warp-uniform bound: the deepest contributor among this warp's 128 pixels
+  const uint32_t warp_last = __reduce_max_sync(0xffffffffu, my_last);
 
   for (int i = 0; i < rounds; ++i) {
     const int buf = i & 1;
     mbar_wait(&s_full[buf], (uint32_t)((i >> 1) & 1));
-    __syncthreads();  // previous batch fully consumed and flushed by every thread
+    __syncthreads();  // previous batch fully consumed by both warps
     if (tid == 0 && i + 1 < rounds) issue(i + 1);
 
-    const int cnt = min(kBwdBatch, total - i * kBwdBatch);
-    const uint32_t pos0 = (uint32_t)i * kBwdBatch;
-    // warp-uniform bound: the deepest contributor among this warp's pixels
-    const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
+    const int cnt = min(kBlendBatch, total - i * kBlendBatch);
+    const uint32_t pos0 = (uint32_t)i * kBlendBatch;
     const int jmax = (int)min((uint32_t)cnt, warp_last > pos0 ? warp_last - pos0 : 0u);
 
     for (int j = 0; j < jmax; ++j) {
       const float4 A = sA[buf][j];
       const float4 B = sB[buf][j];
-      const float2 d = {A.x - pixf.x, A.y - pixf.y};
       const float4 con_o = {A.z, A.w, B.x, B.y};
-      const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-      bool contributes = (pos0 + j < last) && !(power > 0.0f) && !(power < B.z);
-      float G = 0.f, alpha = 0.f;
-      if (contributes) {
-        G = exp(power);
-        alpha = min(0.99f, con_o.w * G);
-        contributes = !(alpha < 1.0f / 255.0f);
-      }
-      if (!__any_sync(0xffffffffu, contributes)) continue;
+      const uint32_t pos = pos0 + j;
 
+      // v = {Mx, My, Mxx, Mxy, Myy, M0, cr, cg, cb}
       float v[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) v[k] = 0.f;
-      if (contributes) {
-        const float4 col = sC[buf][j];
-        const float c[3] = {col.x, col.y, col.z};
-        const float dchannel_dcolor = alpha * T;
-        float dL_dalpha = 0.0f;
+      // gate of all four pixels first: independent chains, one vote for the common miss
+      float pw[kSlots];
+      bool cand[kSlots];
+      bool any_cand = false;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          ar[ch] += T * alpha * c[ch];
-          const float dL_dchannel = dL[ch];
-          v[6 + ch] = dchannel_dcolor * dL_dchannel;
-          dL_dalpha += ((c[ch] * T) - (1.0f / (1.0f - alpha)) * (-ar[ch])) * dL_dchannel;
-        }
-        dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot_dpixel;
-        T *= (1.0f - alpha);
+      for (int q = 0; q < kSlots; ++q) {
+        const float2 d = {A.x - pxf[q], A.y - pyf[q]};
+        const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
+        pw[q] = power;
+        cand[q] = (pos < last[q]) && !(power > 0.0f) && !(power < B.z);
+        any_cand = any_cand || cand[q];
+      }
+      if (!__any_sync(0xffffffffu, any_cand)) continue;  // splat misses this warp's half tile
 
-        const float dL_dG = con_o.w * dL_dalpha;
-        const float gdx = G * d.x;
-        const float gdy = G * d.y;
-        const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-        const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-        v[1] = dL_dG * dG_ddely * ddely_dy;
-        v[2] = -0.5f * gdx * d.x * dL_dG;
-        v[3] = -0.5f * gdx * d.y * dL_dG;
-        v[4] = -0.5f * gdy * d.y * dL_dG;
-        v[5] = G * dL_dalpha;
-      }
-      // warp pre-reduction of the nine partial sums
+      bool contributed = false;
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
+      for (int q = 0; q < kSlots; ++q) {
+        if (!cand[q]) continue;
+        const float G = exp(pw[q]);
+        const float alpha = min(0.99f, con_o.w * G);
+        if (alpha < 1.0f / 255.0f) continue;
+        contributed = true;
+        {
+          const float2 d = {A.x - pxf[q], A.y - pyf[q]};
+          const float4 col = sC[buf][j];
+          const float c[3] = {col.x, col.y, col.z};
+          const float one_m = 1.0f - alpha;
+          const float inv = 1.0f / one_m;
+          const float Ta = T[q] * alpha;
+          float dL_dalpha = 0.0f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+          for (int ch = 0; ch < 3; ++ch) {
+            ar[q][ch] += Ta * c[ch];
+            v[6 + ch] += Ta * dL[q][ch];
+            dL_dalpha += ((c[ch] * T[q]) + inv * ar[q][ch]) * dL[q][ch];
+          }
+          dL_dalpha += (-T_final[q] * inv) * bg_dot[q];
+          T[q] *= one_m;
+
+          const float w = G * dL_dalpha;
+          const float wdx = w * d.x;
+          const float wdy = w * d.y;
+          v[0] += wdx;
+          v[1] += wdy;
+          v[2] += wdx * d.x;
+          v[3] += wdx * d.y;
+          v[4] += wdy * d.y;
+          v[5] += w;
+        }
       }
-      if (lane < 9) {
-        float mine = v[0];
-#pragma unroll
-        for (int k = 1; k < 9; ++k) mine = (lane == k) ? v[k] : mine;
-        atomicAdd(&s_acc[j * kAccStride + lane], mine);
-      }
-    }
-    __syncthreads();
-    // flush this batch: one global reduction per (splat, tile) and component
-    for (int e = tid; e < cnt * kAccStride; e += GSR_TILE_PIX) {
-      const float val = s_acc[e];
-      if (val != 0.f) {
-        const int j = e / kAccStride, k = e - j * kAccStride;
-        const uint32_t g = __float_as_uint(sB[buf][j].w);
-        atomicAdd(&acc[(size_t)g * 12 + k], val);
-        s_acc[e] = 0.f;
+      if (!__any_sync(0xffffffffu, contributed)) continue;
+
+      float s8, s9;
+      warp_reduce9(v, lane, s8, s9);
+      const uint32_t g = __float_as_uint(B.w);
+      if ((lane & 3) == 0) {
+        if (s8 != 0.f) atomicAdd(&acc[(size_t)g * 12 + (lane >> 2)], s8);
+      } else if (lane == 1) {
+        if (s9 != 0.f) atomicAdd(&acc[(size_t)g * 12 + 8], s9);
       }
     }
   }
@@ -182,8 +223,8 @@ int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* max_cont
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s) {
   dim3 grid((W + GSR_TILE_X - 1) / GSR_TILE_X, (H + GSR_TILE_Y - 1) / GSR_TILE_Y, 1);
-  blend_bwd_kernel<<<grid, GSR_TILE_PIX, 0, s>>>(ranges, max_contrib, rec_a, rec_b, rec_c, W, H, bg,
-                                                 final_T, n_contrib, accum_c, dL_dpix, acc);
+  blend_bwd_kernel<<<grid, kBlendThreads, 0, s>>>(ranges, max_contrib, rec_a, rec_b, rec_c, W, H, bg,
+                                                  final_T, n_contrib, accum_c, dL_dpix, acc);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -1,0 +1,24 @@
+// Shared shape of the two blend kernels: a 64-thread CTA per 16x16 tile, each warp owns
+// a 16x8 half tile, each thread owns four pixels — the pixel at (lane&7, lane>>3) of each
+// of the four 8x4 blocks of the half tile.  A "slot" q is one of those blocks, so the 32
+// pixels of a slot are spatially compact: a warp-wide vote per slot tells cheaply whether a
+// splat touches that block at all.
+#pragma once
+#include <stdint.h>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+constexpr int kBlendThreads = 64;
+constexpr int kSlots = 4;
+constexpr int kBlendBatch = 128;  // splat records staged per bulk copy (3 x 2 KB)
+
+__device__ __forceinline__ uint32_t slot_px(uint32_t tile_x, int lane, int q) {
+  return tile_x * GSR_TILE_X + (q & 1) * 8 + (lane & 7);
+}
+__device__ __forceinline__ uint32_t slot_py(uint32_t tile_y, int warp, int lane, int q) {
+  return tile_y * GSR_TILE_Y + warp * 8 + (q >> 1) * 4 + (lane >> 3);
+}
+
+}  // namespace gsr

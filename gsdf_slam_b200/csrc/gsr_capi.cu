@@ -16,6 +16,9 @@
 
 #include <cstdio>
 #include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
 
 #include "gsr_common.cuh"
 
@@ -42,9 +45,57 @@ static uint32_t* pinned_word() {
   }
   return p;
 }
+
+// ---- optional per-stage CUDA-event profiler (bench.py's live roofline measurement) ----
+struct ProfPending { int slot; cudaEvent_t a, b; };
+struct Profiler {
+  bool on = false;
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<long long> count;
+  std::vector<ProfPending> pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+  int slot_of(const char* n) {
+    for (size_t i = 0; i < names.size(); ++i) if (names[i] == n) return (int)i;
+    names.push_back(n); ms.push_back(0.0); count.push_back(0);
+    return (int)names.size() - 1;
+  }
+  void drain() {
+    for (auto& p : pending) {
+      float t = 0.f;
+      if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) {
+        ms[p.slot] += t; count[p.slot] += 1;
+      }
+      pool.push_back({p.a, p.b});
+    }
+    pending.clear();
+  }
+};
+static Profiler g_prof;
+struct ProfScope {
+  cudaStream_t s; int slot = -1; cudaEvent_t a{}, b{};
+  ProfScope(const char* name, cudaStream_t st) : s(st) {
+    if (!g_prof.on) return;
+    slot = g_prof.slot_of(name);
+    if (!g_prof.pool.empty()) { a = g_prof.pool.back().first; b = g_prof.pool.back().second; g_prof.pool.pop_back(); }
+    else { cudaEventCreate(&a); cudaEventCreate(&b); }
+    cudaEventRecord(a, s);
+  }
+  ~ProfScope() {
+    if (slot < 0) return;
+    cudaEventRecord(b, s);
+    g_prof.pending.push_back({slot, a, b});
+  }
+};
 }  // namespace gsr
 
 using namespace gsr;
+#define GSR_PROF(name, call)        \
+  do {                              \
+    ProfScope _ps(name, s);         \
+    int _r = (call);                \
+    if (_r != 0) return _r;         \
+  } while (0)
 
 #define GSR_CUDA(x)                         \
   do {                                      \
@@ -111,12 +162,12 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.radii = a->radii; pp.depths = g.depths; pp.means2D = g.means2D;
   pp.conic_opacity = g.conic_opacity; pp.rgb = g.rgb; pp.clamped = g.clamped;
   pp.tiles_touched = g.tiles_touched; pp.sort_items = g.sort_a; pp.num_visible = &g.hdr->num_visible;
-  GSR_RC(launch_preprocess(pp, s));
+  GSR_PROF("preprocess", launch_preprocess(pp, s));
 
   // depth order of the Gaussians: 32 key bits, 4 passes, result back in sort_a
   uint64_t* order = nullptr;
-  GSR_RC(launch_sort_u64(g.sort_a, g.sort_a, g.sort_b, P, 32, 64, g.sort_tmp, s, &order));
-  GSR_RC(launch_scan_gather(g.tiles_touched, order, P, g.dup_offsets, &g.hdr->num_dup, g.sort_tmp, s));
+  GSR_PROF("sort_depth", launch_sort_u64(g.sort_a, g.sort_a, g.sort_b, P, 32, 64, g.sort_tmp, s, &order));
+  GSR_PROF("scan", launch_scan_gather(g.tiles_touched, order, P, g.dup_offsets, &g.hdr->num_dup, g.sort_tmp, s));
 
   uint32_t* host_R = pinned_word();
   if (!host_R) return GSR_ERR_ALLOC;
@@ -136,17 +187,18 @@ int gsr_forward(const gsr_forward_args* a) {
     // choose the emit target so that the sorted list always ends in items_a
     uint64_t* emit_dst = (npass & 1) ? b.items_b : b.items_a;
     uint64_t* other = (npass & 1) ? b.items_a : b.items_b;
-    GSR_RC(launch_emit(P, order, g.tiles_touched, g.dup_offsets, g.means2D, g.conic_opacity,
-                       a->radii, gx, gy, emit_dst, s));
+    GSR_PROF("emit", launch_emit(P, order, g.tiles_touched, g.dup_offsets, g.means2D, g.conic_opacity,
+                       a->radii, gx, gy, emit_dst, &g.hdr->num_large,
+                       reinterpret_cast<uint32_t*>(g.sort_b), s));
     uint64_t* sorted = nullptr;
     // odd: in=b, out=a, alt=b ; even: in=a, out=a, alt=b
-    GSR_RC(launch_sort_u64(emit_dst, b.items_a, (npass & 1) ? emit_dst : other, R, 32, 32 + tb,
+    GSR_PROF("sort_tile", launch_sort_u64(emit_dst, b.items_a, (npass & 1) ? emit_dst : other, R, 32, 32 + tb,
                            b.sort_tmp, s, &sorted));
   }
   const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
-  GSR_RC(launch_finalize(R, b.items_a, g.means2D, g.conic_opacity, colors, im.ranges, T, b.rec_a,
+  GSR_PROF("finalize", launch_finalize(R, b.items_a, g.means2D, g.conic_opacity, colors, im.ranges, T, b.rec_a,
                          b.rec_b, b.rec_c, s));
-  GSR_RC(launch_blend_fwd(W, H, im.ranges, b.rec_a, b.rec_b, b.rec_c, a->background, a->out_color,
+  GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, b.rec_a, b.rec_b, b.rec_c, a->background, a->out_color,
                           im.final_T, im.n_contrib, im.accum_c, im.max_contrib, s));
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));
@@ -177,7 +229,7 @@ int gsr_backward(const gsr_backward_args* a) {
   GSR_CUDA(cudaMemsetAsync(g.acc, 0, (size_t)P * 12 * sizeof(float), s));
   if (a->R > 0) {
     BinView b = bin_view(a->binning_buffer, (size_t)a->R);
-    GSR_RC(launch_blend_bwd(W, H, im.ranges, im.max_contrib, b.rec_a, b.rec_b, b.rec_c,
+    GSR_PROF("blend_bwd", launch_blend_bwd(W, H, im.ranges, im.max_contrib, b.rec_a, b.rec_b, b.rec_c,
                             a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, s));
   }
   PreBwdParams bp;
@@ -194,11 +246,11 @@ int gsr_backward(const gsr_backward_args* a) {
   bp.focal_y = H / (2.0f * a->tan_fovy);
   bp.focal_x = W / (2.0f * a->tan_fovx);
   bp.tan_fovx = a->tan_fovx; bp.tan_fovy = a->tan_fovy;
-  bp.acc = g.acc;
+  bp.acc = g.acc; bp.conic_opacity = g.conic_opacity; bp.W = W; bp.H = H;
   bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
   bp.dL_dcolor = a->dL_dcolor; bp.dL_dmean3D = a->dL_dmean3D; bp.dL_dcov3D = a->dL_dcov3D;
   bp.dL_ddc = a->dL_ddc; bp.dL_dsh = a->dL_dsh; bp.dL_dscale = a->dL_dscale; bp.dL_drot = a->dL_drot;
-  GSR_RC(launch_preprocess_bwd(bp, s));
+  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, s));
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));
     GSR_CUDA(cudaGetLastError());
@@ -228,7 +280,9 @@ int gsr_knn_mean_dist2(int P, const float* points, float* mean_dist2, void* stre
 int gsr_adam_step(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
                   float grad_scale, void* stream) {
   if (n_groups < 0 || (n_groups > 0 && !groups)) return GSR_ERR_BAD_ARG;
-  return launch_adam(groups, n_groups, beta1, beta2, eps, grad_scale, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GSR_PROF("adam", launch_adam(groups, n_groups, beta1, beta2, eps, grad_scale, s));
+  return GSR_OK;
 }
 
 int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, int P, int R,
@@ -270,6 +324,32 @@ int gsr_export_geometry(const char* geom_buffer, int P, float* depths, float* me
   if (tiles_touched) GSR_CUDA(cudaMemcpyAsync(tiles_touched, g.tiles_touched, n * 4, cudaMemcpyDeviceToDevice, s));
   if (clamped) GSR_CUDA(cudaMemcpyAsync(clamped, g.clamped, n, cudaMemcpyDeviceToDevice, s));
   return GSR_OK;
+}
+
+void gsr_profile_enable(int on) {
+  g_prof.drain();
+  g_prof.on = on != 0;
+  if (on) {
+    for (auto& m : g_prof.ms) m = 0.0;
+    for (auto& c : g_prof.count) c = 0;
+  }
+}
+
+// Writes "name count total_ms\n" lines (NUL terminated) and returns the number of stages.
+int gsr_profile_read(char* out, size_t cap) {
+  g_prof.drain();
+  size_t off = 0;
+  int n = 0;
+  for (size_t i = 0; i < g_prof.names.size(); ++i) {
+    if (g_prof.count[i] == 0) continue;
+    int w = snprintf(out + off, off < cap ? cap - off : 0, "%s %lld %.6f\n", g_prof.names[i].c_str(),
+                     g_prof.count[i], g_prof.ms[i]);
+    if (w < 0 || off + (size_t)w >= cap) break;
+    off += (size_t)w;
+    ++n;
+  }
+  if (cap > 0) out[off < cap ? off : cap - 1] = 0;
+  return n;
 }
 
 size_t gsr_sort_temp_bytes(int64_t n) { return gsr::sort_temp_bytes(n); }

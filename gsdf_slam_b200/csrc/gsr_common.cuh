@@ -31,7 +31,8 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 struct GeomHeader {          // lives at the start of the geometry buffer (256 B)
   uint32_t num_dup;          // R: total (Gaussian,tile) duplicates
   uint32_t num_visible;      // V
-  uint32_t pad[62];
+  uint32_t num_large;        // length of the large-rectangle work queue (binning.cu)
+  uint32_t pad[61];
 };
 
 struct GeomView {
@@ -42,7 +43,7 @@ struct GeomView {
   float* rgb;                // [3P]
   uint32_t* tiles_touched;   // [P] exact number of tiles passing the opacity-aware test
   uint8_t* clamped;          // [P] bit c set <=> channel c was clamped
-  float* acc;                // [12P] backward accumulators (see blend_bwd.cu)
+  float* acc;                // [12P] backward moment sums {Mx,My,Mxx,Mxy,Myy,M0,r,g,b,-,-,-}
   uint64_t* sort_a;          // [P] (depth_bits<<32 | idx) ping
   uint64_t* sort_b;          // [P] pong
   uint32_t* dup_offsets;     // [P] exclusive scan of tiles_touched in depth order
@@ -243,6 +244,61 @@ __device__ __forceinline__ float tile_min_power(const float4 co, const float2 me
 __device__ __forceinline__ float opacity_power_threshold(float opacity) {
   const float opacity_threshold = 1.0f / 255.0f;
   return logf(opacity / opacity_threshold);
+}
+
+// Rectangles up to this many tiles are walked by their own thread; larger ones are
+// walked by the whole warp (32 tiles per step), which removes the heavy tail the
+// reference's one-thread-per-Gaussian loop has on near-camera splats.
+constexpr int kSerialRectTiles = 12;
+
+// Warp-cooperative walk over the tile rectangles of the lanes whose rect is large.
+// Must be called by all 32 lanes.  For every large rect (lane `src`), tiles are
+// visited in row-major order, 32 per step; `on_hits(src, pass_mask, pass, x, y,
+// hits_before)` is called by every lane with the ballot of lanes whose tile passed
+// the test (this lane's tile is (x,y)); the per-rect hit count is returned to its
+// owner lane.
+template <typename OnHits>
+__device__ __forceinline__ uint32_t warp_walk_large_rects(bool has_large, const float4 co,
+                                                          const float2 xy, const uint2 rect_min,
+                                                          const uint2 rect_max, float thr,
+                                                          OnHits on_hits) {
+  const int lane = threadIdx.x & 31;
+  uint32_t my_count = 0;
+  unsigned m = __ballot_sync(0xffffffffu, has_large);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    float4 c;
+    c.x = __shfl_sync(0xffffffffu, co.x, src);
+    c.y = __shfl_sync(0xffffffffu, co.y, src);
+    c.z = __shfl_sync(0xffffffffu, co.z, src);
+    c.w = __shfl_sync(0xffffffffu, co.w, src);
+    float2 p;
+    p.x = __shfl_sync(0xffffffffu, xy.x, src);
+    p.y = __shfl_sync(0xffffffffu, xy.y, src);
+    const int x0 = __shfl_sync(0xffffffffu, (int)rect_min.x, src);
+    const int y0 = __shfl_sync(0xffffffffu, (int)rect_min.y, src);
+    const int w = __shfl_sync(0xffffffffu, (int)(rect_max.x - rect_min.x), src);
+    const int h = __shfl_sync(0xffffffffu, (int)(rect_max.y - rect_min.y), src);
+    const float th = __shfl_sync(0xffffffffu, thr, src);
+    const int area = w * h;
+    uint32_t count = 0;
+    for (int t0 = 0; t0 < area; t0 += 32) {
+      const int t = t0 + lane;
+      bool pass = false;
+      int x = 0, y = 0;
+      if (t < area) {
+        y = y0 + t / w;
+        x = x0 + t - (t / w) * w;
+        pass = tile_min_power(c, p, x, y) <= th;
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, pass);
+      on_hits(src, pm, pass, x, y, count);
+      count += __popc(pm);
+    }
+    if (lane == src) my_count = count;
+  }
+  return my_count;
 }
 
 // ---- launch helpers implemented across the .cu files ------------------------

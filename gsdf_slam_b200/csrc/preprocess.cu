@@ -239,11 +239,19 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const Preproces
   // ---- exact tile count (opacity-aware test) -----------------------------------
   uint32_t ntiles = 0;
   const float4 co = {conic.x, conic.y, conic.z, opacity};
-  if (visible) {
-    const float thr = opacity_power_threshold(opacity);
-    for (int y = rect_min.y; y < (int)rect_max.y; ++y)
-      for (int x = rect_min.x; x < (int)rect_max.x; ++x)
-        ntiles += (tile_min_power(co, point_image, x, y) <= thr) ? 1u : 0u;
+  {
+    const float thr = visible ? opacity_power_threshold(opacity) : 0.f;
+    const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
+    const bool large = visible && area > kSerialRectTiles;
+    if (visible && !large) {
+      for (int y = rect_min.y; y < (int)rect_max.y; ++y)
+        for (int x = rect_min.x; x < (int)rect_max.x; ++x)
+          ntiles += (tile_min_power(co, point_image, x, y) <= thr) ? 1u : 0u;
+    }
+    const uint32_t big = warp_walk_large_rects(
+        large, co, point_image, rect_min, rect_max, thr,
+        [](int, unsigned, bool, int, int, uint32_t) {});
+    if (large) ntiles = big;
   }
 
   // ---- outputs -----------------------------------------------------------------

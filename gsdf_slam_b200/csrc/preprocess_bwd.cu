@@ -39,13 +39,14 @@ __device__ __forceinline__ void store3(float* p, size_t i, V3 v) {
   p[3 * i + 0] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z;
 }
 
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P) return;
+// Per-Gaussian body.  `sh_row` is this Gaussian's dL/dsh row (3*M floats) in SHARED
+// memory, pre-zeroed; the CTA writes the rows out coalesced afterwards.
+__device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const int idx,
+                                                   const bool rendered, float* sh_row) {
   const size_t i = (size_t)idx;
   const int M = a.M;
 
-  if (!(a.radii[idx] > 0)) {
+  if (!rendered) {
     // not rendered: all gradients are zero
     store3(a.dL_dmean2D, i, {0.f, 0.f, 0.f});
     if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -55,8 +56,6 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams 
     if (a.dL_dcov3D)
       for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * i + k] = 0.f;
     store3(a.dL_ddc, i, {0.f, 0.f, 0.f});
-    if (a.dL_dsh)
-      for (int k = 0; k < 3 * M; ++k) a.dL_dsh[(size_t)3 * M * i + k] = 0.f;
     store3(a.dL_dscale, i, {0.f, 0.f, 0.f});
     reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
@@ -66,9 +65,19 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams 
   const float4 acc0 = reinterpret_cast<const float4*>(a.acc)[3 * i + 0];
   const float4 acc1 = reinterpret_cast<const float4*>(a.acc)[3 * i + 1];
   const float4 acc2 = reinterpret_cast<const float4*>(a.acc)[3 * i + 2];
-  const float dmean2D_x = acc0.x, dmean2D_y = acc0.y;
-  const float3 dL_dconic = {acc0.z, acc0.w, acc1.x};  // (x, y, w) of the 2x2 conic gradient
-  const float dopacity = acc1.y;
+  // blend_bwd.cu accumulated, over every (pixel, this splat) pair with w = G*dL/dalpha and
+  // d = mean2D - pixel:  Mx = sum w*dx, My, Mxx = sum w*dx^2, Mxy, Myy, M0 = sum w, colour sums.
+  // The reference's per-pair terms (backward.cu:622-637) are linear in these moments:
+  //   dL/dmean2D.x = sum dL_dG*(-G*(a*dx+b*dy))*0.5W = -op*0.5W*(a*Mx + b*My)     (dL_dG = op*dL/dalpha)
+  //   dL/dconic.x  = sum -0.5*G*dx*dx*dL_dG          = -0.5*op*Mxx   (same for xy, yy)
+  //   dL/dopacity  = sum G*dL/dalpha                 = M0
+  const float4 cop = a.conic_opacity[i];
+  const float Mx = acc0.x, My = acc0.y, Mxx = acc0.z, Mxy = acc0.w, Myy = acc1.x, M0 = acc1.y;
+  const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+  const float dmean2D_x = -cop.w * ddelx_dx * (cop.x * Mx + cop.y * My);
+  const float dmean2D_y = -cop.w * ddely_dy * (cop.z * My + cop.y * Mx);
+  const float3 dL_dconic = {-0.5f * cop.w * Mxx, -0.5f * cop.w * Mxy, -0.5f * cop.w * Myy};
+  const float dopacity = M0;
   V3 dL_dRGB = {acc1.z, acc1.w, acc2.x};
 
   store3(a.dL_dmean2D, i, {dmean2D_x, dmean2D_y, 0.f});
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams 
     const float len = sqrtf(dotv(dir_orig, dir_orig));
     const V3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
     const V3* sh = reinterpret_cast<const V3*>(a.shs) + i * M;
-    V3* dL_dsh = reinterpret_cast<V3*>(a.dL_dsh) + i * M;
+    V3* dL_dsh = reinterpret_cast<V3*>(sh_row);
 
     const uint8_t cl = a.clamped[idx];
     dL_dRGB.x *= (cl & 1) ? 0 : 1;
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams 
         }
       }
     }
-    for (int k = written; k < M; ++k) dL_dsh[k] = {0.f, 0.f, 0.f};
+    (void)written;  // rows beyond the active degree stay zero (pre-zeroed shared row)
 
     V3 dL_ddir = {dotv(dRGBdx, dL_dRGB), dotv(dRGBdy, dL_dRGB), dotv(dRGBdz, dL_dRGB)};
     // dnormvdv (auxiliary.h:122-138)
@@ -305,8 +314,6 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams 
       r.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
       dL_dmean_total += r;
     }
-  } else if (a.dL_dsh) {
-    for (int k = 0; k < 3 * M; ++k) a.dL_dsh[(size_t)3 * M * i + k] = 0.f;
   }
   store3(a.dL_ddc, i, out_ddc);
   store3(a.dL_dmean3D, i, dL_dmean_total);
@@ -354,9 +361,40 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreBwdParams 
   }
 }
 
+constexpr int kPreBwdThreads = 128;
+
+// A CTA owns 128 consecutive Gaussians.  The 12*M-byte dL/dsh rows (180 B at SH-3) are
+// assembled in shared memory and written out as one contiguous float4 stream — zeros
+// included — instead of 45 scattered 4-byte stores per thread.
+__global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const PreBwdParams a) {
+  __shared__ __align__(16) float s_dsh[kPreBwdThreads * 45];
+  const int tid = threadIdx.x;
+  const int base = blockIdx.x * kPreBwdThreads;
+  const int idx = base + tid;
+  const int row = 3 * (a.M < 15 ? a.M : 15);
+  for (int k = tid; k < kPreBwdThreads * row; k += kPreBwdThreads) s_dsh[k] = 0.f;
+  __syncthreads();
+  if (idx < a.P) preprocess_bwd_one(a, idx, a.radii[idx] > 0, &s_dsh[tid * row]);
+  __syncthreads();
+  if (a.dL_dsh != nullptr && row > 0) {
+    const int count = min(kPreBwdThreads, a.P - base);
+    const int n = count * row;
+    float* dst = a.dL_dsh + (size_t)base * row;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      const int n4 = n >> 2;
+      for (int k = tid; k < n4; k += kPreBwdThreads)
+        __stcs(reinterpret_cast<float4*>(dst) + k, reinterpret_cast<const float4*>(s_dsh)[k]);
+      for (int k = n4 * 4 + tid; k < n; k += kPreBwdThreads) dst[k] = s_dsh[k];
+    } else {
+      for (int k = tid; k < n; k += kPreBwdThreads) dst[k] = s_dsh[k];
+    }
+  }
+}
+
 int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s) {
   if (p.P <= 0) return 0;
-  preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, s>>>(p);
+  if (p.M > 15) return GSR_ERR_BAD_ARG;
+  preprocess_bwd_kernel<<<(p.P + kPreBwdThreads - 1) / kPreBwdThreads, kPreBwdThreads, 0, s>>>(p);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

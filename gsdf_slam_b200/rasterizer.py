@@ -46,16 +46,23 @@ class _Scratch:
     analogue of the reference's resizeFunctional (src/rasterize_points.cu:28-36)."""
 
     def __init__(self, device):
-        self.device = device
-        self.t = torch.empty(0, dtype=torch.uint8, device=device)
-        self.cb = _lib.RESIZE_FN(self._resize)
+        holder = [torch.empty(0, dtype=torch.uint8, device=device)]
 
-    def _resize(self, _user, nbytes):
-        try:
-            self.t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            return self.t.data_ptr() if nbytes > 0 else 0
-        except Exception:  # never let an exception cross the C ABI
-            return 0
+        def _resize(_user, nbytes):
+            # closes over `holder` only (no reference cycle through self: the buffers must
+            # be freed by refcount as soon as autograd drops them, not by the cyclic GC)
+            try:
+                holder[0] = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+                return holder[0].data_ptr() if nbytes > 0 else 0
+            except Exception:  # never let an exception cross the C ABI
+                return 0
+
+        self._holder = holder
+        self.cb = _lib.RESIZE_FN(_resize)
+
+    @property
+    def t(self) -> torch.Tensor:
+        return self._holder[0]
 
 
 def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotations, scale_modifier,
@@ -99,9 +106,12 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                                    scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
                                    tan_fovy, dL_dout_color, dc, sh, degree, campos, geomBuffer, R,
                                    binningBuffer, imageBuffer, B, sampleBuffer, debug,
-                                   want_dcov3D: bool = True):
+                                   want_dcov3D: bool = True, out: Optional[dict] = None):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh,
-    dL_dscales, dL_drotations)   (same order as src/rasterize_points.cu:204)"""
+    dL_dscales, dL_drotations)   (same order as src/rasterize_points.cu:204)
+
+    ``out`` (extension): optional dict name -> preallocated contiguous tensor (e.g. views into
+    the flat gradient arena that is all-reduced across GPUs) to receive a gradient in place."""
     L = _lib.lib()
     dev = means3D.device
     P = int(means3D.size(0))
@@ -109,16 +119,24 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     M = int(sh.size(1)) if (sh is not None and sh.dim() >= 2 and sh.size(0) != 0) else 0
     opts = dict(dtype=torch.float32, device=dev)
     # the callee writes every row of every output: no zero-fill needed here
-    alloc = torch.empty if P > 0 else torch.zeros
-    dL_dmeans3D = alloc((P, 3), **opts)
-    dL_dmeans2D = alloc((P, 3), **opts)
-    dL_dcolors = alloc((P, NUM_CHANNELS), **opts)
-    dL_dopacity = alloc((P, 1), **opts)
-    dL_dcov3D = alloc((P, 6), **opts) if want_dcov3D else None
-    dL_ddc = alloc((P, 1, 3), **opts)
-    dL_dsh = alloc((P, M, 3), **opts)
-    dL_dscales = alloc((P, 3), **opts)
-    dL_drotations = alloc((P, 4), **opts)
+    out = out or {}
+
+    def alloc(name, shape):
+        t = out.get(name)
+        if t is not None:
+            assert t.is_contiguous() and t.numel() == int(torch.Size(shape).numel()), name
+            return t
+        return (torch.empty if P > 0 else torch.zeros)(shape, **opts)
+
+    dL_dmeans3D = alloc("dL_dmeans3D", (P, 3))
+    dL_dmeans2D = alloc("dL_dmeans2D", (P, 3))
+    dL_dcolors = alloc("dL_dcolors", (P, NUM_CHANNELS))
+    dL_dopacity = alloc("dL_dopacity", (P, 1))
+    dL_dcov3D = alloc("dL_dcov3D", (P, 6)) if want_dcov3D else None
+    dL_ddc = alloc("dL_ddc", (P, 1, 3))
+    dL_dsh = alloc("dL_dsh", (P, M, 3))
+    dL_dscales = alloc("dL_dscales", (P, 3))
+    dL_drotations = alloc("dL_drotations", (P, 4))
     if P != 0:
         keep = [_f32c(t) if t is not None else None for t in
                 (background, means3D, dc, sh, colors, scales, rotations, cov3D_precomp, viewmatrix,

@@ -157,6 +157,11 @@ size_t gsr_sort_temp_bytes(int64_t n);
 int gsr_sort_u64(const uint64_t* items_in, uint64_t* items_out, uint64_t* items_alt,
                  int64_t n, int begin_bit, int end_bit, char* tmp, void* stream);
 
+/* Optional per-stage CUDA-event timing (bench.py roofline measurement): enable, run steps,
+ * then read "stage count total_ms" lines.  Off by default; adds two event records per stage. */
+void gsr_profile_enable(int on);
+int gsr_profile_read(char* out, size_t cap);
+
 /* Number of kernels this library has launched since load (bench bookkeeping). */
 int64_t gsr_launch_count(void);
 const char* gsr_version(void);
