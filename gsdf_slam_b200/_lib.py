@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsr.so")
+# GSR_LIB_PATH: developer override to A/B kernel variants (tools/); default is the in-tree build
+LIB_PATH = os.environ.get("GSR_LIB_PATH", os.path.join(_HERE, "libgsr.so"))
 
 RESIZE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 

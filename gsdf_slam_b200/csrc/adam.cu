@@ -23,8 +23,17 @@
 namespace gsr {
 
 constexpr int kAdamMaxGroups = 16;
-constexpr int kAdamThreads = 256;
-constexpr int kAdamVecPerThread = 4;                                   // float4 per thread
+#ifndef GSR_ADAM_THREADS
+#define GSR_ADAM_THREADS 256
+#endif
+#ifndef GSR_ADAM_VEC
+#define GSR_ADAM_VEC 4
+#endif
+#ifndef GSR_ADAM_STREAM
+#define GSR_ADAM_STREAM 0
+#endif
+constexpr int kAdamThreads = GSR_ADAM_THREADS;
+constexpr int kAdamVecPerThread = GSR_ADAM_VEC;                        // float4 per thread
 constexpr int kAdamChunk = kAdamThreads * kAdamVecPerThread * 4;      // 4096 elements per CTA
 
 struct AdamGroupDev {
@@ -74,10 +83,17 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const AdamParams a) 
 #pragma unroll
     for (int k = 0; k < kAdamVecPerThread; ++k) {
       const long long e = base / 4 + k * kAdamThreads + threadIdx.x;
+#if GSR_ADAM_STREAM
+      p4[k] = __ldcs(reinterpret_cast<const float4*>(G.p) + e);
+      g4[k] = __ldcs(reinterpret_cast<const float4*>(G.g) + e);
+      m4[k] = __ldcs(reinterpret_cast<const float4*>(G.m) + e);
+      v4[k] = __ldcs(reinterpret_cast<const float4*>(G.v) + e);
+#else
       p4[k] = reinterpret_cast<const float4*>(G.p)[e];
       g4[k] = __ldcs(reinterpret_cast<const float4*>(G.g) + e);
       m4[k] = reinterpret_cast<const float4*>(G.m)[e];
       v4[k] = reinterpret_cast<const float4*>(G.v)[e];
+#endif
     }
 #pragma unroll
     for (int k = 0; k < kAdamVecPerThread; ++k) {
@@ -89,9 +105,15 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const AdamParams a) 
 #pragma unroll
     for (int k = 0; k < kAdamVecPerThread; ++k) {
       const long long e = base / 4 + k * kAdamThreads + threadIdx.x;
+#if GSR_ADAM_STREAM
+      __stcs(reinterpret_cast<float4*>(G.p) + e, p4[k]);
+      __stcs(reinterpret_cast<float4*>(G.m) + e, m4[k]);
+      __stcs(reinterpret_cast<float4*>(G.v) + e, v4[k]);
+#else
       reinterpret_cast<float4*>(G.p)[e] = p4[k];
       reinterpret_cast<float4*>(G.m)[e] = m4[k];
       reinterpret_cast<float4*>(G.v)[e] = v4[k];
+#endif
     }
   } else {
     for (long long e = base + threadIdx.x; e < end; e += kAdamThreads) {

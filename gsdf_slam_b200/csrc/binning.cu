@@ -172,6 +172,59 @@ int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
   return (int)cudaGetLastError();
 }
 
+// Longest-processing-time-first launch order for the blend kernels: a counting sort of the
+// tiles by list length (1024 buckets of 4 entries, longest first).  The blend kernels run
+// one CTA per tile for the whole length of its list, so starting the long lists first keeps
+// the last wave short (matters most for heavy-tailed scenes such as cfg4's ground splats).
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(const uint2* __restrict__ ranges, uint32_t T, uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_cnt[1024];
+  __shared__ uint32_t s_warp[32];
+  const int tid = threadIdx.x;
+  s_cnt[tid] = 0;
+  __syncthreads();
+  for (uint32_t t = tid; t < T; t += 1024) {
+    const uint2 r = ranges[t];
+    const uint32_t b = 1023u - min(1023u, (r.y - r.x) >> 2);  // bucket 0 = longest lists
+    atomicAdd(&s_cnt[b], 1u);
+  }
+  __syncthreads();
+  // exclusive scan of the 1024 bucket counts
+  const uint32_t c = s_cnt[tid];
+  uint32_t inc = c;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += x;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  s_cnt[tid] = inc - c + (warp > 0 ? s_warp[warp - 1] : 0u);
+  __syncthreads();
+  for (uint32_t t = tid; t < T; t += 1024) {
+    const uint2 r = ranges[t];
+    const uint32_t b = 1023u - min(1023u, (r.y - r.x) >> 2);
+    order[atomicAdd(&s_cnt[b], 1u)] = t;
+  }
+}
+
+int launch_tile_order(const uint2* ranges, uint32_t T, uint32_t* order, cudaStream_t s) {
+  tile_order_kernel<<<1, 1024, 0, s>>>(ranges, T, order);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
 // Debug/test export: rebuild the reference's 64-bit sorted keys (tile<<32 | depth bits)
 // and the sorted Gaussian-id list from the packed records.
 __global__ void export_binning_kernel(uint32_t R, const uint64_t* __restrict__ sorted,

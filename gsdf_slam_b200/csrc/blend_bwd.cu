@@ -56,8 +56,8 @@ __device__ __forceinline__ void warp_reduce9(const float (&v)[9], int lane, floa
   out9 = z;
 }
 
-__global__ void __launch_bounds__(kBlendThreads)
-blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ max_contrib,
+__global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_BWD_MINBLOCKS)
+blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ max_contrib,
                  const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
                  const float4* __restrict__ rec_c, int W, int H, const float* __restrict__ bg,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -69,7 +69,10 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   __shared__ __align__(8) uint64_t s_full[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+  // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel)
+  const uint32_t tile_id = tile_order[blockIdx.x];
+  const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
+  const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
   const size_t N = (size_t)W * H;
 
   const uint2 range = ranges[tile_id];
@@ -96,38 +99,41 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   };
   if (tid == 0 && rounds > 0) issue(0);
 
-  // per-pixel state of the four slots
-  float pxf[kSlots], pyf[kSlots], T[kSlots], T_final[kSlots], bg_dot[kSlots];
+  // per-pixel state of the four slots.  The reference tracks, per channel, ar = -(colour still
+  // to be blended behind the current splat) and forms
+  //   dL/dalpha = sum_ch (c_ch*T + ar_ch/(1-alpha)) * dL_ch - T_final/(1-alpha) * (bg . dL)
+  // (backward.cu:609-618).  ar only ever meets dL in a dot product, so one scalar per pixel
+  // suffices:  S = sum_ch ar_ch*dL_ch - T_final*(bg . dL);  each blended splat adds
+  // T*alpha*(c . dL) to it, and  dL/dalpha = T*(c . dL) + S/(1-alpha).
+  float pxf[kSlots], pyf[kSlots], T[kSlots], S[kSlots];
   uint32_t last[kSlots];
-  float ar[kSlots][3], dL[kSlots][3];
+  float dL[kSlots][3];
   const float bgc[3] = {bg[0], bg[1], bg[2]};
   uint32_t my_last = 0;
 #pragma unroll
   for (int q = 0; q < kSlots; ++q) {
-    const uint32_t px = slot_px(blockIdx.x, lane, q);
-    const uint32_t py = slot_py(blockIdx.y, warp, lane, q);
+    const uint32_t px = slot_px(tile_x, lane, q);
+    const uint32_t py = slot_py(tile_y, warp, lane, q);
     const bool inside = px < (uint32_t)W && py < (uint32_t)H;
     const uint32_t pix_id = (uint32_t)W * py + px;
     pxf[q] = (float)px;
     pyf[q] = (float)py;
     T[q] = 1.0f;
-    T_final[q] = 0.f;
+    S[q] = 0.f;
     last[q] = 0;
-    bg_dot[q] = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      ar[q][ch] = 0.f;
-      dL[q][ch] = 0.f;
-    }
+    for (int ch = 0; ch < 3; ++ch) dL[q][ch] = 0.f;
     if (inside) {
-      T_final[q] = final_T[pix_id];
+      const float T_final = final_T[pix_id];
       last[q] = n_contrib[pix_id];
+      float bg_dot = 0.f, ar_dot = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        ar[q][ch] = -accum_c[ch * N + pix_id];  // minus the colour still to be blended
         dL[q][ch] = dL_dpix[ch * N + pix_id];
-        bg_dot[q] += bgc[ch] * dL[q][ch];
+        ar_dot += accum_c[ch * N + pix_id] * dL[q][ch];
+        bg_dot += bgc[ch] * dL[q][ch];
       }
+      S[q] = -ar_dot - T_final * bg_dot;
     }
     my_last = max(my_last, last[q]);
   }
@@ -160,7 +166,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       bool any_cand = false;
 #pragma unroll
       for (int q = 0; q < kSlots; ++q) {
-        const float2 d = {A.x - pxf[q], A.y - pyf[q]};
+        const float2 d = {A.x - pxf[q & 1], A.y - pyf[q & 2]};
         const float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
         pw[q] = power;
         cand[q] = (pos < last[q]) && !(power > 0.0f) && !(power < B.z);
@@ -177,20 +183,17 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         if (alpha < 1.0f / 255.0f) continue;
         contributed = true;
         {
-          const float2 d = {A.x - pxf[q], A.y - pyf[q]};
+          const float2 d = {A.x - pxf[q & 1], A.y - pyf[q & 2]};
           const float4 col = sC[buf][j];
-          const float c[3] = {col.x, col.y, col.z};
           const float one_m = 1.0f - alpha;
-          const float inv = 1.0f / one_m;
+          const float inv = __frcp_rn(one_m);  // == 1.0f / one_m (correctly rounded), no slow path
           const float Ta = T[q] * alpha;
-          float dL_dalpha = 0.0f;
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            ar[q][ch] += Ta * c[ch];
-            v[6 + ch] += Ta * dL[q][ch];
-            dL_dalpha += ((c[ch] * T[q]) + inv * ar[q][ch]) * dL[q][ch];
-          }
-          dL_dalpha += (-T_final[q] * inv) * bg_dot[q];
+          const float cdl = col.x * dL[q][0] + col.y * dL[q][1] + col.z * dL[q][2];
+          v[6] += Ta * dL[q][0];
+          v[7] += Ta * dL[q][1];
+          v[8] += Ta * dL[q][2];
+          S[q] += Ta * cdl;
+          const float dL_dalpha = T[q] * cdl + inv * S[q];
           T[q] *= one_m;
 
           const float w = G * dL_dalpha;
@@ -218,12 +221,13 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
 }
 
-int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* max_contrib,
+int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_order,
+                     const uint32_t* max_contrib,
                      const float4* rec_a, const float4* rec_b, const float4* rec_c, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s) {
-  dim3 grid((W + GSR_TILE_X - 1) / GSR_TILE_X, (H + GSR_TILE_Y - 1) / GSR_TILE_Y, 1);
-  blend_bwd_kernel<<<grid, kBlendThreads, 0, s>>>(ranges, max_contrib, rec_a, rec_b, rec_c, W, H, bg,
+  const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
+  blend_bwd_kernel<<<grid, kBlendThreads, 0, s>>>(ranges, tile_order, max_contrib, rec_a, rec_b, rec_c, W, H, bg,
                                                   final_T, n_contrib, accum_c, dL_dpix, acc);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();

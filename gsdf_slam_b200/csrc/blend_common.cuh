@@ -8,6 +8,14 @@
 
 #include "gsr_common.cuh"
 
+// minimum resident CTAs per SM the compiler must allow (bounds registers per thread)
+#ifndef GSR_BLEND_FWD_MINBLOCKS
+#define GSR_BLEND_FWD_MINBLOCKS 1
+#endif
+#ifndef GSR_BLEND_BWD_MINBLOCKS
+#define GSR_BLEND_BWD_MINBLOCKS 1
+#endif
+
 namespace gsr {
 
 constexpr int kBlendThreads = 64;

@@ -24,8 +24,8 @@
 
 namespace gsr {
 
-__global__ void __launch_bounds__(kBlendThreads)
-blend_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ rec_a,
+__global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_FWD_MINBLOCKS)
+blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const float4* __restrict__ rec_a,
                  const float4* __restrict__ rec_b, const float4* __restrict__ rec_c, int W, int H,
                  const float* __restrict__ bg, float* __restrict__ out_color,
                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
@@ -37,15 +37,18 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ re
   __shared__ uint32_t s_max[kBlendThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+  // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel)
+  const uint32_t tile_id = tile_order[blockIdx.x];
+  const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
+  const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
 
   float pxf[kSlots], pyf[kSlots];
   uint32_t pix_id[kSlots];
   bool inside[kSlots];
 #pragma unroll
   for (int q = 0; q < kSlots; ++q) {
-    const uint32_t px = slot_px(blockIdx.x, lane, q);
-    const uint32_t py = slot_py(blockIdx.y, warp, lane, q);
+    const uint32_t px = slot_px(tile_x, lane, q);
+    const uint32_t py = slot_py(tile_y, warp, lane, q);
     inside[q] = px < (uint32_t)W && py < (uint32_t)H;
     pix_id[q] = (uint32_t)W * py + px;
     pxf[q] = (float)px;
@@ -111,7 +114,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ re
       bool any_cand = false;
 #pragma unroll
       for (int q = 0; q < kSlots; ++q) {
-        float2 d = {xy.x - pxf[q], xy.y - pyf[q]};
+        float2 d = {xy.x - pxf[q & 1], xy.y - pyf[q & 2]};
         float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
         pw[q] = power;
         // power < B.z: certainly alpha < 1/255 (conservative, see finalize_kernel)
@@ -169,11 +172,11 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const float4* __restrict__ re
   }
 }
 
-int launch_blend_fwd(int W, int H, const uint2* ranges, const float4* rec_a, const float4* rec_b,
+int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec_a, const float4* rec_b,
                      const float4* rec_c, const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s) {
-  dim3 grid((W + GSR_TILE_X - 1) / GSR_TILE_X, (H + GSR_TILE_Y - 1) / GSR_TILE_Y, 1);
-  blend_fwd_kernel<<<grid, kBlendThreads, 0, s>>>(ranges, rec_a, rec_b, rec_c, W, H, bg, out_color,
+  const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
+  blend_fwd_kernel<<<grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec_a, rec_b, rec_c, W, H, bg, out_color,
                                                   final_T, n_contrib, accum_c, max_contrib);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();

@@ -4,20 +4,21 @@ set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 ROOT="$(cd "$HERE/../.." && pwd)"
 NVCC="${NVCC:-nvcc}"
-OUT="$HERE/../libgsr.so"
+OUT="${GSR_OUT:-$HERE/../libgsr.so}"
+OBJDIR="${GSR_OBJDIR:-$HERE/obj}"
 FLAGS=(-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC
        -I"$ROOT/include" -I"$HERE" ${GSR_EXTRA_NVCC_FLAGS:-})
 SRCS=(gsr_capi.cu preprocess.cu radix_sort.cu binning.cu blend_fwd.cu blend_bwd.cu preprocess_bwd.cu adam.cu knn.cu)
-mkdir -p "$HERE/obj"
+mkdir -p "$OBJDIR"
 pids=()
 for s in "${SRCS[@]}"; do
-  o="$HERE/obj/${s%.cu}.o"
+  o="$OBJDIR/${s%.cu}.o"
   if [ ! -f "$o" ] || [ "$HERE/$s" -nt "$o" ] || [ -n "$(find "$HERE" "$ROOT/include" -maxdepth 1 \( -name '*.cuh' -o -name '*.h' \) -newer "$o" 2>/dev/null | head -1)" ]; then
     "$NVCC" "${FLAGS[@]}" -c "$HERE/$s" -o "$o" &
     pids+=($!)
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-OBJS=(); for s in "${SRCS[@]}"; do OBJS+=("$HERE/obj/${s%.cu}.o"); done
+OBJS=(); for s in "${SRCS[@]}"; do OBJS+=("$OBJDIR/${s%.cu}.o"); done
 "$NVCC" -shared -o "$OUT" "${OBJS[@]}" -gencode arch=compute_100a,code=sm_100a
 echo "built $OUT"

@@ -198,7 +198,8 @@ int gsr_forward(const gsr_forward_args* a) {
   const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
   GSR_PROF("finalize", launch_finalize(R, b.items_a, g.means2D, g.conic_opacity, colors, im.ranges, T, b.rec_a,
                          b.rec_b, b.rec_c, s));
-  GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, b.rec_a, b.rec_b, b.rec_c, a->background, a->out_color,
+  GSR_PROF("tile_order", launch_tile_order(im.ranges, T, im.tile_order, s));
+  GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec_a, b.rec_b, b.rec_c, a->background, a->out_color,
                           im.final_T, im.n_contrib, im.accum_c, im.max_contrib, s));
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));
@@ -229,7 +230,7 @@ int gsr_backward(const gsr_backward_args* a) {
   GSR_CUDA(cudaMemsetAsync(g.acc, 0, (size_t)P * 12 * sizeof(float), s));
   if (a->R > 0) {
     BinView b = bin_view(a->binning_buffer, (size_t)a->R);
-    GSR_PROF("blend_bwd", launch_blend_bwd(W, H, im.ranges, im.max_contrib, b.rec_a, b.rec_b, b.rec_c,
+    GSR_PROF("blend_bwd", launch_blend_bwd(W, H, im.ranges, im.tile_order, im.max_contrib, b.rec_a, b.rec_b, b.rec_c,
                             a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, s));
   }
   PreBwdParams bp;

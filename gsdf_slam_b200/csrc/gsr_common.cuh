@@ -57,6 +57,7 @@ struct ImageView {
   float* accum_c;            // [3N] blended colour WITHOUT background (planar)
   uint2* ranges;             // [T]
   uint32_t* max_contrib;     // [T]
+  uint32_t* tile_order;      // [T] tiles sorted by list length, longest first (CTA launch order)
 };
 
 struct BinView {
@@ -110,11 +111,12 @@ inline ImageView image_view(char* base, size_t N, size_t T) {
   v.accum_c = carve<float>(p, 3 * N);
   v.ranges = carve<uint2>(p, T);
   v.max_contrib = carve<uint32_t>(p, T);
+  v.tile_order = carve<uint32_t>(p, T);
   return v;
 }
 inline size_t image_bytes(size_t N, size_t T) {
   ImageView v = image_view(nullptr, N, T);
-  return reinterpret_cast<size_t>(v.max_contrib) + T * 4 + 128;
+  return reinterpret_cast<size_t>(v.tile_order) + T * 4 + 128;
 }
 
 inline BinView bin_view(char* base, size_t R) {

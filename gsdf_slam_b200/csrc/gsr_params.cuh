@@ -77,10 +77,12 @@ int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
                     float4* rec_a, float4* rec_b, float4* rec_c, cudaStream_t s);
 int launch_export_binning(uint32_t R, const uint64_t* sorted, const float* depths, uint64_t* keys,
                           uint32_t* point_list, cudaStream_t s);
-int launch_blend_fwd(int W, int H, const uint2* ranges, const float4* rec_a, const float4* rec_b,
+int launch_tile_order(const uint2* ranges, uint32_t T, uint32_t* order, cudaStream_t s);
+int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec_a, const float4* rec_b,
                      const float4* rec_c, const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s);
-int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* max_contrib,
+int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_order,
+                     const uint32_t* max_contrib,
                      const float4* rec_a, const float4* rec_b, const float4* rec_c, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s);

@@ -22,8 +22,11 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItemsPerThread = 16;
-constexpr int kTileItems = kSortThreads * kItemsPerThread;  // 4096
+// Items per thread: 16 (4096-item tiles) for large inputs; 4 (1024-item tiles) for small
+// ones, where a pass is latency-bound and more, shorter CTAs fill the 148 SMs better.
+constexpr int kIptLarge = 16;
+constexpr int kIptSmall = 4;
+constexpr int64_t kSmallSortLimit = 96 * 1024;
 constexpr int kMaxPasses = 8;
 
 constexpr uint32_t kFlagAgg = 1u << 30;   // tile published its own count
@@ -32,7 +35,11 @@ constexpr uint32_t kValMask = (1u << 30) - 1;
 
 // temp layout (uint32 words): ghist[kMaxPasses][256] | tile_counter[kMaxPasses] (padded to 64)
 //                             | lookback[kMaxPasses][num_tiles][256]
-static inline int64_t sort_num_tiles(int64_t n) { return (n + kTileItems - 1) / kTileItems; }
+static inline int sort_ipt(int64_t n) { return n < kSmallSortLimit ? kIptSmall : kIptLarge; }
+static inline int64_t sort_num_tiles(int64_t n) {
+  const int64_t tile = (int64_t)kSortThreads * sort_ipt(n);
+  return (n + tile - 1) / tile;
+}
 static inline size_t sort_header_words() { return (size_t)kMaxPasses * kRadix + 64; }
 
 size_t sort_temp_bytes(int64_t n) {
@@ -101,11 +108,13 @@ sort_histogram_kernel(const uint64_t* __restrict__ items, uint32_t n, int begin_
 // ---------------------------------------------------------------------------
 // One onesweep pass: stable scatter of the items by one 8-bit digit.
 // ---------------------------------------------------------------------------
+template <int kItemsPerThread>
 __global__ void __launch_bounds__(kSortThreads)
 onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n,
                      int shift, uint32_t digit_mask, const uint32_t* __restrict__ ghist,
                      uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ lookback) {
-  __shared__ uint64_t s_items[kTileItems];              // 32 KB
+  constexpr int kTileItems = kSortThreads * kItemsPerThread;
+  __shared__ uint64_t s_items[kTileItems];              // 32 KB at 16 items per thread
   __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];  // 8 KB
   __shared__ uint32_t s_bin_start[kRadix];
   __shared__ uint32_t s_digit_base[kRadix];
@@ -230,9 +239,14 @@ int launch_sort_u64(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t n,
   for (int p = 0; p < npass; ++p) {
     const int sh = begin_bit + p * kRadixBits;
     const int bits = (end_bit - sh) < kRadixBits ? (end_bit - sh) : kRadixBits;
-    onesweep_pass_kernel<<<(unsigned)tiles, kSortThreads, 0, s>>>(
-        src, dst, (uint32_t)n, sh, (1u << bits) - 1u, ghist + (size_t)p * kRadix, counters + p,
-        lookback + (size_t)p * tiles * kRadix);
+    if (sort_ipt(n) == kIptSmall)
+      onesweep_pass_kernel<kIptSmall><<<(unsigned)tiles, kSortThreads, 0, s>>>(
+          src, dst, (uint32_t)n, sh, (1u << bits) - 1u, ghist + (size_t)p * kRadix, counters + p,
+          lookback + (size_t)p * tiles * kRadix);
+    else
+      onesweep_pass_kernel<kIptLarge><<<(unsigned)tiles, kSortThreads, 0, s>>>(
+          src, dst, (uint32_t)n, sh, (1u << bits) - 1u, ghist + (size_t)p * kRadix, counters + p,
+          lookback + (size_t)p * tiles * kRadix);
     GSR_LAUNCHED();
     src = dst;
     dst = (dst == out) ? alt : out;
@@ -258,6 +272,10 @@ scan_gather_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restri
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
+  // The items are depth-sorted with every non-rendered Gaussian (key 0xFFFFFFFF) at the end:
+  // a tile that starts with one holds only zeros, and so do all tiles after it — nobody will
+  // ever look back at them, so they leave at once (typically > 80 % of the tiles).
+  if ((uint32_t)(order_items[(size_t)tile * kScanTile] >> 32) == 0xffffffffu) return;
   const uint32_t base = tile * kScanTile + tid * kScanItems;
   uint32_t v[kScanItems];
   uint32_t sum = 0;
@@ -290,7 +308,7 @@ scan_gather_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restri
       st_volatile_u32(lookback + tile, kFlagInc | (pre + block_total));
     }
     s_prefix = pre;
-    if ((uint64_t)(tile + 1) * kScanTile >= n) *total_out = pre + block_total;
+    if (block_total) atomicAdd(total_out, block_total);  // *total_out is zeroed by the caller
   }
   __syncthreads();
   uint32_t run = s_prefix + excl;
