@@ -29,9 +29,17 @@ emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restri
             const uint32_t* __restrict__ dup_offsets, const float2* __restrict__ means2D,
             const float4* __restrict__ conic_opacity, const int* __restrict__ radii, int grid_x,
             int grid_y, uint64_t* __restrict__ items, uint32_t* __restrict__ large_count,
-            uint32_t* __restrict__ large_list) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+            uint32_t* __restrict__ large_list, const uint32_t* __restrict__ num_valid) {
+  // Only the first num_valid depth-sorted positions own tiles.  In depth order the near
+  // (= large) splats are neighbours, so lane l of a warp takes its Gaussian from the l-th of
+  // 32 depth strata: every warp then walks a similar mix of near and far rectangles.
   const int lane = threadIdx.x & 31;
+  const uint32_t nv = *num_valid;
+  const uint32_t per_lane = (nv + 31u) / 32u;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp_global >= per_lane) return;  // whole warp
+  const uint32_t jj = (uint32_t)lane * per_lane + warp_global;
+  const int j = jj < nv ? (int)jj : P;
   uint32_t g = 0, cnt = 0, off = 0;
   float2 xy = {0.f, 0.f};
   float4 co = {0.f, 0.f, 0.f, 0.f};
@@ -49,21 +57,25 @@ emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restri
     thr = opacity_power_threshold(co.w);
   }
   const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
-  const bool large = cnt != 0 && area > kSerialRectTiles;
-  if (cnt != 0 && !large) {
-    for (int y = rect_min.y; y < (int)rect_max.y; ++y) {
-      for (int x = rect_min.x; x < (int)rect_max.x; ++x) {
-        if (tile_min_power(co, xy, x, y) <= thr) {
-          const uint64_t tile = (uint64_t)(y * grid_x + x);
-          items[off++] = (tile << 32) | g;
-        }
-      }
-    }
-  }
-  // Large rectangles are not walked here: in depth order the near (= huge) splats sit next
-  // to each other, so they would all land in the first few warps.  They are queued and
+  const bool large = cnt != 0 && area > kQueueRectTiles;
+  // All (Gaussian, tile) pairs of the warp are tested 32 per step; a hit claims the next slot
+  // of its owner's reserved range [off, off + cnt).  (The order inside one Gaussian's range is
+  // irrelevant: its tiles are distinct, and the tile sort only needs the ranges of different
+  // Gaussians to stay in depth order.)
+  __shared__ uint32_t s_slot[256 / 32][32];
+  const int warp = threadIdx.x >> 5;
+  s_slot[warp][lane] = 0;
+  __syncwarp();
+  uint32_t* slot = s_slot[warp];
+  warp_walk_rects_flat(cnt != 0 && !large, co, xy, rect_min, rect_max, thr, off, g,
+                       [&](int owner, int x, int y, uint32_t owner_off, uint32_t owner_g) {
+                         const uint32_t k = atomicAdd(&slot[owner], 1u);
+                         const uint64_t tile = (uint64_t)(y * grid_x + x);
+                         items[owner_off + k] = (tile << 32) | owner_g;
+                       });
+  // Very large rectangles are not walked here: in depth order the near (= huge) splats sit
+  // next to each other, so they would all land in the first few warps.  They are queued and
   // spread over the whole GPU by emit_large_kernel.
-  (void)lane;
   if (large) large_list[atomicAdd(large_count, 1u)] = (uint32_t)j;
 }
 
@@ -113,11 +125,11 @@ emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __re
 int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
                 const uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
                 const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
-                uint32_t* large_list, cudaStream_t s) {
+                uint32_t* large_list, const uint32_t* num_valid, cudaStream_t s) {
   if (P <= 0) return 0;
   emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, sorted, tiles_touched, dup_offsets, means2D,
                                               conic_opacity, radii, grid_x, grid_y, items,
-                                              large_count, large_list);
+                                              large_count, large_list, num_valid);
   GSR_LAUNCHED();
   // 148 SMs x 2 CTAs x 8 warps walk the queued large rectangles
   emit_large_kernel<<<148 * 2, 256, 0, s>>>(large_count, large_list, sorted, dup_offsets, means2D,

@@ -189,7 +189,7 @@ int gsr_forward(const gsr_forward_args* a) {
     uint64_t* other = (npass & 1) ? b.items_a : b.items_b;
     GSR_PROF("emit", launch_emit(P, order, g.tiles_touched, g.dup_offsets, g.means2D, g.conic_opacity,
                        a->radii, gx, gy, emit_dst, &g.hdr->num_large,
-                       reinterpret_cast<uint32_t*>(g.sort_b), s));
+                       reinterpret_cast<uint32_t*>(g.sort_b), &g.hdr->num_visible, s));
     uint64_t* sorted = nullptr;
     // odd: in=b, out=a, alt=b ; even: in=a, out=a, alt=b
     GSR_PROF("sort_tile", launch_sort_u64(emit_dst, b.items_a, (npass & 1) ? emit_dst : other, R, 32, 32 + tb,

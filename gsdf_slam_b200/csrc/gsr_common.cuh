@@ -251,7 +251,10 @@ __device__ __forceinline__ float opacity_power_threshold(float opacity) {
 // Rectangles up to this many tiles are walked by their own thread; larger ones are
 // walked by the whole warp (32 tiles per step), which removes the heavy tail the
 // reference's one-thread-per-Gaussian loop has on near-camera splats.
-constexpr int kSerialRectTiles = 12;
+#ifndef GSR_SERIAL_RECT_TILES
+#define GSR_SERIAL_RECT_TILES 12
+#endif
+constexpr int kSerialRectTiles = GSR_SERIAL_RECT_TILES;
 
 // Warp-cooperative walk over the tile rectangles of the lanes whose rect is large.
 // Must be called by all 32 lanes.  For every large rect (lane `src`), tiles are
@@ -301,6 +304,63 @@ __device__ __forceinline__ uint32_t warp_walk_large_rects(bool has_large, const 
     if (lane == src) my_count = count;
   }
   return my_count;
+}
+
+// Flattened warp-cooperative walk over the tile rectangles of ALL lanes of a warp: the
+// (lane, tile) pairs are enumerated 32 per step, so every step tests 32 tiles no matter how
+// the rectangle sizes are distributed over the lanes (a one-thread-per-Gaussian loop runs at
+// ~2 live lanes per warp when few lanes hold visible Gaussians).  Must be called by all 32
+// lanes; `on_hit(owner_lane, x, y, pay0, pay1)` is invoked by each lane whose tile passed the
+// test (pay0/pay1 = the owner lane's payload words), in no particular order.
+constexpr int kQueueRectTiles = 256;  // emit: rectangles larger than this go to the work queue
+
+template <typename OnHit>
+__device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, const float2 xy,
+                                                     const uint2 rect_min, const uint2 rect_max,
+                                                     float thr, uint32_t pay0, uint32_t pay1,
+                                                     OnHit on_hit) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int w_own = has ? (int)(rect_max.x - rect_min.x) : 0;
+  const int area = has ? w_own * (int)(rect_max.y - rect_min.y) : 0;
+  int incl = area;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(full, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(full, incl, 31);
+  const int excl = incl - area;
+  for (int f0 = 0; f0 < total; f0 += 32) {
+    const int f = f0 + lane;
+    // owner = number of lanes whose inclusive prefix is <= f (prefix is non-decreasing)
+    int owner = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int v = __shfl_sync(full, incl, owner + step - 1);
+      if (v <= f) owner += step;
+    }
+    float4 c;
+    c.x = __shfl_sync(full, co.x, owner);
+    c.y = __shfl_sync(full, co.y, owner);
+    c.z = __shfl_sync(full, co.z, owner);
+    c.w = __shfl_sync(full, co.w, owner);
+    float2 p;
+    p.x = __shfl_sync(full, xy.x, owner);
+    p.y = __shfl_sync(full, xy.y, owner);
+    const int x0 = __shfl_sync(full, (int)rect_min.x, owner);
+    const int y0 = __shfl_sync(full, (int)rect_min.y, owner);
+    const int w = __shfl_sync(full, w_own, owner);
+    const float th = __shfl_sync(full, thr, owner);
+    const int t = f - __shfl_sync(full, excl, owner);
+    const uint32_t q0 = __shfl_sync(full, pay0, owner);
+    const uint32_t q1 = __shfl_sync(full, pay1, owner);
+    if (f < total) {
+      const int y = y0 + t / w;
+      const int x = x0 + t - (t / w) * w;
+      if (tile_min_power(c, p, x, y) <= th) on_hit(owner, x, y, q0, q1);
+    }
+  }
 }
 
 // ---- launch helpers implemented across the .cu files ------------------------

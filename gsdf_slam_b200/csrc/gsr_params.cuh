@@ -71,7 +71,7 @@ int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t*
 int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
                 const uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
                 const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
-                uint32_t* large_list, cudaStream_t s);
+                uint32_t* large_list, const uint32_t* num_valid, cudaStream_t s);
 int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
                     const float4* conic_opacity, const float* colors, uint2* ranges, uint32_t T,
                     float4* rec_a, float4* rec_b, float4* rec_c, cudaStream_t s);

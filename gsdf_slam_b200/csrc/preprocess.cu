@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const Preproces
   __shared__ __align__(16) float s_rot[kPreThreads * 4];
   __shared__ __align__(16) float s_dc[kPreThreads * 3];
   __shared__ float s_sh[kPreThreads / 32][32 * kShFloats];  // per-warp SH rows (23 KB)
+  __shared__ uint32_t s_tiles[kPreThreads / 32][32];        // per-warp tile counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int base = blockIdx.x * kPreThreads;
@@ -213,13 +214,32 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const Preproces
       const int ncoef = min(a.M, 15) * 3;
       unsigned m = vis_mask;
       while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const size_t g = (size_t)(base + warp * 32 + src);
-        const float* row = a.shs + g * (size_t)a.M * 3;
-        float* dst = &s_sh[warp][src * kShFloats];
-        if (lane < ncoef) dst[lane] = row[lane];
-        if (lane + 32 < ncoef) dst[lane + 32] = row[lane + 32];
+        // four rows per trip: all eight loads are in flight before the first store
+        int src[4];
+        float v0[4], v1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          src[u] = m ? (__ffs(m) - 1) : -1;
+          m &= m - 1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v0[u] = 0.f;
+          v1[u] = 0.f;
+          if (src[u] >= 0) {
+            const float* row = a.shs + (size_t)(base + warp * 32 + src[u]) * (size_t)a.M * 3;
+            if (lane < ncoef) v0[u] = row[lane];
+            if (lane + 32 < ncoef) v1[u] = row[lane + 32];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (src[u] >= 0) {
+            float* dst = &s_sh[warp][src[u] * kShFloats];
+            if (lane < ncoef) dst[lane] = v0[u];
+            if (lane + 32 < ncoef) dst[lane + 32] = v1[u];
+          }
+        }
       }
       __syncwarp();
     }
@@ -240,18 +260,15 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const Preproces
   uint32_t ntiles = 0;
   const float4 co = {conic.x, conic.y, conic.z, opacity};
   {
+    // all (Gaussian, tile) pairs of the warp, 32 per step (gsr_common.cuh)
     const float thr = visible ? opacity_power_threshold(opacity) : 0.f;
-    const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
-    const bool large = visible && area > kSerialRectTiles;
-    if (visible && !large) {
-      for (int y = rect_min.y; y < (int)rect_max.y; ++y)
-        for (int x = rect_min.x; x < (int)rect_max.x; ++x)
-          ntiles += (tile_min_power(co, point_image, x, y) <= thr) ? 1u : 0u;
-    }
-    const uint32_t big = warp_walk_large_rects(
-        large, co, point_image, rect_min, rect_max, thr,
-        [](int, unsigned, bool, int, int, uint32_t) {});
-    if (large) ntiles = big;
+    s_tiles[warp][lane] = 0;
+    __syncwarp();
+    uint32_t* cnt = s_tiles[warp];
+    warp_walk_rects_flat(visible, co, point_image, rect_min, rect_max, thr, 0u, 0u,
+                         [cnt](int owner, int, int, uint32_t, uint32_t) { atomicAdd(&cnt[owner], 1u); });
+    __syncwarp();
+    ntiles = s_tiles[warp][lane];
   }
 
   // ---- outputs -----------------------------------------------------------------
@@ -273,7 +290,8 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const Preproces
     }
     a.sort_items[idx] = ((uint64_t)depth_bits << 32) | (uint32_t)idx;
   }
-  const unsigned vm = __ballot_sync(0xffffffffu, visible);
+  // number of Gaussians that own at least one tile (= length of the valid depth-sorted prefix)
+  const unsigned vm = __ballot_sync(0xffffffffu, visible && ntiles > 0);
   if (lane == 0 && vm) atomicAdd(a.num_visible, (uint32_t)__popc(vm));
 }
 
