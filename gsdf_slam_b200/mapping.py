@@ -128,7 +128,7 @@ class KeyframeBatchMapper:
         self.render_backward(keyframes[0], self.grad_views)      # first keyframe writes in place
         for kf in keyframes[1:]:
             if self._scratch_arena is None:
-                self._scratch_arena = torch.empty_like(self.arena)
+                self._scratch_arena = torch.zeros_like(self.arena)  # padding slots stay 0
             self.render_backward(kf, self._views(self._scratch_arena))
             self.arena.add_(self._scratch_arena)
 

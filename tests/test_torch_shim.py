@@ -1,0 +1,89 @@
+"""The LibTorch drop-in shim (gsdf_slam_b200/csrc/torch_shim): same C++ symbols as the
+reference's src/rasterize_points.cu, implemented over the C ABI."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "gsdf_slam_b200", "libgsr_torch_shim.so")
+REF_HDR_DIR = "/root/reference/include"
+
+
+def _nm_symbols():
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", SHIM], capture_output=True, text=True).stdout
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(SHIM), reason="torch shim not built")
+def test_shim_exports_reference_symbols():
+    syms = _nm_symbols()
+    for name in ("RasterizeGaussiansCUDA(", "RasterizeGaussiansBackwardCUDA(", "markVisible(", "distCUDA2("):
+        assert name in syms, f"{name} not exported by the shim"
+
+
+@pytest.mark.skipif(not (os.path.exists(SHIM) and os.path.exists(os.path.join(REF_HDR_DIR, "rasterize_points.h"))),
+                    reason="needs the shim and the reference headers (build container only)")
+def test_reference_header_links_against_shim():
+    """A translation unit that includes the REFERENCE's own rasterize_points.h / spatial.h and
+    takes the address of every function must link against the shim: identical signatures."""
+    tdir = os.path.dirname(torch.__file__)
+    src = r'''
+#include "rasterize_points.h"
+#include "spatial.h"
+int main() {
+  auto f = &RasterizeGaussiansCUDA; auto b = &RasterizeGaussiansBackwardCUDA;
+  auto m = &markVisible; auto d = &distCUDA2;
+  return (f && b && m && d) ? 0 : 1;
+}
+'''
+    with tempfile.TemporaryDirectory() as td:
+        cpp = os.path.join(td, "t.cpp")
+        open(cpp, "w").write(src)
+        abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
+        import sysconfig
+        cmd = ["g++", "-std=c++17", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", "-I", REF_HDR_DIR,
+               "-I", "/root/reference/submodules/simple-knn", "-I", os.path.join(tdir, "include"),
+               "-I", os.path.join(tdir, "include/torch/csrc/api/include"), "-I", "/usr/local/cuda/include",
+               "-I", sysconfig.get_paths()["include"], cpp, "-o", os.path.join(td, "t"),
+               "-L", os.path.join(ROOT, "gsdf_slam_b200"), "-l:libgsr_torch_shim.so", "-l:libgsr.so",
+               "-L", os.path.join(tdir, "lib"), "-ltorch", "-ltorch_cpu", "-lc10",
+               f"-Wl,-rpath,{os.path.join(ROOT, 'gsdf_slam_b200')}", f"-Wl,-rpath,{os.path.join(tdir, 'lib')}",
+               "-Wl,--no-as-needed"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(SHIM), reason="torch shim not built")
+def test_shim_matches_ctypes_path():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import run_product_backward, run_product_forward, scenes, to_dev
+    torch.ops.load_library(SHIM)
+    scene = scenes.tiny(seed=61, P=3000, W=176, H=120, degree=3)
+    t = to_dev(scene)
+    cam = scene.cam
+    e = t["empty"]
+    fwd = run_product_forward(scene, t)
+    g = run_product_backward(scene, t, fwd)
+    r = torch.ops.gsr_shim.rasterize_forward(t["bg"], t["means3D"], e, t["opacity"], t["scales"], t["rotations"],
+                                             1.0, e, t["viewmatrix"], t["projmatrix"], cam.tanfovx, cam.tanfovy,
+                                             cam.H, cam.W, t["dc"], t["sh"], 3, t["campos"], False, False)
+    assert r[0] == fwd[0]
+    assert torch.equal(r[2], fwd[2]) and torch.equal(r[3], fwd[3])
+    gb = torch.ops.gsr_shim.rasterize_backward(t["bg"], t["means3D"], r[3], e, t["scales"], t["rotations"], 1.0, e,
+                                               t["viewmatrix"], t["projmatrix"], cam.tanfovx, cam.tanfovy,
+                                               t["dL_dout"], t["dc"], t["sh"], 3, t["campos"], r[4], r[0], r[5],
+                                               r[6], r[1], r[7], False)
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_ddc", "dL_dsh",
+             "dL_dscales", "dL_drotations"]
+    for name, a in zip(names, gb):
+        b = g[name]
+        den = float(b.double().norm())
+        err = float((a.double() - b.double()).norm()) / (den if den > 0 else 1.0)
+        assert err <= 1e-5, (name, err)   # atomics order differs between two runs
+    import gsdf_slam_b200 as gs
+    assert torch.equal(torch.ops.gsr_shim.dist_cuda2(t["means3D"]), gs.distCUDA2(t["means3D"]))
