@@ -252,8 +252,7 @@ def run_product(args, rank, world, dev):
                                           e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy,
                                           kf.dL_dout, p["dc"], p["sh"], mapper.degree, kf.campos, geom, R,
                                           binning, img, B, sample, False, want_dcov3D=False, out=out)
-        mapper.allreduce()
-        mapper.adam_step()
+        mapper.exchange_and_update()
         chk_host.copy_(mapper.grad_views["opacity"].sum().reshape(1), non_blocking=True)
         color.record_stream(copy_stream)
         torch.cuda.current_stream(dev).synchronize()
@@ -505,6 +504,15 @@ def run_reference(args, rank, world, dev):
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) may write to stdout; the contract is
+    # ONE JSON line there, so everything else is sent to stderr and the line is written to the
+    # real stdout at the end.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -525,16 +533,18 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(run_reference(args, rank, world, dev)), flush=True)
+            emit(run_reference(args, rank, world, dev))
         return
 
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     line = run_product(args, rank, world, dev)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

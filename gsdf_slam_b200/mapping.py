@@ -8,7 +8,7 @@ summed with ONE NCCL all-reduce over a flat gradient arena, and every rank appli
 identical fused Adam step (gsr_adam_step) to its replica — no parameter broadcast is needed.
 
 Gradient arena layout (fp32, each segment 16-byte aligned and itself a valid contiguous
-gradient tensor): [xyz 3P | f_dc 3P | f_rest 3MP | opacity P | scaling 3P | rotation 4P].
+gradient tensor): [xyz 3P | f_dc 3P | opacity P | scaling 3P | rotation 4P | f_rest 3MP].
 
 The loss (L1 + SSIM) and the activation functions are outside this path (SURVEY.md §8f-1,
 f-2): the step consumes dL/d(image) per keyframe and works on activated parameters.
@@ -36,12 +36,17 @@ def partition_keyframes(num_keyframes: int, world_size: int, rank: int) -> List[
     return list(range(rank, num_keyframes, world_size))
 
 
+# order of the segments inside the arena: the five small ones first (one 14*P-float chunk),
+# the 3*M*P-float SH block last so that it can be cut into a few large chunks
+ARENA_ORDER = ("means3D", "dc", "opacity", "scales", "rotations", "sh")
+
+
 def arena_layout(P: int, M: int) -> Dict[str, tuple]:
     """name -> (offset, numel, shape); offsets are multiples of 4 floats (16 bytes)."""
     shapes = {"means3D": (P, 3), "dc": (P, 1, 3), "sh": (P, M, 3), "opacity": (P, 1), "scales": (P, 3),
               "rotations": (P, 4)}
     out, off = {}, 0
-    for name in SEGMENTS:
+    for name in ARENA_ORDER:
         n = 1
         for d in shapes[name]:
             n *= d
@@ -142,8 +147,74 @@ class KeyframeBatchMapper:
                  if self.opt_params[k].numel() > 0}
         self.optimizer.step(grads=grads, grad_scale=grad_scale)
 
+    # ---- pipelined exchange: all-reduce chunk k+1 while Adam consumes chunk k -------------
+    def _chunks(self, target_elems: int = 8 * 1024 * 1024):
+        """[(arena_lo, arena_hi, [(segment, lo, hi), ...])]: contiguous arena ranges of roughly
+        32 MB — the five small segments together, the SH block in a few pieces."""
+        small = [n for n in ARENA_ORDER if n != "sh" and self.layout[n][1] > 0]
+        out = []
+        if small:
+            lo = self.layout[small[0]][0]
+            hi = self.layout[small[-1]][0] + self.layout[small[-1]][1]
+            out.append((lo, hi, [(n, 0, self.layout[n][1]) for n in small]))
+        off, n, _ = self.layout["sh"]
+        if n > 0:
+            k = max(1, (n + target_elems - 1) // target_elems)
+            step = ((n + k - 1) // k + 3) // 4 * 4
+            for lo in range(0, n, step):
+                hi = min(n, lo + step)
+                out.append((off + lo, off + hi, [("sh", lo, hi)]))
+        return out
+
+    def _adam_ranges(self, ranges, steps, grad_scale: float) -> None:
+        """One fused Adam launch over sub-ranges [(segment, lo, hi)] of the parameter tensors."""
+        import ctypes as C
+
+        from . import _lib
+        items = []
+        betas = eps = None
+        for name, lo, hi in ranges:
+            p = self.opt_params[name].view(-1)
+            st = self.optimizer._state(self.opt_params[name])
+            g = self.grad_views[name].view(-1)
+            grp = next(gr for gr in self.optimizer.param_groups if gr["params"][0] is self.opt_params[name])
+            betas, eps = grp["betas"], grp["eps"]
+            items.append(_lib.AdamGroup(param=p[lo:hi].data_ptr(), grad=g[lo:hi].data_ptr(),
+                                        exp_avg=st["exp_avg"].view(-1)[lo:hi].data_ptr(),
+                                        exp_avg_sq=st["exp_avg_sq"].view(-1)[lo:hi].data_ptr(),
+                                        numel=hi - lo, lr=float(grp["lr"]), step=int(steps[name])))
+        arr = (_lib.AdamGroup * len(items))(*items)
+        dev = self.arena.device
+        _lib.check(_lib.lib().gsr_adam_step(arr, len(items), float(betas[0]), float(betas[1]), float(eps),
+                                            float(grad_scale),
+                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                   "gsr_adam_step")
+
+    def exchange_and_update(self, grad_scale: float = 1.0) -> None:
+        """Gradient exchange + optimiser.  With more than one rank the arena is all-reduced in
+        ~32 MB chunks on NCCL's stream and the fused Adam consumes each chunk as soon as it has
+        landed, so most of the Adam pass (HBM-bound) hides behind the NVLink transfer."""
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
+        if not multi:
+            self.adam_step(grad_scale)
+            return
+        chunks = self._chunks()
+        works = []
+        for lo, hi, _ in chunks:
+            works.append(dist.all_reduce(self.arena[lo:hi], op=dist.ReduceOp.SUM, group=self.pg,
+                                         async_op=True))
+        steps = {}
+        for name in SEGMENTS:
+            if self.opt_params[name].numel():
+                st = self.optimizer._state(self.opt_params[name])
+                st["step"] += 1
+                steps[name] = st["step"]
+        for (_, _, ranges), w in zip(chunks, works):
+            w.wait()  # the compute stream waits for this chunk only
+            self._adam_ranges(ranges, steps, grad_scale)
+
     def step(self, keyframes: Sequence[Keyframe], grad_scale: float = 1.0) -> None:
         """One mapping iteration over this rank's keyframes."""
         self.accumulate(keyframes)
-        self.allreduce()
-        self.adam_step(grad_scale)
+        self.exchange_and_update(grad_scale)

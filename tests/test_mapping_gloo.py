@@ -40,7 +40,8 @@ def test_arena_layout_is_aligned_and_59_floats_per_gaussian():
     total = lay["_total"][1]
     assert total >= 59 * P and total - 59 * P < 4 * len(SEGMENTS)
     end = 0
-    for name in SEGMENTS:
+    from gsdf_slam_b200.mapping import ARENA_ORDER
+    for name in ARENA_ORDER:
         off, n, shape = lay[name]
         assert off % 4 == 0 and off >= end
         assert n == int(np.prod(shape))
@@ -58,6 +59,18 @@ class _FakeMapper(KeyframeBatchMapper):
                 g.copy_(torch.sin(self.params[name] * (kf + 1) + i))
         return None, None, None
 
+    def _adam_ranges(self, ranges, steps, grad_scale):
+        for name, lo, hi in ranges:
+            self._adam_range(name, lo, hi, steps[name], grad_scale)
+
+    def _adam_range(self, name, lo, hi, step, grad_scale):
+        p = self.opt_params[name]
+        st = self.optimizer._state(p)
+        pn = p.numpy().reshape(-1)[lo:hi]
+        gn = (self.grad_views[name] * grad_scale).numpy().reshape(-1)[lo:hi].copy()
+        ob.adam(pn, gn, st["exp_avg"].numpy().reshape(-1)[lo:hi], st["exp_avg_sq"].numpy().reshape(-1)[lo:hi],
+                DEFAULT_LR[name], step)
+
     def adam_step(self, grad_scale: float = 1.0):
         for name in SEGMENTS:
             p = self.opt_params[name]
@@ -65,9 +78,7 @@ class _FakeMapper(KeyframeBatchMapper):
                 continue
             st = self.optimizer._state(p)
             st["step"] += 1
-            pn, gn = p.numpy().reshape(-1), (self.grad_views[name] * grad_scale).numpy().reshape(-1).copy()
-            ob.adam(pn, gn, st["exp_avg"].numpy().reshape(-1), st["exp_avg_sq"].numpy().reshape(-1),
-                    DEFAULT_LR[name], st["step"])
+            self._adam_range(name, 0, p.numel(), st["step"], grad_scale)
 
 
 def _make_params(P=257, M=15, seed=0):
