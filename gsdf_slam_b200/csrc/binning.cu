@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gsr_capi.h"
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -29,7 +30,8 @@ emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restri
             const uint32_t* __restrict__ dup_offsets, const float2* __restrict__ means2D,
             const float4* __restrict__ conic_opacity, const int* __restrict__ radii, int grid_x,
             int grid_y, uint64_t* __restrict__ items, uint32_t* __restrict__ large_count,
-            uint32_t* __restrict__ large_list, const uint32_t* __restrict__ num_valid) {
+            uint32_t* __restrict__ large_list, uint32_t large_capacity,
+            const uint32_t* __restrict__ num_valid) {
   // Only the first num_valid depth-sorted positions own tiles.  In depth order the near
   // (= large) splats are neighbours, so lane l of a warp takes its Gaussian from the l-th of
   // 32 depth strata: every warp then walks a similar mix of near and far rectangles.
@@ -57,7 +59,21 @@ emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restri
     thr = opacity_power_threshold(co.w);
   }
   const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
-  const bool large = cnt != 0 && area > kQueueRectTiles;
+  // Very large rectangles are not walked here: they are cut into chunks of kQueueRectTiles
+  // tiles, queued as (chunk << 24 | sorted position) and spread over the whole GPU by
+  // emit_large_kernel (a single warp walking a 3000-tile rectangle would be the critical path).
+  bool large = cnt != 0 && area > kQueueRectTiles;
+  if (large) {
+    const uint32_t nchunks = ((uint32_t)area + kQueueRectTiles - 1) / kQueueRectTiles;
+    const uint32_t q0 = atomicAdd(large_count, nchunks);
+    if (q0 + nchunks <= large_capacity && nchunks <= 256u) {
+      for (uint32_t c = 0; c < nchunks; ++c) large_list[q0 + c] = (c << 24) | (uint32_t)j;
+    } else {
+      // queue full (pathological input): poison the reserved entries and walk it right here
+      for (uint32_t c = 0; c < nchunks && q0 + c < large_capacity; ++c) large_list[q0 + c] = 0xffffffffu;
+      large = false;
+    }
+  }
   // All (Gaussian, tile) pairs of the warp are tested 32 per step; a hit claims the next slot
   // of its owner's reserved range [off, off + cnt).  (The order inside one Gaussian's range is
   // irrelevant: its tiles are distinct, and the tile sort only needs the ranges of different
@@ -73,29 +89,29 @@ emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restri
                          const uint64_t tile = (uint64_t)(y * grid_x + x);
                          items[owner_off + k] = (tile << 32) | owner_g;
                        });
-  // Very large rectangles are not walked here: in depth order the near (= huge) splats sit
-  // next to each other, so they would all land in the first few warps.  They are queued and
-  // spread over the whole GPU by emit_large_kernel.
-  if (large) large_list[atomicAdd(large_count, 1u)] = (uint32_t)j;
 }
 
-// One warp per queued large-rectangle Gaussian (grid-stride over the queue): 32 tiles are
-// tested per step and the hits are written in row-major order.
+// One warp per queued chunk (kQueueRectTiles tiles of one large rectangle), grid-stride over
+// the queue.  32 tiles are tested per step; the hits claim slots of the owner's reserved range
+// by advancing dup_offsets[j] atomically (that array is not needed after the emit stage, and
+// the order inside one Gaussian's range is irrelevant).
 __global__ void __launch_bounds__(256)
 emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_list,
-                  const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ dup_offsets,
+                  const uint64_t* __restrict__ sorted, uint32_t* __restrict__ dup_offsets,
                   const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
                   const int* __restrict__ radii, int grid_x, int grid_y,
-                  uint64_t* __restrict__ items) {
+                  uint64_t* __restrict__ items, uint32_t large_capacity) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t count = *large_count;
+  const uint32_t count = min(*large_count, large_capacity);
   const unsigned lanemask_lt = (1u << lane) - 1u;
   for (uint32_t k = warp_global; k < count; k += num_warps) {
-    const uint32_t j = large_list[k];
+    const uint32_t item = large_list[k];
+    if (item == 0xffffffffu) continue;
+    const uint32_t j = item & ((1u << 24) - 1u);
+    const uint32_t chunk = item >> 24;
     const uint32_t g = (uint32_t)(sorted[j] & 0xffffffffu);
-    uint32_t off = dup_offsets[j];
     const float2 xy = means2D[g];
     const float4 co = conic_opacity[g];
     uint2 rect_min, rect_max;
@@ -103,37 +119,45 @@ emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __re
     const float thr = opacity_power_threshold(co.w);
     const int w = (int)(rect_max.x - rect_min.x), h = (int)(rect_max.y - rect_min.y);
     const int area = w * h;
-    for (int t0 = 0; t0 < area; t0 += 32) {
+    const int t_begin = (int)chunk * kQueueRectTiles;
+    const int t_end = min(area, t_begin + kQueueRectTiles);
+    for (int t0 = t_begin; t0 < t_end; t0 += 32) {
       const int t = t0 + lane;
       bool pass = false;
       int x = 0, y = 0;
-      if (t < area) {
+      if (t < t_end) {
         y = (int)rect_min.y + t / w;
         x = (int)rect_min.x + t - (t / w) * w;
         pass = tile_min_power(co, xy, x, y) <= thr;
       }
       const unsigned pm = __ballot_sync(0xffffffffu, pass);
+      if (pm == 0) continue;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&dup_offsets[j], (uint32_t)__popc(pm));
+      base = __shfl_sync(0xffffffffu, base, 0);
       if (pass) {
         const uint64_t tile = (uint64_t)(y * grid_x + x);
-        items[off + __popc(pm & lanemask_lt)] = (tile << 32) | g;
+        items[base + __popc(pm & lanemask_lt)] = (tile << 32) | g;
       }
-      off += __popc(pm);
     }
   }
 }
 
 int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
-                const uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
+                uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
                 const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
                 uint32_t* large_list, const uint32_t* num_valid, cudaStream_t s) {
   if (P <= 0) return 0;
+  if (P >= (1 << 24)) return GSR_ERR_BAD_ARG;  // queue entries hold 24-bit sorted positions
+  const uint32_t large_capacity = 2u * (uint32_t)P;  // the list lives in a P x u64 scratch array
   emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, sorted, tiles_touched, dup_offsets, means2D,
                                               conic_opacity, radii, grid_x, grid_y, items,
-                                              large_count, large_list, num_valid);
+                                              large_count, large_list, large_capacity, num_valid);
   GSR_LAUNCHED();
   // 148 SMs x 2 CTAs x 8 warps walk the queued large rectangles
   emit_large_kernel<<<148 * 2, 256, 0, s>>>(large_count, large_list, sorted, dup_offsets, means2D,
-                                            conic_opacity, radii, grid_x, grid_y, items);
+                                            conic_opacity, radii, grid_x, grid_y, items,
+                                            large_capacity);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

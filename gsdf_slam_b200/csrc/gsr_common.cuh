@@ -312,7 +312,10 @@ __device__ __forceinline__ uint32_t warp_walk_large_rects(bool has_large, const 
 // ~2 live lanes per warp when few lanes hold visible Gaussians).  Must be called by all 32
 // lanes; `on_hit(owner_lane, x, y, pay0, pay1)` is invoked by each lane whose tile passed the
 // test (pay0/pay1 = the owner lane's payload words), in no particular order.
-constexpr int kQueueRectTiles = 256;  // emit: rectangles larger than this go to the work queue
+#ifndef GSR_QUEUE_RECT_TILES
+#define GSR_QUEUE_RECT_TILES 256
+#endif
+constexpr int kQueueRectTiles = GSR_QUEUE_RECT_TILES;  // emit: larger rectangles go to the work queue
 
 template <typename OnHit>
 __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, const float2 xy,

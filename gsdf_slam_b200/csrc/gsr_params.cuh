@@ -69,7 +69,7 @@ int launch_preprocess(const PreprocessParams& p, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
                         cudaStream_t s);
 int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
-                const uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
+                uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
                 const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
                 uint32_t* large_list, const uint32_t* num_valid, cudaStream_t s);
 int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
@@ -86,7 +86,8 @@ int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_ord
                      const float4* rec_a, const float4* rec_b, const float4* rec_c, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s);
-int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s);
+int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,
+                          cudaStream_t s);
 int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
                 float grad_scale, cudaStream_t s);
 size_t knn_temp_bytes(int64_t P);

@@ -18,6 +18,7 @@
 
 #include "gsr_common.cuh"
 #include "gsr_params.cuh"
+#include "tma.cuh"
 
 namespace gsr {
 
@@ -109,7 +110,10 @@ __device__ __forceinline__ float sh_channel(int deg, float x, float y, float z, 
 constexpr int kPreThreads = 128;
 constexpr int kShFloats = 45;  // 15 coefficients x 3 channels
 
-__global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const PreprocessParams a) {
+#ifndef GSR_PRE_MINBLOCKS
+#define GSR_PRE_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_kernel(const PreprocessParams a) {
   // CTA-staged input rows
   __shared__ __align__(16) float s_xyz[kPreThreads * 3];
   __shared__ __align__(16) float s_scale[kPreThreads * 3];
@@ -214,33 +218,15 @@ __global__ void __launch_bounds__(kPreThreads) preprocess_kernel(const Preproces
       const int ncoef = min(a.M, 15) * 3;
       unsigned m = vis_mask;
       while (m) {
-        // four rows per trip: all eight loads are in flight before the first store
-        int src[4];
-        float v0[4], v1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          src[u] = m ? (__ffs(m) - 1) : -1;
-          m &= m - 1;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          v0[u] = 0.f;
-          v1[u] = 0.f;
-          if (src[u] >= 0) {
-            const float* row = a.shs + (size_t)(base + warp * 32 + src[u]) * (size_t)a.M * 3;
-            if (lane < ncoef) v0[u] = row[lane];
-            if (lane + 32 < ncoef) v1[u] = row[lane + 32];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (src[u] >= 0) {
-            float* dst = &s_sh[warp][src[u] * kShFloats];
-            if (lane < ncoef) dst[lane] = v0[u];
-            if (lane + 32 < ncoef) dst[lane + 32] = v1[u];
-          }
-        }
+        // asynchronous copies: every visible row of the warp is in flight at once
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const float* row = a.shs + (size_t)(base + warp * 32 + src) * (size_t)a.M * 3;
+        float* dst = &s_sh[warp][src * kShFloats];
+        if (lane < ncoef) cp_async_f32(dst + lane, row + lane);
+        if (lane + 32 < ncoef) cp_async_f32(dst + lane + 32, row + lane + 32);
       }
+      cp_async_wait_all();
       __syncwarp();
     }
     if (visible) {

@@ -11,6 +11,7 @@
 
 #include "gsr_common.cuh"
 #include "gsr_params.cuh"
+#include "tma.cuh"
 
 namespace gsr {
 
@@ -42,7 +43,8 @@ __device__ __forceinline__ void store3(float* p, size_t i, V3 v) {
 // Per-Gaussian body.  `sh_row` is this Gaussian's dL/dsh row (3*M floats) in SHARED
 // memory, pre-zeroed; the CTA writes the rows out coalesced afterwards.
 __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const int idx,
-                                                   const bool rendered, float* sh_row) {
+                                                   const bool rendered, float* sh_row,
+                                                   const float* sh_in_row) {
   const size_t i = (size_t)idx;
   const int M = a.M;
 
@@ -222,7 +224,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
     const V3 dir_orig = {mean.x - campos.x, mean.y - campos.y, mean.z - campos.z};
     const float len = sqrtf(dotv(dir_orig, dir_orig));
     const V3 dir = {dir_orig.x / len, dir_orig.y / len, dir_orig.z / len};
-    const V3* sh = reinterpret_cast<const V3*>(a.shs) + i * M;
+    const V3* sh = reinterpret_cast<const V3*>(sh_in_row);  // this Gaussian's SH row (staged)
     V3* dL_dsh = reinterpret_cast<V3*>(sh_row);
 
     const uint8_t cl = a.clamped[idx];
@@ -362,39 +364,122 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
 }
 
 constexpr int kPreBwdThreads = 128;
+constexpr int kZeroThreads = 256;
+constexpr int kZeroMaxTensors = 12;
 
-// A CTA owns 128 consecutive Gaussians.  The 12*M-byte dL/dsh rows (180 B at SH-3) are
-// assembled in shared memory and written out as one contiguous float4 stream — zeros
-// included — instead of 45 scattered 4-byte stores per thread.
-__global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const PreBwdParams a) {
-  __shared__ __align__(16) float s_dsh[kPreBwdThreads * 45];
-  const int tid = threadIdx.x;
-  const int base = blockIdx.x * kPreBwdThreads;
-  const int idx = base + tid;
-  const int row = 3 * (a.M < 15 ? a.M : 15);
-  for (int k = tid; k < kPreBwdThreads * row; k += kPreBwdThreads) s_dsh[k] = 0.f;
-  __syncthreads();
-  if (idx < a.P) preprocess_bwd_one(a, idx, a.radii[idx] > 0, &s_dsh[tid * row]);
-  __syncthreads();
-  if (a.dL_dsh != nullptr && row > 0) {
-    const int count = min(kPreBwdThreads, a.P - base);
-    const int n = count * row;
-    float* dst = a.dL_dsh + (size_t)base * row;
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      const int n4 = n >> 2;
-      for (int k = tid; k < n4; k += kPreBwdThreads)
-        __stcs(reinterpret_cast<float4*>(dst) + k, reinterpret_cast<const float4*>(s_dsh)[k]);
-      for (int k = n4 * 4 + tid; k < n; k += kPreBwdThreads) dst[k] = s_dsh[k];
-    } else {
-      for (int k = tid; k < n; k += kPreBwdThreads) dst[k] = s_dsh[k];
-    }
+// ---- pass 1: dense zero fill of every gradient tensor (coalesced float4 stream) ----------
+// The API returns dense [P, ...] gradient tensors while only the rendered Gaussians (~15 % of
+// a mapping view) have non-zero rows.  Writing the zeros as one vectorised multi-tensor stream
+// and then computing only the rendered rows from the compacted depth-sorted list is much
+// cheaper than letting every thread of a P-wide kernel write its own strided zero row.
+struct ZeroParams {
+  float* ptr[kZeroMaxTensors];
+  long long numel[kZeroMaxTensors];
+  int first_block[kZeroMaxTensors + 1];
+  int n;
+};
+constexpr int kZeroChunk = kZeroThreads * 4 * 4;  // floats per CTA
+
+__global__ void __launch_bounds__(kZeroThreads) zero_fill_kernel(const ZeroParams z) {
+  int t = 0;
+#pragma unroll 1
+  for (int k = 1; k < z.n; ++k)
+    if ((int)blockIdx.x >= z.first_block[k]) t = k;
+  float* p = z.ptr[t];
+  const long long n = z.numel[t];
+  const long long base = (long long)(blockIdx.x - z.first_block[t]) * kZeroChunk;
+  const long long end = min(n, base + kZeroChunk);
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0 && end - base == kZeroChunk) {
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      __stcs(reinterpret_cast<float4*>(p) + base / 4 + k * kZeroThreads + threadIdx.x, zero4);
+  } else {
+    for (long long e = base + threadIdx.x; e < end; e += kZeroThreads) p[e] = 0.f;
   }
 }
 
-int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t s) {
+// ---- pass 2: the rendered Gaussians, taken from the depth-sorted list of the forward ------
+// sorted[0 .. *num_valid) are exactly the Gaussians that own at least one tile; every other
+// Gaussian received no gradient from the blend stage, so all of its outputs are zero.
+#ifndef GSR_PREBWD_MINBLOCKS
+#define GSR_PREBWD_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kPreBwdThreads, GSR_PREBWD_MINBLOCKS)
+preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
+                      const uint32_t* __restrict__ num_valid) {
+  // per-warp staging: SH rows in (coalesced 180 B reads), dL/dsh rows out (coalesced writes)
+  __shared__ float s_sh[kPreBwdThreads / 32][32 * 45];
+  __shared__ float s_dsh[kPreBwdThreads / 32][32 * 45];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = 3 * (a.M < 15 ? a.M : 15);
+  const bool has_sh = a.shs != nullptr && row > 0;
+  const uint32_t nv = *num_valid;
+  const uint32_t stride = gridDim.x * kPreBwdThreads;
+  const uint32_t rounds = (nv + stride - 1) / stride;
+  for (uint32_t r = 0; r < rounds; ++r) {
+    const uint32_t t = r * stride + blockIdx.x * kPreBwdThreads + tid;
+    const bool act = t < nv;
+    const int idx = act ? (int)(uint32_t)(sorted[t] & 0xffffffffu) : -1;
+    if (has_sh) {
+      // gather the 32 SH rows with asynchronous copies: all of them are in flight together
+      for (int src = 0; src < 32; ++src) {
+        const int g = __shfl_sync(0xffffffffu, idx, src);
+        if (g < 0) continue;
+        const float* grow = a.shs + (size_t)g * (size_t)a.M * 3;
+        float* dst = &s_sh[warp][src * row];
+        if (lane < row) cp_async_f32(dst + lane, grow + lane);
+        if (lane + 32 < row) cp_async_f32(dst + lane + 32, grow + lane + 32);
+      }
+      cp_async_wait_all();
+    }
+    float* my_row = &s_dsh[warp][lane * row];
+    for (int k = 0; k < row; ++k) my_row[k] = 0.f;
+    __syncwarp();
+    if (act) preprocess_bwd_one(a, idx, true, my_row, &s_sh[warp][lane * row]);
+    __syncwarp();
+    if (a.dL_dsh != nullptr && row > 0) {
+      // each rendered row leaves as one contiguous 12*M-byte segment
+      for (int src = 0; src < 32; ++src) {
+        const int g = __shfl_sync(0xffffffffu, idx, src);
+        if (g < 0) continue;
+        float* dst = a.dL_dsh + (size_t)g * row;
+        const float* srow = &s_dsh[warp][src * row];
+        if (lane < row) dst[lane] = srow[lane];
+        if (lane + 32 < row) dst[lane + 32] = srow[lane + 32];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,
+                          cudaStream_t s) {
   if (p.P <= 0) return 0;
   if (p.M > 15) return GSR_ERR_BAD_ARG;
-  preprocess_bwd_kernel<<<(p.P + kPreBwdThreads - 1) / kPreBwdThreads, kPreBwdThreads, 0, s>>>(p);
+  const long long P = p.P;
+  ZeroParams z;
+  z.n = 0;
+  int blocks = 0;
+  auto add = [&](float* ptr, long long numel) {
+    if (ptr == nullptr || numel <= 0) return;
+    z.ptr[z.n] = ptr;
+    z.numel[z.n] = numel;
+    z.first_block[z.n] = blocks;
+    blocks += (int)((numel + kZeroChunk - 1) / kZeroChunk);
+    ++z.n;
+  };
+  add(p.dL_dmean2D, 3 * P); add(p.dL_dconic, 4 * P); add(p.dL_dopacity, P); add(p.dL_dcolor, 3 * P);
+  add(p.dL_dmean3D, 3 * P); add(p.dL_dcov3D, 6 * P); add(p.dL_ddc, 3 * P);
+  add(p.dL_dsh, 3LL * (p.M < 15 ? p.M : 15) * P); add(p.dL_dscale, 3 * P); add(p.dL_drot, 4 * P);
+  z.first_block[z.n] = blocks;
+  if (blocks > 0) {
+    zero_fill_kernel<<<blocks, kZeroThreads, 0, s>>>(z);
+    GSR_LAUNCHED();
+  }
+  // enough CTAs for one round in the common case (V <= 300 k); grid-stride beyond
+  const int want = (p.P + kPreBwdThreads - 1) / kPreBwdThreads;
+  preprocess_bwd_kernel<<<want < 148 * 16 ? want : 148 * 16, kPreBwdThreads, 0, s>>>(p, sorted, num_valid);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

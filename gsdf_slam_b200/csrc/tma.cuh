@@ -55,3 +55,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 
 }  // namespace gsr
+
+namespace gsr {
+// Ampere-style asynchronous 4-byte global->shared copy (SASS: LDGSTS): no register staging,
+// so a warp can have all the rows it gathers in flight at once.
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+}  // namespace gsr
