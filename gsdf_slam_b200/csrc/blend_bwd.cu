@@ -56,6 +56,31 @@ __device__ __forceinline__ void warp_reduce9(const float (&v)[9], int lane, floa
   out9 = z;
 }
 
+// Same result through shared memory: every lane stores its nine values (conflict-free rows of
+// 36 floats), then four lanes per component add eight of them each (two LDS.128) and finish
+// with two shuffles; the ninth component takes a plain shuffle tree.  ~35 instructions instead
+// of ~63, which matters because this runs once per (splat, half tile).
+constexpr int kRedStride = 36;
+__device__ __forceinline__ void warp_reduce9_smem(const float (&v)[9], int lane, float* s_red /* [8][36] */,
+                                                  float& out8, float& out9) {
+  const unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_red[k * kRedStride + lane] = v[k];
+  __syncwarp();
+  const float4* row = reinterpret_cast<const float4*>(s_red + (lane >> 2) * kRedStride + (lane & 3) * 8);
+  const float4 a = row[0];
+  const float4 b = row[1];
+  float y = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+  y += __shfl_xor_sync(full, y, 1);
+  y += __shfl_xor_sync(full, y, 2);
+  out8 = y;  // total of v[lane >> 2]
+  float z = v[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(full, z, o);
+  out9 = z;
+  __syncwarp();  // rows are rewritten by the next reduction
+}
+
 __global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_BWD_MINBLOCKS)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ max_contrib,
                  const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
@@ -67,6 +92,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   __shared__ __align__(128) float4 sB[2][kBlendBatch];
   __shared__ __align__(128) float4 sC[2][kBlendBatch];
   __shared__ __align__(8) uint64_t s_full[2];
+  __shared__ __align__(16) float s_red[kBlendThreads / 32][8 * kRedStride];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel)
@@ -210,7 +236,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       if (!__any_sync(0xffffffffu, contributed)) continue;
 
       float s8, s9;
-      warp_reduce9(v, lane, s8, s9);
+      warp_reduce9_smem(v, lane, s_red[warp], s8, s9);
       const uint32_t g = __float_as_uint(B.w);
       if ((lane & 3) == 0) {
         if (s8 != 0.f) atomicAdd(&acc[(size_t)g * 12 + (lane >> 2)], s8);
