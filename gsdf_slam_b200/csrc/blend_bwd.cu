@@ -94,24 +94,24 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   __shared__ __align__(8) uint64_t s_full[2];
   __shared__ __align__(16) float s_red[kBlendThreads / 32][8 * kRedStride];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel)
-  const uint32_t tile_id = tile_order[blockIdx.x];
+  const int lane = threadIdx.x;
+  // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel); two CTAs per tile
+  const uint32_t tile_id = tile_order[blockIdx.x >> 1];
+  const int warp = blockIdx.x & 1;  // upper / lower half of the tile
   const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
   const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
   const size_t N = (size_t)W * H;
 
   const uint2 range = ranges[tile_id];
   // nothing behind the deepest contributor of the tile receives gradient
-  const int total = min((int)(range.y - range.x), (int)max_contrib[tile_id]);
-  const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
+  int total = min((int)(range.y - range.x), (int)max_contrib[tile_id]);
 
-  if (tid == 0) {
+  if (lane == 0) {
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     fence_mbar_init();
   }
-  __syncthreads();
+  __syncwarp();
 
   auto issue = [&](int round) {
     const int buf = round & 1;
@@ -123,7 +123,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     bulk_g2s(&sB[buf][0], rec_b + start, bytes, &s_full[buf]);
     bulk_g2s(&sC[buf][0], rec_c + start, bytes, &s_full[buf]);
   };
-  if (tid == 0 && rounds > 0) issue(0);
+
 
   // per-pixel state of the four slots.  The reference tracks, per channel, ar = -(colour still
   // to be blended behind the current splat) and forms
@@ -163,14 +163,18 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     }
     my_last = max(my_last, last[q]);
   }
-  // warp-uniform bound: the deepest contributor among this warp's 128 pixels
+  // warp-uniform bound: the deepest contributor among this half tile's 128 pixels; nothing
+  // behind it is even loaded
   const uint32_t warp_last = __reduce_max_sync(0xffffffffu, my_last);
+  total = min(total, (int)warp_last);
+  const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
+  if (lane == 0 && rounds > 0) issue(0);
 
   for (int i = 0; i < rounds; ++i) {
     const int buf = i & 1;
     mbar_wait(&s_full[buf], (uint32_t)((i >> 1) & 1));
-    __syncthreads();  // previous batch fully consumed by both warps
-    if (tid == 0 && i + 1 < rounds) issue(i + 1);
+    __syncwarp();  // previous batch fully consumed by every lane
+    if (lane == 0 && i + 1 < rounds) issue(i + 1);
 
     const int cnt = min(kBlendBatch, total - i * kBlendBatch);
     const uint32_t pos0 = (uint32_t)i * kBlendBatch;
@@ -236,7 +240,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       if (!__any_sync(0xffffffffu, contributed)) continue;
 
       float s8, s9;
-      warp_reduce9_smem(v, lane, s_red[warp], s8, s9);
+      warp_reduce9_smem(v, lane, s_red[0], s8, s9);
       const uint32_t g = __float_as_uint(B.w);
       if ((lane & 3) == 0) {
         if (s8 != 0.f) atomicAdd(&acc[(size_t)g * 12 + (lane >> 2)], s8);
@@ -253,7 +257,7 @@ int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_ord
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  blend_bwd_kernel<<<grid, kBlendThreads, 0, s>>>(ranges, tile_order, max_contrib, rec_a, rec_b, rec_c, W, H, bg,
+  blend_bwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, max_contrib, rec_a, rec_b, rec_c, W, H, bg,
                                                   final_T, n_contrib, accum_c, dL_dpix, acc);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();

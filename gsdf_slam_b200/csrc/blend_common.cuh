@@ -1,5 +1,6 @@
-// Shared shape of the two blend kernels: a 64-thread CTA per 16x16 tile, each warp owns
-// a 16x8 half tile, each thread owns four pixels — the pixel at (lane&7, lane>>3) of each
+// Shared shape of the two blend kernels: one single-warp CTA per 16x8 HALF tile (two CTAs per
+// 16x16 tile, so the work units are short and the last wave of the launch stays small; no
+// CTA-wide barrier exists in the kernels), each thread owns four pixels — the pixel at (lane&7, lane>>3) of each
 // of the four 8x4 blocks of the half tile.  A "slot" q is one of those blocks, so the 32
 // pixels of a slot are spatially compact: a warp-wide vote per slot tells cheaply whether a
 // splat touches that block at all.
@@ -18,9 +19,9 @@
 
 namespace gsr {
 
-constexpr int kBlendThreads = 64;
+constexpr int kBlendThreads = 32;   // one warp = one 16x8 half tile = one CTA
 constexpr int kSlots = 4;
-constexpr int kBlendBatch = 128;  // splat records staged per bulk copy (3 x 2 KB)
+constexpr int kBlendBatch = 64;    // splat records staged per bulk copy (3 x 1 KB)
 
 __device__ __forceinline__ uint32_t slot_px(uint32_t tile_x, int lane, int q) {
   return tile_x * GSR_TILE_X + (q & 1) * 8 + (lane & 7);

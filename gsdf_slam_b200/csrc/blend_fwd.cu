@@ -34,11 +34,11 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   __shared__ __align__(128) float4 sB[2][kBlendBatch];
   __shared__ __align__(128) float4 sC[2][kBlendBatch];
   __shared__ __align__(8) uint64_t s_full[2];
-  __shared__ uint32_t s_max[kBlendThreads / 32];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel)
-  const uint32_t tile_id = tile_order[blockIdx.x];
+  const int lane = threadIdx.x;
+  // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel); two CTAs per tile
+  const uint32_t tile_id = tile_order[blockIdx.x >> 1];
+  const int warp = blockIdx.x & 1;  // upper / lower half of the tile
   const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
   const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
 
@@ -59,12 +59,12 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const int total = (int)(range.y - range.x);
   const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
 
-  if (tid == 0) {
+  if (lane == 0) {
     mbar_init(&s_full[0], 1);
     mbar_init(&s_full[1], 1);
     fence_mbar_init();
   }
-  __syncthreads();
+  __syncwarp();
 
   auto issue = [&](int round) {
     const int buf = round & 1;
@@ -76,7 +76,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     bulk_g2s(&sB[buf][0], rec_b + start, bytes, &s_full[buf]);
     bulk_g2s(&sC[buf][0], rec_c + start, bytes, &s_full[buf]);
   };
-  if (tid == 0 && rounds > 0) issue(0);
+  if (lane == 0 && rounds > 0) issue(0);
 
   bool done[kSlots];
   float T[kSlots];
@@ -96,10 +96,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     bool all_done = true;
 #pragma unroll
     for (int q = 0; q < kSlots; ++q) all_done = all_done && done[q];
-    // every thread is past the previous batch here; stop when every pixel is saturated
-    const int num_done = __syncthreads_count(all_done);
-    if (num_done == kBlendThreads) break;
-    if (tid == 0 && i + 1 < rounds) issue(i + 1);
+    // every lane is past the previous batch here; stop when every pixel is saturated
+    if (__all_sync(0xffffffffu, all_done)) break;
+    if (lane == 0 && i + 1 < rounds) issue(i + 1);
 
     const int cnt = min(kBlendBatch, total - i * kBlendBatch);
     const uint32_t pos0 = (uint32_t)i * kBlendBatch;
@@ -162,21 +161,16 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
   // deepest list position any pixel of the tile used (bounds the backward replay)
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, my_max);
-  if (lane == 0) s_max[warp] = wmax;
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t m = 0;
-#pragma unroll
-    for (int w = 0; w < kBlendThreads / 32; ++w) m = max(m, s_max[w]);
-    max_contrib[tile_id] = m;
-  }
+  if (lane == 0) atomicMax(&max_contrib[tile_id], wmax);  // zeroed by the launcher
 }
 
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec_a, const float4* rec_b,
                      const float4* rec_c, const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  blend_fwd_kernel<<<grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec_a, rec_b, rec_c, W, H, bg, out_color,
+  cudaError_t e = cudaMemsetAsync(max_contrib, 0, (size_t)grid * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return (int)e;
+  blend_fwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec_a, rec_b, rec_c, W, H, bg, out_color,
                                                   final_T, n_contrib, accum_c, max_contrib);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
