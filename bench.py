@@ -179,6 +179,9 @@ def stage_model(counts, tile_bits):
         "blend_bwd": 48 * counts["sum_max_contrib"] + 32 * N + 72 * R,
         "preprocess_bwd": (87 + 12 * M) * V + 48 * V + (52 + 12 * M) * P + 4 * P,
         "adam": 28 * (14 + 3 * M) * P,
+        # visibility-split Adam: rows without gradient move 24 B/element (grad not read)
+        "adam_rows_zero_grad": 24 * (14 + 3 * M) * (P - V),
+        "adam_rows_with_grad": 28 * (14 + 3 * M) * V,
     }
     f = {"blend_fwd": 25 * E, "blend_bwd": 60 * E}
     return b, f
@@ -233,28 +236,21 @@ def run_product(args, rank, world, dev):
         mapper.bg = stage["bg"]
         kf = Keyframe(stage["viewmatrix"], stage["projmatrix"], stage["campos"], cam.tanfovx, cam.tanfovy,
                       cam.H, cam.W, stage["dL_dout"])
-        p = mapper.params
-        e = torch.empty(0, dtype=torch.float32, device=dev)
-        fwd = gs.RasterizeGaussiansCUDA(mapper.bg, p["means3D"], e, p["opacity"], p["scales"], p["rotations"],
-                                        1.0, e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy, kf.H,
-                                        kf.W, p["dc"], p["sh"], mapper.degree, kf.campos, False, False)
-        R, B, color, radii, geom, binning, img, sample = fwd
-        # read the image back while the backward runs
-        ev_fwd.record(main)
-        copy_stream.wait_event(ev_fwd)
-        with torch.cuda.stream(copy_stream):
-            img_host.copy_(color, non_blocking=True)
-        main.wait_event(ev_h2d)  # dL_dout has landed
-        out = {gname: mapper.grad_views[k] for k, gname in
-               (("means3D", "dL_dmeans3D"), ("dc", "dL_ddc"), ("sh", "dL_dsh"), ("opacity", "dL_dopacity"),
-                ("scales", "dL_dscales"), ("rotations", "dL_drotations"))}
-        gs.RasterizeGaussiansBackwardCUDA(mapper.bg, p["means3D"], radii, e, p["scales"], p["rotations"], 1.0,
-                                          e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy,
-                                          kf.dL_dout, p["dc"], p["sh"], mapper.degree, kf.campos, geom, R,
-                                          binning, img, B, sample, False, want_dcov3D=False, out=out)
-        mapper.exchange_and_update()
+        keep = {}
+
+        def after_forward(_kf, fwd):
+            # read the image back while the backward runs; the backward needs the uploaded dL_dout
+            color = fwd[2]
+            ev_fwd.record(main)
+            copy_stream.wait_event(ev_fwd)
+            with torch.cuda.stream(copy_stream):
+                img_host.copy_(color, non_blocking=True)
+            color.record_stream(copy_stream)
+            main.wait_event(ev_h2d)
+            keep["color"] = color
+
+        mapper.step([kf], on_forward=after_forward)
         chk_host.copy_(mapper.grad_views["opacity"].sum().reshape(1), non_blocking=True)
-        color.record_stream(copy_stream)
         torch.cuda.current_stream(dev).synchronize()
         copy_stream.synchronize()
 
@@ -290,9 +286,11 @@ def run_product(args, rank, world, dev):
     # per-stage durations with CUDA events on the launching stream (separate, untimed loop)
     prof = {}
     L.gsr_profile_enable(1)
+    mapper.serialize_side_stream = True   # per-stage times are taken without stream overlap
     for _ in range(max(5, min(args.steps, 20))):
         step_resident()
     torch.cuda.synchronize()
+    mapper.serialize_side_stream = False
     buf = (__import__("ctypes").create_string_buffer)(8192)
     L.gsr_profile_read(buf, 8192)
     L.gsr_profile_enable(0)

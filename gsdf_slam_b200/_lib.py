@@ -33,6 +33,7 @@ class ForwardArgs(C.Structure):
         ("sample_resize", RESIZE_FN), ("sample_user", C.c_void_p),
         ("stream", C.c_void_p),
         ("num_rendered", C.POINTER(C.c_int)), ("num_buckets", C.POINTER(C.c_int)),
+        ("radii_ready_event", C.c_void_p),
     ]
 
 
@@ -67,7 +68,7 @@ class AdamGroup(C.Structure):
 
 # every symbol include/gsr_capi.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
-    "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step",
+    "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows",
     "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_sort_temp_bytes",
     "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
 ]
@@ -109,6 +110,9 @@ def lib() -> C.CDLL:
     L.gsr_adam_step.argtypes = [C.POINTER(AdamGroup), C.c_int, C.c_double, C.c_double, C.c_double,
                                 C.c_float, C.c_void_p]
     L.gsr_adam_step.restype = C.c_int
+    L.gsr_adam_step_rows.argtypes = [C.POINTER(AdamGroup), C.c_int, C.c_double, C.c_double, C.c_double,
+                                     C.c_float, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    L.gsr_adam_step_rows.restype = C.c_int
     L.gsr_export_binning.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
     L.gsr_export_binning.restype = C.c_int

@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "gsr_capi.h"
 #include "gsr_common.cuh"
@@ -126,11 +127,194 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const AdamParams a) 
   }
 }
 
-int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
-                float grad_scale, cudaStream_t s) {
-  if (n_groups <= 0) return 0;
+// ---------------------------------------------------------------------------
+// Visibility-split Adam (gsr_adam_step_rows).  Every parameter tensor of the
+// Gaussian model is [rows, width]; in one mapping iteration only the rows of
+// the Gaussians that were rendered (radii > 0) have a non-zero gradient.  The
+// update of all OTHER rows (typically 85 %) does not depend on the backward
+// pass at all — their gradient is exactly +0 — so the caller may run it on a
+// side stream while the rasterizer kernels (which barely touch HBM) execute,
+// and only the rendered rows are left for after the backward pass.  The two
+// phases together perform bit-for-bit the update of one gsr_adam_step.
+//   phase 0 (kWithGrad = false): rows with row_mask <= 0, gradient taken as +0.0f, `grad` not read
+//   phase 1 (kWithGrad = true):  rows with row_mask  > 0, gradient read from `grad`
+// ---------------------------------------------------------------------------
+struct AdamRowsParams {
+  AdamParams base;
+  const int* row_mask;
+  unsigned width[kAdamMaxGroups];
+  unsigned magic[kAdamMaxGroups];  // ceil(2^32 / width): o / width == __umulhi(o, magic) for o * width < 2^32
+};
+
+// Phase 0 (rows WITHOUT gradient): a persistent grid-stride sweep over the 4096-element chunks of
+// every group.  The grid is deliberately small (a CTA or two per SM) so that the kernel can sit
+// on a side stream next to the rasterizer kernels without taking their registers away.
+#ifndef GSR_ADAM_ROWS_VEC
+#define GSR_ADAM_ROWS_VEC 2
+#endif
+constexpr int kAdamRowsVec = GSR_ADAM_ROWS_VEC;                    // float4 per thread and array
+constexpr int kAdamRowsChunk = kAdamThreads * kAdamRowsVec * 4;   // 2048 elements per chunk
+
+__device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, int chunk) {
+  const AdamParams& a = ar.base;
+  int gi = 0;
+#pragma unroll 1
+  for (int k = 1; k < a.n_groups; ++k)
+    if (chunk >= a.grp[k].first_block) gi = k;
+  const AdamGroupDev G = a.grp[gi];
+  const unsigned w = ar.width[gi];
+  const unsigned magic = ar.magic[gi];
+  const long long base = (long long)(chunk - G.first_block) * kAdamRowsChunk;
+  const long long end = min(G.numel, base + kAdamRowsChunk);
+  const int* __restrict__ mask = ar.row_mask;
+  // one wide division per chunk; everything below is 32-bit relative to the chunk's first row
+  const unsigned row_base = (unsigned)((unsigned long long)base / w);
+  const unsigned rem_base = (unsigned)((unsigned long long)base - (unsigned long long)row_base * w);
+
+  if (G.vec_ok && end - base == kAdamRowsChunk) {
+    unsigned mine[kAdamRowsVec];  // bit j set <=> element j of the float4 belongs to a row without gradient
+#pragma unroll
+    for (int k = 0; k < kAdamRowsVec; ++k) {
+      const unsigned o = rem_base + 4u * (unsigned)(k * kAdamThreads + threadIdx.x);  // < chunk + width
+      const unsigned q = (w == 1u) ? o : __umulhi(o, magic);
+      const unsigned rem = o - q * w;
+      const unsigned r0 = row_base + q;
+      unsigned bits = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned rr = rem + j;
+        const unsigned row = r0 + (rr >= w) + (rr >= 2 * w) + (rr >= 3 * w);
+        bits |= (__ldg(mask + row) > 0) ? 0u : (1u << j);
+      }
+      mine[k] = bits;
+    }
+    float4 p4[kAdamRowsVec], m4[kAdamRowsVec], v4[kAdamRowsVec];
+#pragma unroll
+    for (int k = 0; k < kAdamRowsVec; ++k) {
+      const long long e = base / 4 + k * kAdamThreads + threadIdx.x;
+      if (mine[k]) {
+        // streaming (evict-first) accesses: this sweep must not push the rasterizer's working
+        // set (splat records, moment sums) out of L2 while it runs beside the blend kernels
+        p4[k] = __ldcs(reinterpret_cast<const float4*>(G.p) + e);
+        m4[k] = __ldcs(reinterpret_cast<const float4*>(G.m) + e);
+        v4[k] = __ldcs(reinterpret_cast<const float4*>(G.v) + e);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kAdamRowsVec; ++k) {
+      if (!mine[k]) continue;
+      adam_elem(p4[k].x, 0.0f, m4[k].x, v4[k].x, a, G);
+      adam_elem(p4[k].y, 0.0f, m4[k].y, v4[k].y, a, G);
+      adam_elem(p4[k].z, 0.0f, m4[k].z, v4[k].z, a, G);
+      adam_elem(p4[k].w, 0.0f, m4[k].w, v4[k].w, a, G);
+      const long long e = base / 4 + k * kAdamThreads + threadIdx.x;
+      if (mine[k] == 15u) {
+        __stcs(reinterpret_cast<float4*>(G.p) + e, p4[k]);
+        __stcs(reinterpret_cast<float4*>(G.m) + e, m4[k]);
+        __stcs(reinterpret_cast<float4*>(G.v) + e, v4[k]);
+      } else {
+        // a float4 that straddles rendered and non-rendered rows: store only the latter's elements
+        const float pe[4] = {p4[k].x, p4[k].y, p4[k].z, p4[k].w};
+        const float me[4] = {m4[k].x, m4[k].y, m4[k].z, m4[k].w};
+        const float ve[4] = {v4[k].x, v4[k].y, v4[k].z, v4[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (mine[k] & (1u << j)) {
+            G.p[e * 4 + j] = pe[j];
+            G.m[e * 4 + j] = me[j];
+            G.v[e * 4 + j] = ve[j];
+          }
+        }
+      }
+    }
+  } else {
+    for (long long e = base + threadIdx.x; e < end; e += kAdamThreads) {
+      const unsigned o = rem_base + (unsigned)(e - base);
+      const unsigned row = row_base + ((w == 1u) ? o : __umulhi(o, magic));
+      if (__ldg(mask + row) > 0) continue;
+      float p = G.p[e], m = G.m[e], v = G.v[e];
+      adam_elem(p, 0.0f, m, v, a, G);
+      G.p[e] = p;
+      G.m[e] = m;
+      G.v[e] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kAdamThreads) adam_rows_zero_grad_kernel(const AdamRowsParams ar, int chunks) {
+  for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) adam_zero_grad_chunk(ar, chunk);
+}
+
+// Phase 1 (rows WITH gradient, typically ~15 % and scattered): row-oriented.  A warp takes 32
+// consecutive rows, ballots their mask and walks the marked rows; the lanes cover the
+// `row_elems` (= 59 for the Gaussian model) elements of a row across all groups, so every lane
+// does useful work and the group / offset of a lane's elements is resolved once, outside the loop.
+constexpr int kAdamRowSlots = 4;  // rows of up to 128 elements
+struct AdamVisParams {
+  AdamRowsParams rows;
+  unsigned prefix[kAdamMaxGroups + 1];  // element offset of each group inside a row
+  unsigned row_elems;
+  unsigned n_rows;
+};
+
+__global__ void __launch_bounds__(256) adam_rows_with_grad_kernel(const AdamVisParams vp) {
+  const AdamParams& a = vp.rows.base;
+  const int lane = threadIdx.x & 31;
+  const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned num_warps = (gridDim.x * blockDim.x) >> 5;
+  const int* __restrict__ mask = vp.rows.row_mask;
+
+  // the (at most kAdamRowSlots) row elements this lane owns: e = lane + 32 * slot
+  float* P[kAdamRowSlots]; const float* Gd[kAdamRowSlots]; float* Mo[kAdamRowSlots]; float* Vo[kAdamRowSlots];
+  unsigned wdt[kAdamRowSlots];
+  float neg_step[kAdamRowSlots], inv_bc2[kAdamRowSlots];
+  bool have[kAdamRowSlots];
+#pragma unroll
+  for (int sl = 0; sl < kAdamRowSlots; ++sl) {
+    const unsigned e = (unsigned)lane + 32u * sl;
+    have[sl] = e < vp.row_elems;
+    int gi = 0;
+    for (int k = 1; k < a.n_groups; ++k)
+      if (e >= vp.prefix[k]) gi = k;
+    const unsigned off = have[sl] ? e - vp.prefix[gi] : 0u;
+    P[sl] = a.grp[gi].p + off; Gd[sl] = a.grp[gi].g + off; Mo[sl] = a.grp[gi].m + off; Vo[sl] = a.grp[gi].v + off;
+    wdt[sl] = vp.rows.width[gi];
+    neg_step[sl] = a.grp[gi].neg_step_size;
+    inv_bc2[sl] = a.grp[gi].inv_sqrt_bc2;
+  }
+  const unsigned n_chunks = (vp.n_rows + 31u) / 32u;
+  for (unsigned c = warp_global; c < n_chunks; c += num_warps) {
+    const unsigned row = c * 32u + lane;
+    unsigned bal = __ballot_sync(0xffffffffu, row < vp.n_rows && __ldg(mask + row) > 0);
+    while (bal) {
+      const unsigned r = c * 32u + (unsigned)(__ffs(bal) - 1);
+      bal &= bal - 1;
+      float p[kAdamRowSlots], g[kAdamRowSlots], m[kAdamRowSlots], v[kAdamRowSlots];
+#pragma unroll
+      for (int sl = 0; sl < kAdamRowSlots; ++sl) {
+        if (have[sl]) {
+          const size_t i = (size_t)r * wdt[sl];
+          p[sl] = P[sl][i]; g[sl] = __ldcs(Gd[sl] + i); m[sl] = Mo[sl][i]; v[sl] = Vo[sl][i];
+        }
+      }
+#pragma unroll
+      for (int sl = 0; sl < kAdamRowSlots; ++sl) {
+        if (have[sl]) {
+          AdamGroupDev Gs;
+          Gs.neg_step_size = neg_step[sl];
+          Gs.inv_sqrt_bc2 = inv_bc2[sl];
+          adam_elem(p[sl], g[sl], m[sl], v[sl], a, Gs);
+          const size_t i = (size_t)r * wdt[sl];
+          P[sl][i] = p[sl]; Mo[sl][i] = m[sl]; Vo[sl][i] = v[sl];
+        }
+      }
+    }
+  }
+}
+
+static int build_adam_params(const gsr_adam_group* groups, int n_groups, double beta1, double beta2,
+                             double eps, float grad_scale, AdamParams& a, int& blocks, int chunk = kAdamChunk) {
   if (n_groups > kAdamMaxGroups) return GSR_ERR_BAD_ARG;
-  AdamParams a;
   a.n_groups = 0;
   // ATen casts the double scalars to the fp32 op-math type inside each kernel
   a.beta1 = (float)beta1;
@@ -140,7 +324,7 @@ int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double
   a.eps = (float)eps;
   a.grad_scale = grad_scale;
   a.use_scale = grad_scale != 1.0f;
-  int blocks = 0;
+  blocks = 0;
   for (int k = 0; k < n_groups; ++k) {
     const gsr_adam_group& g = groups[k];
     if (g.numel <= 0) continue;
@@ -158,10 +342,71 @@ int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double
     d.first_block = blocks;
     const uintptr_t al = (uintptr_t)d.p | (uintptr_t)d.g | (uintptr_t)d.m | (uintptr_t)d.v;
     d.vec_ok = (al & 15) == 0;
-    blocks += (int)((g.numel + kAdamChunk - 1) / kAdamChunk);
+    blocks += (int)((g.numel + chunk - 1) / chunk);
   }
+  return 0;
+}
+
+int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
+                float grad_scale, cudaStream_t s) {
+  if (n_groups <= 0) return 0;
+  AdamParams a;
+  int blocks = 0;
+  const int rc = build_adam_params(groups, n_groups, beta1, beta2, eps, grad_scale, a, blocks);
+  if (rc) return rc;
   if (blocks == 0) return 0;
   adam_kernel<<<blocks, kAdamThreads, 0, s>>>(a);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+int launch_adam_rows(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
+                     float grad_scale, int64_t rows, const int* row_mask, int phase, cudaStream_t s) {
+  if (n_groups <= 0 || rows <= 0) return 0;
+  if (!row_mask || (phase != 0 && phase != 1)) return GSR_ERR_BAD_ARG;
+  AdamRowsParams ar;
+  int blocks = 0;
+  const int rc = build_adam_params(groups, n_groups, beta1, beta2, eps, grad_scale, ar.base, blocks,
+                                   kAdamRowsChunk);
+  if (rc) return rc;
+  if (blocks == 0) return 0;
+  ar.row_mask = row_mask;
+  int k2 = 0;
+  for (int k = 0; k < n_groups; ++k) {
+    if (groups[k].numel <= 0) continue;
+    if (groups[k].numel % rows != 0) return GSR_ERR_BAD_ARG;  // every tensor is [rows, width]
+    const int64_t width = groups[k].numel / rows;
+    if (width > 4096) return GSR_ERR_BAD_ARG;  // the in-CTA division is exact for o * width < 2^32
+    ar.width[k2] = (unsigned)width;
+    ar.magic[k2] = (unsigned)(((1ull << 32) + (uint64_t)width - 1) / (uint64_t)width);
+    ++k2;
+  }
+  if (phase == 0) {
+    // persistent: GSR_ADAM_SIDE_CTAS CTAs per SM (default 2) grid-stride over the chunks
+    static const int per_sm = [] {
+      const char* e = getenv("GSR_ADAM_SIDE_CTAS");
+      const int v = e ? atoi(e) : 2;
+      return v < 1 ? 1 : v;
+    }();
+    const int grid = blocks < 148 * per_sm ? blocks : 148 * per_sm;
+    adam_rows_zero_grad_kernel<<<grid, kAdamThreads, 0, s>>>(ar, blocks);
+  } else {
+    AdamVisParams vp;
+    vp.rows = ar;
+    unsigned off = 0;
+    for (int k = 0; k < ar.base.n_groups; ++k) {
+      vp.prefix[k] = off;
+      off += ar.width[k];
+    }
+    vp.prefix[ar.base.n_groups] = off;
+    if (off > 32u * kAdamRowSlots) return GSR_ERR_BAD_ARG;  // rows wider than 128 elements are not supported
+    vp.row_elems = off;
+    vp.n_rows = (unsigned)rows;
+    const int64_t warps = (rows + 31) / 32;
+    const int64_t want = (warps + 7) / 8;
+    const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+    adam_rows_with_grad_kernel<<<grid, 256, 0, s>>>(vp);
+  }
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -163,6 +163,7 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.conic_opacity = g.conic_opacity; pp.rgb = g.rgb; pp.clamped = g.clamped;
   pp.tiles_touched = g.tiles_touched; pp.sort_items = g.sort_a; pp.num_visible = &g.hdr->num_visible;
   GSR_PROF("preprocess", launch_preprocess(pp, s));
+  if (a->radii_ready_event) GSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->radii_ready_event), s));
 
   // depth order of the Gaussians: 32 key bits, 4 passes, result back in sort_a
   uint64_t* order = nullptr;
@@ -283,6 +284,15 @@ int gsr_adam_step(const gsr_adam_group* groups, int n_groups, double beta1, doub
   if (n_groups < 0 || (n_groups > 0 && !groups)) return GSR_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   GSR_PROF("adam", launch_adam(groups, n_groups, beta1, beta2, eps, grad_scale, s));
+  return GSR_OK;
+}
+
+int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
+                       float grad_scale, int64_t rows, const int32_t* row_mask, int phase, void* stream) {
+  if (n_groups < 0 || (n_groups > 0 && !groups) || rows < 0) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GSR_PROF(phase == GSR_ADAM_ROWS_ZERO_GRAD ? "adam_rows_zero_grad" : "adam_rows_with_grad",
+           launch_adam_rows(groups, n_groups, beta1, beta2, eps, grad_scale, rows, row_mask, phase, s));
   return GSR_OK;
 }
 

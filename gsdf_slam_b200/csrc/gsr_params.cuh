@@ -91,6 +91,8 @@ int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const u
 int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
                 float grad_scale, cudaStream_t s);
 size_t knn_temp_bytes(int64_t P);
+int launch_adam_rows(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
+                     float grad_scale, int64_t rows, const int* row_mask, int phase, cudaStream_t s);
 int launch_knn(int P, const float* points, float* mean_dist2, char* tmp, cudaStream_t s);
 
 }  // namespace gsr

@@ -73,7 +73,7 @@ class KeyframeBatchMapper:
 
     def __init__(self, params: Dict[str, torch.Tensor], degree: int, bg: torch.Tensor,
                  lr: Optional[Dict[str, float]] = None, eps: float = 1e-15,
-                 process_group=None, freeze_render_inputs: bool = False):
+                 process_group=None, freeze_render_inputs: bool = False, overlap_adam: bool = False):
         self.params = {k: params[k].contiguous() for k in SEGMENTS}
         self.degree = int(degree)
         self.bg = bg
@@ -95,6 +95,16 @@ class KeyframeBatchMapper:
                                     if self.opt_params[k].numel() > 0], lr=0.0, eps=eps)
         self.last_radii: Optional[torch.Tensor] = None
         self.last_color: Optional[torch.Tensor] = None
+        # visibility-split Adam (gsr_adam_step_rows): the zero-gradient rows are updated on a
+        # side stream while the blend / backward kernels run.  OFF by default: measured on B200
+        # (cfg2) the streaming sweep slows the co-running blend kernels by as much as it hides
+        # (step 1.08 ms vs 0.99 ms fused), so the fused single launch stays the default
+        self.overlap_adam = bool(overlap_adam) and dev.type == "cuda"
+        self.serialize_side_stream = False   # profiling aid: run the side-stream work on the main stream
+        self.trace = None                    # profiling aid: list collecting (label, timing event) pairs
+        self._side: Optional[torch.cuda.Stream] = None
+        self._ev_radii: Optional[torch.cuda.Event] = None
+        self._ev_side: Optional[torch.cuda.Event] = None
 
     def _views(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
         v = {}
@@ -108,13 +118,25 @@ class KeyframeBatchMapper:
         import torch.distributed as dist
         return dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
 
-    def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor]):
-        """fwd + bwd of one keyframe; parameter gradients are written into grad_views."""
+    def render(self, kf: Keyframe, radii_ready_event=None):
+        """Forward pass of one keyframe -> the reference's 8-tuple (rasterize_points.h:18-39)."""
         p = self.params
         e = torch.empty(0, dtype=torch.float32, device=p["means3D"].device)
-        fwd = RasterizeGaussiansCUDA(self.bg, p["means3D"], e, p["opacity"], p["scales"], p["rotations"],
-                                     1.0, e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy, kf.H,
-                                     kf.W, p["dc"], p["sh"], self.degree, kf.campos, False, False)
+        return RasterizeGaussiansCUDA(self.bg, p["means3D"], e, p["opacity"], p["scales"], p["rotations"],
+                                      1.0, e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy, kf.H,
+                                      kf.W, p["dc"], p["sh"], self.degree, kf.campos, False, False,
+                                      radii_ready_event=radii_ready_event)
+
+    def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor], fwd=None, on_forward=None):
+        """fwd + bwd of one keyframe; parameter gradients are written into grad_views.
+        ``on_forward(kf, fwd)`` runs between the two passes (e.g. to start reading the image back
+        and to make the stream wait for the uploaded dL/d(image))."""
+        p = self.params
+        e = torch.empty(0, dtype=torch.float32, device=p["means3D"].device)
+        if fwd is None:
+            fwd = self.render(kf)
+            if on_forward is not None:
+                on_forward(kf, fwd)
         R, B, color, radii, geom, binning, img, sample = fwd
         out = {GRAD_NAME[k]: grad_views[k] for k in SEGMENTS if grad_views[k].numel() > 0}
         g = RasterizeGaussiansBackwardCUDA(self.bg, p["means3D"], radii, e, p["scales"], p["rotations"], 1.0,
@@ -124,17 +146,17 @@ class KeyframeBatchMapper:
         self.last_radii, self.last_color = radii, color
         return color, radii, g
 
-    def accumulate(self, keyframes: Sequence[Keyframe]) -> None:
+    def accumulate(self, keyframes: Sequence[Keyframe], on_forward=None) -> None:
         """Sum of the local keyframes' gradients -> arena (== K sequential backward() calls
         without zero_grad, the semantics pinned in SURVEY.md §8e)."""
         if len(keyframes) == 0:
             self.arena.zero_()
             return
-        self.render_backward(keyframes[0], self.grad_views)      # first keyframe writes in place
+        self.render_backward(keyframes[0], self.grad_views, on_forward=on_forward)  # writes in place
         for kf in keyframes[1:]:
             if self._scratch_arena is None:
                 self._scratch_arena = torch.zeros_like(self.arena)  # padding slots stay 0
-            self.render_backward(kf, self._views(self._scratch_arena))
+            self.render_backward(kf, self._views(self._scratch_arena), on_forward=on_forward)
             self.arena.add_(self._scratch_arena)
 
     def allreduce(self) -> None:
@@ -214,7 +236,72 @@ class KeyframeBatchMapper:
             w.wait()  # the compute stream waits for this chunk only
             self._adam_ranges(ranges, steps, grad_scale)
 
-    def step(self, keyframes: Sequence[Keyframe], grad_scale: float = 1.0) -> None:
+    # ---- single-rank step with the visibility-split Adam overlapped with the rasterizer -----
+    def _streams(self):
+        dev = self.arena.device
+        if self._side is None:
+            import os
+            # the side kernel is a small persistent grid: give it priority so that its few CTAs are
+            # placed at once and then stream under the rasterizer kernels
+            prio = -1 if os.environ.get("GSR_SIDE_PRIO", "high") == "high" else 0
+            self._side = torch.cuda.Stream(device=dev, priority=prio)
+            self._ev_radii = torch.cuda.Event()
+            self._ev_side = torch.cuda.Event()
+        return torch.cuda.current_stream(dev), self._side
+
+    def _mark(self, label: str, stream) -> None:
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.trace.append((label, ev))
+
+    def _step_overlapped(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
+        """Rows that no local keyframe renders have a zero gradient: their Adam update only needs
+        `radii`, so it is enqueued on a side stream right after the (last) forward pass and runs
+        under the blend / backward kernels; the rendered rows follow the backward pass on the
+        main stream.  Bit-identical to accumulate() + adam_step() (tests/test_gpu_kernels.py)."""
+        main, side = self._streams()
+        if self.serialize_side_stream:
+            side = main
+        opt = self.optimizer
+        grads = {self.opt_params[k]: self.grad_views[k] for k in SEGMENTS if self.opt_params[k].numel() > 0}
+        K = len(keyframes)
+        mask = None
+        self._mark("step_begin", main)
+        for i, kf in enumerate(keyframes):
+            last = i == K - 1
+            fwd = self.render(kf, radii_ready_event=self._ev_radii if (last and K == 1) else None)
+            if on_forward is not None:
+                on_forward(kf, fwd)
+            radii = fwd[3]
+            mask = radii if mask is None else torch.maximum(mask, radii)
+            if last:
+                if K > 1:
+                    self._ev_radii.record(main)
+                side.wait_event(self._ev_radii)
+                mask.record_stream(side)
+                self._mark("forward_end", main)
+                with torch.cuda.stream(side):
+                    self._mark("side_adam_begin", side)
+                    opt.step_rows(mask, opt.ROWS_ZERO_GRAD, grads=None, grad_scale=grad_scale, new_step=True)
+                    self._mark("side_adam_end", side)
+                    self._ev_side.record(side)
+            if i == 0:
+                self.render_backward(kf, self.grad_views, fwd=fwd)
+            else:
+                if self._scratch_arena is None:
+                    self._scratch_arena = torch.zeros_like(self.arena)
+                self.render_backward(kf, self._views(self._scratch_arena), fwd=fwd)
+                self.arena.add_(self._scratch_arena)
+        self._mark("backward_end", main)
+        opt.step_rows(mask, opt.ROWS_WITH_GRAD, grads=grads, grad_scale=grad_scale, new_step=False)
+        self._mark("main_adam_end", main)
+        main.wait_event(self._ev_side)  # later work on this stream sees the complete update
+
+    def step(self, keyframes: Sequence[Keyframe], grad_scale: float = 1.0, on_forward=None) -> None:
         """One mapping iteration over this rank's keyframes."""
-        self.accumulate(keyframes)
+        if self.overlap_adam and self.world_size == 1 and len(keyframes) > 0 and self.P > 0:
+            self._step_overlapped(keyframes, grad_scale, on_forward)
+            return
+        self.accumulate(keyframes, on_forward)
         self.exchange_and_update(grad_scale)

@@ -67,8 +67,13 @@ class _Scratch:
 
 def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                            cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
-                           image_width, dc, sh, degree, campos, prefiltered, debug):
-    """-> (rendered, num_buckets, out_color, radii, geomBuffer, binningBuffer, imgBuffer, sampleBuffer)"""
+                           image_width, dc, sh, degree, campos, prefiltered, debug,
+                           radii_ready_event: Optional["torch.cuda.Event"] = None):
+    """-> (rendered, num_buckets, out_color, radii, geomBuffer, binningBuffer, imgBuffer, sampleBuffer)
+
+    ``radii_ready_event`` (extension): a ``torch.cuda.Event`` recorded on the current stream as
+    soon as ``radii`` is final (after the first kernel of the forward pass), so that a side
+    stream can start the zero-gradient phase of the visibility-split Adam step early."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     L = _lib.lib()
@@ -96,8 +101,13 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
         debug=int(bool(debug)), out_color=_ptr(out_color), radii=_ptr(radii),
         geom_resize=geom.cb, geom_user=None, binning_resize=binning.cb, binning_user=None,
         image_resize=img.cb, image_user=None, sample_resize=sample.cb, sample_user=None,
-        stream=_stream(dev), num_rendered=C.pointer(rendered), num_buckets=C.pointer(buckets))
+        stream=_stream(dev), num_rendered=C.pointer(rendered), num_buckets=C.pointer(buckets),
+        radii_ready_event=None)
     with torch.cuda.device(dev):
+        if radii_ready_event is not None:
+            if not radii_ready_event.cuda_event:      # torch creates the cudaEvent_t lazily
+                radii_ready_event.record(torch.cuda.current_stream(dev))
+            a.radii_ready_event = C.c_void_p(radii_ready_event.cuda_event)
         _lib.check(L.gsr_forward(C.byref(a)), "gsr_forward")
     return (rendered.value, buckets.value, out_color, radii, geom.t, binning.t, img.t, sample.t)
 

@@ -12,8 +12,8 @@
  *                         (called by markVisible,                src/rasterize_points.cu:207-226)
  *   gsr_knn_mean_dist2 <- SimpleKNN::knn                          submodules/simple-knn/simple_knn.h:17
  *                         (called by distCUDA2,                  submodules/simple-knn/spatial.cu:15-26)
- *   gsr_adam_step      <- torch::optim::Adam::step on the 6 parameter groups
- *                         (src/gaussian_model.cpp:319-352, stepped at src/gaussian_mapper.cpp:465)
+ *   gsr_adam_step,     <- torch::optim::Adam::step on the 6 parameter groups
+ *   gsr_adam_step_rows    (src/gaussian_model.cpp:319-352, stepped at src/gaussian_mapper.cpp:465)
  *   gsr_export_*       <- test/debug decoders of the opaque scratch buffers (the
  *                         reference's GeometryState/BinningState/ImageState::fromChunk,
  *                         cuda_rasterizer/rasterizer_impl.cu:274-343)
@@ -76,6 +76,9 @@ typedef struct gsr_forward_args {
   void* stream;                /* cudaStream_t */
   int* num_rendered;           /* host out: number of (Gaussian,tile) duplicates R */
   int* num_buckets;            /* host out: kept for API parity (number of 32-splat buckets) */
+  void* radii_ready_event;     /* optional cudaEvent_t, recorded on `stream` right after the kernel
+                                  that writes `radii` (lets a side stream start gsr_adam_step_rows
+                                  phase 0 while the rest of the forward pass runs); may be NULL */
 } gsr_forward_args;
 
 typedef struct gsr_backward_args {
@@ -138,6 +141,23 @@ typedef struct gsr_adam_group {
 } gsr_adam_group;
 int gsr_adam_step(const gsr_adam_group* groups, int n_groups, double beta1,
                   double beta2, double eps, float grad_scale, void* stream);
+
+/* The same step, split by row visibility so that most of it can overlap the rasterizer.
+ * Every group is a [rows, width] tensor (numel % rows == 0) and row_mask[r] > 0 marks the rows
+ * that received a gradient in this iteration (the `radii` output of gsr_forward, or the
+ * element-wise maximum of several keyframes' / ranks' radii).
+ *   phase GSR_ADAM_ROWS_ZERO_GRAD: updates the rows with row_mask <= 0, whose gradient is
+ *     exactly +0 (the reference's dense torch::optim::Adam still decays their moments and moves
+ *     them); `grad` is not read, so this phase may run on a side stream as soon as the forward
+ *     pass has produced radii, concurrently with the blend / backward kernels;
+ *   phase GSR_ADAM_ROWS_WITH_GRAD: updates the rows with row_mask > 0 from `grad`.
+ * Running both phases (in either order) is bit-identical to one gsr_adam_step whenever the
+ * masked-out rows of `grad` hold +0, which gsr_backward guarantees. */
+#define GSR_ADAM_ROWS_ZERO_GRAD 0
+#define GSR_ADAM_ROWS_WITH_GRAD 1
+int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
+                       double beta2, double eps, float grad_scale, int64_t rows,
+                       const int32_t* row_mask, int phase, void* stream);
 
 /* ---- test / debug exports (device -> device copies out of the opaque buffers) ---- */
 /* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits). */

@@ -92,6 +92,90 @@ def test_fused_adam_matches_libtorch_adam_op_sequence():
     assert max_ulp <= 2, f"parameters differ from LibTorch Adam by {max_ulp} ulp"
 
 
+@pytest.mark.parametrize("rows,vis_frac", [(50_001, 0.15), (4099, 0.5), (130, 0.0), (130, 1.0)])
+def test_visibility_split_adam_is_bit_identical_to_the_fused_step(rows, vis_frac):
+    """gsr_adam_step_rows: phase ZERO_GRAD (rows with radii == 0, gradient not read) + phase
+    WITH_GRAD (rendered rows) == one gsr_adam_step over everything, bit for bit."""
+    from gsdf_slam_b200 import FusedAdam
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    shapes = [(rows, 3), (rows, 1, 3), (rows, 15, 3), (rows, 1), (rows, 3), (rows, 4)]
+    lrs = [1.6e-4, 0.0025, 0.000125, 0.05, 0.005, 0.001]
+    pa = [torch.randn(s, device="cuda", generator=gen) for s in shapes]
+    pb = [p.clone() for p in pa]
+    oa = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(pa, lrs)], lr=0.0, eps=1e-15)
+    ob = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(pb, lrs)], lr=0.0, eps=1e-15)
+    side = torch.cuda.Stream()
+    for step in range(1, 5):
+        radii = (torch.rand(rows, device="cuda", generator=gen) < vis_frac).to(torch.int32) * (step + 2)
+        vis = radii > 0
+        ga, gb = {}, {}
+        for a, b in zip(pa, pb):
+            g = torch.randn(a.shape, device="cuda", generator=gen)
+            g[~vis] = 0.0                       # what gsr_backward writes for non-rendered rows
+            ga[a], gb[b] = g, g.clone()
+        # poison phase 0's view of the gradient: it must not be read there
+        poison = {b: torch.full_like(g, float("nan")) for b, g in gb.items()}
+        oa.step(grads=ga)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            ob.step_rows(radii, ob.ROWS_ZERO_GRAD, grads=poison, new_step=True)
+        ob.step_rows(radii, ob.ROWS_WITH_GRAD, grads=gb)   # concurrently on the main stream
+        torch.cuda.synchronize()
+        for a, b in zip(pa, pb):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+            assert torch.equal(oa.state[a]["exp_avg"].view(torch.int32), ob.state[b]["exp_avg"].view(torch.int32))
+            assert torch.equal(oa.state[a]["exp_avg_sq"].view(torch.int32),
+                               ob.state[b]["exp_avg_sq"].view(torch.int32))
+            assert oa.state[a]["step"] == ob.state[b]["step"] == step
+
+
+def test_adam_step_rows_rejects_bad_arguments():
+    L = _lib.lib()
+    x = torch.zeros(12, device="cuda")
+    mask = torch.zeros(5, dtype=torch.int32, device="cuda")
+    grp = (_lib.AdamGroup * 1)(_lib.AdamGroup(param=x.data_ptr(), grad=x.data_ptr(), exp_avg=x.data_ptr(),
+                                              exp_avg_sq=x.data_ptr(), numel=12, lr=1e-3, step=1))
+    assert L.gsr_adam_step_rows(grp, 1, 0.9, 0.999, 1e-8, 1.0, 5, C.c_void_p(mask.data_ptr()), 0, None) != 0  # 12 % 5
+    assert L.gsr_adam_step_rows(grp, 1, 0.9, 0.999, 1e-8, 1.0, 4, None, 0, None) != 0                          # no mask
+    assert L.gsr_adam_step_rows(grp, 1, 0.9, 0.999, 1e-8, 1.0, 4, C.c_void_p(mask.data_ptr()), 2, None) != 0  # phase
+
+
+def test_overlapped_mapping_step_equals_sequential_step():
+    """KeyframeBatchMapper.step with the Adam update of the non-rendered rows overlapped on a
+    side stream == accumulate() + one fused Adam step, bit for bit (1 and 2 local keyframes)."""
+    from gsdf_slam_b200.mapping import SEGMENTS, Keyframe, KeyframeBatchMapper
+    scene = scenes.tiny(seed=9, P=6000, W=176, H=120, degree=3)
+    t = to_dev(scene)
+    cam = scene.cam
+    kfs = [Keyframe(t["viewmatrix"], t["projmatrix"], t["campos"], cam.tanfovx, cam.tanfovy, cam.H, cam.W,
+                    t["dL_dout"] * s) for s in (1.0, -0.5)]
+    params_init = dict(means3D=t["means3D"], dc=t["dc"], sh=t["sh"], opacity=t["opacity"], scales=t["scales"],
+                       rotations=t["rotations"])
+    for K in (1, 2):
+        res = []
+        for overlap in (False, True):
+            params = dict(means3D=t["means3D"].clone(), dc=t["dc"].clone(), sh=t["sh"].clone(),
+                          opacity=t["opacity"].clone(), scales=t["scales"].clone(), rotations=t["rotations"].clone())
+            m = KeyframeBatchMapper(params, scene.degree, t["bg"], freeze_render_inputs=True, overlap_adam=overlap)
+            for _ in range(3):
+                m.step(kfs[:K])
+            torch.cuda.synchronize()
+            res.append(m)
+        a, b = res
+        hidden = a.last_radii == 0   # same camera for every keyframe: never rendered
+        assert 0 < int(hidden.sum()) < scene.P
+        for k in SEGMENTS:
+            pa_, pb_ = a.opt_params[k], b.opt_params[k]
+            sa, sb = a.optimizer.state[pa_], b.optimizer.state[pb_]
+            assert sa["step"] == sb["step"] == 3
+            # rows without gradient: exact; rendered rows: the blend backward sums with atomics, so
+            # two runs agree to the gradient tolerance (1e-4 rel-L2), not bit for bit
+            assert torch.equal(pa_[hidden].view(torch.int32), pb_[hidden].view(torch.int32)), k
+            assert torch.equal(sa["exp_avg_sq"][hidden], sb["exp_avg_sq"][hidden]), k
+            assert rel_l2(sa["exp_avg"], sb["exp_avg"]) <= 1e-4, k
+            assert rel_l2(pa_ - params_init[k], pb_ - params_init[k]) <= 1e-3, k
+
+
 def _brute_knn(pts: torch.Tensor) -> torch.Tensor:
     out = torch.empty(pts.size(0), device=pts.device)
     for s in range(0, pts.size(0), 2048):
