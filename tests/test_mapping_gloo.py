@@ -52,7 +52,7 @@ def test_arena_layout_is_aligned_and_59_floats_per_gaussian():
 class _FakeMapper(KeyframeBatchMapper):
     """render_backward replaced by a deterministic function of (keyframe id, parameter)."""
 
-    def render_backward(self, kf, grad_views):
+    def render_backward(self, kf, grad_views, fwd=None, on_forward=None):
         for i, name in enumerate(SEGMENTS):
             g = grad_views[name]
             if g.numel():
