@@ -121,24 +121,39 @@ emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __re
     const int area = w * h;
     const int t_begin = (int)chunk * kQueueRectTiles;
     const int t_end = min(area, t_begin + kQueueRectTiles);
-    for (int t0 = t_begin; t0 < t_end; t0 += 32) {
+    // test all tiles of the chunk first (bit `st` = this lane's tile of step `st` passed), reserve
+    // the chunk's slots with ONE atomic (a returning atomic per 32 tiles was the critical path),
+    // then write
+    static_assert(kQueueRectTiles <= 32 * 32, "one pass bit per step");
+    uint32_t passbits = 0, total = 0;
+    int st = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += 32, ++st) {
       const int t = t0 + lane;
       bool pass = false;
-      int x = 0, y = 0;
       if (t < t_end) {
-        y = (int)rect_min.y + t / w;
-        x = (int)rect_min.x + t - (t / w) * w;
+        const int y = (int)rect_min.y + t / w;
+        const int x = (int)rect_min.x + t - (t / w) * w;
         pass = tile_min_power(co, xy, x, y) <= thr;
       }
+      passbits |= pass ? (1u << st) : 0u;
+      total += __popc(__ballot_sync(0xffffffffu, pass));
+    }
+    if (total == 0) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&dup_offsets[j], total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    st = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += 32, ++st) {
+      const bool pass = (passbits >> st) & 1u;
       const unsigned pm = __ballot_sync(0xffffffffu, pass);
-      if (pm == 0) continue;
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&dup_offsets[j], (uint32_t)__popc(pm));
-      base = __shfl_sync(0xffffffffu, base, 0);
       if (pass) {
+        const int t = t0 + lane;
+        const int y = (int)rect_min.y + t / w;
+        const int x = (int)rect_min.x + t - (t / w) * w;
         const uint64_t tile = (uint64_t)(y * grid_x + x);
         items[base + __popc(pm & lanemask_lt)] = (tile << 32) | g;
       }
+      base += __popc(pm);
     }
   }
 }
@@ -162,29 +177,17 @@ int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
   return (int)cudaGetLastError();
 }
 
-// One thread per sorted duplicate: tile boundaries -> ranges (the job of the
-// reference's identifyTileRanges, rasterizer_impl.cu:217-246) and the packed
-// per-duplicate record {xy, conic, opacity, reject threshold, idx, rgb}.
+// One thread per sorted duplicate: the packed per-duplicate record {xy, conic, opacity, reject
+// threshold, idx, rgb}.  (The tile ranges — the job of the reference's identifyTileRanges,
+// rasterizer_impl.cu:217-246 — already exist: tile_meta_kernel scans the exact per-tile counts.)
 __global__ void __launch_bounds__(256)
 finalize_kernel(uint32_t R, const uint64_t* __restrict__ sorted, const float2* __restrict__ means2D,
                 const float4* __restrict__ conic_opacity, const float* __restrict__ colors,
-                uint2* __restrict__ ranges, float4* __restrict__ rec_a, float4* __restrict__ rec_b,
-                float4* __restrict__ rec_c) {
+                float4* __restrict__ rec_a, float4* __restrict__ rec_b, float4* __restrict__ rec_c) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
   const uint64_t it = sorted[i];
-  const uint32_t tile = (uint32_t)(it >> 32);
   const uint32_t g = (uint32_t)(it & 0xffffffffu);
-  if (i == 0) {
-    ranges[tile].x = 0;
-  } else {
-    const uint32_t prev = (uint32_t)(sorted[i - 1] >> 32);
-    if (prev != tile) {
-      ranges[prev].y = i;
-      ranges[tile].x = i;
-    }
-  }
-  if (i == R - 1) ranges[tile].y = R;
 
   const float2 xy = means2D[g];
   const float4 co = conic_opacity[g];
@@ -197,66 +200,103 @@ finalize_kernel(uint32_t R, const uint64_t* __restrict__ sorted, const float2* _
 }
 
 int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
-                    const float4* conic_opacity, const float* colors, uint2* ranges, uint32_t T,
-                    float4* rec_a, float4* rec_b, float4* rec_c, cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)T * sizeof(uint2), s);
-  if (e != cudaSuccess) return (int)e;
+                    const float4* conic_opacity, const float* colors, float4* rec_a, float4* rec_b,
+                    float4* rec_c, cudaStream_t s) {
   if (R == 0) return 0;
-  finalize_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted, means2D, conic_opacity, colors, ranges,
-                                                  rec_a, rec_b, rec_c);
+  finalize_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted, means2D, conic_opacity, colors, rec_a,
+                                                  rec_b, rec_c);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }
 
-// Longest-processing-time-first launch order for the blend kernels: a counting sort of the
-// tiles by list length (1024 buckets of 4 entries, longest first).  The blend kernels run
-// one CTA per tile for the whole length of its list, so starting the long lists first keeps
-// the last wave short (matters most for heavy-tailed scenes such as cfg4's ground splats).
+// Everything that follows from the exact per-tile splat counts (accumulated by preprocess), in
+// one single-CTA kernel right after preprocess:
+//   * ranges[t]   = exclusive scan of the counts (the reference's identifyTileRanges result),
+//   * *num_dup    = R, the total number of duplicates (read back by the host to size the
+//                   binning buffer while the depth sort is already running),
+//   * tile_ghist  = digit histograms of the tile sort (no histogram pass over the R duplicates),
+//   * order       = longest-processing-time-first launch order of the blend kernels: a counting
+//                   sort of the tiles by list length (1024 buckets of 4 entries, longest first) —
+//                   the blend kernels run one CTA per half tile for the whole length of its
+//                   list, so starting the long lists first keeps the last wave short,
+//   * max_contrib = 0 (blend_fwd raises it with atomicMax).
 __global__ void __launch_bounds__(1024)
-tile_order_kernel(const uint2* __restrict__ ranges, uint32_t T, uint32_t* __restrict__ order) {
+tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, int npass,
+                 uint2* __restrict__ ranges, uint32_t* __restrict__ num_dup,
+                 uint32_t* __restrict__ tile_ghist, uint32_t* __restrict__ order,
+                 uint32_t* __restrict__ max_contrib) {
   __shared__ uint32_t s_cnt[1024];
+  __shared__ uint32_t s_hist[kTileHistPasses][256];
   __shared__ uint32_t s_warp[32];
-  const int tid = threadIdx.x;
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_cnt[tid] = 0;
+  (&s_hist[0][0])[tid] = 0;  // kTileHistPasses * 256 == 1024 entries
+  if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (uint32_t t = tid; t < T; t += 1024) {
-    const uint2 r = ranges[t];
-    const uint32_t b = 1023u - min(1023u, (r.y - r.x) >> 2);  // bucket 0 = longest lists
-    atomicAdd(&s_cnt[b], 1u);
-  }
-  __syncthreads();
-  // exclusive scan of the 1024 bucket counts
-  const uint32_t c = s_cnt[tid];
-  uint32_t inc = c;
-  const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += x;
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = s_warp[lane];
+
+  // block-wide inclusive scan of one value per thread (1024 threads); all threads must call
+  auto block_incl_scan = [&](uint32_t v) -> uint32_t {
+    uint32_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t x = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += x;
+      const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += x;
     }
-    s_warp[lane] = w;
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += x;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t r = inc + (warp > 0 ? s_warp[warp - 1] : 0u);
+    __syncthreads();  // s_warp is reused by the next call
+    return r;
+  };
+
+  for (uint32_t t0 = 0; t0 < T; t0 += 1024) {
+    const uint32_t t = t0 + tid;
+    const uint32_t c = t < T ? tile_count[t] : 0u;
+    const uint32_t inc = block_incl_scan(c);
+    const uint32_t carry = s_carry;
+    if (t < T) {
+      ranges[t] = make_uint2(carry + inc - c, carry + inc);
+      max_contrib[t] = 0;
+      if (c) {
+        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p][(t >> (8 * p)) & 0xffu], c);
+      }
+      atomicAdd(&s_cnt[1023u - min(1023u, c >> 2)], 1u);  // bucket 0 = longest lists
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + inc;
+    __syncthreads();
   }
-  __syncthreads();
-  s_cnt[tid] = inc - c + (warp > 0 ? s_warp[warp - 1] : 0u);
+  if (tid == 0) *num_dup = s_carry;
+  for (int i = tid; i < npass * 256; i += 1024) tile_ghist[i] = (&s_hist[0][0])[i];
+
+  // exclusive scan of the 1024 bucket counts, then place the tiles
+  const uint32_t c = s_cnt[tid];
+  const uint32_t inc = block_incl_scan(c);
+  s_cnt[tid] = inc - c;
   __syncthreads();
   for (uint32_t t = tid; t < T; t += 1024) {
-    const uint2 r = ranges[t];
-    const uint32_t b = 1023u - min(1023u, (r.y - r.x) >> 2);
+    const uint32_t b = 1023u - min(1023u, tile_count[t] >> 2);
     order[atomicAdd(&s_cnt[b], 1u)] = t;
   }
 }
 
-int launch_tile_order(const uint2* ranges, uint32_t T, uint32_t* order, cudaStream_t s) {
-  tile_order_kernel<<<1, 1024, 0, s>>>(ranges, T, order);
+int launch_tile_meta(const uint32_t* tile_count, uint32_t T, int tile_bits, uint2* ranges,
+                     uint32_t* num_dup, uint32_t* tile_ghist, uint32_t* order, uint32_t* max_contrib,
+                     cudaStream_t s) {
+  const int npass = (tile_bits + 7) / 8;
+  if (npass > kTileHistPasses) return GSR_ERR_BAD_ARG;
+  tile_meta_kernel<<<1, 1024, 0, s>>>(tile_count, T, npass, ranges, num_dup, tile_ghist, order, max_contrib);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -161,15 +161,13 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
   // deepest list position any pixel of the tile used (bounds the backward replay)
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, my_max);
-  if (lane == 0) atomicMax(&max_contrib[tile_id], wmax);  // zeroed by the launcher
+  if (lane == 0) atomicMax(&max_contrib[tile_id], wmax);  // zeroed by tile_meta_kernel
 }
 
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec_a, const float4* rec_b,
                      const float4* rec_c, const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  cudaError_t e = cudaMemsetAsync(max_contrib, 0, (size_t)grid * sizeof(uint32_t), s);
-  if (e != cudaSuccess) return (int)e;
   blend_fwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec_a, rec_b, rec_c, W, H, bg, out_color,
                                                   final_T, n_contrib, accum_c, max_contrib);
   GSR_LAUNCHED();

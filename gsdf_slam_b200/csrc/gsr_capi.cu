@@ -46,6 +46,12 @@ static uint32_t* pinned_word() {
   return p;
 }
 
+static cudaEvent_t readback_event() {
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+  return ev;
+}
+
 // ---- optional per-stage CUDA-event profiler (bench.py's live roofline measurement) ----
 struct ProfPending { int slot; cudaEvent_t a, b; };
 struct Profiler {
@@ -140,7 +146,9 @@ int gsr_forward(const gsr_forward_args* a) {
   GeomView g = geom_view(geom_base, (size_t)P);
   ImageView im = image_view(img_base, N, T);
 
-  GSR_CUDA(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
+  // one clear per buffer: counters + depth histograms + look-back flags | tile counts + histograms
+  GSR_CUDA(cudaMemsetAsync(g.hdr, 0, g.zero_bytes, s));
+  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));
 
   PreprocessParams pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -162,18 +170,30 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.radii = a->radii; pp.depths = g.depths; pp.means2D = g.means2D;
   pp.conic_opacity = g.conic_opacity; pp.rgb = g.rgb; pp.clamped = g.clamped;
   pp.tiles_touched = g.tiles_touched; pp.sort_items = g.sort_a; pp.num_visible = &g.hdr->num_visible;
+  pp.tile_count = im.tile_count; pp.depth_ghist = sort_ghist(g.sort_tmp);
   GSR_PROF("preprocess", launch_preprocess(pp, s));
   if (a->radii_ready_event) GSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->radii_ready_event), s));
 
-  // depth order of the Gaussians: 32 key bits, 4 passes, result back in sort_a
-  uint64_t* order = nullptr;
-  GSR_PROF("sort_depth", launch_sort_u64(g.sort_a, g.sort_a, g.sort_b, P, 32, 64, g.sort_tmp, s, &order));
-  GSR_PROF("scan", launch_scan_gather(g.tiles_touched, order, P, g.dup_offsets, &g.hdr->num_dup, g.sort_tmp, s));
-
+  // ranges, R, tile-sort histograms and the blend launch order from the exact per-tile counts
+  const int tb = tile_bits(T);
+  GSR_PROF("tile_meta", launch_tile_meta(im.tile_count, T, tb, im.ranges, &g.hdr->num_dup, im.tile_ghist,
+                                         im.tile_order, im.max_contrib, s));
+  // R travels to the host while the depth sort runs: by the time the host needs it (to size the
+  // per-duplicate buffers) the copy has long completed, and the GPU never idles
   uint32_t* host_R = pinned_word();
-  if (!host_R) return GSR_ERR_ALLOC;
+  cudaEvent_t ev_R = readback_event();
+  if (!host_R || !ev_R) return GSR_ERR_ALLOC;
   GSR_CUDA(cudaMemcpyAsync(host_R, &g.hdr->num_dup, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-  GSR_CUDA(cudaStreamSynchronize(s));
+  GSR_CUDA(cudaEventRecord(ev_R, s));
+
+  // depth order of the rendered Gaussians: 32 key bits, 4 passes (the first one also drops the
+  // non-rendered Gaussians), result in sort_a; then their duplicate offsets in that order
+  GSR_PROF("sort_depth", launch_sort_depth(g.sort_a, g.sort_b, P, &g.hdr->num_visible, g.sort_tmp, s));
+  const uint64_t* order = g.sort_a;
+  GSR_PROF("scan", launch_scan_gather(g.tiles_touched, order, P, &g.hdr->num_visible, g.dup_offsets, nullptr,
+                                      g.scan_tmp, s));
+
+  GSR_CUDA(cudaEventSynchronize(ev_R));
   const uint32_t R = *host_R;
   *a->num_rendered = (int)R;
 
@@ -183,7 +203,6 @@ int gsr_forward(const gsr_forward_args* a) {
   BinView b = bin_view(bin_base, (size_t)R);
 
   if (R > 0) {
-    const int tb = tile_bits(T);
     const int npass = (tb + 7) / 8;
     // choose the emit target so that the sorted list always ends in items_a
     uint64_t* emit_dst = (npass & 1) ? b.items_b : b.items_a;
@@ -191,15 +210,13 @@ int gsr_forward(const gsr_forward_args* a) {
     GSR_PROF("emit", launch_emit(P, order, g.tiles_touched, g.dup_offsets, g.means2D, g.conic_opacity,
                        a->radii, gx, gy, emit_dst, &g.hdr->num_large,
                        reinterpret_cast<uint32_t*>(g.sort_b), &g.hdr->num_visible, s));
-    uint64_t* sorted = nullptr;
     // odd: in=b, out=a, alt=b ; even: in=a, out=a, alt=b
-    GSR_PROF("sort_tile", launch_sort_u64(emit_dst, b.items_a, (npass & 1) ? emit_dst : other, R, 32, 32 + tb,
-                           b.sort_tmp, s, &sorted));
+    GSR_PROF("sort_tile", launch_sort_tile(emit_dst, b.items_a, (npass & 1) ? emit_dst : other, R, tb,
+                                           im.tile_ghist, b.sort_tmp, s));
   }
   const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
-  GSR_PROF("finalize", launch_finalize(R, b.items_a, g.means2D, g.conic_opacity, colors, im.ranges, T, b.rec_a,
+  GSR_PROF("finalize", launch_finalize(R, b.items_a, g.means2D, g.conic_opacity, colors, b.rec_a,
                          b.rec_b, b.rec_c, s));
-  GSR_PROF("tile_order", launch_tile_order(im.ranges, T, im.tile_order, s));
   GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec_a, b.rec_b, b.rec_c, a->background, a->out_color,
                           im.final_T, im.n_contrib, im.accum_c, im.max_contrib, s));
   if (a->debug) {

@@ -37,6 +37,13 @@ struct GeomHeader {          // lives at the start of the geometry buffer (256 B
 
 struct GeomView {
   GeomHeader* hdr;
+  // hdr | sort_tmp | scan_tmp are contiguous: ONE memset zeroes the counters, the depth-digit
+  // histograms that preprocess accumulates and the look-back flags of the depth sort and scan
+  char* sort_tmp;            // onesweep temp of the depth sort (starts with the 4x256 histograms)
+  size_t sort_tmp_bytes;
+  char* scan_tmp;            // chained-scan flags
+  size_t scan_tmp_bytes;
+  size_t zero_bytes;         // bytes to clear starting at hdr
   float* depths;             // [P]
   float2* means2D;           // [P]
   float4* conic_opacity;     // [P]
@@ -47,11 +54,14 @@ struct GeomView {
   uint64_t* sort_a;          // [P] (depth_bits<<32 | idx) ping
   uint64_t* sort_b;          // [P] pong
   uint32_t* dup_offsets;     // [P] exclusive scan of tiles_touched in depth order
-  char* sort_tmp;            // onesweep temp for P items
-  size_t sort_tmp_bytes;
 };
 
+constexpr int kTileHistPasses = 4;   // tile ids up to 32 bits
 struct ImageView {
+  // tile_count | tile_ghist are contiguous and zeroed by one memset before preprocess
+  uint32_t* tile_count;      // [T] exact number of splats per tile (accumulated by preprocess)
+  uint32_t* tile_ghist;      // [kTileHistPasses][256] digit histograms of the tile sort (tile_meta_kernel)
+  size_t zero_bytes;         // bytes to clear starting at tile_count
   float* final_T;            // [N]
   uint32_t* n_contrib;       // [N]
   float* accum_c;            // [3N] blended colour WITHOUT background (planar)
@@ -71,6 +81,8 @@ struct BinView {
 };
 
 size_t sort_temp_bytes(int64_t n);
+size_t sort_depth_temp_bytes(int64_t P);
+size_t scan_temp_bytes(int64_t n);
 
 template <typename T>
 __host__ __device__ inline T* carve(char*& p, size_t count) {
@@ -84,6 +96,11 @@ inline GeomView geom_view(char* base, size_t P) {
   GeomView g;
   char* p = base;
   g.hdr = carve<GeomHeader>(p, 1);
+  g.sort_tmp_bytes = align_up(sort_depth_temp_bytes((int64_t)P), 128);
+  g.sort_tmp = carve<char>(p, g.sort_tmp_bytes);
+  g.scan_tmp_bytes = align_up(scan_temp_bytes((int64_t)P), 128);
+  g.scan_tmp = carve<char>(p, g.scan_tmp_bytes);
+  g.zero_bytes = (size_t)(p - reinterpret_cast<char*>(g.hdr));
   g.depths = carve<float>(p, P);
   g.means2D = carve<float2>(p, P);
   g.conic_opacity = carve<float4>(p, P);
@@ -94,18 +111,19 @@ inline GeomView geom_view(char* base, size_t P) {
   g.sort_a = carve<uint64_t>(p, P);
   g.sort_b = carve<uint64_t>(p, P);
   g.dup_offsets = carve<uint32_t>(p, P);
-  g.sort_tmp_bytes = sort_temp_bytes((int64_t)P);
-  g.sort_tmp = carve<char>(p, g.sort_tmp_bytes);
   return g;
 }
 inline size_t geom_bytes(size_t P) {
   GeomView g = geom_view(nullptr, P);
-  return reinterpret_cast<size_t>(g.sort_tmp) + g.sort_tmp_bytes + 128;
+  return reinterpret_cast<size_t>(g.dup_offsets) + P * 4 + 128;
 }
 
 inline ImageView image_view(char* base, size_t N, size_t T) {
   ImageView v;
   char* p = base;
+  v.tile_count = carve<uint32_t>(p, T);
+  v.tile_ghist = carve<uint32_t>(p, (size_t)kTileHistPasses * 256);
+  v.zero_bytes = (size_t)(p - reinterpret_cast<char*>(v.tile_count));
   v.final_T = carve<float>(p, N);
   v.n_contrib = carve<uint32_t>(p, N);
   v.accum_c = carve<float>(p, 3 * N);
@@ -368,8 +386,15 @@ __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, 
 
 // ---- launch helpers implemented across the .cu files ------------------------
 size_t scan_temp_bytes(int64_t n);
-int launch_scan_gather(const uint32_t* counts, const uint64_t* order_items, int64_t n,
-                       uint32_t* offsets, uint32_t* total_out, char* tmp, cudaStream_t s);
+int launch_scan_gather(const uint32_t* counts, const uint64_t* order_items, int64_t n_max,
+                       const uint32_t* n_dev, uint32_t* offsets, uint32_t* total_out, char* tmp,
+                       cudaStream_t s);
+uint32_t* sort_ghist(char* tmp);
+size_t sort_depth_temp_bytes(int64_t P);
+int launch_sort_depth(uint64_t* a, uint64_t* b, int64_t P, const uint32_t* n_valid, char* tmp,
+                      cudaStream_t s);
+int launch_sort_tile(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t R, int tile_bits,
+                     const uint32_t* ghist, char* tmp, cudaStream_t s);
 int launch_sort_u64(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t n, int begin_bit,
                     int end_bit, char* tmp, cudaStream_t s, uint64_t** result);
 

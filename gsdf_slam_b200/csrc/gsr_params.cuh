@@ -34,6 +34,8 @@ struct PreprocessParams {
   uint32_t* tiles_touched;
   uint64_t* sort_items;
   uint32_t* num_visible;
+  uint32_t* tile_count;   // [T] += 1 per (Gaussian, tile) that passes the exact test (zeroed by the caller)
+  uint32_t* depth_ghist;  // [4][256] digit histograms of the depth bits of the rendered Gaussians (zeroed by the caller)
 };
 struct PreBwdParams {
   int P, D, M;
@@ -73,11 +75,13 @@ int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
                 const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
                 uint32_t* large_list, const uint32_t* num_valid, cudaStream_t s);
 int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
-                    const float4* conic_opacity, const float* colors, uint2* ranges, uint32_t T,
-                    float4* rec_a, float4* rec_b, float4* rec_c, cudaStream_t s);
+                    const float4* conic_opacity, const float* colors, float4* rec_a, float4* rec_b,
+                    float4* rec_c, cudaStream_t s);
 int launch_export_binning(uint32_t R, const uint64_t* sorted, const float* depths, uint64_t* keys,
                           uint32_t* point_list, cudaStream_t s);
-int launch_tile_order(const uint2* ranges, uint32_t T, uint32_t* order, cudaStream_t s);
+int launch_tile_meta(const uint32_t* tile_count, uint32_t T, int tile_bits, uint2* ranges,
+                     uint32_t* num_dup, uint32_t* tile_ghist, uint32_t* order, uint32_t* max_contrib,
+                     cudaStream_t s);
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec_a, const float4* rec_b,
                      const float4* rec_c, const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s);

@@ -251,8 +251,15 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
     s_tiles[warp][lane] = 0;
     __syncwarp();
     uint32_t* cnt = s_tiles[warp];
+    uint32_t* tile_count = a.tile_count;
+    const int grid_x = a.grid_x;
     warp_walk_rects_flat(visible, co, point_image, rect_min, rect_max, thr, 0u, 0u,
-                         [cnt](int owner, int, int, uint32_t, uint32_t) { atomicAdd(&cnt[owner], 1u); });
+                         [cnt, tile_count, grid_x](int owner, int x, int y, uint32_t, uint32_t) {
+                           atomicAdd(&cnt[owner], 1u);
+                           // exact per-tile list length: ranges, R and the tile-sort histograms
+                           // all follow from it (binning.cu: tile_meta_kernel)
+                           atomicAdd(&tile_count[y * grid_x + x], 1u);
+                         });
     __syncwarp();
     ntiles = s_tiles[warp][lane];
   }
@@ -276,9 +283,21 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
     }
     a.sort_items[idx] = ((uint64_t)depth_bits << 32) | (uint32_t)idx;
   }
-  // number of Gaussians that own at least one tile (= length of the valid depth-sorted prefix)
-  const unsigned vm = __ballot_sync(0xffffffffu, visible && ntiles > 0);
-  if (lane == 0 && vm) atomicAdd(a.num_visible, (uint32_t)__popc(vm));
+  // number of Gaussians that own at least one tile (= length of the depth-sorted list)
+  const bool rendered = visible && ntiles > 0;
+  const unsigned vm = __ballot_sync(0xffffffffu, rendered);
+  if (vm) {
+    if (lane == 0) atomicAdd(a.num_visible, (uint32_t)__popc(vm));
+    // digit histograms of the depth sort, warp-aggregated (the high digits of neighbouring
+    // depths coincide, so most warps issue one atomic per digit position)
+    const uint32_t bits = __float_as_uint(p_view.z);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t d = (bits >> (8 * p)) & 0xffu;
+      const unsigned peers = __match_any_sync(0xffffffffu, rendered ? d : 0xffffu);
+      if (rendered && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&a.depth_ghist[p * 256 + d], (uint32_t)__popc(peers));
+    }
+  }
 }
 
 int launch_preprocess(const PreprocessParams& p, cudaStream_t s) {

@@ -108,11 +108,16 @@ sort_histogram_kernel(const uint64_t* __restrict__ items, uint32_t n, int begin_
 // ---------------------------------------------------------------------------
 // One onesweep pass: stable scatter of the items by one 8-bit digit.
 // ---------------------------------------------------------------------------
-template <int kItemsPerThread>
+// kDropInvalid: items whose high word is 0xFFFFFFFF (preprocess: Gaussian not rendered) are
+// neither ranked nor written, i.e. the pass doubles as an order-preserving compaction; `ghist`
+// must then count the valid items only.  n_dev (optional) overrides n with a device-side
+// count; CTAs whose tile starts beyond it leave at once (the grid is sized for the host bound).
+template <int kItemsPerThread, bool kDropInvalid>
 __global__ void __launch_bounds__(kSortThreads)
 onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n,
-                     int shift, uint32_t digit_mask, const uint32_t* __restrict__ ghist,
-                     uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ lookback) {
+                     const uint32_t* __restrict__ n_dev, int shift, uint32_t digit_mask,
+                     const uint32_t* __restrict__ ghist, uint32_t* __restrict__ tile_counter,
+                     uint32_t* __restrict__ lookback) {
   constexpr int kTileItems = kSortThreads * kItemsPerThread;
   __shared__ uint64_t s_items[kTileItems];              // 32 KB at 16 items per thread
   __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];  // 8 KB
@@ -122,11 +127,13 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (n_dev != nullptr) n = *n_dev;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t base = tile * (uint32_t)kTileItems;
+  if (base >= n) return;  // whole CTA: nobody looks back at a tile past the end
   const uint32_t tile_count = min((uint32_t)kTileItems, n - base);
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 
@@ -142,7 +149,8 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
 #pragma unroll
   for (int k = 0; k < kItemsPerThread; ++k) {
     const uint32_t li = wbase + k * 32 + lane;
-    const bool valid = li < tile_count;
+    bool valid = li < tile_count;
+    if (kDropInvalid) valid = valid && (uint32_t)(items[k] >> 32) != 0xffffffffu;
     const uint32_t digit = (uint32_t)(items[k] >> shift) & digit_mask;
     const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 0xffffu);
     const uint32_t before = __popc(peers & lanemask_lt);
@@ -167,7 +175,8 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
   uint32_t* my_flag = lookback + (size_t)tile * kRadix + tid;
   st_volatile_u32(my_flag, (tile == 0 ? kFlagInc : kFlagAgg) | total);
 
-  const uint32_t bin_start = block_excl_scan_256(total, s_scan, nullptr);
+  uint32_t kept = tile_count;  // items of this tile that are written (all of them unless kDropInvalid)
+  const uint32_t bin_start = block_excl_scan_256(total, s_scan, kDropInvalid ? &kept : nullptr);
   const uint32_t gcount = ghist[tid];
   const uint32_t gbase = block_excl_scan_256(gcount, s_scan, nullptr);
 
@@ -192,21 +201,36 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
 #pragma unroll
   for (int k = 0; k < kItemsPerThread; ++k) {
     const uint32_t li = wbase + k * 32 + lane;
-    if (li < tile_count) {
+    bool valid = li < tile_count;
+    if (kDropInvalid) valid = valid && (uint32_t)(items[k] >> 32) != 0xffffffffu;
+    if (valid) {
       const uint32_t digit = (uint32_t)(items[k] >> shift) & digit_mask;
       s_items[s_bin_start[digit] + s_warp_hist[warp][digit] + ranks[k]] = items[k];
     }
   }
   __syncthreads();
 #pragma unroll 4
-  for (uint32_t i = tid; i < tile_count; i += kSortThreads) {
+  for (uint32_t i = tid; i < kept; i += kSortThreads) {
     const uint64_t it = s_items[i];
     const uint32_t digit = (uint32_t)(it >> shift) & digit_mask;
     out[s_digit_base[digit] + i] = it;
   }
 }
 
-// Sorts on bits [begin_bit,end_bit). `in` is not modified; the result lands in
+template <bool kDrop>
+static void launch_pass(int ipt, int64_t tiles, const uint64_t* src, uint64_t* dst, uint32_t n,
+                        const uint32_t* n_dev, int sh, uint32_t mask, const uint32_t* ghist,
+                        uint32_t* counter, uint32_t* lookback, cudaStream_t s) {
+  if (ipt == kIptSmall)
+    onesweep_pass_kernel<kIptSmall, kDrop><<<(unsigned)tiles, kSortThreads, 0, s>>>(
+        src, dst, n, n_dev, sh, mask, ghist, counter, lookback);
+  else
+    onesweep_pass_kernel<kIptLarge, kDrop><<<(unsigned)tiles, kSortThreads, 0, s>>>(
+        src, dst, n, n_dev, sh, mask, ghist, counter, lookback);
+  GSR_LAUNCHED();
+}
+
+// Sorts on bits [begin_bit,end_bit).  `in` is not modified; the result lands in
 // `out` (*result == out).  `in`, `out`, `alt` must be distinct when more than
 // one pass is needed (alt may be NULL for a single pass).
 int launch_sort_u64(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t n, int begin_bit,
@@ -239,15 +263,79 @@ int launch_sort_u64(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t n,
   for (int p = 0; p < npass; ++p) {
     const int sh = begin_bit + p * kRadixBits;
     const int bits = (end_bit - sh) < kRadixBits ? (end_bit - sh) : kRadixBits;
-    if (sort_ipt(n) == kIptSmall)
-      onesweep_pass_kernel<kIptSmall><<<(unsigned)tiles, kSortThreads, 0, s>>>(
-          src, dst, (uint32_t)n, sh, (1u << bits) - 1u, ghist + (size_t)p * kRadix, counters + p,
-          lookback + (size_t)p * tiles * kRadix);
-    else
-      onesweep_pass_kernel<kIptLarge><<<(unsigned)tiles, kSortThreads, 0, s>>>(
-          src, dst, (uint32_t)n, sh, (1u << bits) - 1u, ghist + (size_t)p * kRadix, counters + p,
-          lookback + (size_t)p * tiles * kRadix);
-    GSR_LAUNCHED();
+    launch_pass<false>(sort_ipt(n), tiles, src, dst, (uint32_t)n, nullptr, sh, (1u << bits) - 1u,
+                       ghist + (size_t)p * kRadix, counters + p, lookback + (size_t)p * tiles * kRadix, s);
+    src = dst;
+    dst = (dst == out) ? alt : out;
+  }
+  return (int)cudaGetLastError();
+}
+
+// ---- the two sorts of the forward pass, with their histograms computed upstream ----------
+// Depth sort: `tmp` (sort_depth_temp_bytes) starts with the 4 x 256 digit histograms and must
+// be zeroed by the caller BEFORE the kernel that accumulates them (preprocess) runs.
+uint32_t* sort_ghist(char* tmp) { return reinterpret_cast<uint32_t*>(tmp); }
+
+// Depth order of the rendered Gaussians: items (depth_bits<<32 | idx) for all P Gaussians, the
+// non-rendered ones marked with 0xFFFFFFFF in the high word.  Pass 1 reads all P items and
+// keeps only the *n_valid rendered ones; passes 2-4 run on those (grid sized for P, surplus
+// CTAs exit).  ghist (4 x 256, valid items only) was accumulated by preprocess.
+// a -> b -> a -> b -> a: the sorted list ends in `a`.
+int launch_sort_depth(uint64_t* a, uint64_t* b, int64_t P, const uint32_t* n_valid, char* tmp,
+                      cudaStream_t s) {
+  if (P <= 0) return 0;
+  if (P >= (int64_t)kValMask) return -1;
+  uint32_t* words = reinterpret_cast<uint32_t*>(tmp);
+  uint32_t* ghist = words;
+  uint32_t* counters = words + (size_t)kMaxPasses * kRadix;
+  uint32_t* lookback = words + sort_header_words();
+  const int64_t tiles_full = sort_num_tiles(P);
+  // passes over the rendered subset: short tiles unless the scene is very large
+  const int ipt_sub = P <= (int64_t)2 * 1024 * 1024 ? kIptSmall : kIptLarge;
+  const int64_t tiles_sub = (P + (int64_t)kSortThreads * ipt_sub - 1) / ((int64_t)kSortThreads * ipt_sub);
+  // the look-back area was sized (and zeroed) for 4 passes of sort_num_tiles(P) tiles of the
+  // small kind when P < kSmallSortLimit, else of the large kind; tiles_sub may exceed that
+  launch_pass<true>(sort_ipt(P), tiles_full, a, b, (uint32_t)P, nullptr, 32, 0xffu, ghist, counters, lookback, s);
+  const uint64_t* src = b;
+  uint64_t* dst = a;
+  for (int p = 1; p < 4; ++p) {
+    launch_pass<false>(ipt_sub, tiles_sub, src, dst, 0u, n_valid, 32 + 8 * p, 0xffu,
+                       ghist + (size_t)p * kRadix, counters + p,
+                       lookback + (size_t)tiles_full * kRadix + (size_t)(p - 1) * tiles_sub * kRadix, s);
+    uint64_t* t = const_cast<uint64_t*>(src);
+    src = dst;
+    dst = t;
+  }
+  return (int)cudaGetLastError();
+}
+size_t sort_depth_temp_bytes(int64_t P) {
+  if (P < 0) P = 0;
+  const int ipt_sub = P <= (int64_t)2 * 1024 * 1024 ? kIptSmall : kIptLarge;
+  const int64_t tiles_sub = (P + (int64_t)kSortThreads * ipt_sub - 1) / ((int64_t)kSortThreads * ipt_sub);
+  return (sort_header_words() + (size_t)(sort_num_tiles(P) + 3 * tiles_sub) * kRadix) * 4 + 256;
+}
+
+// Tile order of the duplicates: only the tile digits (bits 32..32+tile_bits) are sorted; their
+// histograms come from the per-tile counts (binning.cu: tile_meta_kernel).  Result in `out`.
+int launch_sort_tile(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t R, int tile_bits,
+                     const uint32_t* ghist, char* tmp, cudaStream_t s) {
+  if (R <= 0) return 0;
+  if (R >= (int64_t)kValMask) return -1;
+  const int npass = (tile_bits + kRadixBits - 1) / kRadixBits;
+  if (npass <= 0 || npass > kMaxPasses) return -1;
+  uint32_t* words = reinterpret_cast<uint32_t*>(tmp);
+  uint32_t* counters = words + (size_t)kMaxPasses * kRadix;
+  uint32_t* lookback = words + sort_header_words();
+  const int64_t tiles = sort_num_tiles(R);
+  cudaError_t e = cudaMemsetAsync(counters, 0, (64 + (size_t)npass * tiles * kRadix) * 4, s);
+  if (e != cudaSuccess) return (int)e;
+  const uint64_t* src = in;
+  uint64_t* dst = (npass & 1) ? out : alt;
+  for (int p = 0; p < npass; ++p) {
+    const int sh = 32 + p * kRadixBits;
+    const int bits = (tile_bits - p * kRadixBits) < kRadixBits ? (tile_bits - p * kRadixBits) : kRadixBits;
+    launch_pass<false>(sort_ipt(R), tiles, src, dst, (uint32_t)R, nullptr, sh, (1u << bits) - 1u,
+                       ghist + (size_t)p * kRadix, counters + p, lookback + (size_t)p * tiles * kRadix, s);
     src = dst;
     dst = (dst == out) ? alt : out;
   }
@@ -263,8 +351,9 @@ constexpr int kScanTile = 256 * kScanItems;
 
 __global__ void __launch_bounds__(256)
 scan_gather_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restrict__ order_items,
-                   uint32_t n, uint32_t* __restrict__ offsets, uint32_t* __restrict__ total_out,
-                   uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ lookback) {
+                   const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ offsets,
+                   uint32_t* __restrict__ total_out, uint32_t* __restrict__ tile_counter,
+                   uint32_t* __restrict__ lookback) {
   __shared__ uint32_t s_scan[8];
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_prefix;
@@ -272,10 +361,10 @@ scan_gather_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restri
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
-  // The items are depth-sorted with every non-rendered Gaussian (key 0xFFFFFFFF) at the end:
-  // a tile that starts with one holds only zeros, and so do all tiles after it — nobody will
-  // ever look back at them, so they leave at once (typically > 80 % of the tiles).
-  if ((uint32_t)(order_items[(size_t)tile * kScanTile] >> 32) == 0xffffffffu) return;
+  // only the first *n_dev sorted positions hold rendered Gaussians; the grid is sized for all P,
+  // tiles past the end leave at once (nobody looks back at them)
+  const uint32_t n = *n_dev;
+  if (tile * (uint32_t)kScanTile >= n) return;
   const uint32_t base = tile * kScanTile + tid * kScanItems;
   uint32_t v[kScanItems];
   uint32_t sum = 0;
@@ -308,7 +397,7 @@ scan_gather_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restri
       st_volatile_u32(lookback + tile, kFlagInc | (pre + block_total));
     }
     s_prefix = pre;
-    if (block_total) atomicAdd(total_out, block_total);  // *total_out is zeroed by the caller
+    if (total_out != nullptr && block_total) atomicAdd(total_out, block_total);  // zeroed by the caller
   }
   __syncthreads();
   uint32_t run = s_prefix + excl;
@@ -323,14 +412,14 @@ scan_gather_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restri
 // tmp: (1 + tiles) words, zeroed here.
 size_t scan_temp_bytes(int64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile + 64) * 4; }
 
-int launch_scan_gather(const uint32_t* counts, const uint64_t* order_items, int64_t n,
-                       uint32_t* offsets, uint32_t* total_out, char* tmp, cudaStream_t s) {
-  if (n <= 0) return 0;
-  const int64_t tiles = (n + kScanTile - 1) / kScanTile;
-  cudaError_t e = cudaMemsetAsync(tmp, 0, (size_t)(tiles + 64) * 4, s);
-  if (e != cudaSuccess) return (int)e;
+// n_max bounds *n_dev (sizes the grid); tmp ((tiles + 64) words) must be zeroed by the caller.
+int launch_scan_gather(const uint32_t* counts, const uint64_t* order_items, int64_t n_max,
+                       const uint32_t* n_dev, uint32_t* offsets, uint32_t* total_out, char* tmp,
+                       cudaStream_t s) {
+  if (n_max <= 0) return 0;
+  const int64_t tiles = (n_max + kScanTile - 1) / kScanTile;
   uint32_t* words = reinterpret_cast<uint32_t*>(tmp);
-  scan_gather_kernel<<<(unsigned)tiles, 256, 0, s>>>(counts, order_items, (uint32_t)n, offsets,
+  scan_gather_kernel<<<(unsigned)tiles, 256, 0, s>>>(counts, order_items, n_dev, offsets,
                                                       total_out, words, words + 64);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
