@@ -113,8 +113,8 @@ def lib() -> C.CDLL:
     L.gsr_adam_step_rows.argtypes = [C.POINTER(AdamGroup), C.c_int, C.c_double, C.c_double, C.c_double,
                                      C.c_float, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     L.gsr_adam_step_rows.restype = C.c_int
-    L.gsr_export_binning.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                     C.c_void_p, C.c_void_p]
+    L.gsr_export_binning.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_export_binning.restype = C.c_int
     L.gsr_export_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]

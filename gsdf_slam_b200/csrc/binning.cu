@@ -1,238 +1,52 @@
-// Binning: turn the depth-sorted Gaussians into per-tile, depth-ordered lists.
+// Binning: turn the rendered Gaussians into per-tile, depth-ordered lists of packed splat
+// records.
 //
-// The reference builds one 64-bit key (tile<<32 | depth bits) per (Gaussian,
-// tile) overlap and radix-sorts all R of them on 32+log2(T) bits
-// (duplicateWithKeys + cub SortPairs + identifyTileRanges,
-// rasterizer_impl.cu:139-246, 476-500).  Here the same total order is produced
-// with far less traffic by splitting the LSD sort at bit 32:
-//   * the low 32 key bits (depth) are identical for every duplicate of a
-//     Gaussian, so those four digit passes run on the P un-duplicated Gaussians
-//     (preprocess emits (depth<<32 | idx); launch_sort_u64 orders them);
-//   * duplicates are then emitted in that order (emit_kernel) and only the tile
-//     digits (bits 32..32+log2 T) are sorted on the R duplicates — LSD radix sort
-//     is stable, so the result is exactly the order of sorting the full key,
-//     including ties (equal tile and depth keep ascending Gaussian index).
-// finalize_kernel then derives the tile ranges and writes the packed,
-// tile-contiguous splat records that the blend kernels stream with bulk copies.
+// The reference builds one 64-bit key (tile<<32 | depth bits) per (Gaussian, tile) overlap,
+// radix-sorts all R of them on 32+log2(T) bits with cub and then finds the tile boundaries
+// (duplicateWithKeys + SortPairs + identifyTileRanges, rasterizer_impl.cu:139-246, 476-500):
+// six passes over R keys and values.  That global sort is gone here:
+//   * preprocess already counted, exactly, how many splats every tile receives, so
+//     tile_meta_kernel gets the tile RANGES (and R) from a scan of T counters before a single
+//     duplicate exists;
+//   * emit_kernel drops every duplicate straight into its tile's range (slot order inside a
+//     tile is arbitrary at this point: one atomic per duplicate);
+//   * tile_sort_pack_*_kernel sort each tile's list by (depth bits, Gaussian index) in shared
+//     memory — the 64-bit items are unique, so the result is THE order a stable sort of the
+//     reference's keys produces, ties (equal depth -> ascending index) included — and write
+//     the packed records the blend kernels stream with bulk copies.
+// Per duplicate the pipeline moves 8 B (emit) + 16 B (sort in/out) + 36 B gathered + 48 B
+// record, instead of 152 B of sort traffic plus the same gathers.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "gsr_capi.h"
 #include "gsr_common.cuh"
+#include "gsr_params.cuh"
 
 namespace gsr {
 
-// One thread per depth-sorted Gaussian: re-run the opacity-aware tile test and
-// write (tile<<32 | idx) for every surviving tile, row-major like the reference
-// (rasterizer_impl.cu:177-200).
-__global__ void __launch_bounds__(256)
-emit_kernel(int P, const uint64_t* __restrict__ sorted, const uint32_t* __restrict__ tiles_touched,
-            const uint32_t* __restrict__ dup_offsets, const float2* __restrict__ means2D,
-            const float4* __restrict__ conic_opacity, const int* __restrict__ radii, int grid_x,
-            int grid_y, uint64_t* __restrict__ items, uint32_t* __restrict__ large_count,
-            uint32_t* __restrict__ large_list, uint32_t large_capacity,
-            const uint32_t* __restrict__ num_valid) {
-  // Only the first num_valid depth-sorted positions own tiles.  In depth order the near
-  // (= large) splats are neighbours, so lane l of a warp takes its Gaussian from the l-th of
-  // 32 depth strata: every warp then walks a similar mix of near and far rectangles.
-  const int lane = threadIdx.x & 31;
-  const uint32_t nv = *num_valid;
-  const uint32_t per_lane = (nv + 31u) / 32u;
-  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (warp_global >= per_lane) return;  // whole warp
-  const uint32_t jj = (uint32_t)lane * per_lane + warp_global;
-  const int j = jj < nv ? (int)jj : P;
-  uint32_t g = 0, cnt = 0, off = 0;
-  float2 xy = {0.f, 0.f};
-  float4 co = {0.f, 0.f, 0.f, 0.f};
-  uint2 rect_min = {0, 0}, rect_max = {0, 0};
-  float thr = 0.f;
-  if (j < P) {
-    g = (uint32_t)(sorted[j] & 0xffffffffu);
-    cnt = tiles_touched[g];
-  }
-  if (cnt != 0) {
-    off = dup_offsets[j];
-    xy = means2D[g];
-    co = conic_opacity[g];
-    tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
-    thr = opacity_power_threshold(co.w);
-  }
-  const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
-  // Very large rectangles are not walked here: they are cut into chunks of kQueueRectTiles
-  // tiles, queued as (chunk << 24 | sorted position) and spread over the whole GPU by
-  // emit_large_kernel (a single warp walking a 3000-tile rectangle would be the critical path).
-  bool large = cnt != 0 && area > kQueueRectTiles;
-  if (large) {
-    const uint32_t nchunks = ((uint32_t)area + kQueueRectTiles - 1) / kQueueRectTiles;
-    const uint32_t q0 = atomicAdd(large_count, nchunks);
-    if (q0 + nchunks <= large_capacity && nchunks <= 256u) {
-      for (uint32_t c = 0; c < nchunks; ++c) large_list[q0 + c] = (c << 24) | (uint32_t)j;
-    } else {
-      // queue full (pathological input): poison the reserved entries and walk it right here
-      for (uint32_t c = 0; c < nchunks && q0 + c < large_capacity; ++c) large_list[q0 + c] = 0xffffffffu;
-      large = false;
-    }
-  }
-  // All (Gaussian, tile) pairs of the warp are tested 32 per step; a hit claims the next slot
-  // of its owner's reserved range [off, off + cnt).  (The order inside one Gaussian's range is
-  // irrelevant: its tiles are distinct, and the tile sort only needs the ranges of different
-  // Gaussians to stay in depth order.)
-  __shared__ uint32_t s_slot[256 / 32][32];
-  const int warp = threadIdx.x >> 5;
-  s_slot[warp][lane] = 0;
-  __syncwarp();
-  uint32_t* slot = s_slot[warp];
-  warp_walk_rects_flat(cnt != 0 && !large, co, xy, rect_min, rect_max, thr, off, g,
-                       [&](int owner, int x, int y, uint32_t owner_off, uint32_t owner_g) {
-                         const uint32_t k = atomicAdd(&slot[owner], 1u);
-                         const uint64_t tile = (uint64_t)(y * grid_x + x);
-                         items[owner_off + k] = (tile << 32) | owner_g;
-                       });
-}
-
-// One warp per queued chunk (kQueueRectTiles tiles of one large rectangle), grid-stride over
-// the queue.  32 tiles are tested per step; the hits claim slots of the owner's reserved range
-// by advancing dup_offsets[j] atomically (that array is not needed after the emit stage, and
-// the order inside one Gaussian's range is irrelevant).
-__global__ void __launch_bounds__(256)
-emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_list,
-                  const uint64_t* __restrict__ sorted, uint32_t* __restrict__ dup_offsets,
-                  const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-                  const int* __restrict__ radii, int grid_x, int grid_y,
-                  uint64_t* __restrict__ items, uint32_t large_capacity) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t count = min(*large_count, large_capacity);
-  const unsigned lanemask_lt = (1u << lane) - 1u;
-  for (uint32_t k = warp_global; k < count; k += num_warps) {
-    const uint32_t item = large_list[k];
-    if (item == 0xffffffffu) continue;
-    const uint32_t j = item & ((1u << 24) - 1u);
-    const uint32_t chunk = item >> 24;
-    const uint32_t g = (uint32_t)(sorted[j] & 0xffffffffu);
-    const float2 xy = means2D[g];
-    const float4 co = conic_opacity[g];
-    uint2 rect_min, rect_max;
-    tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
-    const float thr = opacity_power_threshold(co.w);
-    const int w = (int)(rect_max.x - rect_min.x), h = (int)(rect_max.y - rect_min.y);
-    const int area = w * h;
-    const int t_begin = (int)chunk * kQueueRectTiles;
-    const int t_end = min(area, t_begin + kQueueRectTiles);
-    // test all tiles of the chunk first (bit `st` = this lane's tile of step `st` passed), reserve
-    // the chunk's slots with ONE atomic (a returning atomic per 32 tiles was the critical path),
-    // then write
-    static_assert(kQueueRectTiles <= 32 * 32, "one pass bit per step");
-    uint32_t passbits = 0, total = 0;
-    int st = 0;
-    for (int t0 = t_begin; t0 < t_end; t0 += 32, ++st) {
-      const int t = t0 + lane;
-      bool pass = false;
-      if (t < t_end) {
-        const int y = (int)rect_min.y + t / w;
-        const int x = (int)rect_min.x + t - (t / w) * w;
-        pass = tile_min_power(co, xy, x, y) <= thr;
-      }
-      passbits |= pass ? (1u << st) : 0u;
-      total += __popc(__ballot_sync(0xffffffffu, pass));
-    }
-    if (total == 0) continue;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&dup_offsets[j], total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    st = 0;
-    for (int t0 = t_begin; t0 < t_end; t0 += 32, ++st) {
-      const bool pass = (passbits >> st) & 1u;
-      const unsigned pm = __ballot_sync(0xffffffffu, pass);
-      if (pass) {
-        const int t = t0 + lane;
-        const int y = (int)rect_min.y + t / w;
-        const int x = (int)rect_min.x + t - (t / w) * w;
-        const uint64_t tile = (uint64_t)(y * grid_x + x);
-        items[base + __popc(pm & lanemask_lt)] = (tile << 32) | g;
-      }
-      base += __popc(pm);
-    }
-  }
-}
-
-int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
-                uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
-                const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
-                uint32_t* large_list, const uint32_t* num_valid, cudaStream_t s) {
-  if (P <= 0) return 0;
-  if (P >= (1 << 24)) return GSR_ERR_BAD_ARG;  // queue entries hold 24-bit sorted positions
-  const uint32_t large_capacity = 2u * (uint32_t)P;  // the list lives in a P x u64 scratch array
-  emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, sorted, tiles_touched, dup_offsets, means2D,
-                                              conic_opacity, radii, grid_x, grid_y, items,
-                                              large_count, large_list, large_capacity, num_valid);
-  GSR_LAUNCHED();
-  // 148 SMs x 2 CTAs x 8 warps walk the queued large rectangles
-  emit_large_kernel<<<148 * 2, 256, 0, s>>>(large_count, large_list, sorted, dup_offsets, means2D,
-                                            conic_opacity, radii, grid_x, grid_y, items,
-                                            large_capacity);
-  GSR_LAUNCHED();
-  return (int)cudaGetLastError();
-}
-
-// One thread per sorted duplicate: the packed per-duplicate record {xy, conic, opacity, reject
-// threshold, idx, rgb}.  (The tile ranges — the job of the reference's identifyTileRanges,
-// rasterizer_impl.cu:217-246 — already exist: tile_meta_kernel scans the exact per-tile counts.)
-__global__ void __launch_bounds__(256)
-finalize_kernel(uint32_t R, const uint64_t* __restrict__ sorted, const float2* __restrict__ means2D,
-                const float4* __restrict__ conic_opacity, const float* __restrict__ colors,
-                float4* __restrict__ rec_a, float4* __restrict__ rec_b, float4* __restrict__ rec_c) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R) return;
-  const uint64_t it = sorted[i];
-  const uint32_t g = (uint32_t)(it & 0xffffffffu);
-
-  const float2 xy = means2D[g];
-  const float4 co = conic_opacity[g];
-  // power below which opacity*exp(power) is certainly < 1/255 (1 % safety margin):
-  // lets the blend kernels skip the exp for far-away pixels without changing any result.
-  const float reject = -logf(255.0f * co.w) - 0.01f;
-  rec_a[i] = make_float4(xy.x, xy.y, co.x, co.y);
-  rec_b[i] = make_float4(co.z, co.w, reject, __uint_as_float(g));
-  rec_c[i] = make_float4(colors[3 * (size_t)g], colors[3 * (size_t)g + 1], colors[3 * (size_t)g + 2], 0.f);
-}
-
-int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
-                    const float4* conic_opacity, const float* colors, float4* rec_a, float4* rec_b,
-                    float4* rec_c, cudaStream_t s) {
-  if (R == 0) return 0;
-  finalize_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted, means2D, conic_opacity, colors, rec_a,
-                                                  rec_b, rec_c);
-  GSR_LAUNCHED();
-  return (int)cudaGetLastError();
-}
-
-// Everything that follows from the exact per-tile splat counts (accumulated by preprocess), in
-// one single-CTA kernel right after preprocess:
-//   * ranges[t]   = exclusive scan of the counts (the reference's identifyTileRanges result),
-//   * *num_dup    = R, the total number of duplicates (read back by the host to size the
-//                   binning buffer while the depth sort is already running),
-//   * tile_ghist  = digit histograms of the tile sort (no histogram pass over the R duplicates),
-//   * order       = longest-processing-time-first launch order of the blend kernels: a counting
-//                   sort of the tiles by list length (1024 buckets of 4 entries, longest first) —
-//                   the blend kernels run one CTA per half tile for the whole length of its
-//                   list, so starting the long lists first keeps the last wave short,
-//   * max_contrib = 0 (blend_fwd raises it with atomicMax).
+// ---------------------------------------------------------------------------------------------
+// tile_meta: everything that follows from the exact per-tile splat counts, in one single-CTA
+// kernel right after preprocess:
+//   * ranges[t]      = exclusive scan of the counts (the reference's identifyTileRanges result),
+//   * hdr->num_dup   = R, hdr->max_tile_len, hdr->num_long_tiles (lists longer than the small
+//                      shared-memory sort handles),
+//   * order          = longest-processing-time-first launch order for the per-tile kernels: a
+//                      counting sort of the tiles by list length (1024 buckets of 4 entries,
+//                      longest first) — one CTA works on a tile for the whole length of its
+//                      list, so starting the long lists first keeps the last wave short,
+//   * max_contrib    = 0 (blend_fwd raises it with atomicMax).
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, int npass,
-                 uint2* __restrict__ ranges, uint32_t* __restrict__ num_dup,
-                 uint32_t* __restrict__ tile_ghist, uint32_t* __restrict__ order,
+tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, uint2* __restrict__ ranges,
+                 GeomHeader* __restrict__ hdr, uint32_t* __restrict__ order,
                  uint32_t* __restrict__ max_contrib) {
   __shared__ uint32_t s_cnt[1024];
-  __shared__ uint32_t s_hist[kTileHistPasses][256];
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_max, s_long;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_cnt[tid] = 0;
-  (&s_hist[0][0])[tid] = 0;  // kTileHistPasses * 256 == 1024 entries
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) { s_max = 0; s_long = 0; }
   __syncthreads();
 
   // block-wide inclusive scan of one value per thread (1024 threads); all threads must call
@@ -259,65 +73,342 @@ tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, int npass,
     __syncthreads();  // s_warp is reused by the next call
     return r;
   };
+  auto bucket_of = [](uint32_t c) { return 1023u - min(1023u, c >> 2); };  // bucket 0 = longest lists
 
-  for (uint32_t t0 = 0; t0 < T; t0 += 1024) {
-    const uint32_t t = t0 + tid;
-    const uint32_t c = t < T ? tile_count[t] : 0u;
-    const uint32_t inc = block_incl_scan(c);
-    const uint32_t carry = s_carry;
+  // each thread owns `ipt` consecutive tiles: one block scan for any T
+  const uint32_t ipt = (T + 1023u) / 1024u;
+  const uint32_t t_first = (uint32_t)tid * ipt;
+  uint32_t sum = 0, mx = 0, nlong = 0;
+  for (uint32_t k = 0; k < ipt; ++k) {
+    const uint32_t t = t_first + k;
     if (t < T) {
-      ranges[t] = make_uint2(carry + inc - c, carry + inc);
-      max_contrib[t] = 0;
-      if (c) {
-        for (int p = 0; p < npass; ++p) atomicAdd(&s_hist[p][(t >> (8 * p)) & 0xffu], c);
-      }
-      atomicAdd(&s_cnt[1023u - min(1023u, c >> 2)], 1u);  // bucket 0 = longest lists
+      const uint32_t c = tile_count[t];
+      sum += c;
+      mx = max(mx, c);
+      nlong += c >= (uint32_t)kSortSmallCap ? 1u : 0u;
     }
-    __syncthreads();
-    if (tid == 1023) s_carry = carry + inc;
-    __syncthreads();
   }
-  if (tid == 0) *num_dup = s_carry;
-  for (int i = tid; i < npass * 256; i += 1024) tile_ghist[i] = (&s_hist[0][0])[i];
+  const uint32_t inc = block_incl_scan(sum);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  nlong = __reduce_add_sync(0xffffffffu, nlong);
+  if (lane == 0) {
+    if (mx) atomicMax(&s_max, mx);
+    if (nlong) atomicAdd(&s_long, nlong);
+  }
+  uint32_t run = inc - sum;
+  for (uint32_t k = 0; k < ipt; ++k) {  // uniform trip count: the warp votes below need all lanes
+    const uint32_t t = t_first + k;
+    const bool in = t < T;
+    const uint32_t c = in ? tile_count[t] : 0u;
+    if (in) {
+      ranges[t] = make_uint2(run, run + c);
+      max_contrib[t] = 0;
+    }
+    run += c;
+    // warp-aggregated: neighbouring tiles have similar lengths and would collide on a bucket
+    const uint32_t b = in ? bucket_of(c) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (in && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&s_cnt[b], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  if (tid == 1023) {
+    hdr->num_dup = inc;
+    hdr->max_tile_len = s_max;
+    hdr->num_long_tiles = s_long;
+  }
 
   // exclusive scan of the 1024 bucket counts, then place the tiles
   const uint32_t c = s_cnt[tid];
-  const uint32_t inc = block_incl_scan(c);
-  s_cnt[tid] = inc - c;
+  const uint32_t binc = block_incl_scan(c);
+  s_cnt[tid] = binc - c;
   __syncthreads();
-  for (uint32_t t = tid; t < T; t += 1024) {
-    const uint32_t b = 1023u - min(1023u, tile_count[t] >> 2);
-    order[atomicAdd(&s_cnt[b], 1u)] = t;
+  const uint32_t t_end = (T + 31u) & ~31u;
+  for (uint32_t t = tid; t < t_end; t += 1024) {
+    const bool in = t < T;
+    const uint32_t b = in ? bucket_of(tile_count[t]) : 0xffffffffu;
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (in && lane == leader) base = atomicAdd(&s_cnt[b], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (in) order[base + __popc(peers & ((1u << lane) - 1u))] = t;
   }
 }
 
-int launch_tile_meta(const uint32_t* tile_count, uint32_t T, int tile_bits, uint2* ranges,
-                     uint32_t* num_dup, uint32_t* tile_ghist, uint32_t* order, uint32_t* max_contrib,
-                     cudaStream_t s) {
-  const int npass = (tile_bits + 7) / 8;
-  if (npass > kTileHistPasses) return GSR_ERR_BAD_ARG;
-  tile_meta_kernel<<<1, 1024, 0, s>>>(tile_count, T, npass, ranges, num_dup, tile_ghist, order, max_contrib);
+int launch_tile_meta(const uint32_t* tile_count, uint32_t T, uint2* ranges, GeomHeader* hdr,
+                     uint32_t* order, uint32_t* max_contrib, cudaStream_t s) {
+  tile_meta_kernel<<<1, 1024, 0, s>>>(tile_count, T, ranges, hdr, order, max_contrib);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// emit: one thread per rendered Gaussian (compacted list): re-run the opacity-aware tile test
+// and drop (depth_bits<<32 | idx) into the next free slot of every surviving tile's range.
+// `capacity` guards the optimistically sized buffer (gsr_forward re-runs the stage if R
+// exceeded it).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+emit_kernel(const uint64_t* __restrict__ vis_items, const uint32_t* __restrict__ num_visible,
+            const uint32_t* __restrict__ tiles_touched, const float2* __restrict__ means2D,
+            const float4* __restrict__ conic_opacity, const int* __restrict__ radii, int grid_x,
+            int grid_y, const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
+            uint64_t* __restrict__ items, uint32_t capacity, uint32_t* __restrict__ large_count,
+            uint32_t* __restrict__ large_list, uint32_t large_capacity) {
+  const uint32_t nv = *num_visible;
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((j & ~31u) >= nv) return;  // whole warp
+  uint32_t g = 0, depth_bits = 0, cnt = 0;
+  float2 xy = {0.f, 0.f};
+  float4 co = {0.f, 0.f, 0.f, 0.f};
+  uint2 rect_min = {0, 0}, rect_max = {0, 0};
+  float thr = 0.f;
+  if (j < nv) {
+    const uint64_t it = vis_items[j];
+    g = (uint32_t)(it & 0xffffffffu);
+    depth_bits = (uint32_t)(it >> 32);
+    cnt = tiles_touched[g];
+  }
+  if (cnt != 0) {
+    xy = means2D[g];
+    co = conic_opacity[g];
+    tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
+    thr = opacity_power_threshold(co.w);
+  }
+  const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
+  // Very large rectangles are not walked here: they are cut into chunks of kQueueRectTiles
+  // tiles, queued as (chunk << 24 | list position) and spread over the whole GPU by
+  // emit_large_kernel (a single warp walking a 3000-tile rectangle would be the critical path).
+  bool large = cnt != 0 && area > kQueueRectTiles;
+  if (large) {
+    const uint32_t nchunks = ((uint32_t)area + kQueueRectTiles - 1) / kQueueRectTiles;
+    const uint32_t q0 = atomicAdd(large_count, nchunks);
+    if (q0 + nchunks <= large_capacity && nchunks <= 256u) {
+      for (uint32_t c = 0; c < nchunks; ++c) large_list[q0 + c] = (c << 24) | j;
+    } else {
+      // queue full (pathological input): poison the reserved entries and walk it right here
+      for (uint32_t c = 0; c < nchunks && q0 + c < large_capacity; ++c) large_list[q0 + c] = 0xffffffffu;
+      large = false;
+    }
+  }
+  // all (Gaussian, tile) pairs of the warp are tested 32 per step (gsr_common.cuh)
+  warp_walk_rects_flat(cnt != 0 && !large, co, xy, rect_min, rect_max, thr, depth_bits, g,
+                       [&](int, int x, int y, uint32_t owner_depth, uint32_t owner_g) {
+                         const uint32_t tile = (uint32_t)(y * grid_x + x);
+                         const uint32_t pos = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
+                         if (pos < capacity) items[pos] = ((uint64_t)owner_depth << 32) | owner_g;
+                       });
+}
+
+// One warp per queued chunk (kQueueRectTiles tiles of one large rectangle), grid-stride over
+// the queue, 32 tiles per step.
+__global__ void __launch_bounds__(256)
+emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_list,
+                  const uint64_t* __restrict__ vis_items, const float2* __restrict__ means2D,
+                  const float4* __restrict__ conic_opacity, const int* __restrict__ radii, int grid_x,
+                  int grid_y, const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
+                  uint64_t* __restrict__ items, uint32_t capacity, uint32_t large_capacity) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t num_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t count = min(*large_count, large_capacity);
+  for (uint32_t k = warp_global; k < count; k += num_warps) {
+    const uint32_t item = large_list[k];
+    if (item == 0xffffffffu) continue;
+    const uint32_t j = item & ((1u << 24) - 1u);
+    const uint32_t chunk = item >> 24;
+    const uint64_t it = vis_items[j];
+    const uint32_t g = (uint32_t)(it & 0xffffffffu);
+    const float2 xy = means2D[g];
+    const float4 co = conic_opacity[g];
+    uint2 rect_min, rect_max;
+    tile_rect(xy, radii[g], grid_x, grid_y, rect_min, rect_max);
+    const float thr = opacity_power_threshold(co.w);
+    const int w = (int)(rect_max.x - rect_min.x), h = (int)(rect_max.y - rect_min.y);
+    const int area = w * h;
+    const int t_begin = (int)chunk * kQueueRectTiles;
+    const int t_end = min(area, t_begin + kQueueRectTiles);
+    for (int t0 = t_begin; t0 < t_end; t0 += 32) {
+      const int t = t0 + lane;
+      if (t < t_end) {
+        const int y = (int)rect_min.y + t / w;
+        const int x = (int)rect_min.x + t - (t / w) * w;
+        if (tile_min_power(co, xy, x, y) <= thr) {
+          const uint32_t tile = (uint32_t)(y * grid_x + x);
+          const uint32_t pos = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
+          if (pos < capacity) items[pos] = it;
+        }
+      }
+    }
+  }
+}
+
+int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
+                const uint32_t* tiles_touched, const float2* means2D, const float4* conic_opacity,
+                const int* radii, int grid_x, int grid_y, const uint2* ranges, uint32_t* tile_fill,
+                uint64_t* items, uint32_t capacity, uint32_t* large_count, uint32_t* large_list,
+                cudaStream_t s) {
+  if (P <= 0) return 0;
+  if (P >= (1 << 24)) return GSR_ERR_BAD_ARG;  // queue entries hold 24-bit list positions
+  const uint32_t large_capacity = 2u * (uint32_t)P;
+  // the grid covers all P list slots; warps past the *num_visible rendered ones leave at once
+  emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(vis_items, num_visible, tiles_touched, means2D,
+                                              conic_opacity, radii, grid_x, grid_y, ranges, tile_fill,
+                                              items, capacity, large_count, large_list, large_capacity);
+  GSR_LAUNCHED();
+  // 148 SMs x 2 CTAs x 8 warps walk the queued large rectangles
+  emit_large_kernel<<<148 * 2, 256, 0, s>>>(large_count, large_list, vis_items, means2D, conic_opacity,
+                                            radii, grid_x, grid_y, ranges, tile_fill, items, capacity,
+                                            large_capacity);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile_sort_pack: one CTA per tile.  Bitonic sort of the tile's 64-bit items (unique, so the
+// sorted order is unique) and the packed per-duplicate records
+//   {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}.
+// Lists shorter than kSortSmallCap entries are sorted in 16 KB of shared memory by the "small" launch
+// (one CTA per tile, LPT order).  The "long" launch (148 persistent CTAs over the
+// hdr->num_long_tiles longest tiles, which form a prefix of the LPT order) sorts lists up to
+// kSortLargeCap entries in 128 KB of shared memory and anything longer in a padded global
+// scratch area — slow, but correct for any input.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
+  return n <= 1u ? 1u : 1u << (32 - __clz(n - 1u));
+}
+
+// in-place ascending bitonic sort of buf[0, n_pad), n_pad a power of two; all threads of the CTA
+template <int kThreads>
+__device__ __forceinline__ void bitonic_sort(uint64_t* buf, uint32_t n_pad) {
+  const uint32_t half = n_pad >> 1;
+  for (uint32_t k = 2; k <= n_pad; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t p = threadIdx.x; p < half; p += kThreads) {
+        // p-th compare-exchange of this stage: i has bit j clear, partner i | j
+        const uint32_t i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u));
+        const uint32_t l = i | j;
+        const uint64_t a = buf[i], b = buf[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) {
+          buf[i] = b;
+          buf[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int kThreads>
+__device__ __forceinline__ void sort_pack_tile(uint64_t* buf, uint32_t n, uint32_t start,
+                                               uint64_t* __restrict__ items,
+                                               const float2* __restrict__ means2D,
+                                               const float4* __restrict__ conic_opacity,
+                                               const float* __restrict__ colors,
+                                               float4* __restrict__ rec) {
+  const uint32_t n_pad = next_pow2(n);
+  for (uint32_t i = threadIdx.x; i < n_pad; i += kThreads) buf[i] = i < n ? items[start + i] : ~0ull;
+  __syncthreads();
+  bitonic_sort<kThreads>(buf, n_pad);
+  for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
+    const uint64_t it = buf[i];
+    const uint32_t g = (uint32_t)(it & 0xffffffffu);
+    items[start + i] = it;
+    const float2 xy = means2D[g];
+    const float4 co = conic_opacity[g];
+    // power below which opacity*exp(power) is certainly < 1/255 (1 % safety margin):
+    // lets the blend kernels skip the exp for far-away pixels without changing any result.
+    const float reject = -logf(255.0f * co.w) - 0.01f;
+    float4* r = rec + 3 * (size_t)(start + i);
+    r[0] = make_float4(xy.x, xy.y, co.x, co.y);
+    r[1] = make_float4(co.z, co.w, reject, __uint_as_float(g));
+    r[2] = make_float4(colors[3 * (size_t)g], colors[3 * (size_t)g + 1], colors[3 * (size_t)g + 2], 0.f);
+  }
+}
+
+constexpr int kSortSmallThreads = 128;
+constexpr int kSortLargeThreads = 512;
+
+__global__ void __launch_bounds__(kSortSmallThreads)
+tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+                            BinHeader* __restrict__ bin_hdr, uint32_t capacity, uint64_t* __restrict__ items,
+                            const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+                            const float* __restrict__ colors, float4* __restrict__ rec) {
+  __shared__ uint64_t s_buf[kSortSmallCap];
+  if (blockIdx.x == 0 && threadIdx.x == 0) bin_hdr->capacity = capacity;  // read by gsr_export_binning
+  const uint2 range = ranges[order[blockIdx.x]];
+  const uint32_t n = range.y - range.x;
+  if (n == 0 || n >= (uint32_t)kSortSmallCap || range.y > capacity) return;  // long lists: other launch
+  sort_pack_tile<kSortSmallThreads>(s_buf, n, range.x, items, means2D, conic_opacity, colors, rec);
+}
+
+__global__ void __launch_bounds__(kSortLargeThreads)
+tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+                           const GeomHeader* __restrict__ hdr, uint32_t T, uint32_t capacity,
+                           uint64_t* __restrict__ items, uint64_t* __restrict__ scratch,
+                           const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
+                           const float* __restrict__ colors, float4* __restrict__ rec) {
+  extern __shared__ __align__(16) uint64_t s_dyn[];
+  // The lists of kSortSmallCap or more entries are exactly the first num_long_tiles entries of
+  // the LPT order (kSortSmallCap is a multiple of its 4-entry bucket width).
+  const uint32_t limit = min(T, hdr->num_long_tiles);
+  for (uint32_t k = blockIdx.x; k < limit; k += gridDim.x) {
+    const uint2 range = ranges[order[k]];
+    const uint32_t n = range.y - range.x;
+    if (n < (uint32_t)kSortSmallCap || range.y > capacity) continue;
+    if (n <= (uint32_t)kSortLargeCap) {
+      sort_pack_tile<kSortLargeThreads>(s_dyn, n, range.x, items, means2D, conic_opacity, colors, rec);
+    } else {
+      // padded copy at scratch[2 * start, 2 * start + next_pow2(n)): ranges of different tiles
+      // cannot overlap because next_pow2(n) <= 2 n
+      sort_pack_tile<kSortLargeThreads>(scratch + 2 * (size_t)range.x, n, range.x, items, means2D,
+                                        conic_opacity, colors, rec);
+    }
+    __syncthreads();
+  }
+}
+
+int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
+                          BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch, const float2* means2D,
+                          const float4* conic_opacity, const float* colors, float4* rec,
+                          cudaStream_t s) {
+  if (T == 0) return 0;
+  tile_sort_pack_small_kernel<<<T, kSortSmallThreads, 0, s>>>(ranges, order, bin_hdr, capacity, items, means2D,
+                                                              conic_opacity, colors, rec);
+  GSR_LAUNCHED();
+  static bool attr_set = false;
+  const int dyn = kSortLargeCap * (int)sizeof(uint64_t);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tile_sort_pack_long_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  tile_sort_pack_long_kernel<<<148, kSortLargeThreads, dyn, s>>>(ranges, order, hdr, T, capacity, items,
+                                                                 scratch, means2D, conic_opacity, colors,
+                                                                 rec);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }
 
 // Debug/test export: rebuild the reference's 64-bit sorted keys (tile<<32 | depth bits)
-// and the sorted Gaussian-id list from the packed records.
-__global__ void export_binning_kernel(uint32_t R, const uint64_t* __restrict__ sorted,
-                                      const float* __restrict__ depths, uint64_t* keys,
-                                      uint32_t* point_list) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R) return;
-  const uint64_t it = sorted[i];
-  const uint32_t g = (uint32_t)(it & 0xffffffffu);
-  if (keys) keys[i] = (it & 0xffffffff00000000ull) | (uint64_t)__float_as_uint(depths[g]);
-  if (point_list) point_list[i] = g;
+// and the sorted Gaussian-id list from the per-tile lists.  One CTA per tile.
+__global__ void export_binning_kernel(const uint2* __restrict__ ranges, const uint64_t* __restrict__ items,
+                                      uint64_t* keys, uint32_t* point_list) {
+  const uint32_t tile = blockIdx.x;
+  const uint2 range = ranges[tile];
+  for (uint32_t i = range.x + threadIdx.x; i < range.y; i += blockDim.x) {
+    const uint64_t it = items[i];
+    if (keys) keys[i] = ((uint64_t)tile << 32) | (it >> 32);
+    if (point_list) point_list[i] = (uint32_t)(it & 0xffffffffu);
+  }
 }
 
-int launch_export_binning(uint32_t R, const uint64_t* sorted, const float* depths, uint64_t* keys,
+int launch_export_binning(uint32_t T, const uint2* ranges, const uint64_t* items, uint64_t* keys,
                           uint32_t* point_list, cudaStream_t s) {
-  if (R == 0) return 0;
-  export_binning_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted, depths, keys, point_list);
+  if (T == 0) return 0;
+  export_binning_kernel<<<T, 128, 0, s>>>(ranges, items, keys, point_list);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -83,14 +83,11 @@ __device__ __forceinline__ void warp_reduce9_smem(const float (&v)[9], int lane,
 
 __global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_BWD_MINBLOCKS)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ max_contrib,
-                 const float4* __restrict__ rec_a, const float4* __restrict__ rec_b,
-                 const float4* __restrict__ rec_c, int W, int H, const float* __restrict__ bg,
+                 const float4* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ accum_c, const float* __restrict__ dL_dpix,
                  float* __restrict__ acc /* [P][12] */) {
-  __shared__ __align__(128) float4 sA[2][kBlendBatch];
-  __shared__ __align__(128) float4 sB[2][kBlendBatch];
-  __shared__ __align__(128) float4 sC[2][kBlendBatch];
+  __shared__ __align__(128) float4 sR[2][3 * kBlendBatch];  // 48-byte records, one bulk copy per batch
   __shared__ __align__(8) uint64_t s_full[2];
   __shared__ __align__(16) float s_red[kBlendThreads / 32][8 * kRedStride];
 
@@ -117,11 +114,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int buf = round & 1;
     const int start = range.x + round * kBlendBatch;
     const int cnt = min(kBlendBatch, total - round * kBlendBatch);
-    const uint32_t bytes = (uint32_t)cnt * 16u;
-    mbar_expect_tx(&s_full[buf], 3u * bytes);
-    bulk_g2s(&sA[buf][0], rec_a + start, bytes, &s_full[buf]);
-    bulk_g2s(&sB[buf][0], rec_b + start, bytes, &s_full[buf]);
-    bulk_g2s(&sC[buf][0], rec_c + start, bytes, &s_full[buf]);
+    const uint32_t bytes = (uint32_t)cnt * 48u;
+    mbar_expect_tx(&s_full[buf], bytes);
+    bulk_g2s(&sR[buf][0], rec + 3 * (size_t)start, bytes, &s_full[buf]);
   };
 
 
@@ -181,8 +176,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int jmax = (int)min((uint32_t)cnt, warp_last > pos0 ? warp_last - pos0 : 0u);
 
     for (int j = 0; j < jmax; ++j) {
-      const float4 A = sA[buf][j];
-      const float4 B = sB[buf][j];
+      const float4 A = sR[buf][3 * j];
+      const float4 B = sR[buf][3 * j + 1];
       const float4 con_o = {A.z, A.w, B.x, B.y};
       const uint32_t pos = pos0 + j;
 
@@ -214,7 +209,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         contributed = true;
         {
           const float2 d = {A.x - pxf[q & 1], A.y - pyf[q & 2]};
-          const float4 col = sC[buf][j];
+          const float4 col = sR[buf][3 * j + 2];
           const float one_m = 1.0f - alpha;
           const float inv = __frcp_rn(one_m);  // == 1.0f / one_m (correctly rounded), no slow path
           const float Ta = T[q] * alpha;
@@ -253,11 +248,11 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
 int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_order,
                      const uint32_t* max_contrib,
-                     const float4* rec_a, const float4* rec_b, const float4* rec_c, const float* bg,
+                     const float4* rec, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  blend_bwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, max_contrib, rec_a, rec_b, rec_c, W, H, bg,
+  blend_bwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, max_contrib, rec, W, H, bg,
                                                   final_T, n_contrib, accum_c, dL_dpix, acc);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();

@@ -25,14 +25,12 @@
 namespace gsr {
 
 __global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_FWD_MINBLOCKS)
-blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const float4* __restrict__ rec_a,
-                 const float4* __restrict__ rec_b, const float4* __restrict__ rec_c, int W, int H,
+blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const float4* __restrict__ rec,
+                 int W, int H,
                  const float* __restrict__ bg, float* __restrict__ out_color,
                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                 float* __restrict__ accum_c, uint32_t* __restrict__ max_contrib) {
-  __shared__ __align__(128) float4 sA[2][kBlendBatch];
-  __shared__ __align__(128) float4 sB[2][kBlendBatch];
-  __shared__ __align__(128) float4 sC[2][kBlendBatch];
+                 float* __restrict__ accum_c, uint32_t* __restrict__ max_contrib, uint32_t capacity) {
+  __shared__ __align__(128) float4 sR[2][3 * kBlendBatch];  // 48-byte records, one bulk copy per batch
   __shared__ __align__(8) uint64_t s_full[2];
 
   const int lane = threadIdx.x;
@@ -56,7 +54,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
 
   const uint2 range = ranges[tile_id];
-  const int total = (int)(range.y - range.x);
+  // capacity: records the (optimistically sized) buffer holds; a list that did not fit is not
+  // touched — gsr_forward re-runs the stage with the exact size in that case
+  const int total = range.y <= capacity ? (int)(range.y - range.x) : 0;
   const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
 
   if (lane == 0) {
@@ -70,11 +70,9 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int buf = round & 1;
     const int start = range.x + round * kBlendBatch;
     const int cnt = min(kBlendBatch, total - round * kBlendBatch);
-    const uint32_t bytes = (uint32_t)cnt * 16u;
-    mbar_expect_tx(&s_full[buf], 3u * bytes);
-    bulk_g2s(&sA[buf][0], rec_a + start, bytes, &s_full[buf]);
-    bulk_g2s(&sB[buf][0], rec_b + start, bytes, &s_full[buf]);
-    bulk_g2s(&sC[buf][0], rec_c + start, bytes, &s_full[buf]);
+    const uint32_t bytes = (uint32_t)cnt * 48u;
+    mbar_expect_tx(&s_full[buf], bytes);
+    bulk_g2s(&sR[buf][0], rec + 3 * (size_t)start, bytes, &s_full[buf]);
   };
   if (lane == 0 && rounds > 0) issue(0);
 
@@ -103,8 +101,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int cnt = min(kBlendBatch, total - i * kBlendBatch);
     const uint32_t pos0 = (uint32_t)i * kBlendBatch;
     for (int j = 0; !all_done && j < cnt; j++) {
-      const float4 A = sA[buf][j];
-      const float4 B = sB[buf][j];
+      const float4 A = sR[buf][3 * j];
+      const float4 B = sR[buf][3 * j + 1];
       const float2 xy = {A.x, A.y};
       const float4 con_o = {A.z, A.w, B.x, B.y};
       // gate of all four pixels first (independent chains, one branch for the common miss)
@@ -132,7 +130,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
           done[q] = true;
           continue;
         }
-        const float4 col = sC[buf][j];
+        const float4 col = sR[buf][3 * j + 2];
         C[q][0] += col.x * alpha * T[q];
         C[q][1] += col.y * alpha * T[q];
         C[q][2] += col.z * alpha * T[q];
@@ -164,12 +162,13 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   if (lane == 0) atomicMax(&max_contrib[tile_id], wmax);  // zeroed by tile_meta_kernel
 }
 
-int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec_a, const float4* rec_b,
-                     const float4* rec_c, const float* bg, float* out_color, float* final_T,
-                     uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s) {
+int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,
+                     const float* bg, float* out_color, float* final_T,
+                     uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, uint32_t capacity,
+                     cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  blend_fwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec_a, rec_b, rec_c, W, H, bg, out_color,
-                                                  final_T, n_contrib, accum_c, max_contrib);
+  blend_fwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec, W, H, bg, out_color,
+                                                  final_T, n_contrib, accum_c, max_contrib, capacity);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

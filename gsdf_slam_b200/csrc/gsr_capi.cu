@@ -30,11 +30,6 @@ long long g_launch_count = 0;
 #include "gsr_params.cuh"
 
 namespace gsr {
-static inline int tile_bits(uint32_t T) {  // bits needed to hold tile ids 0..T-1
-  int b = 0;
-  while ((1ull << b) < (uint64_t)T) ++b;
-  return b < 1 ? 1 : b;
-}
 
 static uint32_t* pinned_word() {
   static thread_local uint32_t* p = nullptr;
@@ -146,9 +141,8 @@ int gsr_forward(const gsr_forward_args* a) {
   GeomView g = geom_view(geom_base, (size_t)P);
   ImageView im = image_view(img_base, N, T);
 
-  // one clear per buffer: counters + depth histograms + look-back flags | tile counts + histograms
-  GSR_CUDA(cudaMemsetAsync(g.hdr, 0, g.zero_bytes, s));
-  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));
+  GSR_CUDA(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
+  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));  // tile_count | tile_fill
 
   PreprocessParams pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -169,56 +163,66 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.vec_ok = (al & 15) == 0;
   pp.radii = a->radii; pp.depths = g.depths; pp.means2D = g.means2D;
   pp.conic_opacity = g.conic_opacity; pp.rgb = g.rgb; pp.clamped = g.clamped;
-  pp.tiles_touched = g.tiles_touched; pp.sort_items = g.sort_a; pp.num_visible = &g.hdr->num_visible;
-  pp.tile_count = im.tile_count; pp.depth_ghist = sort_ghist(g.sort_tmp);
+  pp.tiles_touched = g.tiles_touched; pp.vis_items = g.vis_items; pp.num_visible = &g.hdr->num_visible;
+  pp.tile_count = im.tile_count;
   GSR_PROF("preprocess", launch_preprocess(pp, s));
   if (a->radii_ready_event) GSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->radii_ready_event), s));
 
-  // ranges, R, tile-sort histograms and the blend launch order from the exact per-tile counts
-  const int tb = tile_bits(T);
-  GSR_PROF("tile_meta", launch_tile_meta(im.tile_count, T, tb, im.ranges, &g.hdr->num_dup, im.tile_ghist,
-                                         im.tile_order, im.max_contrib, s));
-  // R travels to the host while the depth sort runs: by the time the host needs it (to size the
-  // per-duplicate buffers) the copy has long completed, and the GPU never idles
+  // ranges, R and the per-tile launch order from the exact per-tile counts
+  GSR_PROF("tile_meta", launch_tile_meta(im.tile_count, T, im.ranges, g.hdr, im.tile_order, im.max_contrib, s));
   uint32_t* host_R = pinned_word();
   cudaEvent_t ev_R = readback_event();
   if (!host_R || !ev_R) return GSR_ERR_ALLOC;
   GSR_CUDA(cudaMemcpyAsync(host_R, &g.hdr->num_dup, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   GSR_CUDA(cudaEventRecord(ev_R, s));
 
-  // depth order of the rendered Gaussians: 32 key bits, 4 passes (the first one also drops the
-  // non-rendered Gaussians), result in sort_a; then their duplicate offsets in that order
-  GSR_PROF("sort_depth", launch_sort_depth(g.sort_a, g.sort_b, P, &g.hdr->num_visible, g.sort_tmp, s));
-  const uint64_t* order = g.sort_a;
-  GSR_PROF("scan", launch_scan_gather(g.tiles_touched, order, P, &g.hdr->num_visible, g.dup_offsets, nullptr,
-                                      g.scan_tmp, s));
-
-  GSR_CUDA(cudaEventSynchronize(ev_R));
-  const uint32_t R = *host_R;
-  *a->num_rendered = (int)R;
-
-  char* bin_base = a->binning_resize(a->binning_user, bin_bytes((size_t)R));
-  if (!bin_base) return GSR_ERR_ALLOC;
-  if (a->sample_resize) a->sample_resize(a->sample_user, 0);
-  BinView b = bin_view(bin_base, (size_t)R);
-
-  if (R > 0) {
-    const int npass = (tb + 7) / 8;
-    // choose the emit target so that the sorted list always ends in items_a
-    uint64_t* emit_dst = (npass & 1) ? b.items_b : b.items_a;
-    uint64_t* other = (npass & 1) ? b.items_a : b.items_b;
-    GSR_PROF("emit", launch_emit(P, order, g.tiles_touched, g.dup_offsets, g.means2D, g.conic_opacity,
-                       a->radii, gx, gy, emit_dst, &g.hdr->num_large,
-                       reinterpret_cast<uint32_t*>(g.sort_b), &g.hdr->num_visible, s));
-    // odd: in=b, out=a, alt=b ; even: in=a, out=a, alt=b
-    GSR_PROF("sort_tile", launch_sort_tile(emit_dst, b.items_a, (npass & 1) ? emit_dst : other, R, tb,
-                                           im.tile_ghist, b.sort_tmp, s));
+  // The per-duplicate buffer is sized OPTIMISTICALLY from the previous call on this thread, so
+  // the rest of the forward pass is enqueued without waiting for R (no kernel's grid depends on
+  // it; every write is guarded by the capacity).  R is checked once everything is enqueued; if
+  // it did not fit — or on the first call — the tail is (re)run with the exact size.
+  static thread_local uint32_t cap_hint = 0;
+  static thread_local int hint_P = -1, hint_W = -1, hint_H = -1;
+  if (hint_P != P || hint_W != W || hint_H != H) cap_hint = 0;  // a different scene / resolution
+  hint_P = P; hint_W = W; hint_H = H;
+  uint32_t cap = cap_hint;
+  uint32_t R = 0;
+  bool have_R = false;
+  if (cap == 0) {
+    GSR_CUDA(cudaEventSynchronize(ev_R));
+    R = *host_R;
+    have_R = true;
+    cap = R;
   }
   const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
-  GSR_PROF("finalize", launch_finalize(R, b.items_a, g.means2D, g.conic_opacity, colors, b.rec_a,
-                         b.rec_b, b.rec_c, s));
-  GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec_a, b.rec_b, b.rec_c, a->background, a->out_color,
-                          im.final_T, im.n_contrib, im.accum_c, im.max_contrib, s));
+  BinView b;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    char* bin_base = a->binning_resize(a->binning_user, bin_bytes((size_t)cap));
+    if (!bin_base) return GSR_ERR_ALLOC;
+    b = bin_view(bin_base, (size_t)cap);
+    if (attempt > 0) {
+      GSR_CUDA(cudaMemsetAsync(im.tile_fill, 0, (size_t)T * sizeof(uint32_t), s));
+      GSR_CUDA(cudaMemsetAsync(&g.hdr->num_large, 0, sizeof(uint32_t), s));
+    }
+    if (!have_R || R > 0) {
+      GSR_PROF("emit", launch_emit(P, g.vis_items, &g.hdr->num_visible, g.tiles_touched, g.means2D,
+                                   g.conic_opacity, a->radii, gx, gy, im.ranges, im.tile_fill, b.items, cap,
+                                   &g.hdr->num_large, g.large_list, s));
+      GSR_PROF("tile_sort_pack", launch_tile_sort_pack(T, im.ranges, im.tile_order, g.hdr, b.hdr, cap, b.items, b.scratch,
+                                                       g.means2D, g.conic_opacity, colors, b.rec, s));
+    }
+    GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
+                            im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, s));
+    if (!have_R) {
+      GSR_CUDA(cudaEventSynchronize(ev_R));  // completed long ago: the GPU is several kernels further
+      R = *host_R;
+      have_R = true;
+    }
+    if (R <= cap) break;
+    cap = R;  // the optimistic buffer was too small: redo the per-duplicate stages
+  }
+  cap_hint = R + R / 8 + 4096;
+  *a->num_rendered = (int)R;
+  if (a->sample_resize) a->sample_resize(a->sample_user, 0);
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));
     GSR_CUDA(cudaGetLastError());
@@ -247,8 +251,8 @@ int gsr_backward(const gsr_backward_args* a) {
 
   GSR_CUDA(cudaMemsetAsync(g.acc, 0, (size_t)P * 12 * sizeof(float), s));
   if (a->R > 0) {
-    BinView b = bin_view(a->binning_buffer, (size_t)a->R);
-    GSR_PROF("blend_bwd", launch_blend_bwd(W, H, im.ranges, im.tile_order, im.max_contrib, b.rec_a, b.rec_b, b.rec_c,
+    BinView b = bin_view(a->binning_buffer, (size_t)a->R);  // rec does not depend on the capacity
+    GSR_PROF("blend_bwd", launch_blend_bwd(W, H, im.ranges, im.tile_order, im.max_contrib, b.rec,
                             a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, s));
   }
   PreBwdParams bp;
@@ -269,7 +273,7 @@ int gsr_backward(const gsr_backward_args* a) {
   bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
   bp.dL_dcolor = a->dL_dcolor; bp.dL_dmean3D = a->dL_dmean3D; bp.dL_dcov3D = a->dL_dcov3D;
   bp.dL_ddc = a->dL_ddc; bp.dL_dsh = a->dL_dsh; bp.dL_dscale = a->dL_dscale; bp.dL_drot = a->dL_drot;
-  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.sort_a, &g.hdr->num_visible, s));
+  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible, s));
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));
     GSR_CUDA(cudaGetLastError());
@@ -313,14 +317,22 @@ int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
   return GSR_OK;
 }
 
-int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, int P, int R,
-                       uint64_t* keys_sorted, uint32_t* point_list, void* stream) {
+int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+                       int P, int R, int W, int H, uint64_t* keys_sorted, uint32_t* point_list, void* stream) {
+  (void)P; (void)geom_buffer;
   if (R <= 0) return GSR_OK;
-  if (!geom_buffer || !binning_buffer) return GSR_ERR_BAD_ARG;
-  GeomView g = geom_view(const_cast<char*>(geom_buffer), (size_t)P);
-  BinView b = bin_view(const_cast<char*>(binning_buffer), (size_t)R);
-  return launch_export_binning((uint32_t)R, b.items_a, g.depths, keys_sorted, point_list,
-                               static_cast<cudaStream_t>(stream));
+  if (!binning_buffer || !image_buffer) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)W * H;
+  const uint32_t T = (uint32_t)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
+  ImageView im = image_view(const_cast<char*>(image_buffer), N, T);
+  // the sort arrays sit behind the records, whose extent depends on the carved capacity
+  uint64_t cap = 0;
+  GSR_CUDA(cudaMemcpyAsync(&cap, binning_buffer, sizeof(cap), cudaMemcpyDeviceToHost, s));
+  GSR_CUDA(cudaStreamSynchronize(s));
+  if (cap < (uint64_t)R) return GSR_ERR_BAD_ARG;
+  BinView b = bin_view(const_cast<char*>(binning_buffer), (size_t)cap);
+  return launch_export_binning(T, im.ranges, b.items, keys_sorted, point_list, s);
 }
 
 int gsr_export_image(const char* image_buffer, int W, int H, float* final_T, uint32_t* n_contrib,

@@ -30,20 +30,15 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // ----------------------------------------------------------------------------
 struct GeomHeader {          // lives at the start of the geometry buffer (256 B)
   uint32_t num_dup;          // R: total (Gaussian,tile) duplicates
-  uint32_t num_visible;      // V
+  uint32_t max_tile_len;     // longest per-tile list
+  uint32_t num_visible;      // V: rendered Gaussians (length of vis_items)
   uint32_t num_large;        // length of the large-rectangle work queue (binning.cu)
-  uint32_t pad[61];
+  uint32_t num_long_tiles;   // tiles whose list exceeds the small shared-memory sort
+  uint32_t pad[59];
 };
 
 struct GeomView {
   GeomHeader* hdr;
-  // hdr | sort_tmp | scan_tmp are contiguous: ONE memset zeroes the counters, the depth-digit
-  // histograms that preprocess accumulates and the look-back flags of the depth sort and scan
-  char* sort_tmp;            // onesweep temp of the depth sort (starts with the 4x256 histograms)
-  size_t sort_tmp_bytes;
-  char* scan_tmp;            // chained-scan flags
-  size_t scan_tmp_bytes;
-  size_t zero_bytes;         // bytes to clear starting at hdr
   float* depths;             // [P]
   float2* means2D;           // [P]
   float4* conic_opacity;     // [P]
@@ -51,16 +46,15 @@ struct GeomView {
   uint32_t* tiles_touched;   // [P] exact number of tiles passing the opacity-aware test
   uint8_t* clamped;          // [P] bit c set <=> channel c was clamped
   float* acc;                // [12P] backward moment sums {Mx,My,Mxx,Mxy,Myy,M0,r,g,b,-,-,-}
-  uint64_t* sort_a;          // [P] (depth_bits<<32 | idx) ping
-  uint64_t* sort_b;          // [P] pong
-  uint32_t* dup_offsets;     // [P] exclusive scan of tiles_touched in depth order
+  uint64_t* vis_items;       // [P] compacted rendered Gaussians (depth_bits<<32 | idx), unordered
+  uint32_t* large_list;      // [2P] work queue of the large rectangles (emit stage)
 };
 
-constexpr int kTileHistPasses = 4;   // tile ids up to 32 bits
+constexpr int kTileHistPasses = 4;   // (kept for the stand-alone sort API)
 struct ImageView {
-  // tile_count | tile_ghist are contiguous and zeroed by one memset before preprocess
+  // tile_count | tile_fill are contiguous and zeroed by one memset before preprocess
   uint32_t* tile_count;      // [T] exact number of splats per tile (accumulated by preprocess)
-  uint32_t* tile_ghist;      // [kTileHistPasses][256] digit histograms of the tile sort (tile_meta_kernel)
+  uint32_t* tile_fill;       // [T] slots handed out so far by the emit stage
   size_t zero_bytes;         // bytes to clear starting at tile_count
   float* final_T;            // [N]
   uint32_t* n_contrib;       // [N]
@@ -70,19 +64,27 @@ struct ImageView {
   uint32_t* tile_order;      // [T] tiles sorted by list length, longest first (CTA launch order)
 };
 
+// per-tile sort (binning.cu): lists shorter than kSortSmallCap are sorted in static shared
+// memory, lists up to kSortLargeCap in 128 KB of dynamic shared memory, longer ones in global
+// scratch.  kSortSmallCap must be a multiple of 4 and < 4096 (LPT bucket layout of tile_meta_kernel).
+constexpr int kSortSmallCap = 2048;
+constexpr int kSortLargeCap = 16384;
+
+// Per-duplicate buffer.  Its layout must not depend on the exact R (the forward pass sizes it
+// optimistically before R has reached the host): a 128-byte header holding the capacity, then
+// the packed splat records (the only part the backward pass needs), then the sort arrays.
+struct BinHeader {
+  uint64_t capacity;         // records / items the buffer was carved for
+  uint64_t pad[15];
+};
 struct BinView {
-  uint64_t* items_a;         // [R] (tile<<32 | idx) ping
-  uint64_t* items_b;         // [R] pong
-  float4* rec_a;             // [R] {x, y, conic.x, conic.y}
-  float4* rec_b;             // [R] {conic.z, opacity, reject_power, idx bits}
-  float4* rec_c;             // [R] {r, g, b, 0}
-  char* sort_tmp;
-  size_t sort_tmp_bytes;
+  BinHeader* hdr;
+  float4* rec;               // [cap][3] {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}
+  uint64_t* items;           // [cap] (depth_bits<<32 | idx), tile-major; depth-sorted per tile after tile_sort_pack
+  uint64_t* scratch;         // [2*cap] padded lists of the tiles too long for shared memory
 };
 
 size_t sort_temp_bytes(int64_t n);
-size_t sort_depth_temp_bytes(int64_t P);
-size_t scan_temp_bytes(int64_t n);
 
 template <typename T>
 __host__ __device__ inline T* carve(char*& p, size_t count) {
@@ -96,11 +98,6 @@ inline GeomView geom_view(char* base, size_t P) {
   GeomView g;
   char* p = base;
   g.hdr = carve<GeomHeader>(p, 1);
-  g.sort_tmp_bytes = align_up(sort_depth_temp_bytes((int64_t)P), 128);
-  g.sort_tmp = carve<char>(p, g.sort_tmp_bytes);
-  g.scan_tmp_bytes = align_up(scan_temp_bytes((int64_t)P), 128);
-  g.scan_tmp = carve<char>(p, g.scan_tmp_bytes);
-  g.zero_bytes = (size_t)(p - reinterpret_cast<char*>(g.hdr));
   g.depths = carve<float>(p, P);
   g.means2D = carve<float2>(p, P);
   g.conic_opacity = carve<float4>(p, P);
@@ -108,21 +105,20 @@ inline GeomView geom_view(char* base, size_t P) {
   g.tiles_touched = carve<uint32_t>(p, P);
   g.clamped = carve<uint8_t>(p, P);
   g.acc = carve<float>(p, 12 * P);
-  g.sort_a = carve<uint64_t>(p, P);
-  g.sort_b = carve<uint64_t>(p, P);
-  g.dup_offsets = carve<uint32_t>(p, P);
+  g.vis_items = carve<uint64_t>(p, P);
+  g.large_list = carve<uint32_t>(p, 2 * P);
   return g;
 }
 inline size_t geom_bytes(size_t P) {
   GeomView g = geom_view(nullptr, P);
-  return reinterpret_cast<size_t>(g.dup_offsets) + P * 4 + 128;
+  return reinterpret_cast<size_t>(g.large_list) + 2 * P * 4 + 128;
 }
 
 inline ImageView image_view(char* base, size_t N, size_t T) {
   ImageView v;
   char* p = base;
   v.tile_count = carve<uint32_t>(p, T);
-  v.tile_ghist = carve<uint32_t>(p, (size_t)kTileHistPasses * 256);
+  v.tile_fill = carve<uint32_t>(p, T);
   v.zero_bytes = (size_t)(p - reinterpret_cast<char*>(v.tile_count));
   v.final_T = carve<float>(p, N);
   v.n_contrib = carve<uint32_t>(p, N);
@@ -137,22 +133,19 @@ inline size_t image_bytes(size_t N, size_t T) {
   return reinterpret_cast<size_t>(v.tile_order) + T * 4 + 128;
 }
 
-inline BinView bin_view(char* base, size_t R) {
+inline BinView bin_view(char* base, size_t cap) {
   BinView b;
   char* p = base;
-  size_t Rp = R + 8;  // slack so bulk copies may round up to 16 B multiples
-  b.items_a = carve<uint64_t>(p, Rp);
-  b.items_b = carve<uint64_t>(p, Rp);
-  b.rec_a = carve<float4>(p, Rp);
-  b.rec_b = carve<float4>(p, Rp);
-  b.rec_c = carve<float4>(p, Rp);
-  b.sort_tmp_bytes = sort_temp_bytes((int64_t)R);
-  b.sort_tmp = carve<char>(p, b.sort_tmp_bytes);
+  const size_t c = cap + 8;  // slack so bulk copies may round up to 16 B multiples
+  b.hdr = carve<BinHeader>(p, 1);
+  b.rec = carve<float4>(p, 3 * c);
+  b.items = carve<uint64_t>(p, c);
+  b.scratch = carve<uint64_t>(p, 2 * c);
   return b;
 }
-inline size_t bin_bytes(size_t R) {
-  BinView b = bin_view(nullptr, R);
-  return reinterpret_cast<size_t>(b.sort_tmp) + b.sort_tmp_bytes + 128;
+inline size_t bin_bytes(size_t cap) {
+  BinView b = bin_view(nullptr, cap);
+  return reinterpret_cast<size_t>(b.scratch) + 2 * (cap + 8) * 8 + 128;
 }
 
 // ----------------------------------------------------------------------------
@@ -385,16 +378,6 @@ __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, 
 }
 
 // ---- launch helpers implemented across the .cu files ------------------------
-size_t scan_temp_bytes(int64_t n);
-int launch_scan_gather(const uint32_t* counts, const uint64_t* order_items, int64_t n_max,
-                       const uint32_t* n_dev, uint32_t* offsets, uint32_t* total_out, char* tmp,
-                       cudaStream_t s);
-uint32_t* sort_ghist(char* tmp);
-size_t sort_depth_temp_bytes(int64_t P);
-int launch_sort_depth(uint64_t* a, uint64_t* b, int64_t P, const uint32_t* n_valid, char* tmp,
-                      cudaStream_t s);
-int launch_sort_tile(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t R, int tile_bits,
-                     const uint32_t* ghist, char* tmp, cudaStream_t s);
 int launch_sort_u64(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t n, int begin_bit,
                     int end_bit, char* tmp, cudaStream_t s, uint64_t** result);
 

@@ -32,10 +32,9 @@ struct PreprocessParams {
   float* rgb;
   uint8_t* clamped;
   uint32_t* tiles_touched;
-  uint64_t* sort_items;
-  uint32_t* num_visible;
+  uint64_t* vis_items;    // compacted (depth_bits<<32 | idx) of the rendered Gaussians
+  uint32_t* num_visible;  // its length (zeroed by the caller)
   uint32_t* tile_count;   // [T] += 1 per (Gaussian, tile) that passes the exact test (zeroed by the caller)
-  uint32_t* depth_ghist;  // [4][256] digit histograms of the depth bits of the rendered Gaussians (zeroed by the caller)
 };
 struct PreBwdParams {
   int P, D, M;
@@ -70,24 +69,27 @@ struct PreBwdParams {
 int launch_preprocess(const PreprocessParams& p, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
                         cudaStream_t s);
-int launch_emit(int P, const uint64_t* sorted, const uint32_t* tiles_touched,
-                uint32_t* dup_offsets, const float2* means2D, const float4* conic_opacity,
-                const int* radii, int grid_x, int grid_y, uint64_t* items, uint32_t* large_count,
-                uint32_t* large_list, const uint32_t* num_valid, cudaStream_t s);
-int launch_finalize(uint32_t R, const uint64_t* sorted, const float2* means2D,
-                    const float4* conic_opacity, const float* colors, float4* rec_a, float4* rec_b,
-                    float4* rec_c, cudaStream_t s);
-int launch_export_binning(uint32_t R, const uint64_t* sorted, const float* depths, uint64_t* keys,
+struct GeomHeader;
+struct BinHeader;
+int launch_tile_meta(const uint32_t* tile_count, uint32_t T, uint2* ranges, GeomHeader* hdr,
+                     uint32_t* order, uint32_t* max_contrib, cudaStream_t s);
+int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
+                const uint32_t* tiles_touched, const float2* means2D, const float4* conic_opacity,
+                const int* radii, int grid_x, int grid_y, const uint2* ranges, uint32_t* tile_fill,
+                uint64_t* items, uint32_t capacity, uint32_t* large_count, uint32_t* large_list,
+                cudaStream_t s);
+int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
+                          BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch, const float2* means2D,
+                          const float4* conic_opacity, const float* colors, float4* rec,
+                          cudaStream_t s);
+int launch_export_binning(uint32_t T, const uint2* ranges, const uint64_t* items, uint64_t* keys,
                           uint32_t* point_list, cudaStream_t s);
-int launch_tile_meta(const uint32_t* tile_count, uint32_t T, int tile_bits, uint2* ranges,
-                     uint32_t* num_dup, uint32_t* tile_ghist, uint32_t* order, uint32_t* max_contrib,
+int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,
+                     const float* bg, float* out_color, float* final_T,
+                     uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, uint32_t capacity,
                      cudaStream_t s);
-int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec_a, const float4* rec_b,
-                     const float4* rec_c, const float* bg, float* out_color, float* final_T,
-                     uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, cudaStream_t s);
 int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_order,
-                     const uint32_t* max_contrib,
-                     const float4* rec_a, const float4* rec_b, const float4* rec_c, const float* bg,
+                     const uint32_t* max_contrib, const float4* rec, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s);
 int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,

@@ -1,6 +1,6 @@
 // Forward per-Gaussian pass: frustum cull, projection, 3D->2D covariance, conic,
-// 3-sigma radius, SH->RGB, EXACT opacity-aware tile count, and the depth sort
-// item.  One kernel replaces the reference's preprocessCUDA (forward.cu:197-312)
+// 3-sigma radius, SH->RGB, EXACT opacity-aware tile counts (per Gaussian and per
+// tile), and the compacted list of rendered Gaussians.  One kernel replaces the reference's preprocessCUDA (forward.cu:197-312)
 // plus the counting half of duplicateWithKeys (rasterizer_impl.cu:139-212): by
 // running the tile test here, only tiles that will really be rasterised are
 // counted, so no padding keys are ever generated.
@@ -265,10 +265,10 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
   }
 
   // ---- outputs -----------------------------------------------------------------
+  const bool rendered = visible && ntiles > 0;
   if (in_range) {
     a.radii[idx] = visible ? (int)my_radius : 0;
     a.tiles_touched[idx] = ntiles;
-    uint32_t depth_bits = 0xffffffffu;
     if (visible) {
       a.depths[idx] = p_view.z;
       a.means2D[idx] = point_image;
@@ -279,24 +279,19 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
         a.rgb[3 * (size_t)idx + 2] = rgb.z;
         a.clamped[idx] = clamp_bits;
       }
-      if (ntiles > 0) depth_bits = __float_as_uint(p_view.z);
     }
-    a.sort_items[idx] = ((uint64_t)depth_bits << 32) | (uint32_t)idx;
   }
-  // number of Gaussians that own at least one tile (= length of the depth-sorted list)
-  const bool rendered = visible && ntiles > 0;
+  // compacted list of the rendered Gaussians (those that own at least one tile), one
+  // warp-aggregated atomic per warp.  Its order is irrelevant: the emit stage and the backward
+  // preprocess only need the set, the depth order is established per tile (binning.cu).
   const unsigned vm = __ballot_sync(0xffffffffu, rendered);
   if (vm) {
-    if (lane == 0) atomicAdd(a.num_visible, (uint32_t)__popc(vm));
-    // digit histograms of the depth sort, warp-aggregated (the high digits of neighbouring
-    // depths coincide, so most warps issue one atomic per digit position)
-    const uint32_t bits = __float_as_uint(p_view.z);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const uint32_t d = (bits >> (8 * p)) & 0xffu;
-      const unsigned peers = __match_any_sync(0xffffffffu, rendered ? d : 0xffffu);
-      if (rendered && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&a.depth_ghist[p * 256 + d], (uint32_t)__popc(peers));
-    }
+    uint32_t base_pos = 0;
+    if (lane == 0) base_pos = atomicAdd(a.num_visible, (uint32_t)__popc(vm));
+    base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
+    if (rendered)
+      a.vis_items[base_pos + __popc(vm & ((1u << lane) - 1u))] =
+          ((uint64_t)__float_as_uint(p_view.z) << 32) | (uint32_t)idx;
   }
 }
 

@@ -1,7 +1,8 @@
-// Hand-written stable LSD "onesweep" radix sort of 64-bit items and a chained
-// (decoupled look-back) exclusive scan.  Replaces the reference's use of
-// cub::DeviceRadixSort::SortPairs (rasterizer_impl.cu:486-491, simple_knn.cu:210-213)
-// and cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:456-459).
+// Hand-written stable LSD "onesweep" radix sort of 64-bit items (decoupled look-back).
+// Replaces the reference's use of cub::DeviceRadixSort::SortPairs in simple-knn
+// (simple_knn.cu:210-213) and is exposed through gsr_sort_u64.  (The rasterizer's own
+// (tile | depth) ordering no longer needs a global sort: binning.cu sorts every tile's list
+// in shared memory.)
 //
 // Onesweep = one up-front histogram pass for ALL digit positions, then one
 // read + one write per 8-bit digit: every thread block ranks its 4096-item tile
@@ -108,16 +109,11 @@ sort_histogram_kernel(const uint64_t* __restrict__ items, uint32_t n, int begin_
 // ---------------------------------------------------------------------------
 // One onesweep pass: stable scatter of the items by one 8-bit digit.
 // ---------------------------------------------------------------------------
-// kDropInvalid: items whose high word is 0xFFFFFFFF (preprocess: Gaussian not rendered) are
-// neither ranked nor written, i.e. the pass doubles as an order-preserving compaction; `ghist`
-// must then count the valid items only.  n_dev (optional) overrides n with a device-side
-// count; CTAs whose tile starts beyond it leave at once (the grid is sized for the host bound).
-template <int kItemsPerThread, bool kDropInvalid>
+template <int kItemsPerThread>
 __global__ void __launch_bounds__(kSortThreads)
 onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n,
-                     const uint32_t* __restrict__ n_dev, int shift, uint32_t digit_mask,
-                     const uint32_t* __restrict__ ghist, uint32_t* __restrict__ tile_counter,
-                     uint32_t* __restrict__ lookback) {
+                     int shift, uint32_t digit_mask, const uint32_t* __restrict__ ghist,
+                     uint32_t* __restrict__ tile_counter, uint32_t* __restrict__ lookback) {
   constexpr int kTileItems = kSortThreads * kItemsPerThread;
   __shared__ uint64_t s_items[kTileItems];              // 32 KB at 16 items per thread
   __shared__ uint32_t s_warp_hist[kSortWarps][kRadix];  // 8 KB
@@ -127,13 +123,11 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
   __shared__ uint32_t s_tile;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (n_dev != nullptr) n = *n_dev;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   for (int i = tid; i < kSortWarps * kRadix; i += kSortThreads) (&s_warp_hist[0][0])[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t base = tile * (uint32_t)kTileItems;
-  if (base >= n) return;  // whole CTA: nobody looks back at a tile past the end
   const uint32_t tile_count = min((uint32_t)kTileItems, n - base);
   const uint32_t lanemask_lt = (1u << lane) - 1u;
 
@@ -149,8 +143,7 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
 #pragma unroll
   for (int k = 0; k < kItemsPerThread; ++k) {
     const uint32_t li = wbase + k * 32 + lane;
-    bool valid = li < tile_count;
-    if (kDropInvalid) valid = valid && (uint32_t)(items[k] >> 32) != 0xffffffffu;
+    const bool valid = li < tile_count;
     const uint32_t digit = (uint32_t)(items[k] >> shift) & digit_mask;
     const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 0xffffu);
     const uint32_t before = __popc(peers & lanemask_lt);
@@ -175,21 +168,44 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
   uint32_t* my_flag = lookback + (size_t)tile * kRadix + tid;
   st_volatile_u32(my_flag, (tile == 0 ? kFlagInc : kFlagAgg) | total);
 
-  uint32_t kept = tile_count;  // items of this tile that are written (all of them unless kDropInvalid)
-  const uint32_t bin_start = block_excl_scan_256(total, s_scan, kDropInvalid ? &kept : nullptr);
+  const uint32_t bin_start = block_excl_scan_256(total, s_scan, nullptr);
   const uint32_t gcount = ghist[tid];
   const uint32_t gbase = block_excl_scan_256(gcount, s_scan, nullptr);
 
+  // Decoupled look-back, kLookWide predecessors per round trip: the flags of tiles t, t-1, ...
+  // are fetched together (independent loads) and consumed nearest-first until one carries an
+  // inclusive prefix or is not published yet (then the window restarts there).
   uint32_t excl = 0;
   if (tile > 0) {
+    constexpr int kLookWide = 8;
     int t = (int)tile - 1;
-    while (true) {
-      const uint32_t v = ld_volatile_u32(lookback + (size_t)t * kRadix + tid);
-      const uint32_t flag = v & ~kValMask;
-      if (flag == 0) continue;  // predecessor has not published yet
-      excl += v & kValMask;
-      if (flag == kFlagInc) break;
-      --t;
+    bool done = false;
+    while (!done) {
+      uint32_t v[kLookWide];
+#pragma unroll
+      for (int i = 0; i < kLookWide; ++i)
+        v[i] = (t - i >= 0) ? ld_volatile_u32(lookback + (size_t)(t - i) * kRadix + tid) : kFlagInc;
+      int used = kLookWide;
+#pragma unroll
+      for (int i = kLookWide - 1; i >= 0; --i) {  // nearest stop wins: scan far -> near
+        const uint32_t flag = v[i] & ~kValMask;
+        if (flag == 0 || flag == kFlagInc) used = i;
+      }
+      // tiles t .. t-used+1 hold plain aggregates; tile t-used stops the window
+#pragma unroll
+      for (int i = 0; i < kLookWide; ++i)
+        if (i < used) excl += v[i] & kValMask;
+      if (used < kLookWide) {
+        uint32_t stop = 0;
+#pragma unroll
+        for (int i = 0; i < kLookWide; ++i)
+          if (i == used) stop = v[i];
+        if ((stop & ~kValMask) == kFlagInc) {
+          excl += stop & kValMask;
+          done = true;
+        }
+      }
+      t -= used;  // not published yet: look at it again; all consumed: continue further back
     }
     st_volatile_u32(my_flag, kFlagInc | (excl + total));
   }
@@ -201,32 +217,29 @@ onesweep_pass_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out
 #pragma unroll
   for (int k = 0; k < kItemsPerThread; ++k) {
     const uint32_t li = wbase + k * 32 + lane;
-    bool valid = li < tile_count;
-    if (kDropInvalid) valid = valid && (uint32_t)(items[k] >> 32) != 0xffffffffu;
-    if (valid) {
+    if (li < tile_count) {
       const uint32_t digit = (uint32_t)(items[k] >> shift) & digit_mask;
       s_items[s_bin_start[digit] + s_warp_hist[warp][digit] + ranks[k]] = items[k];
     }
   }
   __syncthreads();
 #pragma unroll 4
-  for (uint32_t i = tid; i < kept; i += kSortThreads) {
+  for (uint32_t i = tid; i < tile_count; i += kSortThreads) {
     const uint64_t it = s_items[i];
     const uint32_t digit = (uint32_t)(it >> shift) & digit_mask;
     out[s_digit_base[digit] + i] = it;
   }
 }
 
-template <bool kDrop>
-static void launch_pass(int ipt, int64_t tiles, const uint64_t* src, uint64_t* dst, uint32_t n,
-                        const uint32_t* n_dev, int sh, uint32_t mask, const uint32_t* ghist,
-                        uint32_t* counter, uint32_t* lookback, cudaStream_t s) {
+static void launch_pass(int ipt, int64_t tiles, const uint64_t* src, uint64_t* dst, uint32_t n, int sh,
+                        uint32_t mask, const uint32_t* ghist, uint32_t* counter, uint32_t* lookback,
+                        cudaStream_t s) {
   if (ipt == kIptSmall)
-    onesweep_pass_kernel<kIptSmall, kDrop><<<(unsigned)tiles, kSortThreads, 0, s>>>(
-        src, dst, n, n_dev, sh, mask, ghist, counter, lookback);
+    onesweep_pass_kernel<kIptSmall><<<(unsigned)tiles, kSortThreads, 0, s>>>(src, dst, n, sh, mask, ghist,
+                                                                             counter, lookback);
   else
-    onesweep_pass_kernel<kIptLarge, kDrop><<<(unsigned)tiles, kSortThreads, 0, s>>>(
-        src, dst, n, n_dev, sh, mask, ghist, counter, lookback);
+    onesweep_pass_kernel<kIptLarge><<<(unsigned)tiles, kSortThreads, 0, s>>>(src, dst, n, sh, mask, ghist,
+                                                                             counter, lookback);
   GSR_LAUNCHED();
 }
 
@@ -263,165 +276,11 @@ int launch_sort_u64(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t n,
   for (int p = 0; p < npass; ++p) {
     const int sh = begin_bit + p * kRadixBits;
     const int bits = (end_bit - sh) < kRadixBits ? (end_bit - sh) : kRadixBits;
-    launch_pass<false>(sort_ipt(n), tiles, src, dst, (uint32_t)n, nullptr, sh, (1u << bits) - 1u,
-                       ghist + (size_t)p * kRadix, counters + p, lookback + (size_t)p * tiles * kRadix, s);
+    launch_pass(sort_ipt(n), tiles, src, dst, (uint32_t)n, sh, (1u << bits) - 1u,
+                ghist + (size_t)p * kRadix, counters + p, lookback + (size_t)p * tiles * kRadix, s);
     src = dst;
     dst = (dst == out) ? alt : out;
   }
-  return (int)cudaGetLastError();
-}
-
-// ---- the two sorts of the forward pass, with their histograms computed upstream ----------
-// Depth sort: `tmp` (sort_depth_temp_bytes) starts with the 4 x 256 digit histograms and must
-// be zeroed by the caller BEFORE the kernel that accumulates them (preprocess) runs.
-uint32_t* sort_ghist(char* tmp) { return reinterpret_cast<uint32_t*>(tmp); }
-
-// Depth order of the rendered Gaussians: items (depth_bits<<32 | idx) for all P Gaussians, the
-// non-rendered ones marked with 0xFFFFFFFF in the high word.  Pass 1 reads all P items and
-// keeps only the *n_valid rendered ones; passes 2-4 run on those (grid sized for P, surplus
-// CTAs exit).  ghist (4 x 256, valid items only) was accumulated by preprocess.
-// a -> b -> a -> b -> a: the sorted list ends in `a`.
-int launch_sort_depth(uint64_t* a, uint64_t* b, int64_t P, const uint32_t* n_valid, char* tmp,
-                      cudaStream_t s) {
-  if (P <= 0) return 0;
-  if (P >= (int64_t)kValMask) return -1;
-  uint32_t* words = reinterpret_cast<uint32_t*>(tmp);
-  uint32_t* ghist = words;
-  uint32_t* counters = words + (size_t)kMaxPasses * kRadix;
-  uint32_t* lookback = words + sort_header_words();
-  const int64_t tiles_full = sort_num_tiles(P);
-  // passes over the rendered subset: short tiles unless the scene is very large
-  const int ipt_sub = P <= (int64_t)2 * 1024 * 1024 ? kIptSmall : kIptLarge;
-  const int64_t tiles_sub = (P + (int64_t)kSortThreads * ipt_sub - 1) / ((int64_t)kSortThreads * ipt_sub);
-  // the look-back area was sized (and zeroed) for 4 passes of sort_num_tiles(P) tiles of the
-  // small kind when P < kSmallSortLimit, else of the large kind; tiles_sub may exceed that
-  launch_pass<true>(sort_ipt(P), tiles_full, a, b, (uint32_t)P, nullptr, 32, 0xffu, ghist, counters, lookback, s);
-  const uint64_t* src = b;
-  uint64_t* dst = a;
-  for (int p = 1; p < 4; ++p) {
-    launch_pass<false>(ipt_sub, tiles_sub, src, dst, 0u, n_valid, 32 + 8 * p, 0xffu,
-                       ghist + (size_t)p * kRadix, counters + p,
-                       lookback + (size_t)tiles_full * kRadix + (size_t)(p - 1) * tiles_sub * kRadix, s);
-    uint64_t* t = const_cast<uint64_t*>(src);
-    src = dst;
-    dst = t;
-  }
-  return (int)cudaGetLastError();
-}
-size_t sort_depth_temp_bytes(int64_t P) {
-  if (P < 0) P = 0;
-  const int ipt_sub = P <= (int64_t)2 * 1024 * 1024 ? kIptSmall : kIptLarge;
-  const int64_t tiles_sub = (P + (int64_t)kSortThreads * ipt_sub - 1) / ((int64_t)kSortThreads * ipt_sub);
-  return (sort_header_words() + (size_t)(sort_num_tiles(P) + 3 * tiles_sub) * kRadix) * 4 + 256;
-}
-
-// Tile order of the duplicates: only the tile digits (bits 32..32+tile_bits) are sorted; their
-// histograms come from the per-tile counts (binning.cu: tile_meta_kernel).  Result in `out`.
-int launch_sort_tile(const uint64_t* in, uint64_t* out, uint64_t* alt, int64_t R, int tile_bits,
-                     const uint32_t* ghist, char* tmp, cudaStream_t s) {
-  if (R <= 0) return 0;
-  if (R >= (int64_t)kValMask) return -1;
-  const int npass = (tile_bits + kRadixBits - 1) / kRadixBits;
-  if (npass <= 0 || npass > kMaxPasses) return -1;
-  uint32_t* words = reinterpret_cast<uint32_t*>(tmp);
-  uint32_t* counters = words + (size_t)kMaxPasses * kRadix;
-  uint32_t* lookback = words + sort_header_words();
-  const int64_t tiles = sort_num_tiles(R);
-  cudaError_t e = cudaMemsetAsync(counters, 0, (64 + (size_t)npass * tiles * kRadix) * 4, s);
-  if (e != cudaSuccess) return (int)e;
-  const uint64_t* src = in;
-  uint64_t* dst = (npass & 1) ? out : alt;
-  for (int p = 0; p < npass; ++p) {
-    const int sh = 32 + p * kRadixBits;
-    const int bits = (tile_bits - p * kRadixBits) < kRadixBits ? (tile_bits - p * kRadixBits) : kRadixBits;
-    launch_pass<false>(sort_ipt(R), tiles, src, dst, (uint32_t)R, nullptr, sh, (1u << bits) - 1u,
-                       ghist + (size_t)p * kRadix, counters + p, lookback + (size_t)p * tiles * kRadix, s);
-    src = dst;
-    dst = (dst == out) ? alt : out;
-  }
-  return (int)cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------
-// Chained exclusive scan of counts[order[j]] (j in depth order) -> offsets[j];
-// the grand total is written to *total_out.  One pass over the data.
-// ---------------------------------------------------------------------------
-constexpr int kScanItems = 8;
-constexpr int kScanTile = 256 * kScanItems;
-
-__global__ void __launch_bounds__(256)
-scan_gather_kernel(const uint32_t* __restrict__ counts, const uint64_t* __restrict__ order_items,
-                   const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ offsets,
-                   uint32_t* __restrict__ total_out, uint32_t* __restrict__ tile_counter,
-                   uint32_t* __restrict__ lookback) {
-  __shared__ uint32_t s_scan[8];
-  __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_prefix;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-  // only the first *n_dev sorted positions hold rendered Gaussians; the grid is sized for all P,
-  // tiles past the end leave at once (nobody looks back at them)
-  const uint32_t n = *n_dev;
-  if (tile * (uint32_t)kScanTile >= n) return;
-  const uint32_t base = tile * kScanTile + tid * kScanItems;
-  uint32_t v[kScanItems];
-  uint32_t sum = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const uint32_t j = base + k;
-    uint32_t c = 0;
-    if (j < n) {
-      const uint32_t g = (uint32_t)(order_items[j] & 0xffffffffu);
-      c = counts[g];
-    }
-    v[k] = c;
-    sum += c;
-  }
-  uint32_t block_total;
-  const uint32_t excl = block_excl_scan_256(sum, s_scan, &block_total);
-  if (tid == 0) {
-    st_volatile_u32(lookback + tile, (tile == 0 ? kFlagInc : kFlagAgg) | block_total);
-    uint32_t pre = 0;
-    if (tile > 0) {
-      int t = (int)tile - 1;
-      while (true) {
-        const uint32_t x = ld_volatile_u32(lookback + t);
-        const uint32_t flag = x & ~kValMask;
-        if (flag == 0) continue;
-        pre += x & kValMask;
-        if (flag == kFlagInc) break;
-        --t;
-      }
-      st_volatile_u32(lookback + tile, kFlagInc | (pre + block_total));
-    }
-    s_prefix = pre;
-    if (total_out != nullptr && block_total) atomicAdd(total_out, block_total);  // zeroed by the caller
-  }
-  __syncthreads();
-  uint32_t run = s_prefix + excl;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const uint32_t j = base + k;
-    if (j < n) offsets[j] = run;
-    run += v[k];
-  }
-}
-
-// tmp: (1 + tiles) words, zeroed here.
-size_t scan_temp_bytes(int64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile + 64) * 4; }
-
-// n_max bounds *n_dev (sizes the grid); tmp ((tiles + 64) words) must be zeroed by the caller.
-int launch_scan_gather(const uint32_t* counts, const uint64_t* order_items, int64_t n_max,
-                       const uint32_t* n_dev, uint32_t* offsets, uint32_t* total_out, char* tmp,
-                       cudaStream_t s) {
-  if (n_max <= 0) return 0;
-  const int64_t tiles = (n_max + kScanTile - 1) / kScanTile;
-  uint32_t* words = reinterpret_cast<uint32_t*>(tmp);
-  scan_gather_kernel<<<(unsigned)tiles, 256, 0, s>>>(counts, order_items, n_dev, offsets,
-                                                      total_out, words, words + 64);
-  GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }
 

@@ -25,8 +25,10 @@
  * reference's std::function<char*(size_t)> (rasterizer.h:28-31).
  * All functions return 0 on success, a negative gsr error code or a positive
  * cudaError_t otherwise; nothing throws across this ABI.  All work is enqueued
- * on `stream` (a cudaStream_t); gsr_forward synchronises that stream once
- * internally to size the per-duplicate buffers.
+ * on `stream` (a cudaStream_t).  gsr_forward sizes the per-duplicate buffer
+ * optimistically from its previous call and only waits for the 4-byte count R
+ * after everything is enqueued (first call on a thread: one blocking wait; see
+ * DESIGN.md).
  */
 #ifndef GSR_CAPI_H_
 #define GSR_CAPI_H_
@@ -161,8 +163,9 @@ int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
 
 /* ---- test / debug exports (device -> device copies out of the opaque buffers) ---- */
 /* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits). */
-int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, int P,
-                       int R, uint64_t* keys_sorted, uint32_t* point_list, void* stream);
+int gsr_export_binning(const char* geom_buffer, const char* binning_buffer,
+                       const char* image_buffer, int P, int R, int W, int H,
+                       uint64_t* keys_sorted, uint32_t* point_list, void* stream);
 int gsr_export_image(const char* image_buffer, int W, int H, float* final_T,
                      uint32_t* n_contrib, uint32_t* ranges /*[T,2]*/,
                      uint32_t* max_contrib /*[T]*/, void* stream);

@@ -70,7 +70,8 @@ def product_exports(scene, t, fwd):
     ids = torch.zeros(R, dtype=torch.int32, device=dev)
     p = lambda x: C.c_void_p(x.data_ptr()) if x.numel() else None  # noqa: E731
     if R > 0:
-        _lib.check(L.gsr_export_binning(p(geom), p(binning), P, R, p(keys), p(ids), None), "export_binning")
+        _lib.check(L.gsr_export_binning(p(geom), p(binning), p(img), P, R, W, H, p(keys), p(ids), None),
+                   "export_binning")
     out = dict(keys=keys, ids=ids,
                final_T=torch.zeros(N, dtype=torch.float32, device=dev),
                n_contrib=torch.zeros(N, dtype=torch.int32, device=dev),
