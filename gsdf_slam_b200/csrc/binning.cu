@@ -148,6 +148,11 @@ int launch_tile_meta(const uint32_t* tile_count, uint32_t T, uint2* ranges, Geom
 // `capacity` guards the optimistically sized buffer (gsr_forward re-runs the stage if R
 // exceeded it).
 // ---------------------------------------------------------------------------------------------
+#ifndef GSR_EMIT_OWNERS
+#define GSR_EMIT_OWNERS 8
+#endif
+constexpr int kEmitOwners = GSR_EMIT_OWNERS;
+
 __global__ void __launch_bounds__(256)
 emit_kernel(const uint64_t* __restrict__ vis_items, const uint32_t* __restrict__ num_visible,
             const uint32_t* __restrict__ tiles_touched, const float2* __restrict__ means2D,
@@ -155,9 +160,14 @@ emit_kernel(const uint64_t* __restrict__ vis_items, const uint32_t* __restrict__
             int grid_y, const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_fill,
             uint64_t* __restrict__ items, uint32_t capacity, uint32_t* __restrict__ large_count,
             uint32_t* __restrict__ large_list, uint32_t large_capacity) {
+  // kEmitOwners Gaussians per warp (lanes 0 .. kEmitOwners-1 own one each; all 32 lanes walk
+  // their tiles): the stage is bound by the latency of the slot atomics, so the more warps share
+  // the work the better
+  const int lane = threadIdx.x & 31;
   const uint32_t nv = *num_visible;
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if ((j & ~31u) >= nv) return;  // whole warp
+  const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp_global * kEmitOwners >= nv) return;  // whole warp
+  const uint32_t j = lane < kEmitOwners ? warp_global * kEmitOwners + lane : 0xffffffffu;
   uint32_t g = 0, depth_bits = 0, cnt = 0;
   float2 xy = {0.f, 0.f};
   float4 co = {0.f, 0.f, 0.f, 0.f};
@@ -252,7 +262,8 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
   if (P >= (1 << 24)) return GSR_ERR_BAD_ARG;  // queue entries hold 24-bit list positions
   const uint32_t large_capacity = 2u * (uint32_t)P;
   // the grid covers all P list slots; warps past the *num_visible rendered ones leave at once
-  emit_kernel<<<(P + 255) / 256, 256, 0, s>>>(vis_items, num_visible, tiles_touched, means2D,
+  const long long warps = ((long long)P + kEmitOwners - 1) / kEmitOwners;
+  emit_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(vis_items, num_visible, tiles_touched, means2D,
                                               conic_opacity, radii, grid_x, grid_y, ranges, tile_fill,
                                               items, capacity, large_count, large_list, large_capacity);
   GSR_LAUNCHED();
@@ -268,8 +279,8 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
 // tile_sort_pack: one CTA per tile.  Bitonic sort of the tile's 64-bit items (unique, so the
 // sorted order is unique) and the packed per-duplicate records
 //   {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}.
-// Lists shorter than kSortSmallCap entries are sorted in 16 KB of shared memory by the "small" launch
-// (one CTA per tile, LPT order).  The "long" launch (148 persistent CTAs over the
+// Lists shorter than kSortSmallCap entries are sorted in registers by the "small" launch (one
+// warp per tile, LPT order).  The "long" launch (148 persistent CTAs over the
 // hdr->num_long_tiles longest tiles, which form a prefix of the LPT order) sorts lists up to
 // kSortLargeCap entries in 128 KB of shared memory and anything longer in a padded global
 // scratch area — slow, but correct for any input.
@@ -303,52 +314,152 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* buf, uint32_t n_pad) {
 template <int kThreads>
 __device__ __forceinline__ void sort_pack_tile(uint64_t* buf, uint32_t n, uint32_t start,
                                                uint64_t* __restrict__ items,
-                                               const float2* __restrict__ means2D,
-                                               const float4* __restrict__ conic_opacity,
-                                               const float* __restrict__ colors,
+                                               const float4* __restrict__ splat_rec,
                                                float4* __restrict__ rec) {
   const uint32_t n_pad = next_pow2(n);
   for (uint32_t i = threadIdx.x; i < n_pad; i += kThreads) buf[i] = i < n ? items[start + i] : ~0ull;
   __syncthreads();
   bitonic_sort<kThreads>(buf, n_pad);
-  for (uint32_t i = threadIdx.x; i < n; i += kThreads) {
-    const uint64_t it = buf[i];
-    const uint32_t g = (uint32_t)(it & 0xffffffffu);
-    items[start + i] = it;
-    const float2 xy = means2D[g];
-    const float4 co = conic_opacity[g];
-    // power below which opacity*exp(power) is certainly < 1/255 (1 % safety margin):
-    // lets the blend kernels skip the exp for far-away pixels without changing any result.
-    const float reject = -logf(255.0f * co.w) - 0.01f;
-    float4* r = rec + 3 * (size_t)(start + i);
-    r[0] = make_float4(xy.x, xy.y, co.x, co.y);
-    r[1] = make_float4(co.z, co.w, reject, __uint_as_float(g));
-    r[2] = make_float4(colors[3 * (size_t)g], colors[3 * (size_t)g + 1], colors[3 * (size_t)g + 2], 0.f);
+  for (uint32_t i = threadIdx.x; i < n; i += kThreads) items[start + i] = buf[i];
+  // three consecutive threads copy the three float4 of a record: coalesced on both sides
+  const uint32_t pieces = 3u * n;
+  constexpr int kInFlight = 4;
+  for (uint32_t q0 = 0; q0 < pieces; q0 += kThreads * kInFlight) {
+    float4 t[kInFlight];
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const uint32_t q = q0 + (uint32_t)kThreads * u + threadIdx.x;
+      if (q < pieces) {
+        const uint32_t pos = q / 3u, piece = q - 3u * pos;
+        t[u] = __ldg(splat_rec + 3 * (size_t)(uint32_t)(buf[pos] & 0xffffffffu) + piece);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const uint32_t q = q0 + (uint32_t)kThreads * u + threadIdx.x;
+      if (q < pieces) rec[3 * (size_t)start + q] = t[u];
+    }
   }
 }
 
-constexpr int kSortSmallThreads = 128;
+// ---- lists shorter than kSortSmallCap (= 512): ONE WARP per tile, sorted entirely in registers ----
+// Lane l holds the kE consecutive network positions l*kE .. l*kE+kE-1 (n_pad = 32*kE).  The
+// compare-exchange stages with distance j < kE stay inside a thread; those with j >= kE are
+// exchanges with lane l ^ (j / kE) through shuffles.  No shared memory, no barriers: the CTA-wide
+// shared-memory version of this kernel was bound by the shared-memory pipe (ncu: mio_throttle).
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, lane_mask);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), lane_mask);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+template <int kE>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&v)[kE], int lane) {
+  constexpr int kN = 32 * kE;
+#pragma unroll
+  for (int k = 2; k <= kN; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= kE) {
+        // partner lane; ascending iff bit k of the network position is clear
+        const int lm = j / kE;
+        const bool lower = (lane & lm) == 0;
+        const bool up = (k >= kN) ? true : ((lane & (k / kE)) == 0);
+        const bool take_min = lower == up;
+#pragma unroll
+        for (int e = 0; e < kE; ++e) {
+          const uint64_t o = shfl_xor_u64(v[e], lm);
+          v[e] = take_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < kE; ++e) {
+          if ((e & j) == 0) {
+            const int f = e | j;
+            // bit k of (lane*kE + e): inside the thread when k < kE, else a lane bit
+            const bool up = (k < kE) ? ((e & k) == 0) : ((k >= kN) ? true : ((lane & (k / kE)) == 0));
+            const uint64_t a = v[e], b = v[f];
+            const bool swap = (a > b) == up;
+            v[e] = swap ? b : a;
+            v[f] = swap ? a : b;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int kE>
+__device__ __forceinline__ void warp_sort_pack_tile(uint32_t n, uint32_t start, int lane,
+                                                    uint64_t* __restrict__ items,
+                                                    const float4* __restrict__ splat_rec,
+                                                    float4* __restrict__ rec, uint32_t* s_g) {
+  uint64_t v[kE];
+#pragma unroll
+  for (int e = 0; e < kE; ++e) {
+    const uint32_t i = (uint32_t)lane * kE + e;
+    v[e] = i < n ? items[start + i] : ~0ull;
+  }
+  warp_bitonic_sort<kE>(v, lane);
+  // Sorted position lane*kE + e sits in v[e].  The sorted Gaussian ids go through shared memory
+  // so that each record can be copied by THREE lanes (one float4 each), consecutive lanes
+  // covering consecutive 16-byte pieces: the gathers are 48-byte contiguous reads and the record
+  // stream leaves in full, coalesced lines.
+#pragma unroll
+  for (int e = 0; e < kE; ++e) s_g[lane * kE + e] = (uint32_t)v[e];
+  __syncwarp();
+  const uint32_t pieces = 3u * n;
+  constexpr int kInFlight = 8;  // gathers in flight per lane (the copy is pure latency otherwise)
+  for (uint32_t q0 = 0; q0 < pieces; q0 += 32 * kInFlight) {
+    float4 t[kInFlight];
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const uint32_t q = q0 + 32u * u + lane;
+      if (q < pieces) {
+        const uint32_t pos = q / 3u, piece = q - 3u * pos;  // sorted position and float4 index
+        t[u] = __ldg(splat_rec + 3 * (size_t)s_g[pos] + piece);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kInFlight; ++u) {
+      const uint32_t q = q0 + 32u * u + lane;
+      if (q < pieces) rec[3 * (size_t)start + q] = t[u];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < kE; ++e) {
+    const uint32_t i = (uint32_t)lane * kE + e;
+    if (i < n) items[start + i] = v[e];
+  }
+}
+
+constexpr int kSortSmallThreads = 128;  // four tiles per CTA
 constexpr int kSortLargeThreads = 512;
 
 __global__ void __launch_bounds__(kSortSmallThreads)
-tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, uint32_t T,
                             BinHeader* __restrict__ bin_hdr, uint32_t capacity, uint64_t* __restrict__ items,
-                            const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-                            const float* __restrict__ colors, float4* __restrict__ rec) {
-  __shared__ uint64_t s_buf[kSortSmallCap];
+                            const float4* __restrict__ splat_rec, float4* __restrict__ rec) {
+  __shared__ uint32_t s_g[kSortSmallThreads / 32][kSortSmallCap];  // sorted Gaussian ids, per warp
   if (blockIdx.x == 0 && threadIdx.x == 0) bin_hdr->capacity = capacity;  // read by gsr_export_binning
-  const uint2 range = ranges[order[blockIdx.x]];
+  const int lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * kSortSmallThreads + threadIdx.x) >> 5;
+  if (w >= T) return;
+  const uint2 range = ranges[order[w]];
   const uint32_t n = range.y - range.x;
   if (n == 0 || n >= (uint32_t)kSortSmallCap || range.y > capacity) return;  // long lists: other launch
-  sort_pack_tile<kSortSmallThreads>(s_buf, n, range.x, items, means2D, conic_opacity, colors, rec);
+  if (n <= 32) warp_sort_pack_tile<1>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
+  else if (n <= 64) warp_sort_pack_tile<2>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
+  else if (n <= 128) warp_sort_pack_tile<4>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
+  else if (n <= 256) warp_sort_pack_tile<8>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
+  else warp_sort_pack_tile<16>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(kSortLargeThreads)
 tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
                            const GeomHeader* __restrict__ hdr, uint32_t T, uint32_t capacity,
                            uint64_t* __restrict__ items, uint64_t* __restrict__ scratch,
-                           const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-                           const float* __restrict__ colors, float4* __restrict__ rec) {
+                           const float4* __restrict__ splat_rec, float4* __restrict__ rec) {
   extern __shared__ __align__(16) uint64_t s_dyn[];
   // The lists of kSortSmallCap or more entries are exactly the first num_long_tiles entries of
   // the LPT order (kSortSmallCap is a multiple of its 4-entry bucket width).
@@ -358,24 +469,22 @@ tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
     const uint32_t n = range.y - range.x;
     if (n < (uint32_t)kSortSmallCap || range.y > capacity) continue;
     if (n <= (uint32_t)kSortLargeCap) {
-      sort_pack_tile<kSortLargeThreads>(s_dyn, n, range.x, items, means2D, conic_opacity, colors, rec);
+      sort_pack_tile<kSortLargeThreads>(s_dyn, n, range.x, items, splat_rec, rec);
     } else {
       // padded copy at scratch[2 * start, 2 * start + next_pow2(n)): ranges of different tiles
       // cannot overlap because next_pow2(n) <= 2 n
-      sort_pack_tile<kSortLargeThreads>(scratch + 2 * (size_t)range.x, n, range.x, items, means2D,
-                                        conic_opacity, colors, rec);
+      sort_pack_tile<kSortLargeThreads>(scratch + 2 * (size_t)range.x, n, range.x, items, splat_rec, rec);
     }
     __syncthreads();
   }
 }
 
 int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
-                          BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch, const float2* means2D,
-                          const float4* conic_opacity, const float* colors, float4* rec,
-                          cudaStream_t s) {
+                          BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
+                          const float4* splat_rec, float4* rec, cudaStream_t s) {
   if (T == 0) return 0;
-  tile_sort_pack_small_kernel<<<T, kSortSmallThreads, 0, s>>>(ranges, order, bin_hdr, capacity, items, means2D,
-                                                              conic_opacity, colors, rec);
+  tile_sort_pack_small_kernel<<<(T + 3) / 4, kSortSmallThreads, 0, s>>>(ranges, order, T, bin_hdr, capacity,
+                                                                        items, splat_rec, rec);
   GSR_LAUNCHED();
   static bool attr_set = false;
   const int dyn = kSortLargeCap * (int)sizeof(uint64_t);
@@ -386,8 +495,7 @@ int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order
     attr_set = true;
   }
   tile_sort_pack_long_kernel<<<148, kSortLargeThreads, dyn, s>>>(ranges, order, hdr, T, capacity, items,
-                                                                 scratch, means2D, conic_opacity, colors,
-                                                                 rec);
+                                                                 scratch, splat_rec, rec);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -163,7 +163,7 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.vec_ok = (al & 15) == 0;
   pp.radii = a->radii; pp.depths = g.depths; pp.means2D = g.means2D;
   pp.conic_opacity = g.conic_opacity; pp.rgb = g.rgb; pp.clamped = g.clamped;
-  pp.tiles_touched = g.tiles_touched; pp.vis_items = g.vis_items; pp.num_visible = &g.hdr->num_visible;
+  pp.tiles_touched = g.tiles_touched; pp.splat_rec = g.splat_rec; pp.vis_items = g.vis_items; pp.num_visible = &g.hdr->num_visible;
   pp.tile_count = im.tile_count;
   GSR_PROF("preprocess", launch_preprocess(pp, s));
   if (a->radii_ready_event) GSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->radii_ready_event), s));
@@ -193,7 +193,6 @@ int gsr_forward(const gsr_forward_args* a) {
     have_R = true;
     cap = R;
   }
-  const float* colors = a->colors_precomp ? a->colors_precomp : g.rgb;
   BinView b;
   for (int attempt = 0; attempt < 2; ++attempt) {
     char* bin_base = a->binning_resize(a->binning_user, bin_bytes((size_t)cap));
@@ -208,7 +207,7 @@ int gsr_forward(const gsr_forward_args* a) {
                                    g.conic_opacity, a->radii, gx, gy, im.ranges, im.tile_fill, b.items, cap,
                                    &g.hdr->num_large, g.large_list, s));
       GSR_PROF("tile_sort_pack", launch_tile_sort_pack(T, im.ranges, im.tile_order, g.hdr, b.hdr, cap, b.items, b.scratch,
-                                                       g.means2D, g.conic_opacity, colors, b.rec, s));
+                                                       g.splat_rec, b.rec, s));
     }
     GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
                             im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, s));

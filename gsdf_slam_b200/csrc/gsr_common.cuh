@@ -47,6 +47,7 @@ struct GeomView {
   uint8_t* clamped;          // [P] bit c set <=> channel c was clamped
   float* acc;                // [12P] backward moment sums {Mx,My,Mxx,Mxy,Myy,M0,r,g,b,-,-,-}
   uint64_t* vis_items;       // [P] compacted rendered Gaussians (depth_bits<<32 | idx), unordered
+  float4* splat_rec;         // [P][3] packed splat record of every rendered Gaussian (copied per duplicate)
   uint32_t* large_list;      // [2P] work queue of the large rectangles (emit stage)
 };
 
@@ -64,10 +65,10 @@ struct ImageView {
   uint32_t* tile_order;      // [T] tiles sorted by list length, longest first (CTA launch order)
 };
 
-// per-tile sort (binning.cu): lists shorter than kSortSmallCap are sorted in static shared
-// memory, lists up to kSortLargeCap in 128 KB of dynamic shared memory, longer ones in global
+// per-tile sort (binning.cu): lists shorter than kSortSmallCap are sorted in registers by one
+// warp, lists up to kSortLargeCap in 128 KB of dynamic shared memory, longer ones in global
 // scratch.  kSortSmallCap must be a multiple of 4 and < 4096 (LPT bucket layout of tile_meta_kernel).
-constexpr int kSortSmallCap = 2048;
+constexpr int kSortSmallCap = 512;
 constexpr int kSortLargeCap = 16384;
 
 // Per-duplicate buffer.  Its layout must not depend on the exact R (the forward pass sizes it
@@ -106,6 +107,7 @@ inline GeomView geom_view(char* base, size_t P) {
   g.clamped = carve<uint8_t>(p, P);
   g.acc = carve<float>(p, 12 * P);
   g.vis_items = carve<uint64_t>(p, P);
+  g.splat_rec = carve<float4>(p, 3 * P);
   g.large_list = carve<uint32_t>(p, 2 * P);
   return g;
 }

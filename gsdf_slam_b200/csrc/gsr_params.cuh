@@ -32,6 +32,7 @@ struct PreprocessParams {
   float* rgb;
   uint8_t* clamped;
   uint32_t* tiles_touched;
+  float4* splat_rec;      // [P][3] {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}
   uint64_t* vis_items;    // compacted (depth_bits<<32 | idx) of the rendered Gaussians
   uint32_t* num_visible;  // its length (zeroed by the caller)
   uint32_t* tile_count;   // [T] += 1 per (Gaussian, tile) that passes the exact test (zeroed by the caller)
@@ -79,9 +80,8 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
                 uint64_t* items, uint32_t capacity, uint32_t* large_count, uint32_t* large_list,
                 cudaStream_t s);
 int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
-                          BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch, const float2* means2D,
-                          const float4* conic_opacity, const float* colors, float4* rec,
-                          cudaStream_t s);
+                          BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
+                          const float4* splat_rec, float4* rec, cudaStream_t s);
 int launch_export_binning(uint32_t T, const uint2* ranges, const uint64_t* items, uint64_t* keys,
                           uint32_t* point_list, cudaStream_t s);
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,

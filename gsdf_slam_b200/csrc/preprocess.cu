@@ -289,9 +289,22 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
     uint32_t base_pos = 0;
     if (lane == 0) base_pos = atomicAdd(a.num_visible, (uint32_t)__popc(vm));
     base_pos = __shfl_sync(0xffffffffu, base_pos, 0);
-    if (rendered)
+    if (rendered) {
       a.vis_items[base_pos + __popc(vm & ((1u << lane) - 1u))] =
           ((uint64_t)__float_as_uint(p_view.z) << 32) | (uint32_t)idx;
+      // the packed record the binning stage copies once per (Gaussian, tile) duplicate
+      float3 c = rgb;
+      if (a.colors_precomp != nullptr)
+        c = {a.colors_precomp[3 * (size_t)idx], a.colors_precomp[3 * (size_t)idx + 1],
+             a.colors_precomp[3 * (size_t)idx + 2]};
+      // power below which opacity*exp(power) is certainly < 1/255 (1 % safety margin): lets the
+      // blend kernels skip the exp for far-away pixels without changing any result
+      const float reject = -logf(255.0f * opacity) - 0.01f;
+      float4* r = a.splat_rec + 3 * (size_t)idx;
+      r[0] = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+      r[1] = make_float4(conic.z, opacity, reject, __uint_as_float((uint32_t)idx));
+      r[2] = make_float4(c.x, c.y, c.z, 0.f);
+    }
   }
 }
 
