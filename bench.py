@@ -177,11 +177,12 @@ def stage_model(counts, tile_bits):
         "finalize": 8 * R + 36 * R + 48 * R + 8 * T,
         "blend_fwd": 48 * R + 32 * N + 4 * T,
         "blend_bwd": 48 * counts["sum_max_contrib"] + 32 * N + 72 * R,
-        "preprocess_bwd": (87 + 12 * M) * V + 48 * V + (52 + 12 * M) * P + 4 * P,
+        "preprocess_bwd": (87 + 12 * M) * V + 48 * V + (52 + 12 * M) * V + 4 * V,  # rendered rows only
         "adam": 28 * (14 + 3 * M) * P,
         # visibility-split Adam: rows without gradient move 24 B/element (grad not read)
         "adam_rows_zero_grad": 24 * (14 + 3 * M) * (P - V),
         "adam_rows_with_grad": 28 * (14 + 3 * M) * V,
+        "adam_rows_all": (24 * P + 4 * V) * (14 + 3 * M),
     }
     f = {"blend_fwd": 25 * E, "blend_bwd": 60 * E}
     return b, f
@@ -250,7 +251,7 @@ def run_product(args, rank, world, dev):
             keep["color"] = color
 
         mapper.step([kf], on_forward=after_forward)
-        chk_host.copy_(mapper.grad_views["opacity"].sum().reshape(1), non_blocking=True)
+        chk_host.copy_(mapper.opt_params["opacity"].sum().reshape(1), non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         copy_stream.synchronize()
 
@@ -364,7 +365,9 @@ def run_product(args, rank, world, dev):
                    "P": counts["P"], "sh_degree": scene.degree, "image": [cam.W, cam.H],
                    "keyframes_per_step": world, "parallelism": f"dp{world} (keyframe batch)",
                    "l2_policy": "working set (params+grads+Adam state+scratch ~0.7 GB) exceeds the 126 MB L2",
-                   "adam": "fused, on a raw-parameter shadow copy (render inputs frozen)"},
+                   "adam": ("fused, on a raw-parameter shadow copy (render inputs frozen); single rank: one "
+                            "masked pass (gsr_adam_step_rows ALL) that reads the gradient only for the "
+                            "rendered rows, the backward pass skips the dense zero fill")},
         "counts": counts,
         "e2e": {"value": round(world * 1000.0 / e2e_step, 2), "unit": UNIT, "ms_per_step": round(e2e_step, 4),
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},

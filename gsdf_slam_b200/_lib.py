@@ -54,7 +54,7 @@ class BackwardArgs(C.Structure):
         ("dL_dcolor", C.c_void_p), ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p),
         ("dL_ddc", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p),
-        ("debug", C.c_int), ("stream", C.c_void_p),
+        ("debug", C.c_int), ("stream", C.c_void_p), ("rendered_rows_only", C.c_int),
     ]
 
 

@@ -150,11 +150,15 @@ struct AdamRowsParams {
 // every group.  The grid is deliberately small (a CTA or two per SM) so that the kernel can sit
 // on a side stream next to the rasterizer kernels without taking their registers away.
 #ifndef GSR_ADAM_ROWS_VEC
-#define GSR_ADAM_ROWS_VEC 2
+#define GSR_ADAM_ROWS_VEC 1
 #endif
 constexpr int kAdamRowsVec = GSR_ADAM_ROWS_VEC;                    // float4 per thread and array
-constexpr int kAdamRowsChunk = kAdamThreads * kAdamRowsVec * 4;   // 2048 elements per chunk
+constexpr int kAdamRowsChunk = kAdamThreads * kAdamRowsVec * 4;   // 1024 elements per chunk
 
+// kAll = false: phase 0, rows without gradient only (grad never read).
+// kAll = true : every row; grad is read for the rendered rows and taken as +0 for the others
+//               (whose grad memory may be uninitialised: select, never multiply).
+template <bool kAll>
 __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, int chunk) {
   const AdamParams& a = ar.base;
   int gi = 0;
@@ -172,7 +176,7 @@ __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, i
   const unsigned rem_base = (unsigned)((unsigned long long)base - (unsigned long long)row_base * w);
 
   if (G.vec_ok && end - base == kAdamRowsChunk) {
-    unsigned mine[kAdamRowsVec];  // bit j set <=> element j of the float4 belongs to a row without gradient
+    unsigned mine[kAdamRowsVec];  // bit j set <=> element j of the float4 belongs to a row WITHOUT gradient
 #pragma unroll
     for (int k = 0; k < kAdamRowsVec; ++k) {
       const unsigned o = rem_base + 4u * (unsigned)(k * kAdamThreads + threadIdx.x);  // < chunk + width
@@ -188,11 +192,19 @@ __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, i
       }
       mine[k] = bits;
     }
-    float4 p4[kAdamRowsVec], m4[kAdamRowsVec], v4[kAdamRowsVec];
+    float4 p4[kAdamRowsVec], m4[kAdamRowsVec], v4[kAdamRowsVec], g4[kAdamRowsVec];
 #pragma unroll
     for (int k = 0; k < kAdamRowsVec; ++k) {
       const long long e = base / 4 + k * kAdamThreads + threadIdx.x;
-      if (mine[k]) {
+      g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kAll && mine[k] != 15u) {
+        const float4 g = __ldcs(reinterpret_cast<const float4*>(G.g) + e);
+        g4[k].x = (mine[k] & 1u) ? 0.f : g.x;
+        g4[k].y = (mine[k] & 2u) ? 0.f : g.y;
+        g4[k].z = (mine[k] & 4u) ? 0.f : g.z;
+        g4[k].w = (mine[k] & 8u) ? 0.f : g.w;
+      }
+      if (kAll || mine[k]) {
         // streaming (evict-first) accesses: this sweep must not push the rasterizer's working
         // set (splat records, moment sums) out of L2 while it runs beside the blend kernels
         p4[k] = __ldcs(reinterpret_cast<const float4*>(G.p) + e);
@@ -202,13 +214,13 @@ __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, i
     }
 #pragma unroll
     for (int k = 0; k < kAdamRowsVec; ++k) {
-      if (!mine[k]) continue;
-      adam_elem(p4[k].x, 0.0f, m4[k].x, v4[k].x, a, G);
-      adam_elem(p4[k].y, 0.0f, m4[k].y, v4[k].y, a, G);
-      adam_elem(p4[k].z, 0.0f, m4[k].z, v4[k].z, a, G);
-      adam_elem(p4[k].w, 0.0f, m4[k].w, v4[k].w, a, G);
+      if (!kAll && !mine[k]) continue;
+      adam_elem(p4[k].x, g4[k].x, m4[k].x, v4[k].x, a, G);
+      adam_elem(p4[k].y, g4[k].y, m4[k].y, v4[k].y, a, G);
+      adam_elem(p4[k].z, g4[k].z, m4[k].z, v4[k].z, a, G);
+      adam_elem(p4[k].w, g4[k].w, m4[k].w, v4[k].w, a, G);
       const long long e = base / 4 + k * kAdamThreads + threadIdx.x;
-      if (mine[k] == 15u) {
+      if (kAll || mine[k] == 15u) {
         __stcs(reinterpret_cast<float4*>(G.p) + e, p4[k]);
         __stcs(reinterpret_cast<float4*>(G.m) + e, m4[k]);
         __stcs(reinterpret_cast<float4*>(G.v) + e, v4[k]);
@@ -231,9 +243,10 @@ __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, i
     for (long long e = base + threadIdx.x; e < end; e += kAdamThreads) {
       const unsigned o = rem_base + (unsigned)(e - base);
       const unsigned row = row_base + ((w == 1u) ? o : __umulhi(o, magic));
-      if (__ldg(mask + row) > 0) continue;
+      const bool rendered = __ldg(mask + row) > 0;
+      if (!kAll && rendered) continue;
       float p = G.p[e], m = G.m[e], v = G.v[e];
-      adam_elem(p, 0.0f, m, v, a, G);
+      adam_elem(p, (kAll && rendered) ? G.g[e] : 0.0f, m, v, a, G);
       G.p[e] = p;
       G.m[e] = m;
       G.v[e] = v;
@@ -242,7 +255,10 @@ __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, i
 }
 
 __global__ void __launch_bounds__(kAdamThreads) adam_rows_zero_grad_kernel(const AdamRowsParams ar, int chunks) {
-  for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) adam_zero_grad_chunk(ar, chunk);
+  for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) adam_zero_grad_chunk<false>(ar, chunk);
+}
+__global__ void __launch_bounds__(kAdamThreads) adam_rows_all_kernel(const AdamRowsParams ar) {
+  adam_zero_grad_chunk<true>(ar, (int)blockIdx.x);
 }
 
 // Phase 1 (rows WITH gradient, typically ~15 % and scattered): row-oriented.  A warp takes 32
@@ -363,7 +379,7 @@ int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double
 int launch_adam_rows(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
                      float grad_scale, int64_t rows, const int* row_mask, int phase, cudaStream_t s) {
   if (n_groups <= 0 || rows <= 0) return 0;
-  if (!row_mask || (phase != 0 && phase != 1)) return GSR_ERR_BAD_ARG;
+  if (!row_mask || phase < 0 || phase > 2) return GSR_ERR_BAD_ARG;
   AdamRowsParams ar;
   int blocks = 0;
   const int rc = build_adam_params(groups, n_groups, beta1, beta2, eps, grad_scale, ar.base, blocks,
@@ -390,6 +406,8 @@ int launch_adam_rows(const gsr_adam_group* groups, int n_groups, double beta1, d
     }();
     const int grid = blocks < 148 * per_sm ? blocks : 148 * per_sm;
     adam_rows_zero_grad_kernel<<<grid, kAdamThreads, 0, s>>>(ar, blocks);
+  } else if (phase == 2) {
+    adam_rows_all_kernel<<<blocks, kAdamThreads, 0, s>>>(ar);
   } else {
     AdamVisParams vp;
     vp.rows = ar;

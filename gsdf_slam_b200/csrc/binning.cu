@@ -101,7 +101,8 @@ tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, uint2* __r
     const bool in = t < T;
     const uint32_t c = in ? tile_count[t] : 0u;
     if (in) {
-      ranges[t] = make_uint2(run, run + c);
+      // empty tiles keep (0, 0) like the reference's zero-initialised ranges array
+      ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
       max_contrib[t] = 0;
     }
     run += c;

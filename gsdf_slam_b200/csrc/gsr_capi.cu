@@ -272,7 +272,7 @@ int gsr_backward(const gsr_backward_args* a) {
   bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
   bp.dL_dcolor = a->dL_dcolor; bp.dL_dmean3D = a->dL_dmean3D; bp.dL_dcov3D = a->dL_dcov3D;
   bp.dL_ddc = a->dL_ddc; bp.dL_dsh = a->dL_dsh; bp.dL_dscale = a->dL_dscale; bp.dL_drot = a->dL_drot;
-  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible, s));
+  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible, a->rendered_rows_only == 0, s));
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));
     GSR_CUDA(cudaGetLastError());
@@ -311,7 +311,8 @@ int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
                        float grad_scale, int64_t rows, const int32_t* row_mask, int phase, void* stream) {
   if (n_groups < 0 || (n_groups > 0 && !groups) || rows < 0) return GSR_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  GSR_PROF(phase == GSR_ADAM_ROWS_ZERO_GRAD ? "adam_rows_zero_grad" : "adam_rows_with_grad",
+  GSR_PROF(phase == GSR_ADAM_ROWS_ZERO_GRAD ? "adam_rows_zero_grad"
+           : phase == GSR_ADAM_ROWS_WITH_GRAD ? "adam_rows_with_grad" : "adam_rows_all",
            launch_adam_rows(groups, n_groups, beta1, beta2, eps, grad_scale, rows, row_mask, phase, s));
   return GSR_OK;
 }

@@ -93,7 +93,7 @@ int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_ord
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s);
 int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,
-                          cudaStream_t s);
+                          bool zero_fill, cudaStream_t s);
 int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
                 float grad_scale, cudaStream_t s);
 size_t knn_temp_bytes(int64_t P);

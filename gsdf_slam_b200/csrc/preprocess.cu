@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
   }
 
   // ---- outputs -----------------------------------------------------------------
-  const bool rendered = visible && ntiles > 0;
+  // every Gaussian with radii > 0 is listed (also the few whose tiles all fail the opacity-aware
+  // test): the list is exactly the set of rows the backward pass writes, i.e. the radii mask
+  const bool rendered = visible;
   if (in_range) {
     a.radii[idx] = visible ? (int)my_radius : 0;
     a.tiles_touched[idx] = ntiles;
@@ -281,8 +283,7 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
       }
     }
   }
-  // compacted list of the rendered Gaussians (those that own at least one tile), one
-  // warp-aggregated atomic per warp.  Its order is irrelevant: the emit stage and the backward
+  // compacted list of the visible Gaussians (radii > 0), one warp-aggregated atomic per warp.  Its order is irrelevant: the emit stage and the backward
   // preprocess only need the set, the depth order is established per tile (binning.cu).
   const unsigned vm = __ballot_sync(0xffffffffu, rendered);
   if (vm) {

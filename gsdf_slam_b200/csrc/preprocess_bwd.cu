@@ -454,7 +454,7 @@ preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
 }
 
 int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,
-                          cudaStream_t s) {
+                          bool zero_fill, cudaStream_t s) {
   if (p.P <= 0) return 0;
   if (p.M > 15) return GSR_ERR_BAD_ARG;
   const long long P = p.P;
@@ -473,7 +473,7 @@ int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const u
   add(p.dL_dmean3D, 3 * P); add(p.dL_dcov3D, 6 * P); add(p.dL_ddc, 3 * P);
   add(p.dL_dsh, 3LL * (p.M < 15 ? p.M : 15) * P); add(p.dL_dscale, 3 * P); add(p.dL_drot, 4 * P);
   z.first_block[z.n] = blocks;
-  if (blocks > 0) {
+  if (blocks > 0 && zero_fill) {
     zero_fill_kernel<<<blocks, kZeroThreads, 0, s>>>(z);
     GSR_LAUNCHED();
   }

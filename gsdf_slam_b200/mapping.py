@@ -73,7 +73,8 @@ class KeyframeBatchMapper:
 
     def __init__(self, params: Dict[str, torch.Tensor], degree: int, bg: torch.Tensor,
                  lr: Optional[Dict[str, float]] = None, eps: float = 1e-15,
-                 process_group=None, freeze_render_inputs: bool = False, overlap_adam: bool = False):
+                 process_group=None, freeze_render_inputs: bool = False, overlap_adam: bool = False,
+                 masked_single_view: bool = True):
         self.params = {k: params[k].contiguous() for k in SEGMENTS}
         self.degree = int(degree)
         self.bg = bg
@@ -100,6 +101,11 @@ class KeyframeBatchMapper:
         # (cfg2) the streaming sweep slows the co-running blend kernels by as much as it hides
         # (step 1.08 ms vs 0.99 ms fused), so the fused single launch stays the default
         self.overlap_adam = bool(overlap_adam) and dev.type == "cuda"
+        # single rank, one keyframe: the backward pass writes only the rendered rows (no dense
+        # zero fill) and ONE masked Adam pass reads the gradient only for those rows
+        # (gsr_adam_step_rows, GSR_ADAM_ROWS_ALL) — 276 + 59*4 bytes per non-rendered Gaussian less
+        # HBM traffic per iteration than zero-fill + dense Adam, bit-identical result
+        self.masked_single_view = bool(masked_single_view) and dev.type == "cuda"
         self.serialize_side_stream = False   # profiling aid: run the side-stream work on the main stream
         self.trace = None                    # profiling aid: list collecting (label, timing event) pairs
         self._side: Optional[torch.cuda.Stream] = None
@@ -127,7 +133,8 @@ class KeyframeBatchMapper:
                                       kf.W, p["dc"], p["sh"], self.degree, kf.campos, False, False,
                                       radii_ready_event=radii_ready_event)
 
-    def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor], fwd=None, on_forward=None):
+    def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor], fwd=None, on_forward=None,
+                        rendered_rows_only: bool = False):
         """fwd + bwd of one keyframe; parameter gradients are written into grad_views.
         ``on_forward(kf, fwd)`` runs between the two passes (e.g. to start reading the image back
         and to make the stream wait for the uploaded dL/d(image))."""
@@ -142,7 +149,8 @@ class KeyframeBatchMapper:
         g = RasterizeGaussiansBackwardCUDA(self.bg, p["means3D"], radii, e, p["scales"], p["rotations"], 1.0,
                                            e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy,
                                            kf.dL_dout, p["dc"], p["sh"], self.degree, kf.campos, geom, R,
-                                           binning, img, B, sample, False, want_dcov3D=False, out=out)
+                                           binning, img, B, sample, False, want_dcov3D=False, out=out,
+                                           rendered_rows_only=rendered_rows_only)
         self.last_radii, self.last_color = radii, color
         return color, radii, g
 
@@ -302,6 +310,13 @@ class KeyframeBatchMapper:
         """One mapping iteration over this rank's keyframes."""
         if self.overlap_adam and self.world_size == 1 and len(keyframes) > 0 and self.P > 0:
             self._step_overlapped(keyframes, grad_scale, on_forward)
+            return
+        if self.masked_single_view and self.world_size == 1 and len(keyframes) == 1 and self.P > 0:
+            _, radii, _ = self.render_backward(keyframes[0], self.grad_views, on_forward=on_forward,
+                                               rendered_rows_only=True)
+            grads = {self.opt_params[k]: self.grad_views[k] for k in SEGMENTS if self.opt_params[k].numel() > 0}
+            self.optimizer.step_rows(radii, self.optimizer.ROWS_ALL, grads=grads, grad_scale=grad_scale,
+                                     new_step=True)
             return
         self.accumulate(keyframes, on_forward)
         self.exchange_and_update(grad_scale)

@@ -80,6 +80,7 @@ class FusedAdam:
 
     ROWS_ZERO_GRAD = 0   # gsr_capi.h: GSR_ADAM_ROWS_ZERO_GRAD
     ROWS_WITH_GRAD = 1   # gsr_capi.h: GSR_ADAM_ROWS_WITH_GRAD
+    ROWS_ALL = 2         # gsr_capi.h: GSR_ADAM_ROWS_ALL
 
     @torch.no_grad()
     def step_rows(self, row_mask: torch.Tensor, phase: int, grads=None, grad_scale: float = 1.0,
@@ -90,13 +91,15 @@ class FusedAdam:
         ``row_mask`` is int32 (> 0: the row received a gradient, e.g. the rasterizer's ``radii``).
         ``phase=ROWS_ZERO_GRAD`` updates the other rows with a gradient of exactly zero and does
         not read ``grads`` (so it can run before / while the backward pass executes);
-        ``phase=ROWS_WITH_GRAD`` updates the marked rows.  Pass ``new_step=True`` to exactly one
-        of the two calls of an iteration (the first): it advances the step counters."""
+        ``phase=ROWS_WITH_GRAD`` updates the marked rows; ``phase=ROWS_ALL`` updates every row in
+        one pass, reading ``grads`` only for the marked rows (the other rows of ``grads`` may be
+        uninitialised).  Pass ``new_step=True`` to exactly one call of an iteration (the first):
+        it advances the step counters."""
         L = _lib.lib()
         if row_mask.dtype != torch.int32 or not row_mask.is_contiguous():
             raise RuntimeError("row_mask must be a contiguous int32 tensor")
         rows = int(row_mask.numel())
-        need_grad = phase == self.ROWS_WITH_GRAD
+        need_grad = phase != self.ROWS_ZERO_GRAD
         for (b1, b2, eps, dev), items in self._collect(grads, bump_step=new_step, need_grad=need_grad).items():
             for i in range(0, len(items), 16):
                 chunk = items[i:i + 16]

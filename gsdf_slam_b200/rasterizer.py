@@ -116,12 +116,16 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                                    scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx,
                                    tan_fovy, dL_dout_color, dc, sh, degree, campos, geomBuffer, R,
                                    binningBuffer, imageBuffer, B, sampleBuffer, debug,
-                                   want_dcov3D: bool = True, out: Optional[dict] = None):
+                                   want_dcov3D: bool = True, out: Optional[dict] = None,
+                                   rendered_rows_only: bool = False):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh,
     dL_dscales, dL_drotations)   (same order as src/rasterize_points.cu:204)
 
     ``out`` (extension): optional dict name -> preallocated contiguous tensor (e.g. views into
-    the flat gradient arena that is all-reduced across GPUs) to receive a gradient in place."""
+    the flat gradient arena that is all-reduced across GPUs) to receive a gradient in place.
+    ``rendered_rows_only`` (extension): write only the rows of the rendered Gaussians and leave
+    the others untouched (no dense zero fill) — for consumers that go through the ``radii`` mask
+    (``FusedAdam.step_rows(..., ROWS_ALL)``)."""
     L = _lib.lib()
     dev = means3D.device
     P = int(means3D.size(0))
@@ -165,7 +169,8 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             dL_dmean2D=_ptr(dL_dmeans2D), dL_dconic=None, dL_dopacity=_ptr(dL_dopacity),
             dL_dcolor=_ptr(dL_dcolors), dL_dmean3D=_ptr(dL_dmeans3D), dL_dcov3D=_ptr(dL_dcov3D),
             dL_ddc=_ptr(dL_ddc), dL_dsh=_ptr(dL_dsh), dL_dscale=_ptr(dL_dscales),
-            dL_drot=_ptr(dL_drotations), debug=int(bool(debug)), stream=_stream(dev))
+            dL_drot=_ptr(dL_drotations), debug=int(bool(debug)), stream=_stream(dev),
+            rendered_rows_only=int(bool(rendered_rows_only)))
         with torch.cuda.device(dev):
             _lib.check(L.gsr_backward(C.byref(a)), "gsr_backward")
     if dL_dcov3D is None:

@@ -118,6 +118,11 @@ typedef struct gsr_backward_args {
   float* dL_drot;              /* [P,4] */
   int debug;
   void* stream;
+  int rendered_rows_only;      /* !=0: write only the rows of the rendered Gaussians (radii > 0 and at
+                                  least one tile) and leave every other row of the outputs UNTOUCHED
+                                  instead of zero-filling it — for callers that consume the gradients
+                                  through the radii mask (gsr_adam_step_rows); saves the dense zero
+                                  stream (276 B per Gaussian) */
 } gsr_backward_args;
 
 int gsr_forward(const gsr_forward_args* a);
@@ -157,6 +162,10 @@ int gsr_adam_step(const gsr_adam_group* groups, int n_groups, double beta1,
  * masked-out rows of `grad` hold +0, which gsr_backward guarantees. */
 #define GSR_ADAM_ROWS_ZERO_GRAD 0
 #define GSR_ADAM_ROWS_WITH_GRAD 1
+/* phase GSR_ADAM_ROWS_ALL: one pass over every row; `grad` is read only where row_mask > 0 and
+ * taken as +0 elsewhere, so the masked-out rows of `grad` may hold anything (see
+ * gsr_backward_args.rendered_rows_only).  Same result as gsr_adam_step on a zero-filled grad. */
+#define GSR_ADAM_ROWS_ALL 2
 int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
                        double beta2, double eps, float grad_scale, int64_t rows,
                        const int32_t* row_mask, int phase, void* stream);

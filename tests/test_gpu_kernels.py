@@ -129,6 +129,39 @@ def test_visibility_split_adam_is_bit_identical_to_the_fused_step(rows, vis_frac
             assert oa.state[a]["step"] == ob.state[b]["step"] == step
 
 
+def test_masked_single_pass_adam_ignores_the_masked_out_gradient_rows():
+    """GSR_ADAM_ROWS_ALL == gsr_adam_step on a zero-filled gradient, bit for bit, even when the
+    rows with radii == 0 hold NaN (gsr_backward with rendered_rows_only leaves them untouched)."""
+    from gsdf_slam_b200 import FusedAdam
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    rows = 33_333
+    shapes = [(rows, 3), (rows, 1, 3), (rows, 15, 3), (rows, 1), (rows, 3), (rows, 4)]
+    lrs = [1.6e-4, 0.0025, 0.000125, 0.05, 0.005, 0.001]
+    pa = [torch.randn(s, device="cuda", generator=gen) for s in shapes]
+    pb = [p.clone() for p in pa]
+    oa = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(pa, lrs)], lr=0.0, eps=1e-15)
+    ob = FusedAdam([{"params": [p], "lr": lr} for p, lr in zip(pb, lrs)], lr=0.0, eps=1e-15)
+    for step in range(1, 4):
+        radii = (torch.rand(rows, device="cuda", generator=gen) < 0.2).to(torch.int32) * 7
+        vis = radii > 0
+        ga, gb = {}, {}
+        for a, b in zip(pa, pb):
+            g = torch.randn(a.shape, device="cuda", generator=gen)
+            g[~vis] = 0.0
+            ga[a] = g
+            gp = g.clone()
+            gp[~vis] = float("nan")
+            gb[b] = gp
+        oa.step(grads=ga)
+        ob.step_rows(radii, ob.ROWS_ALL, grads=gb, new_step=True)
+        torch.cuda.synchronize()
+        for a, b in zip(pa, pb):
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32))
+            assert torch.equal(oa.state[a]["exp_avg"].view(torch.int32), ob.state[b]["exp_avg"].view(torch.int32))
+            assert torch.equal(oa.state[a]["exp_avg_sq"].view(torch.int32),
+                               ob.state[b]["exp_avg_sq"].view(torch.int32))
+
+
 def test_adam_step_rows_rejects_bad_arguments():
     L = _lib.lib()
     x = torch.zeros(12, device="cuda")
@@ -137,7 +170,7 @@ def test_adam_step_rows_rejects_bad_arguments():
                                               exp_avg_sq=x.data_ptr(), numel=12, lr=1e-3, step=1))
     assert L.gsr_adam_step_rows(grp, 1, 0.9, 0.999, 1e-8, 1.0, 5, C.c_void_p(mask.data_ptr()), 0, None) != 0  # 12 % 5
     assert L.gsr_adam_step_rows(grp, 1, 0.9, 0.999, 1e-8, 1.0, 4, None, 0, None) != 0                          # no mask
-    assert L.gsr_adam_step_rows(grp, 1, 0.9, 0.999, 1e-8, 1.0, 4, C.c_void_p(mask.data_ptr()), 2, None) != 0  # phase
+    assert L.gsr_adam_step_rows(grp, 1, 0.9, 0.999, 1e-8, 1.0, 4, C.c_void_p(mask.data_ptr()), 3, None) != 0  # phase
 
 
 def test_overlapped_mapping_step_equals_sequential_step():
@@ -156,7 +189,9 @@ def test_overlapped_mapping_step_equals_sequential_step():
         for overlap in (False, True):
             params = dict(means3D=t["means3D"].clone(), dc=t["dc"].clone(), sh=t["sh"].clone(),
                           opacity=t["opacity"].clone(), scales=t["scales"].clone(), rotations=t["rotations"].clone())
-            m = KeyframeBatchMapper(params, scene.degree, t["bg"], freeze_render_inputs=True, overlap_adam=overlap)
+            # reference arm: dense zero-filled gradients + one fused Adam launch
+            m = KeyframeBatchMapper(params, scene.degree, t["bg"], freeze_render_inputs=True, overlap_adam=overlap,
+                                    masked_single_view=False)
             for _ in range(3):
                 m.step(kfs[:K])
             torch.cuda.synchronize()
@@ -174,6 +209,41 @@ def test_overlapped_mapping_step_equals_sequential_step():
             assert torch.equal(sa["exp_avg_sq"][hidden], sb["exp_avg_sq"][hidden]), k
             assert rel_l2(sa["exp_avg"], sb["exp_avg"]) <= 1e-4, k
             assert rel_l2(pa_ - params_init[k], pb_ - params_init[k]) <= 1e-3, k
+
+
+def test_masked_single_view_step_equals_dense_step():
+    """KeyframeBatchMapper.step on one keyframe: backward with rendered_rows_only + one masked Adam
+    pass == zero-filled backward + fused Adam (rows never rendered: bit for bit)."""
+    from gsdf_slam_b200.mapping import SEGMENTS, Keyframe, KeyframeBatchMapper
+    scene = scenes.tiny(seed=10, P=7000, W=176, H=120, degree=3)
+    t = to_dev(scene)
+    cam = scene.cam
+    kf = Keyframe(t["viewmatrix"], t["projmatrix"], t["campos"], cam.tanfovx, cam.tanfovy, cam.H, cam.W,
+                  t["dL_dout"])
+    init = dict(means3D=t["means3D"], dc=t["dc"], sh=t["sh"], opacity=t["opacity"], scales=t["scales"],
+                rotations=t["rotations"])
+    res = []
+    for masked in (False, True):
+        m = KeyframeBatchMapper({k: v.clone() for k, v in init.items()}, scene.degree, t["bg"],
+                                freeze_render_inputs=True, masked_single_view=masked)
+        if masked:
+            m.arena.fill_(float("nan"))   # the non-rendered rows must never be read
+        for _ in range(3):
+            m.step([kf])
+        torch.cuda.synchronize()
+        res.append(m)
+    a, b = res
+    hidden = a.last_radii == 0
+    assert 0 < int(hidden.sum()) < scene.P
+    for k in SEGMENTS:
+        pa_, pb_ = a.opt_params[k], b.opt_params[k]
+        sa, sb = a.optimizer.state[pa_], b.optimizer.state[pb_]
+        assert sa["step"] == sb["step"] == 3
+        assert torch.isfinite(pb_).all(), k
+        assert torch.equal(pa_[hidden].view(torch.int32), pb_[hidden].view(torch.int32)), k
+        assert torch.equal(sa["exp_avg_sq"][hidden], sb["exp_avg_sq"][hidden]), k
+        assert rel_l2(sa["exp_avg"], sb["exp_avg"]) <= 1e-4, k
+        assert rel_l2(pa_ - init[k], pb_ - init[k]) <= 1e-3, k
 
 
 def _brute_knn(pts: torch.Tensor) -> torch.Tensor:

@@ -40,11 +40,30 @@ def _scene(name):
         return scenes.room_scene(60_000, 1200, 680, 600.0, 600.0, seed=2, name="room60k")
     if name == "outdoor_small":
         return scenes.outdoor_scene(50_000, 1241, 376, 718.856, 718.856, seed=4)
+    if name == "depth_ties":
+        # many Gaussians share the exact depth bits: the per-tile order must fall back to the
+        # Gaussian index exactly like the reference's stable radix sort does
+        s = scenes.frustum_scene(20_000, 320, 240, 260.0, 260.0, seed=21, degree=1, sh_coeffs=15, name="ties")
+        s.means3D[:, 2] = np.round(s.means3D[:, 2] * 4.0) / 4.0
+        return s
+    if name == "stacked_mid":
+        # everything projects onto a few tiles: per-tile lists of 512 .. 16384 entries
+        # (binning.cu: the shared-memory path of tile_sort_pack_long_kernel)
+        s = scenes.frustum_scene(9_000, 160, 112, 150.0, 150.0, seed=22, degree=0, sh_coeffs=0, zmin=1.0,
+                                 zmax=4.0, log_scale=0.01, behind_frac=0.0, name="stacked_mid")
+        s.means3D[:, :2] *= 0.08
+        return s
+    if name == "stacked_huge":
+        # per-tile lists beyond 16384 entries: the global-scratch path of the per-tile sort
+        s = scenes.frustum_scene(45_000, 48, 32, 60.0, 60.0, seed=23, degree=0, sh_coeffs=0, zmin=1.0,
+                                 zmax=4.0, log_scale=0.02, op_sigma=0.5, behind_frac=0.0, name="stacked_huge")
+        s.means3D[:, :2] *= 0.3
+        return s
     raise KeyError(name)
 
 
 SCENES = ["tiny_sh3", "tiny_sh1", "tiny_sh0_withrest", "mid_frustum", "cfg1_small", "room_small",
-          "outdoor_small"]
+          "outdoor_small", "depth_ties", "stacked_mid", "stacked_huge"]
 
 
 def _compare_forward(scene, t, fwd, ref):
@@ -107,7 +126,36 @@ def test_forward_backward_vs_reference(name):
     grads = run_product_backward(scene, t, fwd)
     torch.cuda.synchronize()
     worst = _compare_grads(grads, ref["grads"])
+    lens = (ref["ranges"][:, 1] - ref["ranges"][:, 0])
+    if name == "stacked_mid":
+        assert 512 <= int(lens.max()) <= 16384
+    if name == "stacked_huge":
+        assert int(lens.max()) > 16384
+    if name == "depth_ties":
+        d = ref["depths"][ref["radii"] > 0]
+        assert d.unique().numel() < d.numel() // 50
     print(name, info, {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+def test_optimistic_duplicate_buffer_is_regrown_when_the_next_frame_needs_more():
+    """gsr_forward sizes the per-duplicate buffer from its previous call with the same (P, W, H);
+    a frame that needs more than the hint must transparently redo the per-duplicate stages."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libgsdf_ref.so not built")
+    small = scenes.tiny(seed=31, P=4000, W=208, H=144, degree=1)
+    big = scenes.tiny(seed=31, P=4000, W=208, H=144, degree=1)
+    big.scales = (big.scales * 3.0).astype(np.float32)     # same P, W, H but ~9x the duplicates
+    ts, tb = to_dev(small), to_dev(big)
+    f_small = run_product_forward(small, ts)               # sets the hint
+    f_big = run_product_forward(big, tb)                   # hint too small -> regrow
+    torch.cuda.synchronize()
+    assert f_big[0] > f_small[0] * 2
+    ref = run_reference(big, tb)
+    _compare_forward(big, tb, f_big, ref)
+    _compare_grads(run_product_backward(big, tb, f_big), ref["grads"])
+    f_again = run_product_forward(small, ts)               # and shrinking again is fine too
+    torch.cuda.synchronize()
+    _compare_forward(small, ts, f_again, run_reference(small, ts))
 
 
 def test_sh0_empty_rest_drops_colour_gradient():
