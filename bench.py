@@ -167,14 +167,13 @@ def workload_counts(scene, cam, params, dev):
 def stage_model(counts, tile_bits):
     """Algorithmic bytes / flops per launch of each stage."""
     P, V, R, N, T, M, E = (counts[k] for k in ("P", "V", "R", "N", "T", "M", "E"))
-    tile_passes = (tile_bits + 7) // 8
     b = {
         "preprocess": 12 * P + (44 + 12 * M) * V + 16 * P + 43 * V,
-        "sort_depth": P * (8 + 16 * 4),
-        "scan": 8 * P + 4 * V,
-        "emit": 40 * V + 8 * R,
-        "sort_tile": R * (8 + 16 * tile_passes),
-        "finalize": 8 * R + 36 * R + 48 * R + 8 * T,
+        "tile_meta": 4 * T + 16 * T,
+        # emit: list entry + rect inputs per visible Gaussian, one slot atomic (RMW) + one item per duplicate
+        "emit": (8 + 4 + 8 + 16 + 4) * V + (8 + 8) * R,
+        # per-tile sort + pack: items in/out, 48-byte record gathered and written per duplicate
+        "tile_sort_pack": (16 + 48 + 48) * R,
         "blend_fwd": 48 * R + 32 * N + 4 * T,
         "blend_bwd": 48 * counts["sum_max_contrib"] + 32 * N + 72 * R,
         "preprocess_bwd": (87 + 12 * M) * V + 48 * V + (52 + 12 * M) * V + 4 * V,  # rendered rows only
@@ -323,7 +322,8 @@ def run_product(args, rank, world, dev):
             ent.update(algorithmic_flops=int(flops_model[name]), achieved_tflops=round(tf, 3),
                        frac_of_fp32_peak=round(tf / fp32_peak_tflops, 4))
         stages[name] = ent
-    dom = max(prof, key=prof.get) if prof else None
+    modelled = {k: v for k, v in prof.items() if k in bytes_model or k in flops_model}
+    dom = max(modelled, key=modelled.get) if modelled else None
     roofline = None
     if dom is not None:
         if dom in flops_model:

@@ -281,68 +281,11 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
 // sorted order is unique) and the packed per-duplicate records
 //   {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}.
 // Lists shorter than kSortSmallCap entries are sorted in registers by the "small" launch (one
-// warp per tile, LPT order).  The "long" launch (148 persistent CTAs over the
-// hdr->num_long_tiles longest tiles, which form a prefix of the LPT order) sorts lists up to
-// kSortLargeCap entries in 128 KB of shared memory and anything longer in a padded global
-// scratch area — slow, but correct for any input.
+// warp per tile, LPT order, bitonic network).  The "long" launch (persistent CTAs over the
+// hdr->num_long_tiles longest tiles, which form a prefix of the LPT order) runs a stable LSD
+// radix sort per tile, in shared memory up to kSortLongSmemCap entries and through global
+// scratch beyond — any list length works.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t next_pow2(uint32_t n) {
-  return n <= 1u ? 1u : 1u << (32 - __clz(n - 1u));
-}
-
-// in-place ascending bitonic sort of buf[0, n_pad), n_pad a power of two; all threads of the CTA
-template <int kThreads>
-__device__ __forceinline__ void bitonic_sort(uint64_t* buf, uint32_t n_pad) {
-  const uint32_t half = n_pad >> 1;
-  for (uint32_t k = 2; k <= n_pad; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t p = threadIdx.x; p < half; p += kThreads) {
-        // p-th compare-exchange of this stage: i has bit j clear, partner i | j
-        const uint32_t i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u));
-        const uint32_t l = i | j;
-        const uint64_t a = buf[i], b = buf[l];
-        const bool up = (i & k) == 0;
-        if ((a > b) == up) {
-          buf[i] = b;
-          buf[l] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-template <int kThreads>
-__device__ __forceinline__ void sort_pack_tile(uint64_t* buf, uint32_t n, uint32_t start,
-                                               uint64_t* __restrict__ items,
-                                               const float4* __restrict__ splat_rec,
-                                               float4* __restrict__ rec) {
-  const uint32_t n_pad = next_pow2(n);
-  for (uint32_t i = threadIdx.x; i < n_pad; i += kThreads) buf[i] = i < n ? items[start + i] : ~0ull;
-  __syncthreads();
-  bitonic_sort<kThreads>(buf, n_pad);
-  for (uint32_t i = threadIdx.x; i < n; i += kThreads) items[start + i] = buf[i];
-  // three consecutive threads copy the three float4 of a record: coalesced on both sides
-  const uint32_t pieces = 3u * n;
-  constexpr int kInFlight = 4;
-  for (uint32_t q0 = 0; q0 < pieces; q0 += kThreads * kInFlight) {
-    float4 t[kInFlight];
-#pragma unroll
-    for (int u = 0; u < kInFlight; ++u) {
-      const uint32_t q = q0 + (uint32_t)kThreads * u + threadIdx.x;
-      if (q < pieces) {
-        const uint32_t pos = q / 3u, piece = q - 3u * pos;
-        t[u] = __ldg(splat_rec + 3 * (size_t)(uint32_t)(buf[pos] & 0xffffffffu) + piece);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kInFlight; ++u) {
-      const uint32_t q = q0 + (uint32_t)kThreads * u + threadIdx.x;
-      if (q < pieces) rec[3 * (size_t)start + q] = t[u];
-    }
-  }
-}
-
 // ---- lists shorter than kSortSmallCap (= 512): ONE WARP per tile, sorted entirely in registers ----
 // Lane l holds the kE consecutive network positions l*kE .. l*kE+kE-1 (n_pad = 32*kE).  The
 // compare-exchange stages with distance j < kE stay inside a thread; those with j >= kE are
@@ -456,31 +399,166 @@ tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __
   else warp_sort_pack_tile<16>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
 }
 
+// ---- lists of kSortSmallCap or more entries: one CTA per tile, stable LSD radix sort -------------
+// 8-bit digits over the bits in use: the Gaussian index (low word, as many digits as P needs)
+// first, then the four digits of the depth bits.  Lists up to kSortLongSmemCap entries ping-pong
+// between two shared-memory buffers, longer ones between the tile's own range and a scratch range
+// in global memory (L2-resident) — any length works.  Per pass: per-warp digit histograms over
+// contiguous segments (match_any ranking, no atomics), one scan, stable scatter.
+constexpr int kLongWarps = kSortLargeThreads / 32;
+
+// lanes of the warp holding the same 8-bit digit (invalid lanes match nobody): eight ballots.
+// (__match_any_sync does this in one instruction, but its latency grows with the number of
+// distinct values and dominated this kernel: ncu r1, tile_sort_pack_long.)
+__device__ __forceinline__ unsigned warp_peers_8bit(uint32_t d, bool valid) {
+  unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned m = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? m : ~m;
+  }
+  return valid ? peers : 0u;
+}
+
+__device__ __forceinline__ void cta_radix_pass(const uint64_t* in, uint64_t* out, uint32_t n, int shift,
+                                               uint32_t (*s_hist)[256], uint32_t* s_scan) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  constexpr int kBatch = 4;  // rounds whose loads are issued together
+  // contiguous segment of this warp, a multiple of 32 items
+  const uint32_t seg = ((n + kLongWarps * 32 - 1) / (kLongWarps * 32)) * 32;
+  const uint32_t lo = min(n, (uint32_t)warp * seg), hi = min(n, lo + seg);
+  for (int i = tid; i < kLongWarps * 256; i += kSortLargeThreads) (&s_hist[0][0])[i] = 0;
+  __syncthreads();
+  // phase A: per-warp digit counts
+  for (uint32_t i0 = lo; i0 < hi; i0 += 32 * kBatch) {
+    uint32_t d[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const uint32_t i = i0 + 32 * u + lane;
+      d[u] = i < hi ? (uint32_t)(in[i] >> shift) & 0xffu : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (i0 + 32 * u >= hi) break;  // warp-uniform
+      const bool valid = i0 + 32 * u + lane < hi;
+      const unsigned peers = warp_peers_8bit(d[u], valid);
+      if (valid && (peers & lt) == 0) s_hist[warp][d[u]] += (uint32_t)__popc(peers);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // exclusive offsets: digit-major, then warp order inside a digit (keeps the pass stable)
+  uint32_t total = 0;
+  if (tid < 256) {
+#pragma unroll
+    for (int w = 0; w < kLongWarps; ++w) {
+      const uint32_t c = s_hist[w][tid];
+      s_hist[w][tid] = total;
+      total += c;
+    }
+  }
+  uint32_t inc = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += x;
+  }
+  if (lane == 31) s_scan[warp] = inc;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int w = 0; w < kLongWarps; ++w)
+    if (w < warp) wbase += s_scan[w];
+  const uint32_t digit_base = wbase + inc - total;
+  if (tid < 256) {
+#pragma unroll
+    for (int w = 0; w < kLongWarps; ++w) s_hist[w][tid] += digit_base;
+  }
+  __syncthreads();
+  // phase B: stable scatter
+  for (uint32_t i0 = lo; i0 < hi; i0 += 32 * kBatch) {
+    uint64_t it[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const uint32_t i = i0 + 32 * u + lane;
+      it[u] = i < hi ? in[i] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      if (i0 + 32 * u >= hi) break;  // warp-uniform
+      const bool valid = i0 + 32 * u + lane < hi;
+      const uint32_t d = (uint32_t)(it[u] >> shift) & 0xffu;
+      const unsigned peers = warp_peers_8bit(d, valid);
+      uint32_t base = 0;
+      if (valid) base = s_hist[warp][d];
+      __syncwarp();
+      if (valid && (peers & lt) == 0) s_hist[warp][d] = base + (uint32_t)__popc(peers);
+      __syncwarp();
+      if (valid) out[base + __popc(peers & lt)] = it[u];
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kSortLargeThreads)
 tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
-                           const GeomHeader* __restrict__ hdr, uint32_t T, uint32_t capacity,
+                           const GeomHeader* __restrict__ hdr, uint32_t T, uint32_t capacity, int idx_passes,
                            uint64_t* __restrict__ items, uint64_t* __restrict__ scratch,
                            const float4* __restrict__ splat_rec, float4* __restrict__ rec) {
-  extern __shared__ __align__(16) uint64_t s_dyn[];
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  uint32_t (*s_hist)[256] = reinterpret_cast<uint32_t (*)[256]>(s_raw);
+  uint64_t* s_a = reinterpret_cast<uint64_t*>(s_raw + kLongWarps * 256 * sizeof(uint32_t));
+  uint64_t* s_b = s_a + kSortLongSmemCap;
+  __shared__ uint32_t s_scan[kLongWarps];
+  const int tid = threadIdx.x;
   // The lists of kSortSmallCap or more entries are exactly the first num_long_tiles entries of
   // the LPT order (kSortSmallCap is a multiple of its 4-entry bucket width).
   const uint32_t limit = min(T, hdr->num_long_tiles);
   for (uint32_t k = blockIdx.x; k < limit; k += gridDim.x) {
     const uint2 range = ranges[order[k]];
-    const uint32_t n = range.y - range.x;
+    const uint32_t n = range.y - range.x, start = range.x;
     if (n < (uint32_t)kSortSmallCap || range.y > capacity) continue;
-    if (n <= (uint32_t)kSortLargeCap) {
-      sort_pack_tile<kSortLargeThreads>(s_dyn, n, range.x, items, splat_rec, rec);
-    } else {
-      // padded copy at scratch[2 * start, 2 * start + next_pow2(n)): ranges of different tiles
-      // cannot overlap because next_pow2(n) <= 2 n
-      sort_pack_tile<kSortLargeThreads>(scratch + 2 * (size_t)range.x, n, range.x, items, splat_rec, rec);
+    const bool in_smem = n <= (uint32_t)kSortLongSmemCap;
+    uint64_t* a = in_smem ? s_a : items + start;
+    uint64_t* b = in_smem ? s_b : scratch + start;
+    if (in_smem) {
+      for (uint32_t i = tid; i < n; i += kSortLargeThreads) s_a[i] = items[start + i];
+      __syncthreads();
     }
-    __syncthreads();
+    for (int p = 0; p < idx_passes + 4; ++p) {
+      const int shift = p < idx_passes ? 8 * p : 32 + 8 * (p - idx_passes);
+      cta_radix_pass(a, b, n, shift, s_hist, s_scan);
+      uint64_t* t = a; a = b; b = t;
+    }
+    // sorted list in `a`
+    if (a != items + start)
+      for (uint32_t i = tid; i < n; i += kSortLargeThreads) items[start + i] = a[i];
+    // three consecutive threads copy the three float4 of a record: coalesced on both sides
+    const uint32_t pieces = 3u * n;
+    constexpr int kInFlight = 4;
+    for (uint32_t q0 = 0; q0 < pieces; q0 += kSortLargeThreads * kInFlight) {
+      float4 t4[kInFlight];
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u) {
+        const uint32_t q = q0 + (uint32_t)kSortLargeThreads * u + tid;
+        if (q < pieces) {
+          const uint32_t pos = q / 3u, piece = q - 3u * pos;
+          t4[u] = __ldg(splat_rec + 3 * (size_t)(uint32_t)(a[pos] & 0xffffffffu) + piece);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kInFlight; ++u) {
+        const uint32_t q = q0 + (uint32_t)kSortLargeThreads * u + tid;
+        if (q < pieces) rec[3 * (size_t)start + q] = t4[u];
+      }
+    }
+    __syncthreads();  // `a` may be a shared buffer the next tile overwrites
   }
 }
 
-int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
+int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
                           BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
                           const float4* splat_rec, float4* rec, cudaStream_t s) {
   if (T == 0) return 0;
@@ -488,15 +566,19 @@ int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order
                                                                         items, splat_rec, rec);
   GSR_LAUNCHED();
   static bool attr_set = false;
-  const int dyn = kSortLargeCap * (int)sizeof(uint64_t);
+  const int dyn = kLongWarps * 256 * (int)sizeof(uint32_t) + 2 * kSortLongSmemCap * (int)sizeof(uint64_t);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tile_sort_pack_long_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  tile_sort_pack_long_kernel<<<148, kSortLargeThreads, dyn, s>>>(ranges, order, hdr, T, capacity, items,
-                                                                 scratch, splat_rec, rec);
+  int idx_bits = 1;
+  while (idx_bits < 32 && (1ull << idx_bits) < (unsigned long long)P) ++idx_bits;
+  const int idx_passes = (idx_bits + 7) / 8;
+  // two CTAs per SM (80 KB of shared memory each)
+  tile_sort_pack_long_kernel<<<148 * 2, kSortLargeThreads, dyn, s>>>(ranges, order, hdr, T, capacity, idx_passes,
+                                                                     items, scratch, splat_rec, rec);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -206,7 +206,7 @@ int gsr_forward(const gsr_forward_args* a) {
       GSR_PROF("emit", launch_emit(P, g.vis_items, &g.hdr->num_visible, g.tiles_touched, g.means2D,
                                    g.conic_opacity, a->radii, gx, gy, im.ranges, im.tile_fill, b.items, cap,
                                    &g.hdr->num_large, g.large_list, s));
-      GSR_PROF("tile_sort_pack", launch_tile_sort_pack(T, im.ranges, im.tile_order, g.hdr, b.hdr, cap, b.items, b.scratch,
+      GSR_PROF("tile_sort_pack", launch_tile_sort_pack(P, T, im.ranges, im.tile_order, g.hdr, b.hdr, cap, b.items, b.scratch,
                                                        g.splat_rec, b.rec, s));
     }
     GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,

@@ -66,10 +66,11 @@ struct ImageView {
 };
 
 // per-tile sort (binning.cu): lists shorter than kSortSmallCap are sorted in registers by one
-// warp, lists up to kSortLargeCap in 128 KB of dynamic shared memory, longer ones in global
-// scratch.  kSortSmallCap must be a multiple of 4 and < 4096 (LPT bucket layout of tile_meta_kernel).
+// warp; longer ones by a CTA-wide radix sort, in shared memory up to kSortLongSmemCap entries and
+// through global scratch beyond.  kSortSmallCap must be a multiple of 4 and < 4096 (LPT bucket
+// layout of tile_meta_kernel).
 constexpr int kSortSmallCap = 512;
-constexpr int kSortLargeCap = 16384;
+constexpr int kSortLongSmemCap = 4096;
 
 // Per-duplicate buffer.  Its layout must not depend on the exact R (the forward pass sizes it
 // optimistically before R has reached the host): a 128-byte header holding the capacity, then
@@ -82,7 +83,7 @@ struct BinView {
   BinHeader* hdr;
   float4* rec;               // [cap][3] {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}
   uint64_t* items;           // [cap] (depth_bits<<32 | idx), tile-major; depth-sorted per tile after tile_sort_pack
-  uint64_t* scratch;         // [2*cap] padded lists of the tiles too long for shared memory
+  uint64_t* scratch;         // [cap] ping-pong twin of `items` for the lists too long for shared memory
 };
 
 size_t sort_temp_bytes(int64_t n);
@@ -142,12 +143,12 @@ inline BinView bin_view(char* base, size_t cap) {
   b.hdr = carve<BinHeader>(p, 1);
   b.rec = carve<float4>(p, 3 * c);
   b.items = carve<uint64_t>(p, c);
-  b.scratch = carve<uint64_t>(p, 2 * c);
+  b.scratch = carve<uint64_t>(p, c);
   return b;
 }
 inline size_t bin_bytes(size_t cap) {
   BinView b = bin_view(nullptr, cap);
-  return reinterpret_cast<size_t>(b.scratch) + 2 * (cap + 8) * 8 + 128;
+  return reinterpret_cast<size_t>(b.scratch) + (cap + 8) * 8 + 128;
 }
 
 // ----------------------------------------------------------------------------

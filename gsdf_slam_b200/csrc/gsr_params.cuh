@@ -79,7 +79,7 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
                 const int* radii, int grid_x, int grid_y, const uint2* ranges, uint32_t* tile_fill,
                 uint64_t* items, uint32_t capacity, uint32_t* large_count, uint32_t* large_list,
                 cudaStream_t s);
-int launch_tile_sort_pack(uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
+int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
                           BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
                           const float4* splat_rec, float4* rec, cudaStream_t s);
 int launch_export_binning(uint32_t T, const uint2* ranges, const uint64_t* items, uint64_t* keys,
