@@ -119,21 +119,28 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         any_cand = any_cand || cand[q];
       }
       if (!any_cand) continue;
+      // the four exp / alpha chains are evaluated together (4-way ILP, no branches); a chain
+      // of a pixel that is not a candidate computes a value nobody uses
+      float alpha[kSlots];
+      bool live[kSlots];
 #pragma unroll
       for (int q = 0; q < kSlots; ++q) {
-        if (!cand[q]) continue;
-        const float power = pw[q];
-        float alpha = min(0.99f, con_o.w * exp(power));
-        if (alpha < 1.0f / 255.0f) continue;
-        float test_T = T[q] * (1 - alpha);
+        alpha[q] = min(0.99f, con_o.w * exp(pw[q]));
+        live[q] = cand[q] && !(alpha[q] < 1.0f / 255.0f);
+      }
+      if (!(live[0] || live[1] || live[2] || live[3])) continue;
+      const float4 col = sR[buf][3 * j + 2];
+#pragma unroll
+      for (int q = 0; q < kSlots; ++q) {
+        if (!live[q]) continue;
+        const float test_T = T[q] * (1 - alpha[q]);
         if (test_T < 0.0001f) {
           done[q] = true;
           continue;
         }
-        const float4 col = sR[buf][3 * j + 2];
-        C[q][0] += col.x * alpha * T[q];
-        C[q][1] += col.y * alpha * T[q];
-        C[q][2] += col.z * alpha * T[q];
+        C[q][0] += col.x * alpha[q] * T[q];
+        C[q][1] += col.y * alpha[q] * T[q];
+        C[q][2] += col.z * alpha[q] * T[q];
         T[q] = test_T;
         last_contributor[q] = pos0 + j + 1;
       }

@@ -111,7 +111,7 @@ constexpr int kPreThreads = 128;
 constexpr int kShFloats = 45;  // 15 coefficients x 3 channels
 
 #ifndef GSR_PRE_MINBLOCKS
-#define GSR_PRE_MINBLOCKS 1
+#define GSR_PRE_MINBLOCKS 6
 #endif
 __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_kernel(const PreprocessParams a) {
   // CTA-staged input rows
