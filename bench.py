@@ -14,7 +14,8 @@ Weak scaling: one keyframe per rank per step, value = keyframe iterations / s ov
 `value`  : inputs resident in HBM, K steps timed with CUDA events between barriers.
 `e2e`    : the same step through the public API with HOST buffers: every step copies the
            keyframe inputs (camera matrices, background, dL/d(image)) from pinned host memory
-           and reads the rendered image and a gradient checksum back to the host.
+           (the image-sized upload double-buffered on a copy stream) and reads the rendered image
+           back to the host, waiting for it before the next step starts.
 --impl reference : the UNMODIFIED reference CUDA rasterizer compiled for sm_100a
            (oracle/_ref, see oracle/build_ref.sh) + LibTorch's Adam op sequence, same step,
            measured like `e2e`.  (The reference has no CPU implementation; its CPU restatement
@@ -217,11 +218,15 @@ def run_product(args, rank, world, dev):
     # device staging buffers for the e2e path + pinned result buffers
     stage = {k: torch.empty_like(v, device=dev) for k, v in hk.items()}
     img_host = torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory()
-    chk_host = torch.empty(1, dtype=torch.float32).pin_memory()
     h2d_bytes = sum(v.numel() * 4 for v in hk.values())
-    d2h_bytes = img_host.numel() * 4 + 4
+    d2h_bytes = img_host.numel() * 4
     ev_h2d = torch.cuda.Event()
     ev_fwd = torch.cuda.Event()
+    ev_step = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in ev_step:
+        ev.record(torch.cuda.current_stream(dev))
+    dl_stage = [stage["dL_dout"], torch.empty_like(stage["dL_dout"])]
+    counter = [0]
 
     def step_e2e():
         main = torch.cuda.current_stream(dev)
@@ -229,13 +234,17 @@ def run_product(args, rank, world, dev):
         # overlaps the forward (a real mapper uploads the ground-truth image the same way)
         for k in ("viewmatrix", "projmatrix", "campos", "bg"):
             stage[k].copy_(hk[k], non_blocking=True)
-        copy_stream.wait_stream(main)
+        # the image-sized upload is double-buffered: it may start while the previous step's
+        # backward pass still reads the other buffer (two steps back is finished: ev_step[slot])
+        slot = counter[0] & 1
+        counter[0] += 1
+        copy_stream.wait_event(ev_step[slot])
         with torch.cuda.stream(copy_stream):
-            stage["dL_dout"].copy_(hk["dL_dout"], non_blocking=True)
+            dl_stage[slot].copy_(hk["dL_dout"], non_blocking=True)
             ev_h2d.record(copy_stream)
         mapper.bg = stage["bg"]
         kf = Keyframe(stage["viewmatrix"], stage["projmatrix"], stage["campos"], cam.tanfovx, cam.tanfovy,
-                      cam.H, cam.W, stage["dL_dout"])
+                      cam.H, cam.W, dl_stage[slot])
         keep = {}
 
         def after_forward(_kf, fwd):
@@ -250,8 +259,10 @@ def run_product(args, rank, world, dev):
             keep["color"] = color
 
         mapper.step([kf], on_forward=after_forward)
-        chk_host.copy_(mapper.opt_params["opacity"].sum().reshape(1), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        # the step's result (the rendered image) must have reached the host before the next step
+        # starts; the compute stream is NOT drained, so the host prepares step k+1 while the GPU
+        # finishes the backward pass and the optimiser of step k (like a real mapping loop)
+        ev_step[slot].record(main)
         copy_stream.synchronize()
 
     def timed(fn, steps, warmup, sampler=None):
@@ -424,7 +435,6 @@ def run_reference(args, rank, world, dev):
     hk = host_keyframe(scene, cam)
     stage = {k: torch.empty_like(v, device=dev) for k, v in hk.items()}
     img_host = torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory()
-    chk_host = torch.empty(1, dtype=torch.float32).pin_memory()
     names = ("means3D", "dc", "sh", "opacity", "scales", "rotations")
     gname = dict(means3D="dL_dmeans3D", dc="dL_ddc", sh="dL_dsh", opacity="dL_dopacity",
                  scales="dL_dscales", rotations="dL_drotations")
@@ -445,25 +455,50 @@ def run_reference(args, rank, world, dev):
             denom = (v[k].sqrt() / np.sqrt(bc2)).add_(1e-15)
             shadow[k].addcdiv_(m[k], denom, value=-(DEFAULT_LR[k] / bc1))
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_h2d, ev_fwd = torch.cuda.Event(), torch.cuda.Event()
+    ev_step = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in ev_step:
+        ev.record(torch.cuda.current_stream(dev))
+    dl_stage = [stage["dL_dout"], torch.empty_like(stage["dL_dout"])]
+    counter = [0]
+
     def step(debug=False, host_io=True):
+        # host I/O exactly like the product's e2e step: camera block on the compute stream, the
+        # image-sized gradient up and the rendered image down on a copy stream, only the image
+        # read is waited for at the end of the step
         src = stage
+        main = torch.cuda.current_stream(dev)
+        dl = stage["dL_dout"]
         if host_io:
-            for k in hk:
+            for k in ("viewmatrix", "projmatrix", "campos", "bg"):
                 stage[k].copy_(hk[k], non_blocking=True)
+            slot = counter[0] & 1
+            counter[0] += 1
+            dl = dl_stage[slot]
+            copy_stream.wait_event(ev_step[slot])
+            with torch.cuda.stream(copy_stream):
+                dl.copy_(hk["dL_dout"], non_blocking=True)
+                ev_h2d.record(copy_stream)
         # allocations exactly like the reference shim (src/rasterize_points.cu:74-76, 157-166)
         R, B, color, radii = rr.forward(src["bg"], p["means3D"], e, p["opacity"], p["scales"], p["rotations"],
                                         1.0, e, src["viewmatrix"], src["projmatrix"], cam.tanfovx,
                                         cam.tanfovy, cam.H, cam.W, p["dc"], p["sh"], scene.degree,
                                         src["campos"], debug=debug)
         if host_io:
-            img_host.copy_(color, non_blocking=True)
+            ev_fwd.record(main)
+            copy_stream.wait_event(ev_fwd)
+            with torch.cuda.stream(copy_stream):
+                img_host.copy_(color, non_blocking=True)
+            color.record_stream(copy_stream)
+            main.wait_event(ev_h2d)
         g = rr.backward(src["bg"], p["means3D"], radii, e, p["scales"], p["rotations"], 1.0, e,
-                        src["viewmatrix"], src["projmatrix"], cam.tanfovx, cam.tanfovy, src["dL_dout"],
+                        src["viewmatrix"], src["projmatrix"], cam.tanfovx, cam.tanfovy, dl,
                         p["dc"], p["sh"], scene.degree, src["campos"], debug=debug)
         adam(g)
         if host_io:
-            chk_host.copy_(g["dL_dopacity"].sum().reshape(1), non_blocking=True)
-            torch.cuda.synchronize()
+            ev_step[slot].record(main)
+            copy_stream.synchronize()
 
     for k in hk:
         stage[k].copy_(hk[k])
@@ -485,7 +520,7 @@ def run_reference(args, rank, world, dev):
     ms_res = timed(lambda: step(False, False), args.steps, 3)
     ms_dbg = timed(lambda: step(True, False), max(3, args.steps // 2), 2)
     h2d = sum(x.numel() * 4 for x in hk.values())
-    d2h = img_host.numel() * 4 + 4
+    d2h = img_host.numel() * 4
     cb = None if args.no_cpu_baseline else cpu_baseline(args.config)
     line = {"metric": METRIC, "impl": "reference", "value": round(1000.0 / ms_e2e, 2), "unit": UNIT,
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_e2e, 4),
