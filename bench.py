@@ -375,6 +375,10 @@ def run_product(args, rank, world, dev):
                                "fwd+bwd+(allreduce)+fused Adam; loss/activations out of scope",
                    "P": counts["P"], "sh_degree": scene.degree, "image": [cam.W, cam.H],
                    "keyframes_per_step": world, "parallelism": f"dp{world} (keyframe batch)",
+                   "exchange": ("none (single rank)" if world == 1 else
+                                "fused peer-memory kernel: gradient reduction + Adam on a 1/N shard + parameter "
+                                "broadcast over NVLink (gsr_adam_step_peer)" if mapper.peer is not None else
+                                "NCCL all-reduce of the gradient arena, pipelined with fused Adam"),
                    "l2_policy": "working set (params+grads+Adam state+scratch ~0.7 GB) exceeds the 126 MB L2",
                    "adam": ("fused, on a raw-parameter shadow copy (render inputs frozen); single rank: one "
                             "masked pass (gsr_adam_step_rows ALL) that reads the gradient only for the "

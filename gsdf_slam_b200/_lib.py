@@ -66,9 +66,29 @@ class AdamGroup(C.Structure):
     ]
 
 
+GSR_MAX_PEERS = 8
+GSR_PEER_MAX_SEGMENTS = 8
+
+
+class PeerSegment(C.Structure):
+    _fields_ = [("start", C.c_int64), ("numel", C.c_int64), ("width", C.c_int32), ("lr", C.c_double)]
+
+
+class PeerAdamArgs(C.Structure):
+    _fields_ = [
+        ("n_peers", C.c_int), ("rank", C.c_int),
+        ("param_peers", C.c_void_p * GSR_MAX_PEERS), ("grad_peers", C.c_void_p * GSR_MAX_PEERS),
+        ("n_segments", C.c_int), ("segments", PeerSegment * GSR_PEER_MAX_SEGMENTS),
+        ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
+        ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("union_mask", C.c_void_p),
+        ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", C.c_float),
+        ("step", C.c_int64), ("stream", C.c_void_p),
+    ]
+
+
 # every symbol include/gsr_capi.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
-    "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows",
+    "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows", "gsr_adam_step_peer", "gsr_peer_union_mask",
     "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_sort_temp_bytes",
     "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
 ]
@@ -113,6 +133,10 @@ def lib() -> C.CDLL:
     L.gsr_adam_step_rows.argtypes = [C.POINTER(AdamGroup), C.c_int, C.c_double, C.c_double, C.c_double,
                                      C.c_float, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     L.gsr_adam_step_rows.restype = C.c_int
+    L.gsr_adam_step_peer.argtypes = [C.POINTER(PeerAdamArgs)]
+    L.gsr_adam_step_peer.restype = C.c_int
+    L.gsr_peer_union_mask.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.gsr_peer_union_mask.restype = C.c_int
     L.gsr_export_binning.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_export_binning.restype = C.c_int

@@ -1,0 +1,203 @@
+// Multi-GPU optimiser step over NVLink peer memory: gradient reduction, Adam and parameter
+// broadcast in ONE kernel (the "reduce-scatter -> Adam -> all-gather" of a data-parallel step,
+// fused).  Replaces, for N > 1 ranks on one NVSwitch node, the NCCL all-reduce of the 59*P-float
+// gradient arena followed by a full-size Adam pass on every rank (gsdf_slam_b200/mapping.py).
+//
+// Layout: every rank owns a gradient arena and a parameter arena of identical layout in
+// SYMMETRIC memory (peer-mapped; torch.distributed._symmetric_memory hands out the N base
+// pointers).  Rank r is responsible for the element range [lo, hi) of the arena (a 1/N shard):
+//   g      = sum over ranks of grad_peer[k][e]          (N-1 remote loads; skipped — taken as 0 —
+//                                                        for rows no rank rendered: union mask)
+//   m, v   = shard-local Adam moments (only 1/N of the state exists on each rank)
+//   p      = Adam update of the local copy
+//   store p to the parameter arena of EVERY rank       (N-1 remote stores)
+// so each rank reads ~ (N-1)/N * (rendered fraction) * 236 B and writes (N-1)/N * 236 B per
+// Gaussian over NVLink, and touches only 1/N of the Adam state in HBM.  The caller brackets the
+// kernel with two cross-rank barriers (gradients visible / parameters landed).
+//
+// Arithmetic per element is adam_elem of adam.cu (LibTorch op order); the gradient sum runs in
+// rank order 0..N-1 on every rank, so all replicas stay bit-identical.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+
+#include "gsr_capi.h"
+#include "gsr_common.cuh"
+#include "gsr_params.cuh"
+
+namespace gsr {
+
+constexpr int kPeerThreads = 256;
+constexpr int kPeerChunk = kPeerThreads * 4;  // elements per CTA (one float4 per thread)
+
+struct PeerSegDev {
+  long long start;       // first arena element of the segment
+  long long numel;
+  unsigned width;        // elements per row
+  unsigned magic;        // ceil(2^32 / width)
+  float neg_step_size;
+  float inv_sqrt_bc2;
+};
+struct PeerAdamParams {
+  float* param[GSR_MAX_PEERS];
+  const float* grad[GSR_MAX_PEERS];
+  int n_peers;
+  int n_segs;
+  PeerSegDev seg[GSR_PEER_MAX_SEGMENTS];
+  long long lo, hi;      // this rank's shard of the arena (multiples of 4 elements)
+  float* exp_avg;        // [hi - lo] shard-local
+  float* exp_avg_sq;     // [hi - lo]
+  const int* union_mask; // [rows] > 0 <=> some rank rendered the row
+  float beta1, one_minus_beta1, beta2, one_minus_beta2, eps, grad_scale;
+  int use_scale;
+};
+
+__device__ __forceinline__ void peer_adam_elem(float& p, float g, float& m, float& v, const PeerAdamParams& a,
+                                               float neg_step_size, float inv_sqrt_bc2) {
+  if (a.use_scale) g = __fmul_rn(g, a.grad_scale);
+  const float m1 = __fmul_rn(m, a.beta1);
+  const float m2 = __fmaf_rn(a.one_minus_beta1, g, m1);
+  const float v1 = __fmul_rn(v, a.beta2);
+  const float v2 = __fmaf_rn(a.one_minus_beta2, __fmul_rn(g, g), v1);
+  const float d0 = __fmul_rn(__fsqrt_rn(v2), inv_sqrt_bc2);
+  const float d = __fadd_rn(d0, a.eps);
+  p = __fmaf_rn(neg_step_size, __fdiv_rn(m2, d), p);
+  m = m2;
+  v = v2;
+}
+
+__global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamParams a, int my_rank) {
+  const long long base = a.lo + (long long)blockIdx.x * kPeerChunk;
+  const long long e = base + 4LL * threadIdx.x;
+  if (e >= a.hi) return;
+  // segment of this float4 (segments start on 4-element boundaries, so it lies in exactly one)
+  int si = 0;
+#pragma unroll 1
+  for (int k = 1; k < a.n_segs; ++k)
+    if (e >= a.seg[k].start) si = k;
+  const PeerSegDev S = a.seg[si];
+  // rows of the four elements: one wide division per thread, then small offsets
+  const unsigned long long off = (unsigned long long)(e - S.start);
+  const unsigned r0 = (unsigned)(off / S.width);
+  const unsigned rem = (unsigned)(off - (unsigned long long)r0 * S.width);
+  const long long seg_end = S.start + S.numel;
+  unsigned rendered = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned rr = rem + j;
+    const unsigned row = r0 + (rr >= S.width) + (rr >= 2 * S.width) + (rr >= 3 * S.width);
+    if (e + j < seg_end && __ldg(a.union_mask + row) > 0) rendered |= 1u << j;
+  }
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rendered) {
+    // fixed rank order on every rank: identical sums, replicas stay bit-identical
+    for (int k = 0; k < a.n_peers; ++k) {
+      const float4 x = *reinterpret_cast<const float4*>(a.grad[k] + e);
+      g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+    }
+    if (!(rendered & 1u)) g.x = 0.f;
+    if (!(rendered & 2u)) g.y = 0.f;
+    if (!(rendered & 4u)) g.z = 0.f;
+    if (!(rendered & 8u)) g.w = 0.f;
+  }
+  float4 p = *reinterpret_cast<const float4*>(a.param[my_rank] + e);
+  float4 m = __ldcs(reinterpret_cast<const float4*>(a.exp_avg + (e - a.lo)));
+  float4 v = __ldcs(reinterpret_cast<const float4*>(a.exp_avg_sq + (e - a.lo)));
+  peer_adam_elem(p.x, g.x, m.x, v.x, a, S.neg_step_size, S.inv_sqrt_bc2);
+  peer_adam_elem(p.y, g.y, m.y, v.y, a, S.neg_step_size, S.inv_sqrt_bc2);
+  peer_adam_elem(p.z, g.z, m.z, v.z, a, S.neg_step_size, S.inv_sqrt_bc2);
+  peer_adam_elem(p.w, g.w, m.w, v.w, a, S.neg_step_size, S.inv_sqrt_bc2);
+  __stcs(reinterpret_cast<float4*>(a.exp_avg + (e - a.lo)), m);
+  __stcs(reinterpret_cast<float4*>(a.exp_avg_sq + (e - a.lo)), v);
+  for (int k = 0; k < a.n_peers; ++k) *reinterpret_cast<float4*>(a.param[k] + e) = p;
+}
+
+// union[row] = max over ranks of radii_peer[k][row]
+struct PeerMaskParams {
+  const int* radii[GSR_MAX_PEERS];
+  int n_peers;
+};
+__global__ void __launch_bounds__(256) peer_union_mask_kernel(const PeerMaskParams a, long long rows,
+                                                              int* __restrict__ union_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  int m = 0;
+  for (int k = 0; k < a.n_peers; ++k) m = max(m, a.radii[k][i]);
+  union_out[i] = m;
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+int gsr_peer_union_mask(const int32_t* const* radii_peers, int n_peers, int64_t rows, int32_t* union_out,
+                        void* stream) {
+  if (n_peers < 1 || n_peers > GSR_MAX_PEERS || rows < 0 || !radii_peers || (rows > 0 && !union_out))
+    return GSR_ERR_BAD_ARG;
+  if (rows == 0) return GSR_OK;
+  PeerMaskParams a;
+  a.n_peers = n_peers;
+  for (int k = 0; k < n_peers; ++k) {
+    if (!radii_peers[k]) return GSR_ERR_BAD_ARG;
+    a.radii[k] = radii_peers[k];
+  }
+  peer_union_mask_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, rows, union_out);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+int gsr_adam_step_peer(const gsr_peer_adam_args* in) {
+  if (!in || in->n_peers < 1 || in->n_peers > GSR_MAX_PEERS || in->rank < 0 || in->rank >= in->n_peers ||
+      in->n_segments < 1 || in->n_segments > GSR_PEER_MAX_SEGMENTS || in->shard_lo < 0 ||
+      in->shard_hi < in->shard_lo || (in->shard_lo & 3) || !in->union_mask || in->step < 1)
+    return GSR_ERR_BAD_ARG;
+  if (in->shard_hi == in->shard_lo) return GSR_OK;
+  if (!in->exp_avg || !in->exp_avg_sq) return GSR_ERR_BAD_ARG;
+  PeerAdamParams a;
+  a.n_peers = in->n_peers;
+  for (int k = 0; k < in->n_peers; ++k) {
+    if (!in->param_peers[k] || !in->grad_peers[k]) return GSR_ERR_BAD_ARG;
+    if (((uintptr_t)in->param_peers[k] | (uintptr_t)in->grad_peers[k]) & 15) return GSR_ERR_BAD_ARG;
+    a.param[k] = in->param_peers[k];
+    a.grad[k] = in->grad_peers[k];
+  }
+  if (((uintptr_t)in->exp_avg | (uintptr_t)in->exp_avg_sq) & 15) return GSR_ERR_BAD_ARG;
+  const double bc1 = 1.0 - std::pow(in->beta1, (double)in->step);
+  const double bc2 = 1.0 - std::pow(in->beta2, (double)in->step);
+  a.n_segs = in->n_segments;
+  long long prev_end = 0;
+  for (int k = 0; k < in->n_segments; ++k) {
+    const gsr_peer_segment& s = in->segments[k];
+    if (s.start < prev_end || (s.start & 3) || s.numel < 0 || s.width < 1 || s.width > 4096) return GSR_ERR_BAD_ARG;
+    a.seg[k].start = s.start;
+    a.seg[k].numel = s.numel;
+    a.seg[k].width = (unsigned)s.width;
+    a.seg[k].magic = 0;
+    a.seg[k].neg_step_size = (float)(-(s.lr / bc1));
+    a.seg[k].inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
+    prev_end = s.start + s.numel;
+  }
+  a.lo = in->shard_lo;
+  a.hi = in->shard_hi;
+  a.exp_avg = in->exp_avg;
+  a.exp_avg_sq = in->exp_avg_sq;
+  a.union_mask = in->union_mask;
+  a.beta1 = (float)in->beta1;
+  a.beta2 = (float)in->beta2;
+  a.one_minus_beta1 = (float)(1.0 - in->beta1);
+  a.one_minus_beta2 = (float)(1.0 - in->beta2);
+  a.eps = (float)in->eps;
+  a.grad_scale = in->grad_scale;
+  a.use_scale = in->grad_scale != 1.0f;
+  const long long n = a.hi - a.lo;
+  peer_adam_kernel<<<(unsigned)((n + kPeerChunk - 1) / kPeerChunk), kPeerThreads, 0,
+                     static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -74,7 +74,7 @@ class KeyframeBatchMapper:
     def __init__(self, params: Dict[str, torch.Tensor], degree: int, bg: torch.Tensor,
                  lr: Optional[Dict[str, float]] = None, eps: float = 1e-15,
                  process_group=None, freeze_render_inputs: bool = False, overlap_adam: bool = False,
-                 masked_single_view: bool = True):
+                 masked_single_view: bool = True, peer_exchange: Optional[bool] = None):
         self.params = {k: params[k].contiguous() for k in SEGMENTS}
         self.degree = int(degree)
         self.bg = bg
@@ -96,6 +96,14 @@ class KeyframeBatchMapper:
                                     if self.opt_params[k].numel() > 0], lr=0.0, eps=eps)
         self.last_radii: Optional[torch.Tensor] = None
         self.last_color: Optional[torch.Tensor] = None
+        # N > 1 ranks on one NVLink node: gradient reduction + Adam + parameter broadcast fused in
+        # one kernel over peer memory (gsr_adam_step_peer) instead of NCCL all-reduce + full Adam
+        self.peer = None
+        if peer_exchange is None:
+            import os
+            peer_exchange = os.environ.get("GSR_PEER_EXCHANGE", "1") != "0"
+        if peer_exchange and dev.type == "cuda" and self.world_size > 1:
+            self._setup_peer_exchange(lr, eps)
         # visibility-split Adam (gsr_adam_step_rows): the zero-gradient rows are updated on a
         # side stream while the blend / backward kernels run.  OFF by default: measured on B200
         # (cfg2) the streaming sweep slows the co-running blend kernels by as much as it hides
@@ -111,6 +119,104 @@ class KeyframeBatchMapper:
         self._side: Optional[torch.cuda.Stream] = None
         self._ev_radii: Optional[torch.cuda.Event] = None
         self._ev_side: Optional[torch.cuda.Event] = None
+
+    # ---- peer-memory exchange (N > 1) ------------------------------------------------------------
+    def _setup_peer_exchange(self, lr: Dict[str, float], eps: float) -> None:
+        """Moves the gradient arena and the optimised parameters into symmetric (peer-mapped)
+        memory and shards the Adam state.  Falls back to the NCCL path (with a warning) when
+        symmetric memory cannot be set up on this system."""
+        import sys
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else dist.group.WORLD
+            dev = self.arena.device
+            total = self.layout["_total"][1]
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+            if world > 8:
+                raise RuntimeError("more than GSR_MAX_PEERS ranks")
+            g_arena = symm.empty(total, dtype=torch.float32, device=dev)
+            p_arena = symm.empty(total, dtype=torch.float32, device=dev)
+            radii = symm.empty(max(self.P, 1), dtype=torch.int32, device=dev)
+            g_arena.zero_(); p_arena.zero_(); radii.zero_()
+            hg = symm.rendezvous(g_arena, group)
+            hp = symm.rendezvous(p_arena, group)
+            hr = symm.rendezvous(radii, group)
+        except Exception as exc:  # noqa: BLE001
+            print(f"[gsdf_slam_b200] peer-memory exchange unavailable ({exc!r}); using the NCCL all-reduce path",
+                  file=sys.stderr)
+            return
+        # parameters the optimiser updates now live in the symmetric parameter arena
+        p_views = self._views(p_arena)
+        frozen = self.opt_params is not self.params
+        for k in SEGMENTS:
+            p_views[k].copy_(self.opt_params[k])
+        self.opt_params = p_views
+        if not frozen:
+            self.params = p_views
+        self.arena = g_arena
+        self.grad_views = self._views(g_arena)
+        shard = ((total + world - 1) // world + 3) // 4 * 4
+        lo = min(total, rank * shard)
+        hi = min(total, lo + shard)
+        self.peer = dict(world=world, rank=rank, hg=hg, hp=hp, hr=hr, g_arena=g_arena, p_arena=p_arena,
+                         radii=radii, lo=lo, hi=hi, step=0, eps=float(eps), lr=dict(lr),
+                         exp_avg=torch.zeros(max(hi - lo, 4), dtype=torch.float32, device=dev),
+                         exp_avg_sq=torch.zeros(max(hi - lo, 4), dtype=torch.float32, device=dev),
+                         union=torch.zeros(max(self.P, 1), dtype=torch.int32, device=dev))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)
+
+    def _step_peer(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
+        import ctypes as C
+
+        from . import _lib
+        pe = self.peer
+        dev = self.arena.device
+        mask = None
+        if len(keyframes) == 0:
+            self.arena.zero_()
+        for i, kf in enumerate(keyframes):
+            views = self.grad_views if i == 0 else None
+            if i > 0:
+                if self._scratch_arena is None:
+                    self._scratch_arena = torch.zeros_like(self.arena)
+                views = self._views(self._scratch_arena)
+            _, radii, _ = self.render_backward(kf, views, on_forward=on_forward)
+            if i > 0:
+                self.arena.add_(self._scratch_arena)
+            mask = radii if mask is None else torch.maximum(mask, radii)
+        if mask is None:
+            pe["radii"].zero_()
+        else:
+            pe["radii"].copy_(mask)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        L = _lib.lib()
+        pe["hg"].barrier(channel=0)          # every rank's gradients and radii are written
+        rptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hr"].buffer_ptrs])
+        _lib.check(L.gsr_peer_union_mask(rptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
+                   "gsr_peer_union_mask")
+        pe["step"] += 1
+        a = _lib.PeerAdamArgs()
+        a.n_peers, a.rank = pe["world"], pe["rank"]
+        for k in range(pe["world"]):
+            a.param_peers[k] = int(pe["hp"].buffer_ptrs[k])
+            a.grad_peers[k] = int(pe["hg"].buffer_ptrs[k])
+        segs = [n for n in ARENA_ORDER if self.layout[n][1] > 0]
+        a.n_segments = len(segs)
+        for i, n in enumerate(segs):
+            off, numel, _shape = self.layout[n]
+            a.segments[i].start, a.segments[i].numel = off, numel
+            a.segments[i].width = numel // self.P
+            a.segments[i].lr = float(pe["lr"][n])
+        a.shard_lo, a.shard_hi = pe["lo"], pe["hi"]
+        a.exp_avg, a.exp_avg_sq = pe["exp_avg"].data_ptr(), pe["exp_avg_sq"].data_ptr()
+        a.union_mask = pe["union"].data_ptr()
+        a.beta1, a.beta2, a.eps, a.grad_scale = 0.9, 0.999, pe["eps"], float(grad_scale)
+        a.step = pe["step"]
+        a.stream = stream
+        _lib.check(L.gsr_adam_step_peer(C.byref(a)), "gsr_adam_step_peer")
+        pe["hp"].barrier(channel=0)          # every rank's parameter stores have landed
 
     def _views(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
         v = {}
@@ -308,6 +414,9 @@ class KeyframeBatchMapper:
 
     def step(self, keyframes: Sequence[Keyframe], grad_scale: float = 1.0, on_forward=None) -> None:
         """One mapping iteration over this rank's keyframes."""
+        if self.peer is not None and self.P > 0:
+            self._step_peer(keyframes, grad_scale, on_forward)
+            return
         if self.overlap_adam and self.world_size == 1 and len(keyframes) > 0 and self.P > 0:
             self._step_overlapped(keyframes, grad_scale, on_forward)
             return

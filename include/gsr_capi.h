@@ -170,6 +170,46 @@ int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
                        double beta2, double eps, float grad_scale, int64_t rows,
                        const int32_t* row_mask, int phase, void* stream);
 
+/* ---- multi-GPU optimiser step over NVLink peer memory (one node, N <= GSR_MAX_PEERS ranks) ----
+ * Fuses the gradient reduction, the Adam update and the parameter broadcast of a data-parallel
+ * mapping step into one kernel: rank `rank` owns the element range [shard_lo, shard_hi) of a flat
+ * arena, sums the N peers' gradient arenas over it (remote loads, skipped for rows whose
+ * union_mask is 0), updates ITS copy of the parameters with shard-local Adam moments and stores the
+ * result into every rank's parameter arena (remote stores).  All arenas share one layout, described
+ * by `segments` (ascending, 4-element aligned starts; `width` = elements per Gaussian row, `lr` per
+ * segment).  param_peers / grad_peers are the N peer-mapped base pointers of the arenas (e.g. from
+ * torch.distributed._symmetric_memory).  The caller must bracket the call with cross-rank barriers:
+ * all gradients written before, all ranks' kernels finished before parameters are read again.
+ * Replaces torch::optim::Adam::step + the gradient all-reduce a multi-GPU port of
+ * src/gaussian_mapper.cpp:465 would need. */
+#define GSR_MAX_PEERS 8
+#define GSR_PEER_MAX_SEGMENTS 8
+typedef struct gsr_peer_segment {
+  int64_t start;   /* first arena element */
+  int64_t numel;
+  int32_t width;   /* elements per row */
+  double lr;
+} gsr_peer_segment;
+typedef struct gsr_peer_adam_args {
+  int n_peers, rank;
+  float* param_peers[GSR_MAX_PEERS];
+  const float* grad_peers[GSR_MAX_PEERS];
+  int n_segments;
+  gsr_peer_segment segments[GSR_PEER_MAX_SEGMENTS];
+  int64_t shard_lo, shard_hi;   /* multiples of 4 elements */
+  float* exp_avg;               /* [shard_hi - shard_lo], local */
+  float* exp_avg_sq;
+  const int32_t* union_mask;    /* [rows]: > 0 <=> some rank rendered the row (gsr_peer_union_mask) */
+  double beta1, beta2, eps;
+  float grad_scale;
+  int64_t step;                 /* step count AFTER this update (>= 1) */
+  void* stream;
+} gsr_peer_adam_args;
+int gsr_adam_step_peer(const gsr_peer_adam_args* a);
+/* union_out[row] = max over the N ranks of radii_peers[k][row] (peer-mapped radii buffers). */
+int gsr_peer_union_mask(const int32_t* const* radii_peers, int n_peers, int64_t rows,
+                        int32_t* union_out, void* stream);
+
 /* ---- test / debug exports (device -> device copies out of the opaque buffers) ---- */
 /* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits). */
 int gsr_export_binning(const char* geom_buffer, const char* binning_buffer,

@@ -246,6 +246,21 @@ def test_masked_single_view_step_equals_dense_step():
         assert rel_l2(pa_ - init[k], pb_ - init[k]) <= 1e-3, k
 
 
+def test_peer_exchange_matches_nccl_path_on_two_gpus():
+    """gsr_adam_step_peer (fused reduction + Adam + broadcast over peer memory) against the NCCL
+    all-reduce + fused Adam path; needs two GPUs (skipped on the single-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "check_peer.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "peer exchange OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def _brute_knn(pts: torch.Tensor) -> torch.Tensor:
     out = torch.empty(pts.size(0), device=pts.device)
     for s in range(0, pts.size(0), 2048):
