@@ -309,6 +309,27 @@ def run_product(args, rank, world, dev):
         name, cnt, tot = line.split()
         prof[name] = float(tot) / max(1, int(cnt))
 
+    # multi-rank: where the step time goes on every rank (render = fwd + bwd of this rank's view;
+    # wait = first barrier, i.e. waiting for the slowest rank's view; exchange = union mask + fused
+    # peer kernel + second barrier)
+    rank_breakdown = None
+    if world > 1 and mapper.peer is not None:
+        acc = torch.zeros(3, device=dev, dtype=torch.float64)
+        n_tr = 10
+        for _ in range(n_tr):
+            mapper.trace = []
+            step_resident()
+            torch.cuda.synchronize()
+            ev = dict(mapper.trace)
+            acc[0] += ev["step_begin"].elapsed_time(ev["render_end"])
+            acc[1] += ev["render_end"].elapsed_time(ev["barrier1_end"])
+            acc[2] += ev["barrier1_end"].elapsed_time(ev["step_end"])
+        mapper.trace = None
+        acc /= n_tr
+        allr = [torch.zeros_like(acc) for _ in range(world)]
+        dist.all_gather(allr, acc)
+        rank_breakdown = [{"rank": r, "render_ms": round(float(x[0]), 4), "wait_ms": round(float(x[1]), 4),
+                           "exchange_ms": round(float(x[2]), 4)} for r, x in enumerate(allr)]
     if world > 1:
         lt = torch.tensor([launches], device=dev, dtype=torch.float64)
         dist.all_reduce(lt)
@@ -392,6 +413,8 @@ def run_product(args, rank, world, dev):
         "roofline_hbm": roofline_hbm,
         "stages": stages,
     }
+    if rank_breakdown is not None:
+        line["rank_breakdown"] = rank_breakdown
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config)
     return line

@@ -174,6 +174,7 @@ class KeyframeBatchMapper:
         pe = self.peer
         dev = self.arena.device
         mask = None
+        self._mark("step_begin", torch.cuda.current_stream(dev))
         if len(keyframes) == 0:
             self.arena.zero_()
         for i, kf in enumerate(keyframes):
@@ -192,7 +193,9 @@ class KeyframeBatchMapper:
             pe["radii"].copy_(mask)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         L = _lib.lib()
+        self._mark("render_end", torch.cuda.current_stream(dev))
         pe["hg"].barrier(channel=0)          # every rank's gradients and radii are written
+        self._mark("barrier1_end", torch.cuda.current_stream(dev))
         rptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hr"].buffer_ptrs])
         _lib.check(L.gsr_peer_union_mask(rptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
                    "gsr_peer_union_mask")
@@ -216,7 +219,9 @@ class KeyframeBatchMapper:
         a.step = pe["step"]
         a.stream = stream
         _lib.check(L.gsr_adam_step_peer(C.byref(a)), "gsr_adam_step_peer")
+        self._mark("peer_adam_end", torch.cuda.current_stream(dev))
         pe["hp"].barrier(channel=0)          # every rank's parameter stores have landed
+        self._mark("step_end", torch.cuda.current_stream(dev))
 
     def _views(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
         v = {}
