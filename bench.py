@@ -131,11 +131,15 @@ def make_scene(cfg: str, rank: int):
     return scene, cam
 
 
-def host_keyframe(scene, cam):
-    """Pinned host copies of one step's inputs."""
+def host_keyframe(scene, cam, with_loss=False):
+    """Pinned host copies of one step's inputs.  The image-sized input ("dL_dout") is the seeded
+    dL/d(image), or — with --with-loss — a seeded ground-truth image for the L1+SSIM loss."""
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    big = scene.dL_dout
+    if with_loss:
+        big = np.random.default_rng(77).uniform(0.0, 1.0, scene.dL_dout.shape).astype(np.float32)
     return dict(viewmatrix=pin(cam.viewmatrix), projmatrix=pin(cam.projmatrix), campos=pin(cam.campos),
-                bg=pin(scene.bg), dL_dout=pin(scene.dL_dout))
+                bg=pin(scene.bg), dL_dout=pin(big))
 
 
 def workload_counts(scene, cam, params, dev):
@@ -201,10 +205,16 @@ def run_product(args, rank, world, dev):
     params = dict(means3D=t(scene.means3D), dc=t(scene.dc), sh=t(scene.sh), opacity=t(scene.opacity),
                   scales=t(scene.scales), rotations=t(scene.rotations))
     mapper = KeyframeBatchMapper(params, scene.degree, t(scene.bg), freeze_render_inputs=True)
-    kf_dev = Keyframe(t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos), cam.tanfovx, cam.tanfovy,
-                      cam.H, cam.W, t(scene.dL_dout))
+    hk = host_keyframe(scene, cam, args.with_loss)
+    big_dev = hk["dL_dout"].to(dev)
+
+    def make_kf(view, proj, campos, big):
+        if args.with_loss:
+            return Keyframe(view, proj, campos, cam.tanfovx, cam.tanfovy, cam.H, cam.W, gt_image=big)
+        return Keyframe(view, proj, campos, cam.tanfovx, cam.tanfovy, cam.H, cam.W, big)
+
+    kf_dev = make_kf(t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos), big_dev)
     counts = workload_counts(scene, cam, params, dev)
-    hk = host_keyframe(scene, cam)
     copy_stream = torch.cuda.Stream(device=dev)
 
     def barrier():
@@ -243,8 +253,7 @@ def run_product(args, rank, world, dev):
             dl_stage[slot].copy_(hk["dL_dout"], non_blocking=True)
             ev_h2d.record(copy_stream)
         mapper.bg = stage["bg"]
-        kf = Keyframe(stage["viewmatrix"], stage["projmatrix"], stage["campos"], cam.tanfovx, cam.tanfovy,
-                      cam.H, cam.W, dl_stage[slot])
+        kf = make_kf(stage["viewmatrix"], stage["projmatrix"], stage["campos"], dl_stage[slot])
         keep = {}
 
         def after_forward(_kf, fwd):
@@ -393,7 +402,9 @@ def run_product(args, rank, world, dev):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {scene.name}, one keyframe per GPU per step, "
-                               "fwd+bwd+(allreduce)+fused Adam; loss/activations out of scope",
+                               + ("fwd + fused L1+SSIM loss + bwd + exchange + Adam; activations out of scope"
+                                  if args.with_loss else
+                                  "fwd+bwd+(exchange)+fused Adam; loss/activations out of scope"),
                    "P": counts["P"], "sh_degree": scene.degree, "image": [cam.W, cam.H],
                    "keyframes_per_step": world, "parallelism": f"dp{world} (keyframe batch)",
                    "exchange": ("none (single rank)" if world == 1 else
@@ -459,10 +470,11 @@ def run_reference(args, rank, world, dev):
              scales=t(scene.scales), rotations=t(scene.rotations))
     e = torch.empty(0, dtype=torch.float32, device=dev)
     rr = rb.RefRasterizer()
-    hk = host_keyframe(scene, cam)
+    hk = host_keyframe(scene, cam, args.with_loss)
     stage = {k: torch.empty_like(v, device=dev) for k, v in hk.items()}
     img_host = torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory()
     names = ("means3D", "dc", "sh", "opacity", "scales", "rotations")
+    from gsdf_slam_b200.loss import reference_loss
     gname = dict(means3D="dL_dmeans3D", dc="dL_ddc", sh="dL_dsh", opacity="dL_dopacity",
                  scales="dL_dscales", rotations="dL_drotations")
     from gsdf_slam_b200.mapping import DEFAULT_LR
@@ -519,6 +531,11 @@ def run_reference(args, rank, world, dev):
                 img_host.copy_(color, non_blocking=True)
             color.record_stream(copy_stream)
             main.wait_event(ev_h2d)
+        if args.with_loss:
+            # the reference's loss: LibTorch op sequence + autograd (src/gaussian_mapper.cpp:414-431)
+            x = color.detach().requires_grad_(True)
+            reference_loss(x, dl, None, 0.2).backward()
+            dl = x.grad
         g = rr.backward(src["bg"], p["means3D"], radii, e, p["scales"], p["rotations"], 1.0, e,
                         src["viewmatrix"], src["projmatrix"], cam.tanfovx, cam.tanfovy, dl,
                         p["dc"], p["sh"], scene.degree, src["campos"], debug=debug)
@@ -554,7 +571,8 @@ def run_reference(args, rank, world, dev):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {scene.name}; UNMODIFIED reference CUDA rasterizer "
-                                   "recompiled for sm_100a (oracle/_ref) + LibTorch Adam op sequence; "
+                                   "recompiled for sm_100a (oracle/_ref) + LibTorch Adam op sequence"
+                                   + (" + LibTorch L1+SSIM loss with autograd" if args.with_loss else "") + "; "
                                    "host buffers copied every step like the product's e2e",
                        "reference_debug_flag": False},
             "e2e": {"value": round(1000.0 / ms_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -583,6 +601,10 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-loss", action="store_true",
+                    help="include the photometric L1+SSIM loss (SURVEY row f-1) in the step: fused kernels in "
+                         "the product arm, the reference's LibTorch op sequence + autograd in the reference arm; "
+                         "the image-sized input is then the ground-truth image instead of dL/d(image)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
 

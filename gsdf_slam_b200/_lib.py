@@ -89,6 +89,7 @@ class PeerAdamArgs(C.Structure):
 # every symbol include/gsr_capi.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
     "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows", "gsr_adam_step_peer", "gsr_peer_union_mask",
+    "gsr_l1_ssim_loss", "gsr_l1_ssim_workspace_bytes",
     "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_sort_temp_bytes",
     "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
 ]
@@ -137,6 +138,11 @@ def lib() -> C.CDLL:
     L.gsr_adam_step_peer.restype = C.c_int
     L.gsr_peer_union_mask.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     L.gsr_peer_union_mask.restype = C.c_int
+    L.gsr_l1_ssim_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    L.gsr_l1_ssim_workspace_bytes.restype = C.c_size_t
+    L.gsr_l1_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsr_l1_ssim_loss.restype = C.c_int
     L.gsr_export_binning.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_export_binning.restype = C.c_int

@@ -10,8 +10,9 @@ identical fused Adam step (gsr_adam_step) to its replica — no parameter broadc
 Gradient arena layout (fp32, each segment 16-byte aligned and itself a valid contiguous
 gradient tensor): [xyz 3P | f_dc 3P | opacity P | scaling 3P | rotation 4P | f_rest 3MP].
 
-The loss (L1 + SSIM) and the activation functions are outside this path (SURVEY.md §8f-1,
-f-2): the step consumes dL/d(image) per keyframe and works on activated parameters.
+A keyframe either carries dL/d(image) (the caller owns the loss) or a ground-truth image, in
+which case the fused L1 + SSIM loss of loss.py runs between the two passes.
+The activation functions are outside this path (f-2): the step works on activated parameters.
 """
 from __future__ import annotations
 
@@ -65,7 +66,9 @@ class Keyframe:
     tanfovy: float
     H: int
     W: int
-    dL_dout: torch.Tensor  # [3,H,W] gradient of the (out-of-scope) loss w.r.t. the rendered image
+    dL_dout: Optional[torch.Tensor] = None   # [3,H,W] dL/d(rendered image), if the caller owns the loss
+    gt_image: Optional[torch.Tensor] = None  # [3,H,W] ground truth: dL_dout then comes from the fused
+    mask: Optional[torch.Tensor] = None      # [H,W]   L1 + SSIM loss (loss.py)
 
 
 class KeyframeBatchMapper:
@@ -74,7 +77,8 @@ class KeyframeBatchMapper:
     def __init__(self, params: Dict[str, torch.Tensor], degree: int, bg: torch.Tensor,
                  lr: Optional[Dict[str, float]] = None, eps: float = 1e-15,
                  process_group=None, freeze_render_inputs: bool = False, overlap_adam: bool = False,
-                 masked_single_view: bool = True, peer_exchange: Optional[bool] = None):
+                 masked_single_view: bool = True, peer_exchange: Optional[bool] = None,
+                 lambda_dssim: float = 0.2):
         self.params = {k: params[k].contiguous() for k in SEGMENTS}
         self.degree = int(degree)
         self.bg = bg
@@ -96,6 +100,8 @@ class KeyframeBatchMapper:
                                     if self.opt_params[k].numel() > 0], lr=0.0, eps=eps)
         self.last_radii: Optional[torch.Tensor] = None
         self.last_color: Optional[torch.Tensor] = None
+        self.lambda_dssim = float(lambda_dssim)
+        self.last_loss: Optional[torch.Tensor] = None   # device [3] {loss, L1, SSIM} of the last keyframe
         # N > 1 ranks on one NVLink node: gradient reduction + Adam + parameter broadcast fused in
         # one kernel over peer memory (gsr_adam_step_peer) instead of NCCL all-reduce + full Adam
         self.peer = None
@@ -256,10 +262,18 @@ class KeyframeBatchMapper:
             if on_forward is not None:
                 on_forward(kf, fwd)
         R, B, color, radii, geom, binning, img, sample = fwd
+        dL_dout = kf.dL_dout
+        if dL_dout is None:
+            # photometric loss of the reference's mapping iteration (src/gaussian_mapper.cpp:414-431),
+            # forward + backward in two kernels
+            from .loss import l1_ssim_loss
+            if kf.gt_image is None:
+                raise RuntimeError("Keyframe needs either dL_dout or gt_image")
+            self.last_loss, dL_dout = l1_ssim_loss(color, kf.gt_image, kf.mask, self.lambda_dssim)
         out = {GRAD_NAME[k]: grad_views[k] for k in SEGMENTS if grad_views[k].numel() > 0}
         g = RasterizeGaussiansBackwardCUDA(self.bg, p["means3D"], radii, e, p["scales"], p["rotations"], 1.0,
                                            e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy,
-                                           kf.dL_dout, p["dc"], p["sh"], self.degree, kf.campos, geom, R,
+                                           dL_dout, p["dc"], p["sh"], self.degree, kf.campos, geom, R,
                                            binning, img, B, sample, False, want_dcov3D=False, out=out,
                                            rendered_rows_only=rendered_rows_only)
         self.last_radii, self.last_color = radii, color

@@ -170,6 +170,19 @@ int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
                        double beta2, double eps, float grad_scale, int64_t rows,
                        const int32_t* row_mask, int phase, void* stream);
 
+/* ---- fused L1 + SSIM photometric loss, forward + backward ----
+ * Replaces loss_utils::l1_loss + loss_utils::ssim and their autograd backward as used by
+ * GaussianMapper::trainForOneIteration (include/loss_utils.h:28-124, src/gaussian_mapper.cpp:414-431):
+ *   masked = where(mask > 0, image, 1);  loss = (1 - l) * mean|masked - where(mask > 0, gt, 1)|
+ *                                             + l * (1 - SSIM(masked, gt))      (11x11, sigma 1.5)
+ * image, gt, dL_dimage: [3,H,W]; mask: [H,W] or NULL; loss_out: device [3] {loss, L1, SSIM} or NULL.
+ * dL_dimage = d loss / d image, ready to be passed to gsr_backward as dL_dpix.
+ * workspace: gsr_l1_ssim_workspace_bytes(H, W) bytes of device memory. */
+size_t gsr_l1_ssim_workspace_bytes(int H, int W);
+int gsr_l1_ssim_loss(const float* image, const float* gt, const float* mask, int H, int W,
+                     float lambda_dssim, float* loss_out, float* dL_dimage, char* workspace,
+                     void* stream);
+
 /* ---- multi-GPU optimiser step over NVLink peer memory (one node, N <= GSR_MAX_PEERS ranks) ----
  * Fuses the gradient reduction, the Adam update and the parameter broadcast of a data-parallel
  * mapping step into one kernel: rank `rank` owns the element range [shard_lo, shard_hi) of a flat
