@@ -353,7 +353,10 @@ __device__ __forceinline__ void warp_sort_pack_tile(uint32_t n, uint32_t start, 
   for (int e = 0; e < kE; ++e) s_g[lane * kE + e] = (uint32_t)v[e];
   __syncwarp();
   const uint32_t pieces = 3u * n;
-  constexpr int kInFlight = 8;  // gathers in flight per lane (the copy is pure latency otherwise)
+#ifndef GSR_TSP_INFLIGHT
+#define GSR_TSP_INFLIGHT 8
+#endif
+  constexpr int kInFlight = GSR_TSP_INFLIGHT;  // gathers in flight per lane (the copy is pure latency otherwise)
   for (uint32_t q0 = 0; q0 < pieces; q0 += 32 * kInFlight) {
     float4 t[kInFlight];
 #pragma unroll
@@ -380,7 +383,10 @@ __device__ __forceinline__ void warp_sort_pack_tile(uint32_t n, uint32_t start, 
 constexpr int kSortSmallThreads = 128;  // four tiles per CTA
 constexpr int kSortLargeThreads = 512;
 
-__global__ void __launch_bounds__(kSortSmallThreads)
+#ifndef GSR_TSP_MINBLOCKS
+#define GSR_TSP_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kSortSmallThreads, GSR_TSP_MINBLOCKS)
 tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, uint32_t T,
                             BinHeader* __restrict__ bin_hdr, uint32_t capacity, uint64_t* __restrict__ items,
                             const float4* __restrict__ splat_rec, float4* __restrict__ rec) {
