@@ -33,7 +33,7 @@ class ForwardArgs(C.Structure):
         ("sample_resize", RESIZE_FN), ("sample_user", C.c_void_p),
         ("stream", C.c_void_p),
         ("num_rendered", C.POINTER(C.c_int)), ("num_buckets", C.POINTER(C.c_int)),
-        ("radii_ready_event", C.c_void_p),
+        ("raw_params", C.c_int), ("radii_ready_event", C.c_void_p),
     ]
 
 
@@ -54,7 +54,7 @@ class BackwardArgs(C.Structure):
         ("dL_dcolor", C.c_void_p), ("dL_dmean3D", C.c_void_p), ("dL_dcov3D", C.c_void_p),
         ("dL_ddc", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p),
-        ("debug", C.c_int), ("stream", C.c_void_p), ("rendered_rows_only", C.c_int),
+        ("debug", C.c_int), ("stream", C.c_void_p), ("raw_params", C.c_int), ("rendered_rows_only", C.c_int),
     ]
 
 

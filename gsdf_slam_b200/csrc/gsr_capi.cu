@@ -158,6 +158,7 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.focal_x = W / (2.0f * a->tan_fovx);
   pp.grid_x = gx; pp.grid_y = gy;
   pp.prefiltered = a->prefiltered;
+  pp.activate = a->raw_params != 0;
   const uintptr_t al = (uintptr_t)a->means3D | (uintptr_t)pp.scales | (uintptr_t)pp.rotations |
                        (uintptr_t)a->dc;
   pp.vec_ok = (al & 15) == 0;
@@ -257,6 +258,9 @@ int gsr_backward(const gsr_backward_args* a) {
   PreBwdParams bp;
   std::memset(&bp, 0, sizeof(bp));
   bp.P = P; bp.D = a->D; bp.M = a->M;
+  bp.activate = a->raw_params != 0;
+  bp.opacities = a->opacities;
+  if (bp.activate && a->cov3D_precomp) return GSR_ERR_BAD_ARG;  // raw scale / rotation needed
   bp.means3D = a->means3D; bp.radii = a->radii; bp.dc = a->dc;
   bp.shs = (a->colors_precomp || a->M <= 0) ? nullptr : a->shs;
   bp.clamped = g.clamped;

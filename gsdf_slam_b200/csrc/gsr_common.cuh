@@ -211,6 +211,19 @@ __device__ __forceinline__ float ndc_to_pix(float v, int S) {
   return ((v + 1.0) * S - 1.0) * 0.5;
 }
 
+// Parameter activations of the Gaussian model (reference GaussianModel::get*Activation,
+// src/gaussian_model.cpp:48-71: torch::sigmoid, torch::exp, torch::nn::functional::normalize with
+// eps = 1e-12), for the entry points that take RAW parameters.
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float3 act_exp3(float3 s) { return {expf(s.x), expf(s.y), expf(s.z)}; }
+__device__ __forceinline__ float quat_norm(float4 q) {
+  return fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+}
+__device__ __forceinline__ float4 act_normalize4(float4 q) {
+  const float n = quat_norm(q);
+  return {q.x / n, q.y / n, q.z / n, q.w / n};
+}
+
 // tile rectangle of a disc (reference getRect, auxiliary.h:38-51)
 __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, int gx, int gy,
                                           uint2& rect_min, uint2& rect_max) {

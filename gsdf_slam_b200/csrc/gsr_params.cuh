@@ -25,6 +25,7 @@ struct PreprocessParams {
   int grid_x, grid_y;
   int prefiltered;
   int vec_ok;
+  int activate;           // opacities / scales / rotations are RAW parameters (row f-2)
   int* radii;
   float* depths;
   float2* means2D;
@@ -39,6 +40,8 @@ struct PreprocessParams {
 };
 struct PreBwdParams {
   int P, D, M;
+  int activate;                 // gradients w.r.t. the RAW opacity / scale / rotation (row f-2)
+  const float* opacities;       // raw opacities (needed only when activate)
   const float* means3D;
   const int* radii;
   const float* dc;

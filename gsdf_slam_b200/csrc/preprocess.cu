@@ -155,6 +155,13 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
     }
   }
   __syncthreads();
+  // raw-parameter entry point (row f-2): every thread activates its own staged row in place, so
+  // the geometry code below is the same instruction stream for both entry points
+  if (a.activate && a.scales != nullptr && tid < count) {
+    const float3 s3 = act_exp3({s_scale[3 * tid], s_scale[3 * tid + 1], s_scale[3 * tid + 2]});
+    s_scale[3 * tid] = s3.x; s_scale[3 * tid + 1] = s3.y; s_scale[3 * tid + 2] = s3.z;
+    reinterpret_cast<float4*>(s_rot)[tid] = act_normalize4(reinterpret_cast<const float4*>(s_rot)[tid]);
+  }
 
   // ---- per-Gaussian geometry ---------------------------------------------------
   bool visible = false;
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
         if ((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y) != 0) {
           visible = true;
           opacity = a.opacities[idx];
+          if (a.activate) opacity = act_sigmoid(opacity);
         }
       }
     }

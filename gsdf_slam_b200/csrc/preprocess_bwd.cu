@@ -85,7 +85,8 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
   store3(a.dL_dmean2D, i, {dmean2D_x, dmean2D_y, 0.f});
   if (a.dL_dconic)
     reinterpret_cast<float4*>(a.dL_dconic)[i] = make_float4(dL_dconic.x, dL_dconic.y, 0.f, dL_dconic.z);
-  a.dL_dopacity[i] = dopacity;
+  // raw-parameter entry point: chain through sigmoid (sigma' = o (1 - o), o = the activated opacity)
+  a.dL_dopacity[i] = a.activate ? dopacity * cop.w * (1.0f - cop.w) : dopacity;
   store3(a.dL_dcolor, i, dL_dRGB);
 
   const float3 mean = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
@@ -94,10 +95,16 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
   float cov3D[6];
   float3 scale = {0.f, 0.f, 0.f};
   float4 q = {0.f, 0.f, 0.f, 0.f};
+  float q_norm = 1.0f;
   M3 R, Mm;
   if (a.scales != nullptr) {
     scale = {a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2]};
     q = reinterpret_cast<const float4*>(a.rotations)[i];
+    if (a.activate) {
+      q_norm = quat_norm(q);
+      scale = act_exp3(scale);
+      q = {q.x / q_norm, q.y / q_norm, q.z / q_norm, q.w / q_norm};
+    }
     const float r = q.x, x = q.y, y = q.z, z = q.w;
     R = m3_make(1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y),
                 2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x),
@@ -339,6 +346,8 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
     dscale.x = dot3(Rt[0], dL_dMt[0]);
     dscale.y = dot3(Rt[1], dL_dMt[1]);
     dscale.z = dot3(Rt[2], dL_dMt[2]);
+    // raw-parameter entry point: d exp(s)/ds = exp(s) = the activated scale
+    if (a.activate) dscale = {dscale.x * scale.x, dscale.y * scale.y, dscale.z * scale.z};
     store3(a.dL_dscale, i, dscale);
 
 #pragma unroll
@@ -356,6 +365,12 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
               2 * z * (dL_dMt[1][2] + dL_dMt[2][1]) - 4 * y * (dL_dMt[2][2] + dL_dMt[0][0]);
     dL_dq.w = 2 * r * (dL_dMt[0][1] - dL_dMt[1][0]) + 2 * x * (dL_dMt[2][0] + dL_dMt[0][2]) +
               2 * y * (dL_dMt[1][2] + dL_dMt[2][1]) - 4 * z * (dL_dMt[1][1] + dL_dMt[0][0]);
+    if (a.activate) {
+      // q = raw / |raw|: d raw = (dq - q (q . dq)) / |raw|
+      const float qd = q.x * dL_dq.x + q.y * dL_dq.y + q.z * dL_dq.z + q.w * dL_dq.w;
+      dL_dq = {(dL_dq.x - q.x * qd) / q_norm, (dL_dq.y - q.y * qd) / q_norm, (dL_dq.z - q.z * qd) / q_norm,
+               (dL_dq.w - q.w * qd) / q_norm};
+    }
     reinterpret_cast<float4*>(a.dL_drot)[i] = dL_dq;
   } else {
     store3(a.dL_dscale, i, {0.f, 0.f, 0.f});

@@ -78,7 +78,7 @@ class KeyframeBatchMapper:
                  lr: Optional[Dict[str, float]] = None, eps: float = 1e-15,
                  process_group=None, freeze_render_inputs: bool = False, overlap_adam: bool = False,
                  masked_single_view: bool = True, peer_exchange: Optional[bool] = None,
-                 lambda_dssim: float = 0.2):
+                 lambda_dssim: float = 0.2, raw_params: bool = False):
         self.params = {k: params[k].contiguous() for k in SEGMENTS}
         self.degree = int(degree)
         self.bg = bg
@@ -101,6 +101,10 @@ class KeyframeBatchMapper:
         self.last_radii: Optional[torch.Tensor] = None
         self.last_color: Optional[torch.Tensor] = None
         self.lambda_dssim = float(lambda_dssim)
+        # raw_params: `params` holds the model's RAW opacity / scaling / rotation;
+        # the activations and their backward run inside the preprocess kernels, so the gradients in
+        # the arena are those of the leaf parameters and Adam trains the model itself
+        self.raw_params = bool(raw_params)
         self.last_loss: Optional[torch.Tensor] = None   # device [3] {loss, L1, SSIM} of the last keyframe
         # N > 1 ranks on one NVLink node: gradient reduction + Adam + parameter broadcast fused in
         # one kernel over peer memory (gsr_adam_step_peer) instead of NCCL all-reduce + full Adam
@@ -248,7 +252,7 @@ class KeyframeBatchMapper:
         return RasterizeGaussiansCUDA(self.bg, p["means3D"], e, p["opacity"], p["scales"], p["rotations"],
                                       1.0, e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy, kf.H,
                                       kf.W, p["dc"], p["sh"], self.degree, kf.campos, False, False,
-                                      radii_ready_event=radii_ready_event)
+                                      radii_ready_event=radii_ready_event, raw_params=self.raw_params)
 
     def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor], fwd=None, on_forward=None,
                         rendered_rows_only: bool = False):
@@ -275,7 +279,8 @@ class KeyframeBatchMapper:
                                            e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy,
                                            dL_dout, p["dc"], p["sh"], self.degree, kf.campos, geom, R,
                                            binning, img, B, sample, False, want_dcov3D=False, out=out,
-                                           rendered_rows_only=rendered_rows_only)
+                                           rendered_rows_only=rendered_rows_only,
+                                           raw_opacity=p["opacity"] if self.raw_params else None)
         self.last_radii, self.last_color = radii, color
         return color, radii, g
 

@@ -68,12 +68,15 @@ class _Scratch:
 def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                            cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                            image_width, dc, sh, degree, campos, prefiltered, debug,
-                           radii_ready_event: Optional["torch.cuda.Event"] = None):
+                           radii_ready_event: Optional["torch.cuda.Event"] = None, raw_params: bool = False):
     """-> (rendered, num_buckets, out_color, radii, geomBuffer, binningBuffer, imgBuffer, sampleBuffer)
 
     ``radii_ready_event`` (extension): a ``torch.cuda.Event`` recorded on the current stream as
     soon as ``radii`` is final (after the first kernel of the forward pass), so that a side
-    stream can start the zero-gradient phase of the visibility-split Adam step early."""
+    stream can start the zero-gradient phase of the visibility-split Adam step early.
+    ``raw_params`` (extension): ``opacity`` / ``scales`` / ``rotations`` are the
+    model's RAW parameters; sigmoid / exp / normalize (src/gaussian_model.cpp:48-71) are applied
+    inside the preprocess kernel instead of by three LibTorch ops per view."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     L = _lib.lib()
@@ -102,7 +105,7 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
         geom_resize=geom.cb, geom_user=None, binning_resize=binning.cb, binning_user=None,
         image_resize=img.cb, image_user=None, sample_resize=sample.cb, sample_user=None,
         stream=_stream(dev), num_rendered=C.pointer(rendered), num_buckets=C.pointer(buckets),
-        radii_ready_event=None)
+        raw_params=int(bool(raw_params)), radii_ready_event=None)
     with torch.cuda.device(dev):
         if radii_ready_event is not None:
             if not radii_ready_event.cuda_event:      # torch creates the cudaEvent_t lazily
@@ -117,7 +120,7 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                                    tan_fovy, dL_dout_color, dc, sh, degree, campos, geomBuffer, R,
                                    binningBuffer, imageBuffer, B, sampleBuffer, debug,
                                    want_dcov3D: bool = True, out: Optional[dict] = None,
-                                   rendered_rows_only: bool = False):
+                                   rendered_rows_only: bool = False, raw_opacity: Optional[torch.Tensor] = None):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh,
     dL_dscales, dL_drotations)   (same order as src/rasterize_points.cu:204)
 
@@ -125,7 +128,10 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     the flat gradient arena that is all-reduced across GPUs) to receive a gradient in place.
     ``rendered_rows_only`` (extension): write only the rows of the rendered Gaussians and leave
     the others untouched (no dense zero fill) — for consumers that go through the ``radii`` mask
-    (``FusedAdam.step_rows(..., ROWS_ALL)``)."""
+    (``FusedAdam.step_rows(..., ROWS_ALL)``).
+    ``raw_opacity`` (extension, row f-2): the forward ran with ``raw_params``; ``scales`` /
+    ``rotations`` are raw too and dL_dopacity / dL_dscales / dL_drotations come back w.r.t. the RAW
+    parameters (chain rule through sigmoid / exp / normalize inside the backward preprocess)."""
     L = _lib.lib()
     dev = means3D.device
     P = int(means3D.size(0))
@@ -157,10 +163,11 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                  projmatrix, campos, dL_dout_color)]
         (bg_c, means_c, dc_c, sh_c, col_c, sc_c, rot_c, cov_c, view_c, proj_c, cam_c, dpix_c) = keep
         radii_c = radii.contiguous()
+        raw_op_c = _f32c(raw_opacity) if raw_opacity is not None else None
         a = _lib.BackwardArgs(
             P=P, D=int(degree), M=M, R=int(R), B=int(B), W=W, H=H,
             background=_ptr(bg_c), means3D=_ptr(means_c), dc=_ptr(dc_c), shs=_ptr(sh_c),
-            colors_precomp=_ptr(col_c), opacities=None, scales=_ptr(sc_c),
+            colors_precomp=_ptr(col_c), opacities=_ptr(raw_op_c), scales=_ptr(sc_c),
             scale_modifier=float(scale_modifier), rotations=_ptr(rot_c), cov3D_precomp=_ptr(cov_c),
             viewmatrix=_ptr(view_c), projmatrix=_ptr(proj_c), campos=_ptr(cam_c),
             tan_fovx=float(tan_fovx), tan_fovy=float(tan_fovy), radii=_ptr(radii_c),
@@ -170,7 +177,7 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             dL_dcolor=_ptr(dL_dcolors), dL_dmean3D=_ptr(dL_dmeans3D), dL_dcov3D=_ptr(dL_dcov3D),
             dL_ddc=_ptr(dL_ddc), dL_dsh=_ptr(dL_dsh), dL_dscale=_ptr(dL_dscales),
             dL_drot=_ptr(dL_drotations), debug=int(bool(debug)), stream=_stream(dev),
-            rendered_rows_only=int(bool(rendered_rows_only)))
+            raw_params=int(raw_opacity is not None), rendered_rows_only=int(bool(rendered_rows_only)))
         with torch.cuda.device(dev):
             _lib.check(L.gsr_backward(C.byref(a)), "gsr_backward")
     if dL_dcov3D is None:

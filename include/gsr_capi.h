@@ -78,6 +78,9 @@ typedef struct gsr_forward_args {
   void* stream;                /* cudaStream_t */
   int* num_rendered;           /* host out: number of (Gaussian,tile) duplicates R */
   int* num_buckets;            /* host out: kept for API parity (number of 32-splat buckets) */
+  int raw_params;              /* !=0 (extension): opacities / scales / rotations are the
+                                  model's RAW parameters; the callee applies sigmoid / exp / normalize
+                                  (GaussianModel::get*Activation, src/gaussian_model.cpp:48-71) itself */
   void* radii_ready_event;     /* optional cudaEvent_t, recorded on `stream` right after the kernel
                                   that writes `radii` (lets a side stream start gsr_adam_step_rows
                                   phase 0 while the rest of the forward pass runs); may be NULL */
@@ -118,6 +121,9 @@ typedef struct gsr_backward_args {
   float* dL_drot;              /* [P,4] */
   int debug;
   void* stream;
+  int raw_params;              /* !=0: the forward ran with raw_params; `opacities` (raw, required),
+                                  `scales`, `rotations` are raw and dL_dopacity / dL_dscale / dL_drot are
+                                  returned w.r.t. the RAW parameters (chain rule through the activations) */
   int rendered_rows_only;      /* !=0: write only the rows of the rendered Gaussians (radii > 0 and at
                                   least one tile) and leave every other row of the outputs UNTOUCHED
                                   instead of zero-filling it — for callers that consume the gradients

@@ -40,7 +40,8 @@ def test_fused_l1_ssim_matches_the_libtorch_op_sequence(H, W, mask_kind, lam):
     ref.backward()
     stats, grad = l1_ssim_loss(img, gt, mask, lam)
     torch.cuda.synchronize()
-    assert abs(float(stats[0]) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref))), (float(stats[0]), float(ref))
+    rv = float(ref.detach())
+    assert abs(float(stats[0]) - rv) <= 1e-5 * max(1.0, abs(rv)), (float(stats[0]), rv)
     assert torch.isfinite(grad).all()
     err = rel_l2(grad, x.grad)
     assert err <= 1e-4, f"dL/dimage relative L2 {err:.3e}"
