@@ -210,6 +210,33 @@ def cfg2(P: int = 500_000) -> Scene:
     return room_scene(P, 1200, 680, 600.0, 600.0, seed=2, name="cfg2_replica_1200x680_sh3")
 
 
+def cfg3_sequence(P0: int = 100_000, P1: int = 400_000, iters: int = 200, seed: int = 3):
+    """cfg3: TUM-style 640x480 mapping loop whose Gaussian count follows
+    P0 -> P1 with clone / split / prune events every 10 iterations (random 5 % split x2, 3 %
+    prune), and whose every 4th iteration renders at a pyramid level (80x60, 160x120, 320x240), so
+    P, R, T, N all change from call to call.  Yields (iteration, Scene)."""
+    rng = np.random.default_rng(seed)
+    base = frustum_scene(P1 + P1 // 4, 640, 480, 517.306, 516.469, seed=seed, degree=3, sh_coeffs=15,
+                         name="cfg3_pool")
+    alive = np.zeros(base.P, dtype=bool)
+    alive[rng.permutation(base.P)[:P0]] = True
+    grow = (P1 / P0) ** (1.0 / max(1, iters // 10))
+    levels = [(80, 60), (160, 120), (320, 240)]
+    for it in range(iters):
+        if it > 0 and it % 10 == 0:
+            idx = np.flatnonzero(alive)
+            alive[rng.choice(idx, size=max(1, int(0.03 * idx.size)), replace=False)] = False        # prune
+            want = min(int(alive.sum() * grow), P1)
+            dead = np.flatnonzero(~alive)
+            add = min(dead.size, max(0, want - int(alive.sum())) + int(0.05 * idx.size))            # split / clone
+            alive[rng.choice(dead, size=add, replace=False)] = True
+        W, H = (640, 480) if it % 4 else levels[(it // 4) % 3]
+        cam = make_camera(W, H, 517.306 * W / 640.0, 516.469 * H / 480.0)
+        sel = np.flatnonzero(alive)
+        yield it, Scene(f"cfg3_it{it}", cam, 3, base.means3D[sel], base.scales[sel], base.rotations[sel],
+                        base.opacity[sel], base.dc[sel], base.sh[sel], base.bg, _grad_image(rng, H, W))
+
+
 def cfg4(P: int = 2_000_000) -> Scene:
     return outdoor_scene(P, 1241, 376, 718.856, 718.856, seed=4, name="cfg4_kitti_1241x376_sh3")
 

@@ -246,6 +246,35 @@ def test_masked_single_view_step_equals_dense_step():
         assert rel_l2(pa_ - init[k], pb_ - init[k]) <= 1e-3, k
 
 
+def test_keyframe_batch_accumulation_equals_sum_of_single_view_gradients():
+    """BASELINE configs[4] semantics on one rank: a batch of K keyframes accumulates the SUM of the
+    K single-view gradients (== K backward() calls without zero_grad), then one Adam step."""
+    from gsdf_slam_b200.mapping import SEGMENTS, Keyframe, KeyframeBatchMapper
+    scene = scenes.room_scene(20_000, 320, 184, 160.0, 160.0, seed=5, name="room20k")
+    cams = scenes.ring_cameras(4, 320, 184, 160.0, 160.0, radius=0.3)
+    t = to_dev(scene)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    kfs = [Keyframe(tt(c.viewmatrix), tt(c.projmatrix), tt(c.campos), c.tanfovx, c.tanfovy, c.H, c.W, t["dL_dout"])
+           for c in cams]
+    params = dict(means3D=t["means3D"], dc=t["dc"], sh=t["sh"], opacity=t["opacity"], scales=t["scales"],
+                  rotations=t["rotations"])
+    m = KeyframeBatchMapper({k: v.clone() for k, v in params.items()}, scene.degree, t["bg"],
+                            freeze_render_inputs=True)
+    m.accumulate(kfs)
+    torch.cuda.synchronize()
+    total = {k: m.grad_views[k].clone() for k in SEGMENTS}
+    ref = {k: torch.zeros_like(v) for k, v in total.items()}
+    for kf in kfs:
+        m.accumulate([kf])
+        for k in SEGMENTS:
+            ref[k] += m.grad_views[k]
+    torch.cuda.synchronize()
+    for k in SEGMENTS:
+        assert rel_l2(total[k], ref[k]) <= 1e-5, k
+    visible_anywhere = sum((m.render(kf)[3] > 0).long() for kf in kfs) > 0
+    assert 0.2 < float(visible_anywhere.float().mean()) <= 1.0
+
+
 def test_peer_exchange_matches_nccl_path_on_two_gpus():
     """gsr_adam_step_peer (fused reduction + Adam + broadcast over peer memory) against the NCCL
     all-reduce + fused Adam path; needs two GPUs (skipped on the single-GPU box)."""

@@ -137,6 +137,24 @@ def test_forward_backward_vs_reference(name):
     print(name, info, {k: f"{v:.2e}" for k, v in worst.items()})
 
 
+def test_cfg3_mapping_loop_with_changing_gaussian_count_and_resolution():
+    """BASELINE configs[2]: P, R and the image size change from call to call (densify / prune
+    events, image-pyramid levels); every call must still match the reference bit for bit."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libgsdf_ref.so not built")
+    seen = set()
+    for it, scene in scenes.cfg3_sequence(P0=6_000, P1=24_000, iters=24, seed=3):
+        t = to_dev(scene)
+        ref = run_reference(scene, t)
+        fwd = run_product_forward(scene, t)
+        torch.cuda.synchronize()
+        _compare_forward(scene, t, fwd, ref)
+        if it % 3 == 0:
+            _compare_grads(run_product_backward(scene, t, fwd), ref["grads"])
+        seen.add((scene.P, scene.cam.W))
+    assert len(seen) >= 8       # the sequence really varied P and the resolution
+
+
 def test_optimistic_duplicate_buffer_is_regrown_when_the_next_frame_needs_more():
     """gsr_forward sizes the per-duplicate buffer from its previous call with the same (P, W, H);
     a frame that needs more than the hint must transparently redo the per-duplicate stages."""
