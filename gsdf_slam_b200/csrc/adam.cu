@@ -184,11 +184,20 @@ __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, i
       const unsigned rem = o - q * w;
       const unsigned r0 = row_base + q;
       unsigned bits = 0;
+      if (w >= 3u) {
+        // a float4 spans at most two rows: elements 0 .. w-rem-1 lie in r0, the rest in r0 + 1
+        const unsigned in_r0 = min(4u, w - rem);
+        const unsigned b0 = (__ldg(mask + r0) > 0) ? 0u : 15u;
+        const unsigned b1 = (in_r0 < 4u && __ldg(mask + r0 + 1) > 0) ? 0u : 15u;
+        const unsigned first = (1u << in_r0) - 1u;
+        bits = (b0 & first) | (b1 & ~first & 15u);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned rr = rem + j;
-        const unsigned row = r0 + (rr >= w) + (rr >= 2 * w) + (rr >= 3 * w);
-        bits |= (__ldg(mask + row) > 0) ? 0u : (1u << j);
+        for (int j = 0; j < 4; ++j) {
+          const unsigned rr = rem + j;
+          const unsigned row = r0 + (rr >= w) + (rr >= 2 * w) + (rr >= 3 * w);
+          bits |= (__ldg(mask + row) > 0) ? 0u : (1u << j);
+        }
       }
       mine[k] = bits;
     }
