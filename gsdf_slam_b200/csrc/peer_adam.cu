@@ -91,11 +91,15 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
   }
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rendered) {
-    // fixed rank order on every rank: identical sums, replicas stay bit-identical
-    for (int k = 0; k < a.n_peers; ++k) {
-      const float4 x = *reinterpret_cast<const float4*>(a.grad[k] + e);
-      g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
-    }
+    // all N loads are issued before the first sum (NVLink round trips overlap); fixed rank order
+    // of the additions on every rank: identical sums, replicas stay bit-identical
+    float4 x[GSR_MAX_PEERS];
+#pragma unroll
+    for (int k = 0; k < GSR_MAX_PEERS; ++k)
+      if (k < a.n_peers) x[k] = __ldcs(reinterpret_cast<const float4*>(a.grad[k] + e));
+#pragma unroll
+    for (int k = 0; k < GSR_MAX_PEERS; ++k)
+      if (k < a.n_peers) { g.x += x[k].x; g.y += x[k].y; g.z += x[k].z; g.w += x[k].w; }
     if (!(rendered & 1u)) g.x = 0.f;
     if (!(rendered & 2u)) g.y = 0.f;
     if (!(rendered & 4u)) g.z = 0.f;
@@ -110,7 +114,9 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
   peer_adam_elem(p.w, g.w, m.w, v.w, a, S.neg_step_size, S.inv_sqrt_bc2);
   __stcs(reinterpret_cast<float4*>(a.exp_avg + (e - a.lo)), m);
   __stcs(reinterpret_cast<float4*>(a.exp_avg_sq + (e - a.lo)), v);
-  for (int k = 0; k < a.n_peers; ++k) *reinterpret_cast<float4*>(a.param[k] + e) = p;
+#pragma unroll
+  for (int k = 0; k < GSR_MAX_PEERS; ++k)
+    if (k < a.n_peers) *reinterpret_cast<float4*>(a.param[k] + e) = p;
 }
 
 // union[row] = max over ranks of radii_peer[k][row]
