@@ -238,8 +238,11 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, int gx
 // (tx,ty) (reference max_contrib_power_rect_gaussian_float<15,15> and
 // evaluate_opacity_factor, rasterizer_impl.cu:59-118).  The tile is kept iff the
 // returned value <= logf(opacity * 255)  (rasterizer_impl.cu:169-170,193).
-__device__ __forceinline__ float tile_min_power(const float4 co, const float2 mean, int tx,
-                                                int ty) {
+// rcp_x = __frcp_rn(15 * 15 * co.x), rcp_z = __frcp_rn(15 * 15 * co.z): per-Gaussian constants,
+// hoisted out of the per-tile evaluation by the warp-cooperative walks (same operations on the
+// same inputs, so the result is bit-identical to evaluating them here)
+__device__ __forceinline__ float tile_min_power_pre(const float4 co, const float2 mean, int tx, int ty,
+                                                    float rcp_dxdxcox, float rcp_dydycoz) {
   const float rminx = (float)(tx * GSR_TILE_X), rminy = (float)(ty * GSR_TILE_Y);
   const float rmaxx = (float)((tx + 1) * GSR_TILE_X - 1), rmaxy = (float)((ty + 1) * GSR_TILE_Y - 1);
   const float PW = 15.0f, PH = 15.0f;
@@ -259,8 +262,6 @@ __device__ __forceinline__ float tile_min_power(const float4 co, const float2 me
     const float dy = copysign(PH, y_min_diff);
     const float diffx = mean.x - px;
     const float diffy = mean.y - py;
-    const float rcp_dxdxcox = __frcp_rn(15 * 15 * co.x);
-    const float rcp_dydycoz = __frcp_rn(15 * 15 * co.z);
     const float tx_ = not_in_y_range * __saturatef((dx * co.x * diffx + dx * co.y * diffy) * rcp_dxdxcox);
     const float ty_ = not_in_x_range * __saturatef((dy * co.y * diffx + dy * co.z * diffy) * rcp_dydycoz);
     const float mx = px + tx_ * dx, my = py + ty_ * dy;
@@ -268,6 +269,10 @@ __device__ __forceinline__ float tile_min_power(const float4 co, const float2 me
     result = 0.5f * (co.x * ddx * ddx + co.z * ddy * ddy) + co.y * ddx * ddy;
   }
   return result;
+}
+__device__ __forceinline__ float tile_min_power(const float4 co, const float2 mean, int tx,
+                                                int ty) {
+  return tile_min_power_pre(co, mean, tx, ty, __frcp_rn(15 * 15 * co.x), __frcp_rn(15 * 15 * co.z));
 }
 
 __device__ __forceinline__ float opacity_power_threshold(float opacity) {
@@ -361,6 +366,7 @@ __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, 
   }
   const int total = __shfl_sync(full, incl, 31);
   const int excl = incl - area;
+  const float rcp_x = __frcp_rn(15 * 15 * co.x), rcp_z = __frcp_rn(15 * 15 * co.z);  // per Gaussian
   for (int f0 = 0; f0 < total; f0 += 32) {
     const int f = f0 + lane;
     // owner = number of lanes whose inclusive prefix is <= f (prefix is non-decreasing)
@@ -385,10 +391,12 @@ __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, 
     const int t = f - __shfl_sync(full, excl, owner);
     const uint32_t q0 = __shfl_sync(full, pay0, owner);
     const uint32_t q1 = __shfl_sync(full, pay1, owner);
+    const float rx = __shfl_sync(full, rcp_x, owner);
+    const float rz = __shfl_sync(full, rcp_z, owner);
     if (f < total) {
       const int y = y0 + t / w;
       const int x = x0 + t - (t / w) * w;
-      if (tile_min_power(c, p, x, y) <= th) on_hit(owner, x, y, q0, q1);
+      if (tile_min_power_pre(c, p, x, y, rx, rz) <= th) on_hit(owner, x, y, q0, q1);
     }
   }
 }
