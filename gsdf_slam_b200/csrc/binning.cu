@@ -187,14 +187,14 @@ emit_kernel(const uint64_t* __restrict__ vis_items, const uint32_t* __restrict__
     thr = opacity_power_threshold(co.w);
   }
   const int area = (int)((rect_max.x - rect_min.x) * (rect_max.y - rect_min.y));
-  // Very large rectangles are not walked here: they are cut into chunks of kQueueRectTiles
+  // Very large rectangles are not walked here: they are cut into chunks of about kQueueRectTiles
   // tiles, queued as (chunk << 24 | list position) and spread over the whole GPU by
   // emit_large_kernel (a single warp walking a 3000-tile rectangle would be the critical path).
   bool large = cnt != 0 && area > kQueueRectTiles;
   if (large) {
-    const uint32_t nchunks = ((uint32_t)area + kQueueRectTiles - 1) / kQueueRectTiles;
+    const uint32_t nchunks = queue_chunks((uint32_t)area);
     const uint32_t q0 = atomicAdd(large_count, nchunks);
-    if (q0 + nchunks <= large_capacity && nchunks <= 256u) {
+    if (q0 + nchunks <= large_capacity) {
       for (uint32_t c = 0; c < nchunks; ++c) large_list[q0 + c] = (c << 24) | j;
     } else {
       // queue full (pathological input): poison the reserved entries and walk it right here
@@ -237,8 +237,9 @@ emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __re
     const float thr = opacity_power_threshold(co.w);
     const int w = (int)(rect_max.x - rect_min.x), h = (int)(rect_max.y - rect_min.y);
     const int area = w * h;
-    const int t_begin = (int)chunk * kQueueRectTiles;
-    const int t_end = min(area, t_begin + kQueueRectTiles);
+    const int per_chunk = (area + (int)queue_chunks((uint32_t)area) - 1) / (int)queue_chunks((uint32_t)area);
+    const int t_begin = (int)chunk * per_chunk;
+    const int t_end = min(area, t_begin + per_chunk);
     for (int t0 = t_begin; t0 < t_end; t0 += 32) {
       const int t = t0 + lane;
       if (t < t_end) {

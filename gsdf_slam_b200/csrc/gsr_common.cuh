@@ -345,9 +345,14 @@ __device__ __forceinline__ uint32_t warp_walk_large_rects(bool has_large, const 
 // lanes; `on_hit(owner_lane, x, y, pay0, pay1)` is invoked by each lane whose tile passed the
 // test (pay0/pay1 = the owner lane's payload words), in no particular order.
 #ifndef GSR_QUEUE_RECT_TILES
-#define GSR_QUEUE_RECT_TILES 256
+#define GSR_QUEUE_RECT_TILES 64
 #endif
 constexpr int kQueueRectTiles = GSR_QUEUE_RECT_TILES;  // emit: larger rectangles go to the work queue
+// a queued rectangle is cut into at most 256 chunks (8-bit chunk id) of >= kQueueRectTiles tiles
+__host__ __device__ inline uint32_t queue_chunks(uint32_t area) {
+  const uint32_t n = (area + kQueueRectTiles - 1) / kQueueRectTiles;
+  return n < 256u ? n : 256u;
+}
 
 template <typename OnHit>
 __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, const float2 xy,
