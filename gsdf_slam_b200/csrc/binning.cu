@@ -282,128 +282,141 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
 // sorted order is unique) and the packed per-duplicate records
 //   {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}.
 // Lists shorter than kSortSmallCap entries are sorted in registers by the "small" launch (one
-// warp per tile, LPT order, bitonic network).  The "long" launch (persistent CTAs over the
+// 2-warp CTA per tile, LPT order, bitonic network).  The "long" launch (persistent CTAs over the
 // hdr->num_long_tiles longest tiles, which form a prefix of the LPT order) runs a stable LSD
 // radix sort per tile, in shared memory up to kSortLongSmemCap entries and through global
 // scratch beyond — any list length works.
 // ---------------------------------------------------------------------------------------------
-// ---- lists shorter than kSortSmallCap (= 512): ONE WARP per tile, sorted entirely in registers ----
-// Lane l holds the kE consecutive network positions l*kE .. l*kE+kE-1 (n_pad = 32*kE).  The
-// compare-exchange stages with distance j < kE stay inside a thread; those with j >= kE are
-// exchanges with lane l ^ (j / kE) through shuffles.  No shared memory, no barriers: the CTA-wide
-// shared-memory version of this kernel was bound by the shared-memory pipe (ncu: mio_throttle).
+// ---- lists shorter than kSortSmallCap (= 512): one 2-warp CTA per tile, sorted in registers -----
+// Thread t (0..63) holds the kE consecutive network positions t*kE .. t*kE+kE-1 (n_pad = 64*kE).
+// Compare-exchange stages with distance j < kE stay inside a thread; kE <= j < 32*kE are
+// exchanges with lane t ^ (j / kE) through shuffles; the single stage with j = 32*kE (the other
+// warp) goes through shared memory.  Two warps per tile halve the dependent instruction chain of
+// a tile — the kernel is one short wave whose duration is the latency of its longest lists.
+// (A CTA-wide shared-memory network was bound by the shared-memory pipe: ncu mio_throttle.)
+constexpr int kSortSmallThreads = 64;
+
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask) {
   const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, lane_mask);
   const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), lane_mask);
   return ((uint64_t)hi << 32) | lo;
 }
 
-template <int kE>
-__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&v)[kE], int lane) {
-  constexpr int kN = 32 * kE;
+// One stage (merge level K, distance J) — template parameters, so every register index is a
+// compile-time constant and the whole network is straight-line code.
+template <int kE, int K, int J>
+__device__ __forceinline__ void bitonic_stage(uint64_t (&v)[kE], int t, uint64_t* s_x) {
+  constexpr int kT = kSortSmallThreads;
+  constexpr int kN = kT * kE;
+  if constexpr (J >= kE) {
+    constexpr int tm = J / kE;  // partner thread = t ^ tm
+    const bool lower = (t & tm) == 0;
+    const bool up = (K >= kN) ? true : ((t & (K / kE)) == 0);  // bit K of the position is clear
+    const bool take_min = lower == up;
+    if constexpr (tm < 32) {
 #pragma unroll
-  for (int k = 2; k <= kN; k <<= 1) {
+      for (int e = 0; e < kE; ++e) {
+        const uint64_t o = shfl_xor_u64(v[e], tm);
+        v[e] = take_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+      }
+    } else {
+      // the other warp: element-major staging, consecutive threads touch consecutive words
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= kE) {
-        // partner lane; ascending iff bit k of the network position is clear
-        const int lm = j / kE;
-        const bool lower = (lane & lm) == 0;
-        const bool up = (k >= kN) ? true : ((lane & (k / kE)) == 0);
-        const bool take_min = lower == up;
+      for (int e = 0; e < kE; ++e) s_x[e * kT + t] = v[e];
+      __syncthreads();
 #pragma unroll
-        for (int e = 0; e < kE; ++e) {
-          const uint64_t o = shfl_xor_u64(v[e], lm);
-          v[e] = take_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
-        }
-      } else {
+      for (int e = 0; e < kE; ++e) {
+        const uint64_t o = s_x[e * kT + (t ^ tm)];
+        v[e] = take_min ? (v[e] < o ? v[e] : o) : (v[e] < o ? o : v[e]);
+      }
+      __syncthreads();
+    }
+  } else {
 #pragma unroll
-        for (int e = 0; e < kE; ++e) {
-          if ((e & j) == 0) {
-            const int f = e | j;
-            // bit k of (lane*kE + e): inside the thread when k < kE, else a lane bit
-            const bool up = (k < kE) ? ((e & k) == 0) : ((k >= kN) ? true : ((lane & (k / kE)) == 0));
-            const uint64_t a = v[e], b = v[f];
-            const bool swap = (a > b) == up;
-            v[e] = swap ? b : a;
-            v[f] = swap ? a : b;
-          }
-        }
+    for (int e = 0; e < kE; ++e) {
+      if ((e & J) == 0) {
+        // bit K of (t*kE + e): inside the thread when K < kE, else a thread bit
+        const bool up = (K < kE) ? ((e & K) == 0) : ((K >= kN) ? true : ((t & (K / kE)) == 0));
+        const uint64_t a = v[e], b = v[e | J];
+        const bool swap = (a > b) == up;
+        v[e] = swap ? b : a;
+        v[e | J] = swap ? a : b;
       }
     }
   }
 }
+template <int kE, int K, int J>
+struct BitonicStages {
+  static __device__ __forceinline__ void run(uint64_t (&v)[kE], int t, uint64_t* s_x) {
+    bitonic_stage<kE, K, J>(v, t, s_x);
+    if constexpr (J > 1) BitonicStages<kE, K, J / 2>::run(v, t, s_x);
+  }
+};
+template <int kE, int K>
+struct BitonicLevels {
+  static __device__ __forceinline__ void run(uint64_t (&v)[kE], int t, uint64_t* s_x) {
+    BitonicStages<kE, K, K / 2>::run(v, t, s_x);
+    if constexpr (K < kSortSmallThreads * kE) BitonicLevels<kE, K * 2>::run(v, t, s_x);
+  }
+};
 
 template <int kE>
-__device__ __forceinline__ void warp_sort_pack_tile(uint32_t n, uint32_t start, int lane,
-                                                    uint64_t* __restrict__ items,
-                                                    const float4* __restrict__ splat_rec,
-                                                    float4* __restrict__ rec, uint32_t* s_g) {
+__device__ __forceinline__ void cta_sort_pack_tile(uint32_t n, uint32_t start, uint64_t* __restrict__ items,
+                                                   const float4* __restrict__ splat_rec,
+                                                   float4* __restrict__ rec, uint64_t* s_x) {
+  const int t = threadIdx.x;
   uint64_t v[kE];
 #pragma unroll
   for (int e = 0; e < kE; ++e) {
-    const uint32_t i = (uint32_t)lane * kE + e;
+    const uint32_t i = (uint32_t)t * kE + e;
     v[e] = i < n ? items[start + i] : ~0ull;
   }
-  warp_bitonic_sort<kE>(v, lane);
-  // Sorted position lane*kE + e sits in v[e].  The sorted Gaussian ids go through shared memory
-  // so that each record can be copied by THREE lanes (one float4 each), consecutive lanes
+  BitonicLevels<kE, 2>::run(v, t, s_x);
+  // Sorted position t*kE + e sits in v[e].  The sorted Gaussian ids go through shared memory
+  // so that each record can be copied by THREE threads (one float4 each), consecutive threads
   // covering consecutive 16-byte pieces: the gathers are 48-byte contiguous reads and the record
   // stream leaves in full, coalesced lines.
+  uint32_t* s_g = reinterpret_cast<uint32_t*>(s_x);  // (the exchanges are over)
 #pragma unroll
-  for (int e = 0; e < kE; ++e) s_g[lane * kE + e] = (uint32_t)v[e];
-  __syncwarp();
+  for (int e = 0; e < kE; ++e) {
+    const uint32_t i = (uint32_t)t * kE + e;
+    if (i < n) items[start + i] = v[e];
+    s_g[i] = (uint32_t)v[e];
+  }
+  __syncthreads();
   const uint32_t pieces = 3u * n;
-#ifndef GSR_TSP_INFLIGHT
-#define GSR_TSP_INFLIGHT 8
-#endif
-  constexpr int kInFlight = GSR_TSP_INFLIGHT;  // gathers in flight per lane (the copy is pure latency otherwise)
-  for (uint32_t q0 = 0; q0 < pieces; q0 += 32 * kInFlight) {
-    float4 t[kInFlight];
+  constexpr int kInFlight = 8;  // gathers in flight per thread (the copy is pure latency otherwise)
+  for (uint32_t q0 = 0; q0 < pieces; q0 += kSortSmallThreads * kInFlight) {
+    float4 r4[kInFlight];
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u) {
-      const uint32_t q = q0 + 32u * u + lane;
+      const uint32_t q = q0 + (uint32_t)kSortSmallThreads * u + t;
       if (q < pieces) {
         const uint32_t pos = q / 3u, piece = q - 3u * pos;  // sorted position and float4 index
-        t[u] = __ldg(splat_rec + 3 * (size_t)s_g[pos] + piece);
+        r4[u] = __ldg(splat_rec + 3 * (size_t)s_g[pos] + piece);
       }
     }
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u) {
-      const uint32_t q = q0 + 32u * u + lane;
-      if (q < pieces) rec[3 * (size_t)start + q] = t[u];
+      const uint32_t q = q0 + (uint32_t)kSortSmallThreads * u + t;
+      if (q < pieces) rec[3 * (size_t)start + q] = r4[u];
     }
-  }
-#pragma unroll
-  for (int e = 0; e < kE; ++e) {
-    const uint32_t i = (uint32_t)lane * kE + e;
-    if (i < n) items[start + i] = v[e];
   }
 }
 
-constexpr int kSortSmallThreads = 128;  // four tiles per CTA
-constexpr int kSortLargeThreads = 512;
-
-#ifndef GSR_TSP_MINBLOCKS
-#define GSR_TSP_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(kSortSmallThreads, GSR_TSP_MINBLOCKS)
+__global__ void __launch_bounds__(kSortSmallThreads)
 tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, uint32_t T,
                             BinHeader* __restrict__ bin_hdr, uint32_t capacity, uint64_t* __restrict__ items,
                             const float4* __restrict__ splat_rec, float4* __restrict__ rec) {
-  __shared__ uint32_t s_g[kSortSmallThreads / 32][kSortSmallCap];  // sorted Gaussian ids, per warp
+  __shared__ uint64_t s_x[kSortSmallCap];  // 4 KB: cross-warp exchange, then the sorted ids
   if (blockIdx.x == 0 && threadIdx.x == 0) bin_hdr->capacity = capacity;  // read by gsr_export_binning
-  const int lane = threadIdx.x & 31;
-  const uint32_t w = (blockIdx.x * kSortSmallThreads + threadIdx.x) >> 5;
-  if (w >= T) return;
-  const uint2 range = ranges[order[w]];
+  const uint2 range = ranges[order[blockIdx.x]];
   const uint32_t n = range.y - range.x;
   if (n == 0 || n >= (uint32_t)kSortSmallCap || range.y > capacity) return;  // long lists: other launch
-  if (n <= 32) warp_sort_pack_tile<1>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
-  else if (n <= 64) warp_sort_pack_tile<2>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
-  else if (n <= 128) warp_sort_pack_tile<4>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
-  else if (n <= 256) warp_sort_pack_tile<8>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
-  else warp_sort_pack_tile<16>(n, range.x, lane, items, splat_rec, rec, s_g[threadIdx.x >> 5]);
+  if (n <= 64) cta_sort_pack_tile<1>(n, range.x, items, splat_rec, rec, s_x);
+  else if (n <= 128) cta_sort_pack_tile<2>(n, range.x, items, splat_rec, rec, s_x);
+  else if (n <= 256) cta_sort_pack_tile<4>(n, range.x, items, splat_rec, rec, s_x);
+  else cta_sort_pack_tile<8>(n, range.x, items, splat_rec, rec, s_x);
 }
 
 // ---- lists of kSortSmallCap or more entries: one CTA per tile, stable LSD radix sort -------------
@@ -412,6 +425,7 @@ tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __
 // between two shared-memory buffers, longer ones between the tile's own range and a scratch range
 // in global memory (L2-resident) — any length works.  Per pass: per-warp digit histograms over
 // contiguous segments (match_any ranking, no atomics), one scan, stable scatter.
+constexpr int kSortLargeThreads = 512;
 constexpr int kLongWarps = kSortLargeThreads / 32;
 
 // lanes of the warp holding the same 8-bit digit (invalid lanes match nobody): eight ballots.
@@ -569,7 +583,7 @@ int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t
                           BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
                           const float4* splat_rec, float4* rec, cudaStream_t s) {
   if (T == 0) return 0;
-  tile_sort_pack_small_kernel<<<(T + 3) / 4, kSortSmallThreads, 0, s>>>(ranges, order, T, bin_hdr, capacity,
+  tile_sort_pack_small_kernel<<<T, kSortSmallThreads, 0, s>>>(ranges, order, T, bin_hdr, capacity,
                                                                         items, splat_rec, rec);
   GSR_LAUNCHED();
   static bool attr_set = false;
