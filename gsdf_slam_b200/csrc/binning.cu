@@ -287,14 +287,17 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
 // radix sort per tile, in shared memory up to kSortLongSmemCap entries and through global
 // scratch beyond — any list length works.
 // ---------------------------------------------------------------------------------------------
-// ---- lists shorter than kSortSmallCap (= 512): one 2-warp CTA per tile, sorted in registers -----
-// Thread t (0..63) holds the kE consecutive network positions t*kE .. t*kE+kE-1 (n_pad = 64*kE).
+// ---- lists shorter than kSortSmallCap (= 512): one 4-warp CTA per tile, sorted in registers -----
+// Thread t holds the kE consecutive network positions t*kE .. t*kE+kE-1 (n_pad = threads*kE).
 // Compare-exchange stages with distance j < kE stay inside a thread; kE <= j < 32*kE are
-// exchanges with lane t ^ (j / kE) through shuffles; the single stage with j = 32*kE (the other
-// warp) goes through shared memory.  Two warps per tile halve the dependent instruction chain of
+// exchanges with lane t ^ (j / kE) through shuffles; the stages with j >= 32*kE (another
+// warp) go through shared memory.  Several warps per tile shorten the dependent instruction chain of
 // a tile — the kernel is one short wave whose duration is the latency of its longest lists.
 // (A CTA-wide shared-memory network was bound by the shared-memory pipe: ncu mio_throttle.)
-constexpr int kSortSmallThreads = 64;
+#ifndef GSR_TSP_THREADS
+#define GSR_TSP_THREADS 128
+#endif
+constexpr int kSortSmallThreads = GSR_TSP_THREADS;
 
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask) {
   const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, lane_mask);
@@ -413,9 +416,11 @@ tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __
   const uint2 range = ranges[order[blockIdx.x]];
   const uint32_t n = range.y - range.x;
   if (n == 0 || n >= (uint32_t)kSortSmallCap || range.y > capacity) return;  // long lists: other launch
-  if (n <= 64) cta_sort_pack_tile<1>(n, range.x, items, splat_rec, rec, s_x);
-  else if (n <= 128) cta_sort_pack_tile<2>(n, range.x, items, splat_rec, rec, s_x);
-  else if (n <= 256) cta_sort_pack_tile<4>(n, range.x, items, splat_rec, rec, s_x);
+  constexpr int kT = kSortSmallThreads;
+  static_assert(kT * 8 >= kSortSmallCap, "the largest instantiation must hold kSortSmallCap entries");
+  if (n <= kT) cta_sort_pack_tile<1>(n, range.x, items, splat_rec, rec, s_x);
+  else if (n <= 2 * kT) cta_sort_pack_tile<2>(n, range.x, items, splat_rec, rec, s_x);
+  else if (n <= 4 * kT || kT * 4 >= kSortSmallCap) cta_sort_pack_tile<4>(n, range.x, items, splat_rec, rec, s_x);
   else cta_sort_pack_tile<8>(n, range.x, items, splat_rec, rec, s_x);
 }
 
