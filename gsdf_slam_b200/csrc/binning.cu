@@ -43,10 +43,10 @@ tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, uint2* __r
                  uint32_t* __restrict__ max_contrib) {
   __shared__ uint32_t s_cnt[1024];
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_max, s_long;
+  __shared__ uint32_t s_max, s_long, s_huge;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_cnt[tid] = 0;
-  if (tid == 0) { s_max = 0; s_long = 0; }
+  if (tid == 0) { s_max = 0; s_long = 0; s_huge = 0; }
   __syncthreads();
 
   // block-wide inclusive scan of one value per thread (1024 threads); all threads must call
@@ -78,7 +78,7 @@ tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, uint2* __r
   // each thread owns `ipt` consecutive tiles: one block scan for any T
   const uint32_t ipt = (T + 1023u) / 1024u;
   const uint32_t t_first = (uint32_t)tid * ipt;
-  uint32_t sum = 0, mx = 0, nlong = 0;
+  uint32_t sum = 0, mx = 0, nlong = 0, nhuge = 0;
   for (uint32_t k = 0; k < ipt; ++k) {
     const uint32_t t = t_first + k;
     if (t < T) {
@@ -86,14 +86,17 @@ tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, uint2* __r
       sum += c;
       mx = max(mx, c);
       nlong += c >= (uint32_t)kSortSmallCap ? 1u : 0u;
+      nhuge += c >= (uint32_t)kSortMidCap ? 1u : 0u;
     }
   }
   const uint32_t inc = block_incl_scan(sum);
   mx = __reduce_max_sync(0xffffffffu, mx);
   nlong = __reduce_add_sync(0xffffffffu, nlong);
+  nhuge = __reduce_add_sync(0xffffffffu, nhuge);
   if (lane == 0) {
     if (mx) atomicMax(&s_max, mx);
     if (nlong) atomicAdd(&s_long, nlong);
+    if (nhuge) atomicAdd(&s_huge, nhuge);
   }
   uint32_t run = inc - sum;
   for (uint32_t k = 0; k < ipt; ++k) {  // uniform trip count: the warp votes below need all lanes
@@ -116,6 +119,7 @@ tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, uint2* __r
     hdr->num_dup = inc;
     hdr->max_tile_len = s_max;
     hdr->num_long_tiles = s_long;
+    hdr->num_huge_tiles = s_huge;
   }
 
   // exclusive scan of the 1024 bucket counts, then place the tiles
@@ -307,9 +311,8 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int lane_mask) {
 
 // One stage (merge level K, distance J) — template parameters, so every register index is a
 // compile-time constant and the whole network is straight-line code.
-template <int kE, int K, int J>
+template <int kE, int kT, int K, int J>
 __device__ __forceinline__ void bitonic_stage(uint64_t (&v)[kE], int t, uint64_t* s_x) {
-  constexpr int kT = kSortSmallThreads;
   constexpr int kN = kT * kE;
   if constexpr (J >= kE) {
     constexpr int tm = J / kE;  // partner thread = t ^ tm
@@ -348,22 +351,23 @@ __device__ __forceinline__ void bitonic_stage(uint64_t (&v)[kE], int t, uint64_t
     }
   }
 }
-template <int kE, int K, int J>
+template <int kE, int kT, int K, int J>
 struct BitonicStages {
   static __device__ __forceinline__ void run(uint64_t (&v)[kE], int t, uint64_t* s_x) {
-    bitonic_stage<kE, K, J>(v, t, s_x);
-    if constexpr (J > 1) BitonicStages<kE, K, J / 2>::run(v, t, s_x);
+    bitonic_stage<kE, kT, K, J>(v, t, s_x);
+    if constexpr (J > 1) BitonicStages<kE, kT, K, J / 2>::run(v, t, s_x);
   }
 };
-template <int kE, int K>
+template <int kE, int kT, int K>
 struct BitonicLevels {
   static __device__ __forceinline__ void run(uint64_t (&v)[kE], int t, uint64_t* s_x) {
-    BitonicStages<kE, K, K / 2>::run(v, t, s_x);
-    if constexpr (K < kSortSmallThreads * kE) BitonicLevels<kE, K * 2>::run(v, t, s_x);
+    BitonicStages<kE, kT, K, K / 2>::run(v, t, s_x);
+    if constexpr (K < kT * kE) BitonicLevels<kE, kT, K * 2>::run(v, t, s_x);
   }
 };
 
-template <int kE>
+// s_x: kT * kE 64-bit words of shared memory
+template <int kE, int kT>
 __device__ __forceinline__ void cta_sort_pack_tile(uint32_t n, uint32_t start, uint64_t* __restrict__ items,
                                                    const float4* __restrict__ splat_rec,
                                                    float4* __restrict__ rec, uint64_t* s_x) {
@@ -374,7 +378,7 @@ __device__ __forceinline__ void cta_sort_pack_tile(uint32_t n, uint32_t start, u
     const uint32_t i = (uint32_t)t * kE + e;
     v[e] = i < n ? items[start + i] : ~0ull;
   }
-  BitonicLevels<kE, 2>::run(v, t, s_x);
+  BitonicLevels<kE, kT, 2>::run(v, t, s_x);
   // Sorted position t*kE + e sits in v[e].  The sorted Gaussian ids go through shared memory
   // so that each record can be copied by THREE threads (one float4 each), consecutive threads
   // covering consecutive 16-byte pieces: the gathers are 48-byte contiguous reads and the record
@@ -389,11 +393,11 @@ __device__ __forceinline__ void cta_sort_pack_tile(uint32_t n, uint32_t start, u
   __syncthreads();
   const uint32_t pieces = 3u * n;
   constexpr int kInFlight = 8;  // gathers in flight per thread (the copy is pure latency otherwise)
-  for (uint32_t q0 = 0; q0 < pieces; q0 += kSortSmallThreads * kInFlight) {
+  for (uint32_t q0 = 0; q0 < pieces; q0 += kT * kInFlight) {
     float4 r4[kInFlight];
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u) {
-      const uint32_t q = q0 + (uint32_t)kSortSmallThreads * u + t;
+      const uint32_t q = q0 + (uint32_t)kT * u + t;
       if (q < pieces) {
         const uint32_t pos = q / 3u, piece = q - 3u * pos;  // sorted position and float4 index
         r4[u] = __ldg(splat_rec + 3 * (size_t)s_g[pos] + piece);
@@ -401,7 +405,7 @@ __device__ __forceinline__ void cta_sort_pack_tile(uint32_t n, uint32_t start, u
     }
 #pragma unroll
     for (int u = 0; u < kInFlight; ++u) {
-      const uint32_t q = q0 + (uint32_t)kSortSmallThreads * u + t;
+      const uint32_t q = q0 + (uint32_t)kT * u + t;
       if (q < pieces) rec[3 * (size_t)start + q] = r4[u];
     }
   }
@@ -418,13 +422,38 @@ tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __
   if (n == 0 || n >= (uint32_t)kSortSmallCap || range.y > capacity) return;  // long lists: other launch
   constexpr int kT = kSortSmallThreads;
   static_assert(kT * 8 >= kSortSmallCap, "the largest instantiation must hold kSortSmallCap entries");
-  if (n <= kT) cta_sort_pack_tile<1>(n, range.x, items, splat_rec, rec, s_x);
-  else if (n <= 2 * kT) cta_sort_pack_tile<2>(n, range.x, items, splat_rec, rec, s_x);
-  else if (n <= 4 * kT || kT * 4 >= kSortSmallCap) cta_sort_pack_tile<4>(n, range.x, items, splat_rec, rec, s_x);
-  else cta_sort_pack_tile<8>(n, range.x, items, splat_rec, rec, s_x);
+  if (n <= kT) cta_sort_pack_tile<1, kT>(n, range.x, items, splat_rec, rec, s_x);
+  else if (n <= 2 * kT) cta_sort_pack_tile<2, kT>(n, range.x, items, splat_rec, rec, s_x);
+  else if (n <= 4 * kT || kT * 4 >= kSortSmallCap) cta_sort_pack_tile<4, kT>(n, range.x, items, splat_rec, rec, s_x);
+  else cta_sort_pack_tile<8, kT>(n, range.x, items, splat_rec, rec, s_x);
 }
 
-// ---- lists of kSortSmallCap or more entries: one CTA per tile, stable LSD radix sort -------------
+// ---- lists of kSortSmallCap .. kSortMidCap-1 entries: the same network on a 512-thread CTA --------
+// (2, 4 or 8 positions per thread; persistent CTAs over the slice of the LPT order that holds
+// these lists)
+constexpr int kSortMidThreads = 512;
+
+__global__ void __launch_bounds__(kSortMidThreads)
+tile_sort_pack_mid_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
+                          const GeomHeader* __restrict__ hdr, uint32_t T, uint32_t capacity,
+                          uint64_t* __restrict__ items, const float4* __restrict__ splat_rec,
+                          float4* __restrict__ rec) {
+  __shared__ uint64_t s_x[kSortMidThreads * 8];  // 32 KB
+  // In the LPT order the lists of >= kSortMidCap entries come first, then those of
+  // kSortSmallCap .. kSortMidCap-1 entries (both caps are bucket boundaries of that order).
+  const uint32_t first = min(T, hdr->num_huge_tiles), limit = min(T, hdr->num_long_tiles);
+  for (uint32_t k = first + blockIdx.x; k < limit; k += gridDim.x) {
+    const uint2 range = ranges[order[k]];
+    const uint32_t n = range.y - range.x;
+    if (n < (uint32_t)kSortSmallCap || n >= (uint32_t)kSortMidCap || range.y > capacity) continue;
+    if (n <= 2 * kSortMidThreads) cta_sort_pack_tile<2, kSortMidThreads>(n, range.x, items, splat_rec, rec, s_x);
+    else if (n <= 4 * kSortMidThreads) cta_sort_pack_tile<4, kSortMidThreads>(n, range.x, items, splat_rec, rec, s_x);
+    else cta_sort_pack_tile<8, kSortMidThreads>(n, range.x, items, splat_rec, rec, s_x);
+    __syncthreads();  // s_x is reused by the next tile of this CTA
+  }
+}
+
+// ---- lists of kSortMidCap or more entries: one CTA per tile, stable LSD radix sort -----------------
 // 8-bit digits over the bits in use: the Gaussian index (low word, as many digits as P needs)
 // first, then the four digits of the depth bits.  Lists up to kSortLongSmemCap entries ping-pong
 // between two shared-memory buffers, longer ones between the tile's own range and a scratch range
@@ -539,13 +568,13 @@ tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
   uint64_t* s_b = s_a + kSortLongSmemCap;
   __shared__ uint32_t s_scan[kLongWarps];
   const int tid = threadIdx.x;
-  // The lists of kSortSmallCap or more entries are exactly the first num_long_tiles entries of
-  // the LPT order (kSortSmallCap is a multiple of its 4-entry bucket width).
-  const uint32_t limit = min(T, hdr->num_long_tiles);
+  // The lists of kSortMidCap or more entries are exactly the first num_huge_tiles entries of
+  // the LPT order (kSortMidCap is the lower edge of its last bucket).
+  const uint32_t limit = min(T, hdr->num_huge_tiles);
   for (uint32_t k = blockIdx.x; k < limit; k += gridDim.x) {
     const uint2 range = ranges[order[k]];
     const uint32_t n = range.y - range.x, start = range.x;
-    if (n < (uint32_t)kSortSmallCap || range.y > capacity) continue;
+    if (n < (uint32_t)kSortMidCap || range.y > capacity) continue;
     const bool in_smem = n <= (uint32_t)kSortLongSmemCap;
     uint64_t* a = in_smem ? s_a : items + start;
     uint64_t* b = in_smem ? s_b : scratch + start;
@@ -590,6 +619,10 @@ int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t
   if (T == 0) return 0;
   tile_sort_pack_small_kernel<<<T, kSortSmallThreads, 0, s>>>(ranges, order, T, bin_hdr, capacity,
                                                                         items, splat_rec, rec);
+  GSR_LAUNCHED();
+  // persistent: 2 CTAs of 16 warps per SM over the mid-length lists (exits at once if there are none)
+  tile_sort_pack_mid_kernel<<<148 * 2, kSortMidThreads, 0, s>>>(ranges, order, hdr, T, capacity, items, splat_rec,
+                                                               rec);
   GSR_LAUNCHED();
   static bool attr_set = false;
   const int dyn = kLongWarps * 256 * (int)sizeof(uint32_t) + 2 * kSortLongSmemCap * (int)sizeof(uint64_t);

@@ -33,8 +33,9 @@ struct GeomHeader {          // lives at the start of the geometry buffer (256 B
   uint32_t max_tile_len;     // longest per-tile list
   uint32_t num_visible;      // V: rendered Gaussians (length of vis_items)
   uint32_t num_large;        // length of the large-rectangle work queue (binning.cu)
-  uint32_t num_long_tiles;   // tiles whose list exceeds the small shared-memory sort
-  uint32_t pad[59];
+  uint32_t num_long_tiles;   // tiles with >= kSortSmallCap entries (mid + huge)
+  uint32_t num_huge_tiles;   // tiles with >= kSortMidCap entries
+  uint32_t pad[58];
 };
 
 struct GeomView {
@@ -70,6 +71,7 @@ struct ImageView {
 // through global scratch beyond.  kSortSmallCap must be a multiple of 4 and < 4096 (LPT bucket
 // layout of tile_meta_kernel).
 constexpr int kSortSmallCap = 512;
+constexpr int kSortMidCap = 4092;   // the lower edge of the last bucket of the LPT order
 constexpr int kSortLongSmemCap = 4096;
 
 // Per-duplicate buffer.  Its layout must not depend on the exact R (the forward pass sizes it
@@ -345,7 +347,7 @@ __device__ __forceinline__ uint32_t warp_walk_large_rects(bool has_large, const 
 // lanes; `on_hit(owner_lane, x, y, pay0, pay1)` is invoked by each lane whose tile passed the
 // test (pay0/pay1 = the owner lane's payload words), in no particular order.
 #ifndef GSR_QUEUE_RECT_TILES
-#define GSR_QUEUE_RECT_TILES 64
+#define GSR_QUEUE_RECT_TILES 128
 #endif
 constexpr int kQueueRectTiles = GSR_QUEUE_RECT_TILES;  // emit: larger rectangles go to the work queue
 // a queued rectangle is cut into at most 256 chunks (8-bit chunk id) of >= kQueueRectTiles tiles
