@@ -86,10 +86,35 @@ class PeerAdamArgs(C.Structure):
     ]
 
 
+GSR_STORE_GROUPS = 6
+
+
+class GaussianStoreC(C.Structure):
+    """gsr_gaussian_store (include/gsr_capi.h)."""
+    _fields_ = [
+        ("rows", C.c_int64), ("capacity", C.c_int64), ("n_rest", C.c_int32),
+        ("param", C.c_void_p * GSR_STORE_GROUPS), ("exp_avg", C.c_void_p * GSR_STORE_GROUPS),
+        ("exp_avg_sq", C.c_void_p * GSR_STORE_GROUPS),
+        ("exist_since_iter", C.c_void_p), ("xyz_gradient_accum", C.c_void_p), ("denom", C.c_void_p),
+        ("max_radii2D", C.c_void_p),
+    ]
+
+
+class DensifyArgs(C.Structure):
+    _fields_ = [
+        ("max_grad", C.c_float), ("min_opacity", C.c_float), ("extent", C.c_float),
+        ("percent_dense", C.c_float), ("max_screen_size", C.c_int32), ("n_split", C.c_int32),
+        ("noise", C.c_void_p), ("seed", C.c_uint64),
+    ]
+
+
 # every symbol include/gsr_capi.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
     "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows", "gsr_adam_step_peer", "gsr_peer_union_mask",
     "gsr_l1_ssim_loss", "gsr_l1_ssim_workspace_bytes",
+    "gsr_store_workspace_bytes", "gsr_prune_points", "gsr_densify_and_prune", "gsr_densification_postfix",
+    "gsr_add_densification_stats", "gsr_reset_opacity", "gsr_voxel_dedup_workspace_bytes", "gsr_voxel_dedup",
+    "gsr_select_rows", "gsr_increase_pcd_rows",
     "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_sort_temp_bytes",
     "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
 ]
@@ -143,6 +168,32 @@ def lib() -> C.CDLL:
     L.gsr_l1_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_l1_ssim_loss.restype = C.c_int
+    SP = C.POINTER(GaussianStoreC)
+    L.gsr_store_workspace_bytes.argtypes = [C.c_int64]
+    L.gsr_store_workspace_bytes.restype = C.c_size_t
+    L.gsr_prune_points.argtypes = [SP, SP, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+    L.gsr_prune_points.restype = C.c_int
+    L.gsr_densify_and_prune.argtypes = [SP, SP, C.POINTER(DensifyArgs), C.c_void_p, C.POINTER(C.c_int64),
+                                        C.c_void_p]
+    L.gsr_densify_and_prune.restype = C.c_int
+    L.gsr_densification_postfix.argtypes = [SP, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_void_p]
+    L.gsr_densification_postfix.restype = C.c_int
+    L.gsr_add_densification_stats.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+    L.gsr_add_densification_stats.restype = C.c_int
+    L.gsr_reset_opacity.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
+    L.gsr_reset_opacity.restype = C.c_int
+    L.gsr_voxel_dedup_workspace_bytes.argtypes = [C.c_int64]
+    L.gsr_voxel_dedup_workspace_bytes.restype = C.c_size_t
+    L.gsr_voxel_dedup.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    L.gsr_voxel_dedup.restype = C.c_int
+    L.gsr_select_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_int64), C.c_void_p]
+    L.gsr_select_rows.restype = C.c_int
+    L.gsr_increase_pcd_rows.argtypes = [SP, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                        C.c_int32, C.c_void_p]
+    L.gsr_increase_pcd_rows.restype = C.c_int
     L.gsr_export_binning.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_export_binning.restype = C.c_int

@@ -14,6 +14,11 @@
  *                         (called by distCUDA2,                  submodules/simple-knn/spatial.cu:15-26)
  *   gsr_adam_step,     <- torch::optim::Adam::step on the 6 parameter groups
  *   gsr_adam_step_rows    (src/gaussian_model.cpp:319-352, stepped at src/gaussian_mapper.cpp:465)
+ *   gsr_prune_points, gsr_densify_and_prune, gsr_densification_postfix, gsr_reset_opacity,
+ *   gsr_add_densification_stats, gsr_voxel_dedup, gsr_select_rows, gsr_increase_pcd_rows
+ *                      <- GaussianModel::prunePoints / densifyAndPrune / densificationPostfix /
+ *                         resetOpacity / addDensificationStats / increasePcd
+ *                         (src/gaussian_model.cpp:201-317, 399-681)
  *   gsr_export_*       <- test/debug decoders of the opaque scratch buffers (the
  *                         reference's GeometryState/BinningState/ImageState::fromChunk,
  *                         cuda_rasterizer/rasterizer_impl.cu:274-343)
@@ -228,6 +233,122 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* a);
 /* union_out[row] = max over the N ranks of radii_peers[k][row] (peer-mapped radii buffers). */
 int gsr_peer_union_mask(const int32_t* const* radii_peers, int n_peers, int64_t rows,
                         int32_t* union_out, void* stream);
+
+/* ---- Gaussian-store surgery: densify / prune / increasePcd ----
+ * The reference keeps the map as six parameter tensors, twelve Adam moment tensors and four
+ * per-Gaussian statistics, and re-creates ALL of them with index / cat / zeros_like on every
+ * densification (src/gaussian_model.cpp:431-665) and every new frame (increasePcd, :201-317).
+ * Here the store is one struct of row arrays with spare capacity and every reference method is one
+ * pass: classify each source row, scan, scatter every surviving / new row to its final place.
+ * Row order, values and Adam state of the result equal the reference's op sequence (bit-exact for
+ * copied rows; see tests/test_gpu_densify.py for the tolerance of the computed ones). */
+#define GSR_STORE_GROUPS 6
+typedef struct gsr_gaussian_store {
+  int64_t rows;       /* P: Gaussians held */
+  int64_t capacity;   /* rows every array can hold */
+  int32_t n_rest;     /* M: features_rest_ is [P,M,3] */
+  /* xyz [P,3], features_dc [P,1,3], features_rest [P,M,3], opacity [P,1], scaling [P,3],
+   * rotation [P,4]: the reference's param_groups order (src/gaussian_model.cpp:325-345) */
+  float* param[GSR_STORE_GROUPS];
+  float* exp_avg[GSR_STORE_GROUPS];     /* Adam moments, same shapes; NULL = no state yet */
+  float* exp_avg_sq[GSR_STORE_GROUPS];
+  int32_t* exist_since_iter;            /* [P] */
+  float* xyz_gradient_accum;            /* [P,1] */
+  float* denom;                         /* [P,1] */
+  float* max_radii2D;                   /* [P] */
+} gsr_gaussian_store;
+
+/* Bytes of device scratch the store operations below need for a store of `rows` rows. */
+size_t gsr_store_workspace_bytes(int64_t rows);
+
+/* GaussianModel::prunePoints (src/gaussian_model.cpp:431-490): dst = the rows of src whose
+ * prune_mask byte is 0, in order — parameters, both Adam moments and the four statistics.
+ * src and dst must not overlap.  counts_out_host[0] = rows kept (the call waits for it, like the
+ * reference's boolean-mask index does); dst->rows is NOT written (dst is const: the caller sets it). */
+int gsr_prune_points(const gsr_gaussian_store* src, const gsr_gaussian_store* dst,
+                     const uint8_t* prune_mask, char* workspace, int64_t* counts_out_host,
+                     void* stream);
+
+/* GaussianModel::densifyAndPrune (src/gaussian_model.cpp:644-665) = densifyAndClone (:614-642) +
+ * densifyAndSplit (:571-612, N copies, originals removed) + prunePoints(opacity / size mask), fused.
+ * Resulting row order = the reference's: surviving originals, surviving clones, surviving split
+ * copies (copy 0 of every selected row, then copy 1, ...).  New rows get zero Adam moments; the three
+ * statistics of EVERY row are zero afterwards (densificationPostfix resets them, :566-568), which also
+ * makes the reference's max_radii2D > max_screen_size test vacuous — kept that way.
+ * Split positions: xyz + R(rotation) * (z * exp(scaling)), z ~ N(0,1).  `noise` supplies z explicitly:
+ * row (c * S + j) of noise[., 3] belongs to copy c of the j-th split-selected Gaussian (S = number
+ * selected — the layout at::normal sees in the reference, so a caller that does not know S yet passes
+ * n_split * rows rows and the first n_split * S are used); with noise == NULL z is drawn on the
+ * device from Philox-4x32-10 keyed by (seed, c * S + j).
+ * dst must not overlap src.  If dst->capacity is below the worst case (2 * rows, or n_split * rows)
+ * the real size is checked before anything is written: GSR_ERR_ALLOC with counts_out_host[0] = rows
+ * needed means "grow dst and call again".
+ * counts_out_host[4] = {rows in dst, originals kept, clones kept, split-selected S} (waited for). */
+typedef struct gsr_densify_args {
+  float max_grad;         /* densify_grad_threshold; must be > 0 */
+  float min_opacity;
+  float extent;           /* scene extent (cameras_extent_) */
+  float percent_dense;
+  int32_t max_screen_size;/* 0 = skip the size tests (src/gaussian_model.cpp:655-660) */
+  int32_t n_split;        /* N, the reference uses 2; 1..4 */
+  const float* noise;     /* [n_split * S, 3] standard normal, or NULL */
+  uint64_t seed;
+} gsr_densify_args;
+int gsr_densify_and_prune(const gsr_gaussian_store* src, const gsr_gaussian_store* dst,
+                          const gsr_densify_args* args, char* workspace, int64_t* counts_out_host,
+                          void* stream);
+
+/* GaussianModel::densificationPostfix (src/gaussian_model.cpp:492-569) for rows that already exist
+ * as arrays: appends n_new rows (new_param[g] in the store's group order, new_exist_since_iter) after
+ * store->rows, zero Adam moments for them, and zeroes the three statistics of all rows.  Needs
+ * store->rows + n_new <= store->capacity. */
+int gsr_densification_postfix(const gsr_gaussian_store* store, const float* const* new_param,
+                              const int32_t* new_exist_since_iter, int64_t n_new, void* stream);
+
+/* The per-iteration bookkeeping of GaussianMapper::trainForOneIteration (src/gaussian_mapper.cpp:
+ * 443-447) + GaussianModel::addDensificationStats (src/gaussian_model.cpp:667-681), one pass: for
+ * rows with radii > 0: max_radii2D = max(max_radii2D, radii); xyz_gradient_accum += |dL_dmeans2D.xy|;
+ * denom += 1.  dL_dmeans2D is [P,3] (z unused). */
+int gsr_add_densification_stats(int64_t P, const int32_t* radii, const float* dL_dmeans2D,
+                                float* max_radii2D, float* xyz_gradient_accum, float* denom,
+                                void* stream);
+
+/* GaussianModel::resetOpacity (src/gaussian_model.cpp:399-408) incl. replaceTensorToOptimizer
+ * (:410-429): opacity = inverse_sigmoid(min(sigmoid(opacity), cap)), both Adam moments of the group
+ * zeroed.  NOTE the reference builds its cap as ones_like(opacity * 0.01) == 1, i.e. cap = 1 (the
+ * values only make a sigmoid / logit round trip); pass cap = 1.0f for reference behaviour, 0.01f
+ * for what the original 3DGS code does. */
+int gsr_reset_opacity(int64_t P, float* opacity, float* exp_avg, float* exp_avg_sq, float cap,
+                      void* stream);
+
+/* The voxel-hash duplicate test of GaussianModel::increasePcd (src/gaussian_model.cpp:214-232):
+ * keep_out[i] = 0 if a Gaussian of `existing` lies in the same voxel hash
+ * (int64 floor(x/v)*73856093 + floor(y/v)*19349663 + floor(z/v)*83492791) as new point i, else 1.
+ * Replaces torch::isin on two int64 key tensors by a device hash set.
+ * workspace: gsr_voxel_dedup_workspace_bytes(n_existing). */
+size_t gsr_voxel_dedup_workspace_bytes(int64_t n_existing);
+int gsr_voxel_dedup(const float* existing_xyz, int64_t n_existing, const float* new_xyz,
+                    int64_t n_new, float voxel_size, uint8_t* keep_out, char* workspace,
+                    void* stream);
+
+/* Compacted ascending list of the rows whose mask byte is non-zero (invert: zero):
+ * idx_out[0..count), count written to the device word count_out_dev and, if counts_out_host is
+ * non-NULL, waited for and stored there.  (nonzero().squeeze() of src/gaussian_model.cpp:233.)
+ * workspace: gsr_store_workspace_bytes(rows). */
+int gsr_select_rows(const uint8_t* mask, int64_t rows, int invert, uint32_t* idx_out,
+                    uint32_t* count_out_dev, char* workspace, int64_t* counts_out_host, void* stream);
+
+/* The new-Gaussian initialisation of increasePcd (src/gaussian_model.cpp:235-290) for the points
+ * selected by idx[0..n): gathers xyz / colour, features_dc = RGB2SH(colour), features_rest = 0,
+ * scaling = log(sqrt(max(dist2, 1e-7))) (dist2 = gsr_knn_mean_dist2 of the gathered points),
+ * rotation = (1,0,0,0), opacity = inverse_sigmoid(0.1), exist_since_iter = iteration — written
+ * straight into rows [store->rows, store->rows + n) of the store with zero Adam moments, and the
+ * statistics of all rows zeroed (the densificationPostfix at :305).  Two calls: stage 0 gathers the
+ * points into the store's xyz rows (so that the caller can run gsr_knn_mean_dist2 on them), stage 1
+ * needs dist2 and fills the rest. */
+int gsr_increase_pcd_rows(const gsr_gaussian_store* store, const float* new_xyz,
+                          const float* new_rgb, const uint32_t* idx, int64_t n, int stage,
+                          const float* dist2, int32_t iteration, void* stream);
 
 /* ---- test / debug exports (device -> device copies out of the opaque buffers) ---- */
 /* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits). */
