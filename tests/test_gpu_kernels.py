@@ -301,7 +301,7 @@ def _brute_knn(pts: torch.Tensor) -> torch.Tensor:
     return out
 
 
-@pytest.mark.parametrize("P", [4, 1000, 1025, 40_000])
+@pytest.mark.parametrize("P", [4, 33, 1000, 1025, 40_000, 300_000])
 def test_knn_mean_dist2(P):
     import gsdf_slam_b200 as gs
     gen = torch.Generator(device="cuda").manual_seed(P)
@@ -318,6 +318,31 @@ def test_knn_mean_dist2(P):
     if rb.available():
         ref = rb.ref_knn(pts)
         assert torch.equal(mine, ref), f"max diff {(mine - ref).abs().max().item()}"
+
+
+@pytest.mark.parametrize("kind", ["plane_with_duplicates", "two_far_clusters", "line", "grid_ties"])
+def test_knn_structured_clouds_bit_equal_to_reference(kind):
+    """Clouds that stress the AABB-tree pruning: degenerate boxes, empty space, exact ties."""
+    import gsdf_slam_b200 as gs
+    from oracle import ref_binding as rb
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    P = 50_000
+    if kind == "plane_with_duplicates":
+        pts = torch.rand((P, 3), device="cuda", generator=gen) * torch.tensor([8.0, 6.0, 0.0], device="cuda")
+        pts[P // 2:] = pts[: P - P // 2]                     # every point exists twice
+    elif kind == "two_far_clusters":
+        pts = torch.randn((P, 3), device="cuda", generator=gen) * 0.05
+        pts[P // 3:] += torch.tensor([100.0, -40.0, 7.0], device="cuda")
+    elif kind == "line":
+        pts = torch.zeros((P, 3), device="cuda")
+        pts[:, 0] = torch.rand(P, device="cuda", generator=gen) * 50.0
+    else:
+        g = torch.arange(40, device="cuda", dtype=torch.float32) * 0.25
+        pts = torch.stack(torch.meshgrid(g, g, g[:30], indexing="ij"), -1).reshape(-1, 3).contiguous()
+    mine = gs.distCUDA2(pts)
+    assert rel_l2(mine, _brute_knn(pts)) < 1e-5
+    if rb.available():
+        assert torch.equal(mine, rb.ref_knn(pts))
 
 
 def test_knn_tiny_inputs():
