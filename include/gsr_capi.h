@@ -19,6 +19,7 @@
  *                      <- GaussianModel::prunePoints / densifyAndPrune / densificationPostfix /
  *                         resetOpacity / addDensificationStats / increasePcd
  *                         (src/gaussian_model.cpp:201-317, 399-681)
+ *   gsr_colorize_points <- colorize_launcher, cuda_colorize/colorize_pointcloud.cu:57-107 (row f-4)
  *   gsr_export_*       <- test/debug decoders of the opaque scratch buffers (the
  *                         reference's GeometryState/BinningState/ImageState::fromChunk,
  *                         cuda_rasterizer/rasterizer_impl.cu:274-343)
@@ -349,6 +350,20 @@ int gsr_select_rows(const uint8_t* mask, int64_t rows, int invert, uint32_t* idx
 int gsr_increase_pcd_rows(const gsr_gaussian_store* store, const float* new_xyz,
                           const float* new_rgb, const uint32_t* idx, int64_t n, int stage,
                           const float* dist2, int32_t iteration, void* stream);
+
+/* ---- frame ingest ----
+ * colorize_launcher (cuda_colorize/colorize_pointcloud.cu:57-107): every LiDAR point is taken to the
+ * camera (Tr_velo_to_cam, row-major 4x4, rows 0..2 used) and projected (proj_mat, row-major 3x4); points
+ * with camera z <= 0.2 or outside the image are dropped; the survivors are moved to the world frame
+ * (lidar_pose, row-major 4x4) and take the colour of their pixel (image: [H,W,3] float).  Outputs are the
+ * COMPACTED survivors in input order: points_out / colors_out [count,3], both with room for n rows.
+ * The count is waited for and stored in *count_out_host when that is non-NULL.
+ * workspace: gsr_colorize_workspace_bytes(n). */
+size_t gsr_colorize_workspace_bytes(int64_t n);
+int gsr_colorize_points(const float* points, int64_t n, const float* lidar_pose, const float* proj_mat,
+                        const float* Tr_velo_to_cam, const float* image, int img_width, int img_height,
+                        float* points_out, float* colors_out, char* workspace, int64_t* count_out_host,
+                        void* stream);
 
 /* ---- test / debug exports (device -> device copies out of the opaque buffers) ---- */
 /* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits). */

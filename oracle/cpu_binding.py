@@ -149,3 +149,19 @@ def mark_visible(means3D, viewmatrix):
     out = np.zeros(m.shape[0], np.uint8)
     lib().oracle_mark_visible(C.c_int(m.shape[0]), _p(m), _p(v), _p(out))
     return out.astype(bool)
+
+
+def colorize(points, image, proj, Tr, pose):
+    """CPU restatement of colorize_launcher (cuda_colorize/colorize_pointcloud.cu:57-107):
+    returns (world points [k,3], colours [k,3]) of the points that project into the image."""
+    L = lib()
+    L.oracle_colorize.restype = C.c_longlong
+    pts = _f(points)
+    img = _f(image)
+    H, W = img.shape[0], img.shape[1]
+    n = pts.shape[0]
+    po = np.empty((n, 3), np.float32)
+    co = np.empty((n, 3), np.float32)
+    k = L.oracle_colorize(C.c_longlong(n), _p(pts), _p(_f(pose).ravel()), _p(_f(proj).ravel()), _p(_f(Tr).ravel()),
+                          _p(img), C.c_int(W), C.c_int(H), _p(po), _p(co))
+    return po[:k].copy(), co[:k].copy()

@@ -653,4 +653,35 @@ void oracle_mark_visible(int P, const float* means3D, const float* view, uint8_t
   }
 }
 
+
+// colorize_kernel + the compaction of colorize_launcher, cuda_colorize/colorize_pointcloud.cu:3-107.
+// points [n,3] (LiDAR frame), image [H,W,3] float, proj row-major 3x4, Tr / pose row-major 4x4.
+// Writes the surviving points (world frame) and their colours compacted in input order; returns the count.
+static inline void oracle_transform_point(const float* m, const float* p, float* o) {
+  o[0] = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3];
+  o[1] = m[4] * p[0] + m[5] * p[1] + m[6] * p[2] + m[7];
+  o[2] = m[8] * p[0] + m[9] * p[1] + m[10] * p[2] + m[11];
+}
+long long oracle_colorize(long long n, const float* points, const float* pose, const float* proj,
+                          const float* Tr, const float* image, int W, int H, float* points_out,
+                          float* colors_out) {
+  long long k = 0;
+  for (long long i = 0; i < n; ++i) {
+    const float* p = points + 3 * i;
+    float cam[3], pr[3], world[3];
+    oracle_transform_point(Tr, p, cam);     // :31
+    oracle_transform_point(proj, cam, pr);  // :32
+    if (cam[2] <= 0.2f) continue;           // :33-37
+    const int px = static_cast<int>(pr[0] / pr[2]);  // :40-41
+    const int py = static_cast<int>(pr[1] / pr[2]);
+    if (px < 0 || px >= W || py < 0 || py >= H) continue;  // :43-47
+    oracle_transform_point(pose, p, world);  // :50
+    for (int c = 0; c < 3; ++c) {
+      points_out[3 * k + c] = world[c];
+      colors_out[3 * k + c] = image[3 * ((size_t)py * W + px) + c];  // :49
+    }
+    ++k;
+  }
+  return k;
+}
 }  // extern "C"
