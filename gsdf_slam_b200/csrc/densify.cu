@@ -948,3 +948,94 @@ int gsr_increase_pcd_rows(const gsr_gaussian_store* st, const float* new_xyz, co
 }
 
 }  // extern "C"
+
+// ---- PLY vertex rows (GaussianModel::savePly / loadPly, src/gaussian_model.cpp:688-953) ----
+// The on-disk vertex is x y z nx ny nz f_dc_0..2 f_rest_0..3M-1 opacity scale_0..2 rot_0..3 (17 + 3M
+// floats), f_rest CHANNEL-major (features_rest_.transpose(1,2).flatten(1)).  The reference moves seven
+// tensors to the host (after two transposing copies) and lets tinyply interleave them property by
+// property; here one kernel builds the interleaved rows in device memory (coalesced writes, the row is
+// produced word by word) and the host side is a header plus one copy.
+namespace gsr {
+namespace {
+
+__global__ void __launch_bounds__(256)
+ply_pack_kernel(int64_t P, int M, const float* __restrict__ xyz, const float* __restrict__ dc,
+                const float* __restrict__ rest, const float* __restrict__ opacity,
+                const float* __restrict__ scaling, const float* __restrict__ rotation, float* __restrict__ rows) {
+  const int wpr = 17 + 3 * M;
+  const int64_t total = P * wpr;
+  for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < total; w += (int64_t)gridDim.x * 256) {
+    const int64_t i = w / wpr;
+    const int c = (int)(w - i * wpr);
+    float v;
+    if (c < 3) v = xyz[3 * i + c];
+    else if (c < 6) v = 0.f;                                       // normals
+    else if (c < 9) v = dc[3 * i + (c - 6)];                       // [P,1,3] transposed = same order
+    else if (c < 9 + 3 * M) {
+      const int k = c - 9, ch = k / M, m = k - ch * M;             // file index ch*M + m <- rest[i][m][ch]
+      v = rest[(size_t)i * 3 * M + 3 * m + ch];
+    } else if (c < 10 + 3 * M) v = opacity[i];
+    else if (c < 13 + 3 * M) v = scaling[3 * i + (c - 10 - 3 * M)];
+    else v = rotation[4 * i + (c - 13 - 3 * M)];
+    rows[w] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ply_unpack_kernel(int64_t P, int M, const float* __restrict__ rows, float* __restrict__ xyz, float* __restrict__ dc,
+                  float* __restrict__ rest, float* __restrict__ opacity, float* __restrict__ scaling,
+                  float* __restrict__ rotation) {
+  const int wpr = 17 + 3 * M;
+  const int64_t total = P * wpr;
+  for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < total; w += (int64_t)gridDim.x * 256) {
+    const int64_t i = w / wpr;
+    const int c = (int)(w - i * wpr);
+    const float v = rows[w];
+    if (c < 3) xyz[3 * i + c] = v;
+    else if (c < 6) {}
+    else if (c < 9) dc[3 * i + (c - 6)] = v;
+    else if (c < 9 + 3 * M) {
+      const int k = c - 9, ch = k / M, m = k - ch * M;
+      rest[(size_t)i * 3 * M + 3 * m + ch] = v;
+    } else if (c < 10 + 3 * M) opacity[i] = v;
+    else if (c < 13 + 3 * M) scaling[3 * i + (c - 10 - 3 * M)] = v;
+    else rotation[4 * i + (c - 13 - 3 * M)] = v;
+  }
+}
+
+}  // namespace
+}  // namespace gsr
+
+extern "C" {
+
+int gsr_ply_pack_rows(int64_t P, int n_rest, const float* xyz, const float* features_dc, const float* features_rest,
+                      const float* opacity, const float* scaling, const float* rotation, float* rows, void* stream) {
+  if (P < 0 || n_rest < 0 || n_rest > 1024) return GSR_ERR_BAD_ARG;
+  if (P == 0) return GSR_OK;
+  if (!xyz || !features_dc || (n_rest > 0 && !features_rest) || !opacity || !scaling || !rotation || !rows)
+    return GSR_ERR_BAD_ARG;
+  const int64_t total = P * (17 + 3 * (int64_t)n_rest);
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
+  gsr::ply_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, n_rest, xyz, features_dc, features_rest,
+                                                                           opacity, scaling, rotation, rows);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+int gsr_ply_unpack_rows(int64_t P, int n_rest, const float* rows, float* xyz, float* features_dc, float* features_rest,
+                        float* opacity, float* scaling, float* rotation, void* stream) {
+  if (P < 0 || n_rest < 0 || n_rest > 1024) return GSR_ERR_BAD_ARG;
+  if (P == 0) return GSR_OK;
+  if (!xyz || !features_dc || (n_rest > 0 && !features_rest) || !opacity || !scaling || !rotation || !rows)
+    return GSR_ERR_BAD_ARG;
+  const int64_t total = P * (17 + 3 * (int64_t)n_rest);
+  const int64_t want = (total + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 32 ? want : 148 * 32);
+  gsr::ply_unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P, n_rest, rows, xyz, features_dc,
+                                                                             features_rest, opacity, scaling, rotation);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

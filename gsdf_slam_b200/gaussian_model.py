@@ -10,6 +10,8 @@ Same method names and argument meaning as /root/reference/src/gaussian_model.cpp
   src/gaussian_mapper.cpp:443-447
 * ``resetOpacity()``                         — :399-408
 * ``increasePcd(points, colors, iteration)`` — :201-317
+* ``createFromPcd(points, colors, spatial_lr_scale)`` — :130-199
+* ``savePly(path)`` / ``loadPly(path)``       — :861-953 / :688-859 (ply.py)
 * ``step(grads)``                            — optimizer_->step() over the six groups (:319-352)
 
 What differs from the reference is where the rows live.  The reference holds 22 separately
@@ -354,6 +356,41 @@ class GaussianModel:
                        "gsr_increase_pcd_rows")
         self._cur.rows += n
         return n
+
+    @torch.no_grad()
+    def createFromPcd(self, point_cloud: torch.Tensor, color: torch.Tensor, spatial_lr_scale: float = 1.0) -> None:
+        """Initialise the map from a coloured point cloud (src/gaussian_model.cpp:130-199).  The reference
+        computes a voxel-unique index set there but discards the result of its index_select calls, so every
+        point becomes a Gaussian; features_dc = RGB2SH(colour), scaling from distCUDA2, identity rotation,
+        opacity inverse_sigmoid(0.1), exist_since_iter 0."""
+        L = _lib.lib()
+        self.spatial_lr_scale_ = float(spatial_lr_scale)
+        n = int(point_cloud.shape[0])
+        pts = point_cloud.to(device=self.device, dtype=torch.float32).contiguous()
+        rgb = color.to(device=self.device, dtype=torch.float32).contiguous()
+        self._cur.rows = 0
+        self._reserve(n)
+        idx = torch.arange(n, dtype=torch.int32, device=self.device)
+        stream = _stream(self.device)
+        with torch.cuda.device(self.device):
+            s = self._cur.c_struct()
+            args = (C.byref(s), C.c_void_p(pts.data_ptr()), C.c_void_p(rgb.data_ptr()), C.c_void_p(idx.data_ptr()), n)
+            _lib.check(L.gsr_increase_pcd_rows(*args, 0, None, 0, stream), "gsr_increase_pcd_rows")
+            dist2 = distCUDA2(self._cur.param[0][: 3 * n].view(n, 3)) if n else pts.new_empty(0)
+            _lib.check(L.gsr_increase_pcd_rows(*args, 1, C.c_void_p(dist2.data_ptr()) if n else None, 0, stream),
+                       "gsr_increase_pcd_rows")
+        self._cur.rows = n
+        self.adam_step_ = 0
+
+    def savePly(self, result_path) -> None:
+        """src/gaussian_model.cpp:861-953 (see ply.py)."""
+        from . import ply
+        ply.savePly(self, result_path)
+
+    def loadPly(self, ply_path) -> None:
+        """src/gaussian_model.cpp:688-859 (see ply.py)."""
+        from . import ply
+        ply.loadPly(self, ply_path)
 
     @torch.no_grad()
     def step(self, grads: Sequence[Optional[torch.Tensor]], row_mask: Optional[torch.Tensor] = None) -> None:

@@ -351,6 +351,17 @@ int gsr_increase_pcd_rows(const gsr_gaussian_store* store, const float* new_xyz,
                           const float* new_rgb, const uint32_t* idx, int64_t n, int stage,
                           const float* dist2, int32_t iteration, void* stream);
 
+/* PLY interchange rows (GaussianModel::savePly / loadPly, src/gaussian_model.cpp:688-953): one vertex =
+ * x y z nx ny nz f_dc_0..2 f_rest_0..3M-1 opacity scale_0..2 rot_0..3 = 17 + 3M little-endian floats, normals
+ * zero, f_rest channel-major (file index ch*M + m holds features_rest[m][ch]).  pack builds the [P, 17+3M]
+ * rows in device memory from the model's arrays, unpack is the inverse (normals ignored). */
+int gsr_ply_pack_rows(int64_t P, int n_rest, const float* xyz, const float* features_dc,
+                      const float* features_rest, const float* opacity, const float* scaling,
+                      const float* rotation, float* rows, void* stream);
+int gsr_ply_unpack_rows(int64_t P, int n_rest, const float* rows, float* xyz, float* features_dc,
+                        float* features_rest, float* opacity, float* scaling, float* rotation,
+                        void* stream);
+
 /* ---- frame ingest ----
  * colorize_launcher (cuda_colorize/colorize_pointcloud.cu:57-107): every LiDAR point is taken to the
  * camera (Tr_velo_to_cam, row-major 4x4, rows 0..2 used) and projected (proj_mat, row-major 3x4); points

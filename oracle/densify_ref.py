@@ -202,6 +202,28 @@ def increase_pcd(st, new_points, new_colors, iteration, max_sh_degree, dist_fn, 
     return densification_postfix(st, pts, f_dc, f_rest, opac, scales, rots, exist), int(pts.shape[0])
 
 
+def create_from_pcd(point_cloud, color, max_sh_degree, dist_fn):
+    """GaussianModel::createFromPcd, src/gaussian_model.cpp:130-199 (the voxel-unique selection at :135-146 is
+    computed and then discarded by the reference: index_select's result is not assigned)."""
+    dev = point_cloud.device
+    fused = (color - 0.5) / float(torch.tensor(C0, dtype=torch.float32))
+    k = (max_sh_degree + 1) ** 2
+    n = point_cloud.shape[0]
+    features = torch.zeros((n, 3, k), dtype=torch.float32, device=dev)
+    features[:, :3, 0] = fused
+    dist2 = torch.clamp_min(dist_fn(point_cloud.clone()), 0.0000001)
+    scales = torch.log(torch.sqrt(dist2)).unsqueeze(1).repeat(1, 3)
+    rots = torch.zeros((n, 4), device=dev)
+    rots[:, 0] = 1
+    x = 0.1 * torch.ones((n, 1), dtype=torch.float32, device=dev)
+    st = {"xyz_": point_cloud, "features_dc_": features[:, :, 0:1].transpose(1, 2).contiguous(),
+          "features_rest_": features[:, :, 1:].transpose(1, 2).contiguous(), "opacity_": torch.log(x / (1 - x)),
+          "scaling_": scales, "rotation_": rots,
+          "exist_since_iter_": torch.zeros((n,), dtype=torch.int32, device=dev),
+          "max_radii2D_": torch.zeros((n,), device=dev)}
+    return st
+
+
 def random_state(P, M, seed, device="cpu", with_moments=True):
     """A seeded model state whose densification decisions are all exercised."""
     g = torch.Generator().manual_seed(seed)

@@ -193,6 +193,26 @@ def test_increase_pcd_matches_the_libtorch_sequence():
     assert torch.equal(got["xyz_"][P:], pts[keep_ref])
 
 
+def test_create_from_pcd_matches_the_libtorch_sequence():
+    import gsdf_slam_b200 as gs
+    from gsdf_slam_b200.gaussian_model import GaussianModel
+    g = torch.Generator(device="cuda").manual_seed(12)
+    n = 80_001
+    pts = torch.randn((n, 3), device="cuda", generator=g) * 3.0
+    pts[100:200] = pts[:100]                       # duplicates: distance 0 -> the 1e-7 clamp
+    cols = torch.rand((n, 3), device="cuda", generator=g)
+    m = GaussianModel(sh_degree=3, device="cuda")
+    m.createFromPcd(pts, cols, 1.0)
+    ref = R.create_from_pcd(pts, cols, 3, gs.distCUDA2)
+    assert m.P == n
+    assert torch.equal(m.xyz_, ref["xyz_"]) and torch.equal(m.rotation_, ref["rotation_"])
+    assert torch.equal(m.features_rest_, ref["features_rest_"]) and torch.equal(m.exist_since_iter_, ref["exist_since_iter_"])
+    assert torch.allclose(m.features_dc_, ref["features_dc_"], rtol=3e-7, atol=1e-7)
+    assert torch.allclose(m.scaling_, ref["scaling_"], rtol=1e-6, atol=1e-6)
+    assert torch.allclose(m.opacity_, ref["opacity_"], rtol=1e-6, atol=0)
+    assert float(m.max_radii2D_.abs().sum()) == 0.0 and float(m.exp_avg(2).abs().sum()) == 0.0
+
+
 def test_voxel_dedup_edge_cases():
     from gsdf_slam_b200.gaussian_model import GaussianModel
     m = GaussianModel(sh_degree=0, device="cuda")
