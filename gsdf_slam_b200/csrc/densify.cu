@@ -13,10 +13,12 @@
 //                 -> one flag byte per row + four counts per 1024-row CTA
 //   2. scan       one CTA: exclusive scan of the per-CTA counts, the four totals
 //   3. scatter    one CTA per 1024 source rows: in-CTA ranks -> final destination of the kept
-//                 original, its clone and its N split copies; then every array is streamed once
-//                 (coalesced 4-byte words, 8 loads in flight per thread) and every surviving /
-//                 new row written exactly once; Adam moments of new rows and the statistics of
-//                 all rows are written as zeros in the same pass.
+//                 original, its clone and its N split copies; then every array's slab is streamed
+//                 once through a 3-stage shared-memory ring filled by TMA bulk copies
+//                 (cp.async.bulk + mbarrier, 24 KB in flight per CTA without holding registers) and
+//                 every surviving row written exactly once; the few rows that spawn clones / split
+//                 copies are listed in shared memory and handled in a second, sparse pass; Adam
+//                 moments of new rows and the statistics of all rows are written as zeros.
 // HBM traffic = one read of the source store + one write of the destination store (the
 // reference: >= 4 reads + 4 writes of everything, plus the masks' nonzero passes).
 #include <cuda_runtime.h>
@@ -25,6 +27,7 @@
 #include "gsr_capi.h"
 #include "gsr_common.cuh"
 #include "gsr_params.cuh"
+#include "tma.cuh"
 
 namespace gsr {
 
@@ -33,7 +36,6 @@ namespace {
 constexpr int kStoreThreads = 256;
 constexpr int kRowsPerThread = 4;
 constexpr int kRowsPerCta = kStoreThreads * kRowsPerThread;  // 1024
-constexpr int kInFlight = 8;  // 4-byte loads in flight per thread in the scatter stream
 
 // flag byte of a source row
 constexpr uint32_t kKeep = 1;      // the row itself survives
@@ -280,18 +282,78 @@ struct ScatterParams {
   uint64_t seed;
 };
 
+// Shared-memory plan of one CTA (dynamic): a 3-stage ring of 12 KB source chunks filled by TMA bulk
+// copies (one elected thread issues them two chunks ahead, completion on an mbarrier), then the
+// destination tables of its 1024 rows.
+constexpr int kChunkWords = 3072;  // 12 KB
+constexpr int kStages = 3;
+constexpr size_t kScatterSmem = (size_t)kStages * kChunkWords * 4 + 4 * kRowsPerCta * 4 + kRowsPerCta * 2 + 64;
+
 __global__ void __launch_bounds__(kStoreThreads)
 scatter_rows_kernel(StoreArrays A, const uint8_t* __restrict__ flags, const uint4* __restrict__ block_base,
                     const uint4* __restrict__ totals, ScatterParams p) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_raw);                       // [kStages][kChunkWords]
+  int* s_keep = reinterpret_cast<int*>(s_raw + (size_t)kStages * kChunkWords * 4);  // [kRowsPerCta] each
+  int* s_clone = s_keep + kRowsPerCta;
+  int* s_split = s_clone + kRowsPerCta;
+  int* s_noise = s_split + kRowsPerCta;
+  uint16_t* s_list = reinterpret_cast<uint16_t*>(s_noise + kRowsPerCta);        // rows that produce new rows
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_list + kRowsPerCta);         // [kStages]
   __shared__ uint4 s_warp[kStoreThreads / 32];
-  __shared__ int s_keep[kRowsPerCta];
-  __shared__ int s_clone[kRowsPerCta];
-  __shared__ int s_split[kRowsPerCta];
-  __shared__ int s_noise[kRowsPerCta];
+  __shared__ int s_nlist;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t cta_row0 = (int64_t)blockIdx.x * kRowsPerCta;
   const int nrows = (int)min((int64_t)kRowsPerCta, p.rows - cta_row0);
+  if (tid == 0) {
+    for (int k = 0; k < kStages; ++k) mbar_init(&s_full[k], 1);
+    fence_mbar_init();
+    s_nlist = 0;
+  }
+
+  // the chunk sequence: for every array that is read, its slab [cta_row0*wpr, +nrows*wpr) in pieces
+  auto chunk_words = [&](int a) { return (uint32_t)nrows * A.wpr[a]; };
+  auto reads = [&](int a) { return A.kind[a] != kZero && A.src[a] != nullptr; };
+  struct Cursor { int a; uint32_t off; };
+  auto first = [&](Cursor& c) {
+    c.a = 0;
+    c.off = 0;
+    while (c.a < A.n && !reads(c.a)) ++c.a;
+  };
+  auto advance = [&](Cursor& c) {
+    c.off += kChunkWords;
+    if (c.off >= chunk_words(c.a)) {
+      c.off = 0;
+      ++c.a;
+      while (c.a < A.n && !reads(c.a)) ++c.a;
+    }
+  };
+  // words of the chunk that arrive through the bulk copy (16-byte granules, 16-byte aligned source)
+  auto bulk_words = [&](const Cursor& c) {
+    const uint32_t n = min((uint32_t)kChunkWords, chunk_words(c.a) - c.off);
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(A.src[c.a] + (size_t)cta_row0 * A.wpr[c.a] + c.off);
+    return (addr & 15) ? 0u : (n & ~3u);
+  };
+  auto issue = [&](const Cursor& c, int stage) {
+    const uint32_t bw = bulk_words(c);
+    if (bw == 0) return;
+    mbar_expect_tx(&s_full[stage], bw * 4);
+    bulk_g2s(s_stage + (size_t)stage * kChunkWords, A.src[c.a] + (size_t)cta_row0 * A.wpr[c.a] + c.off, bw * 4,
+             &s_full[stage]);
+  };
+  __syncthreads();
+  Cursor prod;
+  first(prod);
+  if (tid == 0) {
+    Cursor c = prod;
+    for (int k = 0; k < kStages - 1 && c.a < A.n; ++k) {
+      issue(c, k);
+      advance(c);
+    }
+  }
+  for (int k = 0; k < kStages - 1 && prod.a < A.n; ++k) advance(prod);  // every thread tracks the producer cursor
+
   const uint4 tot = *totals;
   const uint4 base = block_base[blockIdx.x];
 
@@ -324,50 +386,87 @@ scatter_rows_kernel(StoreArrays A, const uint8_t* __restrict__ flags, const uint
     s_clone[r] = (f[k] & kClone) ? (int)(K + run.y) : -1;
     s_split[r] = (f[k] & kSplit) ? (int)(K + Cn + run.z) : -1;
     s_noise[r] = (int)run.w;
+    if (f[k] & (kClone | kSplit)) s_list[atomicAdd(&s_nlist, 1)] = (uint16_t)r;
     run = add4(run, flag_counts(f[k]));
   }
   __syncthreads();
 
-  // stream every array once
-  for (int a = 0; a < A.n; ++a) {
+  // ---- pass 1: the kept rows, streamed through the TMA ring ----
+  Cursor cur;
+  first(cur);
+  uint32_t phase = 0;  // one parity bit per stage, flipped whenever that stage's barrier has been waited on
+  for (int it = 0; cur.a < A.n; ++it) {
+    const int stage = it % kStages;
+    // the stage consumed in the previous iteration is free (trailing barrier): refill it with the chunk
+    // kStages-1 ahead, so that two chunks are in flight while this one is being scattered
+    if (prod.a < A.n) {
+      if (tid == 0) issue(prod, (it + kStages - 1) % kStages);
+      advance(prod);
+    }
+    const int a = cur.a;
     const uint32_t wpr = A.wpr[a], magic = A.magic[a];
-    const int kind = A.kind[a];
-    const uint32_t nw = (uint32_t)nrows * wpr;
-    const uint32_t* __restrict__ src = A.src[a] ? A.src[a] + (size_t)cta_row0 * wpr : nullptr;
+    const uint32_t n = min((uint32_t)kChunkWords, chunk_words(a) - cur.off);
+    const uint32_t bw = bulk_words(cur);
+    const uint32_t* __restrict__ src = A.src[a] + (size_t)cta_row0 * wpr + cur.off;
     uint32_t* __restrict__ dst = A.dst[a];
-    const bool read = kind != kZero && src != nullptr;
-    const bool new_zero = kind == kMoment || kind == kZero;
+    if (bw) {
+      mbar_wait(&s_full[stage], (phase >> stage) & 1u);
+      phase ^= 1u << stage;
+    }
+    const uint32_t* __restrict__ sm = s_stage + (size_t)stage * kChunkWords;
+#pragma unroll 4
+    for (uint32_t w = tid; w < n; w += kStoreThreads) {
+      const uint32_t v = w < bw ? sm[w] : src[w];
+      const uint32_t g = cur.off + w;
+      const uint32_t r = wpr == 1 ? g : __umulhi(g, magic);
+      const int dk = s_keep[r];
+      if (dk >= 0) dst[(size_t)dk * wpr + (g - r * wpr)] = v;
+    }
+    __syncthreads();  // the stage is free again
+    advance(cur);
+  }
+  // arrays that are all zeros (statistics after a densification): kept rows
+  for (int a = 0; a < A.n; ++a) {
+    if (reads(a) || A.kind[a] == kKeepOnly) continue;
+    const uint32_t wpr = A.wpr[a], magic = A.magic[a], nw = (uint32_t)nrows * wpr;
+    uint32_t* __restrict__ dst = A.dst[a];
+    for (uint32_t g = tid; g < nw; g += kStoreThreads) {
+      const uint32_t r = wpr == 1 ? g : __umulhi(g, magic);
+      const int dk = s_keep[r];
+      if (dk >= 0) dst[(size_t)dk * wpr + (g - r * wpr)] = 0u;
+    }
+  }
+
+  // ---- pass 2: the new rows (clones and split copies) of the listed source rows ----
+  const int nlist = s_nlist;
+  if (nlist == 0) return;
+  for (int a = 0; a < A.n; ++a) {
+    const int kind = A.kind[a];
+    if (kind == kKeepOnly) continue;
+    const uint32_t wpr = A.wpr[a], magic = A.magic[a];
+    const bool new_zero = kind == kMoment || kind == kZero || A.src[a] == nullptr;
     const bool split_copy = kind == kCopyAll || kind == kMoment || kind == kZero;
-    for (uint32_t w0 = tid; w0 < nw; w0 += kStoreThreads * kInFlight) {
-      uint32_t v[kInFlight];
-#pragma unroll
-      for (int u = 0; u < kInFlight; ++u) {
-        const uint32_t w = w0 + u * kStoreThreads;
-        v[u] = (read && w < nw) ? src[w] : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < kInFlight; ++u) {
-        const uint32_t w = w0 + u * kStoreThreads;
-        if (w >= nw) break;
-        const uint32_t r = wpr == 1 ? w : __umulhi(w, magic);
-        const uint32_t c = w - r * wpr;
-        const int dk = s_keep[r];
-        if (dk >= 0) dst[(size_t)dk * wpr + c] = v[u];
-        if (kind == kKeepOnly) continue;
-        const uint32_t nv = new_zero ? 0u : v[u];
-        const int dc = s_clone[r];
-        if (dc >= 0) dst[(size_t)dc * wpr + c] = nv;
-        const int ds = s_split[r];
-        if (ds >= 0 && split_copy) {
-          for (int cp = 0; cp < p.n_split; ++cp) dst[((size_t)ds + (size_t)cp * Ss) * wpr + c] = nv;
-        }
+    const uint32_t* __restrict__ src = new_zero ? nullptr : A.src[a] + (size_t)cta_row0 * wpr;
+    uint32_t* __restrict__ dst = A.dst[a];
+    const uint32_t nw = (uint32_t)nlist * wpr;
+    for (uint32_t t = tid; t < nw; t += kStoreThreads) {
+      const uint32_t li = wpr == 1 ? t : __umulhi(t, magic);
+      const uint32_t c = t - li * wpr;
+      const uint32_t r = s_list[li];
+      const uint32_t v = new_zero ? 0u : src[r * wpr + c];
+      const int dc = s_clone[r];
+      if (dc >= 0) dst[(size_t)dc * wpr + c] = v;
+      const int ds = s_split[r];
+      if (ds >= 0 && split_copy) {
+        for (int cp = 0; cp < p.n_split; ++cp) dst[((size_t)ds + (size_t)cp * Ss) * wpr + c] = v;
       }
     }
   }
 
   // split copies: position and scaling are computed (gaussian_model.cpp:586-594)
   if (A.xyz != nullptr) {
-    for (int r = tid; r < nrows; r += kStoreThreads) {
+    for (int li = tid; li < nlist; li += kStoreThreads) {
+      const int r = s_list[li];
       const int ds = s_split[r];
       if (ds < 0) continue;
       const size_t i = (size_t)(cta_row0 + r);
@@ -416,6 +515,15 @@ scatter_rows_kernel(StoreArrays A, const uint8_t* __restrict__ flags, const uint
       }
     }
   }
+}
+
+int launch_scatter(const StoreArrays& A, const Workspace& w, const ScatterParams& p, cudaStream_t s) {
+  static const cudaError_t attr = cudaFuncSetAttribute(scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                       (int)kScatterSmem);
+  if (attr != cudaSuccess) return (int)attr;
+  scatter_rows_kernel<<<w.nblk, kStoreThreads, kScatterSmem, s>>>(A, w.flags, w.block_base, w.totals, p);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
 }
 
 // ---- select: compacted ascending index list ----
@@ -709,10 +817,10 @@ int gsr_prune_points(const gsr_gaussian_store* src, const gsr_gaussian_store* ds
   ScatterParams p{};
   p.rows = rows;
   p.n_split = 0;
-  scatter_rows_kernel<<<w.nblk, kStoreThreads, 0, s>>>(A, w.flags, w.block_base, w.totals, p);
-  GSR_LAUNCHED();
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
+  {
+    const int rc = launch_scatter(A, w, p, s);
+    if (rc) return rc;
+  }
   if (counts_out_host) {
     uint4 t;
     const int rc = read_totals(w.totals, t, s);
@@ -788,10 +896,10 @@ int gsr_densify_and_prune(const gsr_gaussian_store* src, const gsr_gaussian_stor
   p.inv_split_div = dp.inv_split_div;
   p.noise = a->noise;
   p.seed = a->seed;
-  scatter_rows_kernel<<<w.nblk, kStoreThreads, 0, s>>>(A, w.flags, w.block_base, w.totals, p);
-  GSR_LAUNCHED();
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return (int)e;
+  {
+    const int rc = launch_scatter(A, w, p, s);
+    if (rc) return rc;
+  }
   if (counts_out_host) {
     const int rc = read_totals(w.totals, t, s);
     if (rc) return rc;
