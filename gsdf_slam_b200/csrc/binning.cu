@@ -454,8 +454,9 @@ tile_sort_pack_mid_kernel(const uint2* __restrict__ ranges, const uint32_t* __re
 }
 
 // ---- lists of kSortMidCap or more entries: one CTA per tile, stable LSD radix sort -----------------
-// 8-bit digits over the bits in use: the Gaussian index (low word, as many digits as P needs)
-// first, then the four digits of the depth bits.  Lists up to kSortLongSmemCap entries ping-pong
+// 8-bit digits: the four digits of the depth bits, then a neighbour-compare fix-up of the (rare) runs of
+// equal depth; the digits of the Gaussian index (low word, as many as P needs) are only sorted when a
+// long run of equal depths exists (see the kernel).  Lists up to kSortLongSmemCap entries ping-pong
 // between two shared-memory buffers, longer ones between the tile's own range and a scratch range
 // in global memory (L2-resident) — any length works.  Per pass: per-warp digit histograms over
 // contiguous segments (match_any ranking, no atomics), one scan, stable scatter.
@@ -582,10 +583,48 @@ tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
       for (uint32_t i = tid; i < n; i += kSortLargeThreads) s_a[i] = items[start + i];
       __syncthreads();
     }
-    for (int p = 0; p < idx_passes + 4; ++p) {
-      const int shift = p < idx_passes ? 8 * p : 32 + 8 * (p - idx_passes);
-      cta_radix_pass(a, b, n, shift, s_hist, s_scan);
+    // The order wanted is (depth bits, Gaussian index).  Equal depths are rare (a handful of pairs per
+    // list), so the index digits are NOT sorted first: four passes over the depth bits, then every run
+    // of equal depths — found by comparing neighbours — is put into index order by the thread that owns
+    // its first element (insertion sort, runs of up to kTieRun entries).  Only when a longer run exists
+    // (degenerate scenes: thousands of splats at one depth) does the list take the full LSD sequence,
+    // index digits then depth digits, which is correct from any starting order.
+    for (int p = 0; p < 4; ++p) {
+      cta_radix_pass(a, b, n, 32 + 8 * p, s_hist, s_scan);
       uint64_t* t = a; a = b; b = t;
+    }
+    if (tid == 0) s_scan[0] = 0;
+    __syncthreads();
+    constexpr uint32_t kTieRun = 32;
+    for (uint32_t i = tid; i + 1 < n; i += kSortLargeThreads) {
+      const uint32_t d = (uint32_t)(a[i] >> 32);
+      if ((uint32_t)(a[i + 1] >> 32) != d) continue;
+      if (i > 0 && (uint32_t)(a[i - 1] >> 32) == d) continue;  // not the head of its run
+      uint32_t len = 2;
+      while (i + len < n && len <= kTieRun && (uint32_t)(a[i + len] >> 32) == d) ++len;
+      if (len > kTieRun) {
+        s_scan[0] = 1;  // benign race: every writer stores 1
+        continue;
+      }
+      for (uint32_t j = 1; j < len; ++j) {
+        const uint64_t x = a[i + j];
+        uint32_t k = j;
+        while (k > 0 && a[i + k - 1] > x) {
+          a[i + k] = a[i + k - 1];
+          --k;
+        }
+        a[i + k] = x;
+      }
+    }
+    __syncthreads();
+    const bool long_runs = s_scan[0] != 0;
+    __syncthreads();  // s_scan is reused by the passes below
+    if (long_runs) {
+      for (int p = 0; p < idx_passes + 4; ++p) {
+        const int shift = p < idx_passes ? 8 * p : 32 + 8 * (p - idx_passes);
+        cta_radix_pass(a, b, n, shift, s_hist, s_scan);
+        uint64_t* t = a; a = b; b = t;
+      }
     }
     // sorted list in `a`
     if (a != items + start)
