@@ -3,6 +3,7 @@
 // error codes into the exceptions the reference throws.
 #include "rasterize_points.h"
 
+#include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
 #include <stdexcept>
@@ -165,6 +166,41 @@ void FusedAdamStep(std::vector<torch::Tensor>& params, const std::vector<torch::
           "gsr_adam_step");
 }
 
+// ---- frame ingest: same symbol as the reference's colorize_launcher ----
+// (cuda_colorize/colorize_pointcloud.h:4-11, implementation colorize_pointcloud.cu:57-107, called from
+// submodules/data_loader/data_loader.cpp:189): `points` and `colors` are re-bound to the compacted
+// survivors (world-frame positions, pixel colours); no device-wide synchronisation.
+void colorize_launcher(torch::Tensor& points, torch::Tensor& colors, torch::Tensor& proj, torch::Tensor& Tr,
+                       torch::Tensor& pose, torch::Tensor& image) {
+  if (!points.is_cuda()) points = points.to(torch::kCUDA);
+  const auto dev = points.device();
+  auto pts = points.to(torch::kFloat32).contiguous();
+  auto img = image.to(dev).to(torch::kFloat32).contiguous();
+  auto proj_mat = proj.to(dev).to(torch::kFloat32).contiguous();
+  auto Tr_velo_to_cam = Tr.to(dev).to(torch::kFloat32).contiguous();
+  auto lidar_pose = pose.to(dev).to(torch::kFloat32).contiguous();
+  TORCH_CHECK(pts.dim() == 2 && pts.size(1) == 3, "points must have dimensions (num_points, 3)");
+  TORCH_CHECK(img.dim() == 3 && img.size(2) == 3, "image must have dimensions (H, W, 3)");
+  TORCH_CHECK(proj_mat.numel() == 12 && Tr_velo_to_cam.numel() == 16 && lidar_pose.numel() == 16,
+              "proj must have 12 elements, Tr and pose 16");
+  const int64_t n = pts.size(0);
+  auto out_p = torch::empty({n, 3}, pts.options());
+  auto out_c = torch::empty({n, 3}, pts.options());
+  int64_t count = 0;
+  if (n > 0) {
+    c10::cuda::CUDAGuard guard(dev);
+    auto ws = torch::empty({(int64_t)gsr_colorize_workspace_bytes(n)}, pts.options().dtype(torch::kByte));
+    check(gsr_colorize_points(pts.data_ptr<float>(), n, lidar_pose.data_ptr<float>(), proj_mat.data_ptr<float>(),
+                              Tr_velo_to_cam.data_ptr<float>(), img.data_ptr<float>(), (int)img.size(1),
+                              (int)img.size(0), out_p.data_ptr<float>(), out_c.data_ptr<float>(),
+                              reinterpret_cast<char*>(ws.data_ptr()), &count,
+                              c10::cuda::getCurrentCUDAStream(dev.index()).stream()),
+          "gsr_colorize_points");
+  }
+  points = out_p.slice(0, 0, count).contiguous();
+  colors = out_c.slice(0, 0, count).contiguous();
+}
+
 // Also reachable from Python (torch.ops.gsr_shim.*) so the shim itself is covered by tests.
 TORCH_LIBRARY(gsr_shim, m) {
   m.def("rasterize_forward", [](const torch::Tensor& bg, const torch::Tensor& means3D, const torch::Tensor& colors,
@@ -193,4 +229,10 @@ TORCH_LIBRARY(gsr_shim, m) {
                                           campos, geom, (int)R, binning, img, (int)B, sample, debug);
   });
   m.def("dist_cuda2", [](const torch::Tensor& pts) { return distCUDA2(pts); });
+  m.def("colorize", [](const torch::Tensor& points, const torch::Tensor& proj, const torch::Tensor& Tr,
+                       const torch::Tensor& pose, const torch::Tensor& image) {
+    torch::Tensor p = points, c = torch::zeros_like(points), pr = proj, t = Tr, po = pose, im = image;
+    colorize_launcher(p, c, pr, t, po, im);
+    return std::make_tuple(p, c);
+  });
 }

@@ -46,3 +46,8 @@ void FusedAdamStep(std::vector<torch::Tensor>& params, const std::vector<torch::
                    std::vector<torch::Tensor>& exp_avgs, std::vector<torch::Tensor>& exp_avg_sqs,
                    const std::vector<double>& lrs, const std::vector<int64_t>& steps, double beta1,
                    double beta2, double eps);
+
+// reference: cuda_colorize/colorize_pointcloud.h:4-11.  points / colors are re-bound to
+// the compacted survivors, as the reference does.
+void colorize_launcher(torch::Tensor& points, torch::Tensor& colors, torch::Tensor& proj, torch::Tensor& Tr,
+                       torch::Tensor& pose, torch::Tensor& image);

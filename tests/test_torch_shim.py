@@ -21,7 +21,8 @@ def _nm_symbols():
 @pytest.mark.skipif(not os.path.exists(SHIM), reason="torch shim not built")
 def test_shim_exports_reference_symbols():
     syms = _nm_symbols()
-    for name in ("RasterizeGaussiansCUDA(", "RasterizeGaussiansBackwardCUDA(", "markVisible(", "distCUDA2("):
+    for name in ("RasterizeGaussiansCUDA(", "RasterizeGaussiansBackwardCUDA(", "markVisible(", "distCUDA2(",
+                 "colorize_launcher("):
         assert name in syms, f"{name} not exported by the shim"
 
 
@@ -34,10 +35,11 @@ def test_reference_header_links_against_shim():
     src = r'''
 #include "rasterize_points.h"
 #include "spatial.h"
+#include "cuda_colorize/colorize_pointcloud.h"
 int main() {
   auto f = &RasterizeGaussiansCUDA; auto b = &RasterizeGaussiansBackwardCUDA;
-  auto m = &markVisible; auto d = &distCUDA2;
-  return (f && b && m && d) ? 0 : 1;
+  auto m = &markVisible; auto d = &distCUDA2; auto c = &colorize_launcher;
+  return (f && b && m && d && c) ? 0 : 1;
 }
 '''
     with tempfile.TemporaryDirectory() as td:
@@ -46,7 +48,7 @@ int main() {
         abi = int(torch._C._GLIBCXX_USE_CXX11_ABI)
         import sysconfig
         cmd = ["g++", "-std=c++17", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", "-I", REF_HDR_DIR,
-               "-I", "/root/reference/submodules/simple-knn", "-I", os.path.join(tdir, "include"),
+               "-I", "/root/reference/submodules/simple-knn", "-I", "/root/reference", "-I", os.path.join(tdir, "include"),
                "-I", os.path.join(tdir, "include/torch/csrc/api/include"), "-I", "/usr/local/cuda/include",
                "-I", sysconfig.get_paths()["include"], cpp, "-o", os.path.join(td, "t"),
                "-L", os.path.join(ROOT, "gsdf_slam_b200"), "-l:libgsr_torch_shim.so", "-l:libgsr.so",
@@ -87,3 +89,10 @@ def test_shim_matches_ctypes_path():
         assert err <= 1e-5, (name, err)   # atomics order differs between two runs
     import gsdf_slam_b200 as gs
     assert torch.equal(torch.ops.gsr_shim.dist_cuda2(t["means3D"]), gs.distCUDA2(t["means3D"]))
+    # row f-4 through the C++ symbol the data loader calls
+    import ingest_scenes
+    from gsdf_slam_b200.ingest import colorize_launcher
+    s = {k: torch.from_numpy(v).cuda() for k, v in ingest_scenes.kitti_like(30_000, 8).items()}
+    p1, c1 = torch.ops.gsr_shim.colorize(s["points"], s["proj"], s["Tr"], s["pose"], s["image"])
+    p2, c2 = colorize_launcher(s["points"], s["points"], s["proj"], s["Tr"], s["pose"], s["image"])
+    assert p1.shape[0] > 0 and torch.equal(p1, p2) and torch.equal(c1, c2)
