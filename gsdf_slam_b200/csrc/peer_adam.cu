@@ -6,12 +6,12 @@
 // Layout: every rank owns a gradient arena and a parameter arena of identical layout in
 // SYMMETRIC memory (peer-mapped; torch.distributed._symmetric_memory hands out the N base
 // pointers).  Rank r is responsible for the element range [lo, hi) of the arena (a 1/N shard):
-//   g      = sum over ranks of grad_peer[k][e]          (N-1 remote loads; skipped — taken as 0 —
-//                                                        for rows no rank rendered: union mask)
+//   g      = sum over the ranks that RENDERED the row of grad_peer[k][e]   (remote loads only from those
+//                                                        ranks: per-row rank bitmask, gsr_peer_union_mask)
 //   m, v   = shard-local Adam moments (only 1/N of the state exists on each rank)
 //   p      = Adam update of the local copy
-//   store p to the parameter arena of EVERY rank       (N-1 remote stores)
-// so each rank reads ~ (N-1)/N * (rendered fraction) * 236 B and writes (N-1)/N * 236 B per
+//   store p to the parameter arena of EVERY rank       (N-1 remote stores, skipped when p is unchanged)
+// so each rank reads ~ sum_k (fraction rank k rendered) / N * 236 B and writes (N-1)/N * 236 B per
 // Gaussian over NVLink, and touches only 1/N of the Adam state in HBM.  The caller brackets the
 // kernel with two cross-rank barriers (gradients visible / parameters landed).
 //
@@ -82,30 +82,37 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
   const unsigned r0 = (unsigned)(off / S.width);
   const unsigned rem = (unsigned)(off - (unsigned long long)r0 * S.width);
   const long long seg_end = S.start + S.numel;
-  unsigned rendered = 0;
+  // per element: which ranks rendered its row (bit k of the row's mask, gsr_peer_union_mask)
+  unsigned who[4], want = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const unsigned rr = rem + j;
     const unsigned row = r0 + (rr >= S.width) + (rr >= 2 * S.width) + (rr >= 3 * S.width);
-    if (e + j < seg_end && __ldg(a.union_mask + row) > 0) rendered |= 1u << j;
+    who[j] = (e + j < seg_end) ? (unsigned)__ldg(a.union_mask + row) : 0u;
+    want |= who[j];
   }
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (rendered) {
-    // all N loads are issued before the first sum (NVLink round trips overlap); fixed rank order
-    // of the additions on every rank: identical sums, replicas stay bit-identical
+  if (want) {
+    // Only the arenas of the ranks that rendered one of these rows are read (a view sees a fraction of the
+    // map, so most of the N-1 remote loads disappear, and the ranks need not zero-fill the rows they did
+    // not render).  All loads are issued before the first sum (NVLink round trips overlap); the additions
+    // run in rank order on the one rank that owns the element, so every replica receives the same value.
     float4 x[GSR_MAX_PEERS];
 #pragma unroll
     for (int k = 0; k < GSR_MAX_PEERS; ++k)
-      if (k < a.n_peers) x[k] = __ldcs(reinterpret_cast<const float4*>(a.grad[k] + e));
+      if (k < a.n_peers && ((want >> k) & 1u)) x[k] = __ldcs(reinterpret_cast<const float4*>(a.grad[k] + e));
 #pragma unroll
-    for (int k = 0; k < GSR_MAX_PEERS; ++k)
-      if (k < a.n_peers) { g.x += x[k].x; g.y += x[k].y; g.z += x[k].z; g.w += x[k].w; }
-    if (!(rendered & 1u)) g.x = 0.f;
-    if (!(rendered & 2u)) g.y = 0.f;
-    if (!(rendered & 4u)) g.z = 0.f;
-    if (!(rendered & 8u)) g.w = 0.f;
+    for (int k = 0; k < GSR_MAX_PEERS; ++k) {
+      if (k < a.n_peers && ((want >> k) & 1u)) {
+        if ((who[0] >> k) & 1u) g.x += x[k].x;
+        if ((who[1] >> k) & 1u) g.y += x[k].y;
+        if ((who[2] >> k) & 1u) g.z += x[k].z;
+        if ((who[3] >> k) & 1u) g.w += x[k].w;
+      }
+    }
   }
-  float4 p = *reinterpret_cast<const float4*>(a.param[my_rank] + e);
+  const float4 p_old = *reinterpret_cast<const float4*>(a.param[my_rank] + e);
+  float4 p = p_old;
   float4 m = __ldcs(reinterpret_cast<const float4*>(a.exp_avg + (e - a.lo)));
   float4 v = __ldcs(reinterpret_cast<const float4*>(a.exp_avg_sq + (e - a.lo)));
   peer_adam_elem(p.x, g.x, m.x, v.x, a, S.neg_step_size, S.inv_sqrt_bc2);
@@ -114,12 +121,18 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
   peer_adam_elem(p.w, g.w, m.w, v.w, a, S.neg_step_size, S.inv_sqrt_bc2);
   __stcs(reinterpret_cast<float4*>(a.exp_avg + (e - a.lo)), m);
   __stcs(reinterpret_cast<float4*>(a.exp_avg_sq + (e - a.lo)), v);
+  // every replica holds p_old already: values that did not change (rows whose moments and gradient are
+  // all zero) need not travel
+  const bool changed = __float_as_uint(p.x) != __float_as_uint(p_old.x) || __float_as_uint(p.y) != __float_as_uint(p_old.y) ||
+                       __float_as_uint(p.z) != __float_as_uint(p_old.z) || __float_as_uint(p.w) != __float_as_uint(p_old.w);
+  if (changed) {
 #pragma unroll
-  for (int k = 0; k < GSR_MAX_PEERS; ++k)
-    if (k < a.n_peers) *reinterpret_cast<float4*>(a.param[k] + e) = p;
+    for (int k = 0; k < GSR_MAX_PEERS; ++k)
+      if (k < a.n_peers) *reinterpret_cast<float4*>(a.param[k] + e) = p;
+  }
 }
 
-// union[row] = max over ranks of radii_peer[k][row]
+// union[row] = bit k set <=> rank k rendered the row (radii_peer[k][row] > 0)
 struct PeerMaskParams {
   const int* radii[GSR_MAX_PEERS];
   int n_peers;
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(256) peer_union_mask_kernel(const PeerMaskPara
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   int m = 0;
-  for (int k = 0; k < a.n_peers; ++k) m = max(m, a.radii[k][i]);
+  for (int k = 0; k < a.n_peers; ++k) m |= (a.radii[k][i] > 0) ? (1 << k) : 0;
   union_out[i] = m;
 }
 

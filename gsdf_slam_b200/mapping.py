@@ -193,7 +193,10 @@ class KeyframeBatchMapper:
                 if self._scratch_arena is None:
                     self._scratch_arena = torch.zeros_like(self.arena)
                 views = self._views(self._scratch_arena)
-            _, radii, _ = self.render_backward(kf, views, on_forward=on_forward)
+            # one keyframe per rank: rows this rank did not render are never read by the exchange (per-row
+            # rank bitmask), so the backward pass may skip the dense zero fill
+            _, radii, _ = self.render_backward(kf, views, on_forward=on_forward,
+                                               rendered_rows_only=(len(keyframes) == 1))
             if i > 0:
                 self.arena.add_(self._scratch_arena)
             mask = radii if mask is None else torch.maximum(mask, radii)

@@ -224,14 +224,16 @@ typedef struct gsr_peer_adam_args {
   int64_t shard_lo, shard_hi;   /* multiples of 4 elements */
   float* exp_avg;               /* [shard_hi - shard_lo], local */
   float* exp_avg_sq;
-  const int32_t* union_mask;    /* [rows]: > 0 <=> some rank rendered the row (gsr_peer_union_mask) */
+  const int32_t* union_mask;    /* [rows]: bit k <=> rank k rendered the row (gsr_peer_union_mask) */
   double beta1, beta2, eps;
   float grad_scale;
   int64_t step;                 /* step count AFTER this update (>= 1) */
   void* stream;
 } gsr_peer_adam_args;
 int gsr_adam_step_peer(const gsr_peer_adam_args* a);
-/* union_out[row] = max over the N ranks of radii_peers[k][row] (peer-mapped radii buffers). */
+/* union_out[row] = bitmask of the ranks that rendered the row: bit k set <=> radii_peers[k][row] > 0
+ * (peer-mapped radii buffers).  gsr_adam_step_peer reads rank k's gradient of a row only when bit k is
+ * set, so a rank may leave the rows it did not render unwritten (gsr_backward rendered_rows_only). */
 int gsr_peer_union_mask(const int32_t* const* radii_peers, int n_peers, int64_t rows,
                         int32_t* union_out, void* stream);
 

@@ -19,17 +19,26 @@ base = dict(means3D=t(scene.means3D), dc=t(scene.dc), sh=t(scene.sh), opacity=t(
             scales=t(scene.scales), rotations=t(scene.rotations))
 kf = Keyframe(t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos), cam.tanfovx, cam.tanfovy, cam.H, cam.W,
               t(scene.dL_dout))
-res = {}
-for peer in (False, True):
+cam2 = cams[(rank + 3) % 8]
+kf2 = Keyframe(t(cam2.viewmatrix), t(cam2.projmatrix), t(cam2.campos), cam2.tanfovx, cam2.tanfovy, cam2.H, cam2.W,
+               t(scene.dL_dout))
+worst = 0.0
+# one keyframe per rank (the backward skips the zero fill, the exchange reads only rendering ranks) and two
+# keyframes per rank (dense accumulation)
+for kfs in ([kf], [kf, kf2]):
+  res = {}
+  for peer in (False, True):
     m = KeyframeBatchMapper({k: v.clone() for k, v in base.items()}, scene.degree, t(scene.bg),
                             freeze_render_inputs=True, peer_exchange=peer)
     assert (m.peer is not None) == peer, "peer path not active"
+    if peer:
+        m.arena.fill_(float("nan"))   # rows nobody renders must never be read
     for _ in range(3):
-        m.step([kf])
+        m.step(kfs)
     torch.cuda.synchronize()
     res[peer] = {k: m.opt_params[k].clone() for k in SEGMENTS}
-worst = 0.0
-for k in SEGMENTS:
+    del m
+  for k in SEGMENTS:
     a, b = res[False][k].double(), res[True][k].double()
     d0 = (res[False][k] - base[k]).double()
     rel = float((a - b).norm() / max(float(d0.norm()), 1e-30))
@@ -39,8 +48,9 @@ for k in SEGMENTS:
     dist.all_gather(g, res[True][k].contiguous())
     same = all(torch.equal(g[0].view(torch.int32), x.view(torch.int32)) for x in g)
     if rank == 0:
-        print(f"{k:10s} rel-L2(update) peer vs nccl {rel:.3e}  replicas bit-identical: {same}")
+        print(f"K={len(kfs)} {k:10s} rel-L2(update) peer vs nccl {rel:.3e}  replicas bit-identical: {same}")
     assert same, k
+    assert bool(torch.isfinite(res[True][k]).all()), k
 assert worst <= 2e-3, worst
 if rank == 0:
     print("peer exchange OK")
