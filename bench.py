@@ -323,7 +323,7 @@ def run_product(args, rank, world, dev):
     # peer kernel + second barrier)
     rank_breakdown = None
     if world > 1 and mapper.peer is not None:
-        acc = torch.zeros(3, device=dev, dtype=torch.float64)
+        acc = torch.zeros(6, device=dev, dtype=torch.float64)
         n_tr = 10
         for _ in range(n_tr):
             mapper.trace = []
@@ -333,12 +333,17 @@ def run_product(args, rank, world, dev):
             acc[0] += ev["step_begin"].elapsed_time(ev["render_end"])
             acc[1] += ev["render_end"].elapsed_time(ev["barrier1_end"])
             acc[2] += ev["barrier1_end"].elapsed_time(ev["step_end"])
+            acc[3] += ev["barrier1_end"].elapsed_time(ev["mask_end"])
+            acc[4] += ev["mask_end"].elapsed_time(ev["peer_adam_end"])
+            acc[5] += ev["peer_adam_end"].elapsed_time(ev["step_end"])
         mapper.trace = None
         acc /= n_tr
         allr = [torch.zeros_like(acc) for _ in range(world)]
         dist.all_gather(allr, acc)
         rank_breakdown = [{"rank": r, "render_ms": round(float(x[0]), 4), "wait_ms": round(float(x[1]), 4),
-                           "exchange_ms": round(float(x[2]), 4)} for r, x in enumerate(allr)]
+                           "exchange_ms": round(float(x[2]), 4), "mask_ms": round(float(x[3]), 4),
+                           "peer_adam_ms": round(float(x[4]), 4), "barrier2_ms": round(float(x[5]), 4)}
+                          for r, x in enumerate(allr)]
     if world > 1:
         lt = torch.tensor([launches], device=dev, dtype=torch.float64)
         dist.all_reduce(lt)

@@ -82,7 +82,7 @@ class PeerAdamArgs(C.Structure):
         ("shard_lo", C.c_int64), ("shard_hi", C.c_int64),
         ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("union_mask", C.c_void_p),
         ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", C.c_float),
-        ("step", C.c_int64), ("stream", C.c_void_p),
+        ("step", C.c_int64), ("stream", C.c_void_p), ("shard_chunk", C.c_int64),
     ]
 
 
@@ -110,7 +110,7 @@ class DensifyArgs(C.Structure):
 
 # every symbol include/gsr_capi.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
-    "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows", "gsr_adam_step_peer", "gsr_peer_union_mask",
+    "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows", "gsr_adam_step_peer", "gsr_peer_union_mask", "gsr_peer_rank_mask_u8",
     "gsr_l1_ssim_loss", "gsr_l1_ssim_workspace_bytes",
     "gsr_store_workspace_bytes", "gsr_prune_points", "gsr_densify_and_prune", "gsr_densification_postfix",
     "gsr_add_densification_stats", "gsr_reset_opacity", "gsr_voxel_dedup_workspace_bytes", "gsr_voxel_dedup",
@@ -164,6 +164,8 @@ def lib() -> C.CDLL:
     L.gsr_adam_step_peer.restype = C.c_int
     L.gsr_peer_union_mask.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     L.gsr_peer_union_mask.restype = C.c_int
+    L.gsr_peer_rank_mask_u8.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    L.gsr_peer_rank_mask_u8.restype = C.c_int
     L.gsr_l1_ssim_workspace_bytes.argtypes = [C.c_int, C.c_int]
     L.gsr_l1_ssim_workspace_bytes.restype = C.c_size_t
     L.gsr_l1_ssim_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p,

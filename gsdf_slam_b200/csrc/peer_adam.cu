@@ -46,7 +46,9 @@ struct PeerAdamParams {
   int n_segs;
   PeerSegDev seg[GSR_PEER_MAX_SEGMENTS];
   long long lo, hi;      // this rank's shard of the arena (multiples of 4 elements)
-  float* exp_avg;        // [hi - lo] shard-local
+  long long chunk;       // > 0: the shard is every n_peers-th chunk of `chunk` elements of [0, hi) instead
+  int ctas_per_chunk;
+  float* exp_avg;        // [hi - lo] shard-local (chunked: the owned chunks back to back)
   float* exp_avg_sq;     // [hi - lo]
   const int* union_mask; // [rows] > 0 <=> some rank rendered the row
   float beta1, one_minus_beta1, beta2, one_minus_beta2, eps, grad_scale;
@@ -68,9 +70,23 @@ __device__ __forceinline__ void peer_adam_elem(float& p, float g, float& m, floa
 }
 
 __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamParams a, int my_rank) {
-  const long long base = a.lo + (long long)blockIdx.x * kPeerChunk;
-  const long long e = base + 4LL * threadIdx.x;
+  // element handled by this thread and its slot in the shard-local moment arrays
+  long long e, mo;
+  if (a.chunk > 0) {
+    const long long c_local = blockIdx.x / a.ctas_per_chunk;
+    const long long in_chunk = (long long)(blockIdx.x % a.ctas_per_chunk) * kPeerChunk + 4LL * threadIdx.x;
+    if (in_chunk >= a.chunk) return;
+    e = (c_local * a.n_peers + my_rank) * a.chunk + in_chunk;
+    mo = c_local * a.chunk + in_chunk;
+  } else {
+    e = a.lo + (long long)blockIdx.x * kPeerChunk + 4LL * threadIdx.x;
+    mo = e - a.lo;
+  }
   if (e >= a.hi) return;
+  // local state first: these HBM reads overlap the NVLink round trips below
+  const float4 p_old = *reinterpret_cast<const float4*>(a.param[my_rank] + e);
+  float4 m = __ldcs(reinterpret_cast<const float4*>(a.exp_avg + mo));
+  float4 v = __ldcs(reinterpret_cast<const float4*>(a.exp_avg_sq + mo));
   // segment of this float4 (segments start on 4-element boundaries, so it lies in exactly one)
   int si = 0;
 #pragma unroll 1
@@ -79,8 +95,14 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
   const PeerSegDev S = a.seg[si];
   // rows of the four elements: one wide division per thread, then small offsets
   const unsigned long long off = (unsigned long long)(e - S.start);
-  const unsigned r0 = (unsigned)(off / S.width);
-  const unsigned rem = (unsigned)(off - (unsigned long long)r0 * S.width);
+  unsigned r0, rem;
+  if (off <= 0xffffffffull) {  // 32-bit division: the 64-bit one is ~100 instructions per thread
+    r0 = (unsigned)off / S.width;
+    rem = (unsigned)off - r0 * S.width;
+  } else {
+    r0 = (unsigned)(off / S.width);
+    rem = (unsigned)(off - (unsigned long long)r0 * S.width);
+  }
   const long long seg_end = S.start + S.numel;
   // per element: which ranks rendered its row (bit k of the row's mask, gsr_peer_union_mask)
   unsigned who[4], want = 0;
@@ -111,16 +133,13 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
       }
     }
   }
-  const float4 p_old = *reinterpret_cast<const float4*>(a.param[my_rank] + e);
   float4 p = p_old;
-  float4 m = __ldcs(reinterpret_cast<const float4*>(a.exp_avg + (e - a.lo)));
-  float4 v = __ldcs(reinterpret_cast<const float4*>(a.exp_avg_sq + (e - a.lo)));
   peer_adam_elem(p.x, g.x, m.x, v.x, a, S.neg_step_size, S.inv_sqrt_bc2);
   peer_adam_elem(p.y, g.y, m.y, v.y, a, S.neg_step_size, S.inv_sqrt_bc2);
   peer_adam_elem(p.z, g.z, m.z, v.z, a, S.neg_step_size, S.inv_sqrt_bc2);
   peer_adam_elem(p.w, g.w, m.w, v.w, a, S.neg_step_size, S.inv_sqrt_bc2);
-  __stcs(reinterpret_cast<float4*>(a.exp_avg + (e - a.lo)), m);
-  __stcs(reinterpret_cast<float4*>(a.exp_avg_sq + (e - a.lo)), v);
+  __stcs(reinterpret_cast<float4*>(a.exp_avg + mo), m);
+  __stcs(reinterpret_cast<float4*>(a.exp_avg_sq + mo), v);
   // every replica holds p_old already: values that did not change (rows whose moments and gradient are
   // all zero) need not travel
   const bool changed = __float_as_uint(p.x) != __float_as_uint(p_old.x) || __float_as_uint(p.y) != __float_as_uint(p_old.y) ||
@@ -146,6 +165,38 @@ __global__ void __launch_bounds__(256) peer_union_mask_kernel(const PeerMaskPara
   union_out[i] = m;
 }
 
+// the same from one-byte "rendered" flags, four rows per thread (a quarter of the remote traffic)
+struct PeerFlagParams {
+  const uint8_t* flags[GSR_MAX_PEERS];
+  int n_peers;
+};
+__global__ void __launch_bounds__(256) peer_rank_mask_u8_kernel(const PeerFlagParams a, long long rows,
+                                                                int* __restrict__ mask_out) {
+  const long long i = 4 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= rows) return;
+  int m[4] = {0, 0, 0, 0};
+  if (i + 3 < rows) {
+    uint32_t w[GSR_MAX_PEERS];
+#pragma unroll
+    for (int k = 0; k < GSR_MAX_PEERS; ++k)
+      if (k < a.n_peers) w[k] = *reinterpret_cast<const uint32_t*>(a.flags[k] + i);
+#pragma unroll
+    for (int k = 0; k < GSR_MAX_PEERS; ++k) {
+      if (k < a.n_peers) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] |= ((w[k] >> (8 * j)) & 0xffu) ? (1 << k) : 0;
+      }
+    }
+    *reinterpret_cast<int4*>(mask_out + i) = make_int4(m[0], m[1], m[2], m[3]);
+  } else {
+    for (int j = 0; i + j < rows; ++j) {
+      int mm = 0;
+      for (int k = 0; k < a.n_peers; ++k) mm |= a.flags[k][i + j] ? (1 << k) : 0;
+      mask_out[i + j] = mm;
+    }
+  }
+}
+
 }  // namespace gsr
 
 using namespace gsr;
@@ -165,6 +216,25 @@ int gsr_peer_union_mask(const int32_t* const* radii_peers, int n_peers, int64_t 
   }
   peer_union_mask_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       a, rows, union_out);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_t rows, int32_t* mask_out,
+                          void* stream) {
+  if (n_peers < 1 || n_peers > GSR_MAX_PEERS || rows < 0 || !flags_peers || (rows > 0 && !mask_out))
+    return GSR_ERR_BAD_ARG;
+  if (rows == 0) return GSR_OK;
+  PeerFlagParams a;
+  a.n_peers = n_peers;
+  for (int k = 0; k < n_peers; ++k) {
+    if (!flags_peers[k] || ((uintptr_t)flags_peers[k] & 3)) return GSR_ERR_BAD_ARG;
+    a.flags[k] = flags_peers[k];
+  }
+  if ((uintptr_t)mask_out & 15) return GSR_ERR_BAD_ARG;
+  const long long threads = (rows + 3) / 4;
+  peer_rank_mask_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, rows, mask_out);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }
@@ -212,9 +282,19 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* in) {
   a.eps = (float)in->eps;
   a.grad_scale = in->grad_scale;
   a.use_scale = in->grad_scale != 1.0f;
-  const long long n = a.hi - a.lo;
-  peer_adam_kernel<<<(unsigned)((n + kPeerChunk - 1) / kPeerChunk), kPeerThreads, 0,
-                     static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
+  a.chunk = in->shard_chunk;
+  a.ctas_per_chunk = 1;
+  long long ctas = (a.hi - a.lo + kPeerChunk - 1) / kPeerChunk;
+  if (a.chunk > 0) {
+    // interleaved sharding: rank r owns the chunks c with c % n_peers == r of [0, shard_hi)
+    if ((a.chunk & 3) || in->shard_lo != 0) return GSR_ERR_BAD_ARG;
+    a.ctas_per_chunk = (int)((a.chunk + kPeerChunk - 1) / kPeerChunk);
+    const long long n_chunks = (a.hi + a.chunk - 1) / a.chunk;
+    const long long owned = n_chunks > in->rank ? (n_chunks - in->rank + in->n_peers - 1) / in->n_peers : 0;
+    ctas = owned * a.ctas_per_chunk;
+    if (ctas == 0) return GSR_OK;
+  }
+  peer_adam_kernel<<<(unsigned)ctas, kPeerThreads, 0, static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -147,7 +147,7 @@ class KeyframeBatchMapper:
                 raise RuntimeError("more than GSR_MAX_PEERS ranks")
             g_arena = symm.empty(total, dtype=torch.float32, device=dev)
             p_arena = symm.empty(total, dtype=torch.float32, device=dev)
-            radii = symm.empty(max(self.P, 1), dtype=torch.int32, device=dev)
+            radii = symm.empty(max(self.P, 1) + 16, dtype=torch.uint8, device=dev)   # one "rendered" byte per row
             g_arena.zero_(); p_arena.zero_(); radii.zero_()
             hg = symm.rendezvous(g_arena, group)
             hp = symm.rendezvous(p_arena, group)
@@ -166,14 +166,20 @@ class KeyframeBatchMapper:
             self.params = p_views
         self.arena = g_arena
         self.grad_views = self._views(g_arena)
-        shard = ((total + world - 1) // world + 3) // 4 * 4
-        lo = min(total, rank * shard)
-        hi = min(total, lo + shard)
+        # interleaved sharding: rank r owns every world-th 64 Ki-element chunk of the arena, so every rank
+        # gets the same mix of narrow (xyz, opacity, ...) and wide (sh) rows — a contiguous 1/N range gave
+        # the ranks holding the narrow segments 30 % more parameter stores (measured at N = 8)
+        chunk = 65536
+        n_chunks = (total + chunk - 1) // chunk
+        owned = (n_chunks - rank + world - 1) // world if n_chunks > rank else 0
+        lo, hi = 0, total
+        n_mom = max(owned * chunk, 4)
         self.peer = dict(world=world, rank=rank, hg=hg, hp=hp, hr=hr, g_arena=g_arena, p_arena=p_arena,
                          radii=radii, lo=lo, hi=hi, step=0, eps=float(eps), lr=dict(lr),
-                         exp_avg=torch.zeros(max(hi - lo, 4), dtype=torch.float32, device=dev),
-                         exp_avg_sq=torch.zeros(max(hi - lo, 4), dtype=torch.float32, device=dev),
-                         union=torch.zeros(max(self.P, 1), dtype=torch.int32, device=dev))
+                         chunk=chunk, exp_avg=torch.zeros(n_mom, dtype=torch.float32, device=dev),
+                         exp_avg_sq=torch.zeros(n_mom, dtype=torch.float32, device=dev),
+                         union=torch.zeros(max(self.P, 1) + 4, dtype=torch.int32, device=dev),
+                         flag_tmp=torch.zeros(max(self.P, 1), dtype=torch.bool, device=dev))
         torch.cuda.synchronize(dev)
         dist.barrier(group)
 
@@ -203,15 +209,17 @@ class KeyframeBatchMapper:
         if mask is None:
             pe["radii"].zero_()
         else:
-            pe["radii"].copy_(mask)
+            torch.gt(mask, 0, out=pe["flag_tmp"])
+            pe["radii"][: self.P].copy_(pe["flag_tmp"])
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         L = _lib.lib()
         self._mark("render_end", torch.cuda.current_stream(dev))
         pe["hg"].barrier(channel=0)          # every rank's gradients and radii are written
         self._mark("barrier1_end", torch.cuda.current_stream(dev))
         rptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hr"].buffer_ptrs])
-        _lib.check(L.gsr_peer_union_mask(rptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
-                   "gsr_peer_union_mask")
+        _lib.check(L.gsr_peer_rank_mask_u8(rptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
+                   "gsr_peer_rank_mask_u8")
+        self._mark("mask_end", torch.cuda.current_stream(dev))
         pe["step"] += 1
         a = _lib.PeerAdamArgs()
         a.n_peers, a.rank = pe["world"], pe["rank"]
@@ -225,7 +233,7 @@ class KeyframeBatchMapper:
             a.segments[i].start, a.segments[i].numel = off, numel
             a.segments[i].width = numel // self.P
             a.segments[i].lr = float(pe["lr"][n])
-        a.shard_lo, a.shard_hi = pe["lo"], pe["hi"]
+        a.shard_lo, a.shard_hi, a.shard_chunk = pe["lo"], pe["hi"], pe["chunk"]
         a.exp_avg, a.exp_avg_sq = pe["exp_avg"].data_ptr(), pe["exp_avg_sq"].data_ptr()
         a.union_mask = pe["union"].data_ptr()
         a.beta1, a.beta2, a.eps, a.grad_scale = 0.9, 0.999, pe["eps"], float(grad_scale)

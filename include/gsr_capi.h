@@ -229,6 +229,11 @@ typedef struct gsr_peer_adam_args {
   float grad_scale;
   int64_t step;                 /* step count AFTER this update (>= 1) */
   void* stream;
+  /* 0: the rank owns the contiguous range [shard_lo, shard_hi).  > 0 (a multiple of 4): interleaved
+   * sharding — the arena [0, shard_hi) is cut into chunks of shard_chunk elements and rank r owns the
+   * chunks c with c % n_peers == r (shard_lo must be 0); exp_avg / exp_avg_sq hold the owned chunks back
+   * to back.  Every rank then gets the same mix of narrow and wide parameter rows, i.e. the same work. */
+  int64_t shard_chunk;
 } gsr_peer_adam_args;
 int gsr_adam_step_peer(const gsr_peer_adam_args* a);
 /* union_out[row] = bitmask of the ranks that rendered the row: bit k set <=> radii_peers[k][row] > 0
@@ -236,6 +241,10 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* a);
  * set, so a rank may leave the rows it did not render unwritten (gsr_backward rendered_rows_only). */
 int gsr_peer_union_mask(const int32_t* const* radii_peers, int n_peers, int64_t rows,
                         int32_t* union_out, void* stream);
+/* The same mask from one-byte flags (flags_peers[k][row] != 0 <=> rank k rendered the row; 4-byte aligned
+ * peer-mapped buffers, mask_out 16-byte aligned): a quarter of the NVLink traffic of the radii version. */
+int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_t rows,
+                          int32_t* mask_out, void* stream);
 
 /* ---- Gaussian-store surgery: densify / prune / increasePcd ----
  * The reference keeps the map as six parameter tensors, twelve Adam moment tensors and four
