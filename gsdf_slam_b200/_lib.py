@@ -104,7 +104,7 @@ class DensifyArgs(C.Structure):
     _fields_ = [
         ("max_grad", C.c_float), ("min_opacity", C.c_float), ("extent", C.c_float),
         ("percent_dense", C.c_float), ("max_screen_size", C.c_int32), ("n_split", C.c_int32),
-        ("noise", C.c_void_p), ("seed", C.c_uint64),
+        ("noise", C.c_void_p), ("seed", C.c_uint64), ("noise_rows", C.c_int64),
     ]
 
 

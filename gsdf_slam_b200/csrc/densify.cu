@@ -278,8 +278,9 @@ struct ScatterParams {
   int64_t rows;
   int n_split;
   float inv_split_div;   // 1 / (0.8 N) as ATen forms it (float reciprocal of the scalar)
-  const float* noise;    // [N * S, 3] or NULL
+  const float* noise;    // [noise_rows, 3] or NULL
   uint64_t seed;
+  long long noise_rows;
 };
 
 // Shared-memory plan of one CTA (dynamic): a 3-stage ring of 12 KB source chunks filled by TMA bulk
@@ -496,7 +497,7 @@ scatter_rows_kernel(StoreArrays A, const uint8_t* __restrict__ flags, const uint
       for (int cp = 0; cp < p.n_split; ++cp) {
         const uint32_t nidx = (uint32_t)cp * Sall + (uint32_t)s_noise[r];
         float zn[3];
-        if (p.noise) {
+        if (p.noise && (long long)nidx < p.noise_rows) {
           zn[0] = p.noise[3 * (size_t)nidx];
           zn[1] = p.noise[3 * (size_t)nidx + 1];
           zn[2] = p.noise[3 * (size_t)nidx + 2];
@@ -896,6 +897,7 @@ int gsr_densify_and_prune(const gsr_gaussian_store* src, const gsr_gaussian_stor
   p.inv_split_div = dp.inv_split_div;
   p.noise = a->noise;
   p.seed = a->seed;
+  p.noise_rows = a->noise ? a->noise_rows : 0;
   {
     const int rc = launch_scatter(A, w, p, s);
     if (rc) return rc;

@@ -254,6 +254,7 @@ class GaussianModel:
         if noise is not None:
             noise = noise.to(device=self.device, dtype=torch.float32).contiguous()
             a.noise = noise.data_ptr()
+            a.noise_rows = int(noise.numel() // 3)
         counts = (C.c_int64 * 4)()
         want = int(n * self.growth) + 4096
         with torch.cuda.device(self.device):

@@ -303,8 +303,9 @@ typedef struct gsr_densify_args {
   float percent_dense;
   int32_t max_screen_size;/* 0 = skip the size tests (src/gaussian_model.cpp:655-660) */
   int32_t n_split;        /* N, the reference uses 2; 1..4 */
-  const float* noise;     /* [n_split * S, 3] standard normal, or NULL */
+  const float* noise;     /* [noise_rows, 3] standard normal, or NULL */
   uint64_t seed;
+  int64_t noise_rows;     /* rows `noise` holds; draws beyond them come from the device generator */
 } gsr_densify_args;
 int gsr_densify_and_prune(const gsr_gaussian_store* src, const gsr_gaussian_store* dst,
                           const gsr_densify_args* args, char* workspace, int64_t* counts_out_host,

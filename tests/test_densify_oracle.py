@@ -103,4 +103,4 @@ def test_store_struct_layout_matches_header():
     from gsdf_slam_b200 import _lib
     # int64, int64, int32 (+pad), 18 pointers, 4 pointers
     assert C.sizeof(_lib.GaussianStoreC) == 8 + 8 + 8 + 18 * 8 + 4 * 8
-    assert C.sizeof(_lib.DensifyArgs) == 4 * 4 + 2 * 4 + 8 + 8
+    assert C.sizeof(_lib.DensifyArgs) == 4 * 4 + 2 * 4 + 8 + 8 + 8
