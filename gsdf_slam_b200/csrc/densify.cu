@@ -519,8 +519,9 @@ scatter_rows_kernel(StoreArrays A, const uint8_t* __restrict__ flags, const uint
 }
 
 int launch_scatter(const StoreArrays& A, const Workspace& w, const ScatterParams& p, cudaStream_t s) {
-  static const cudaError_t attr = cudaFuncSetAttribute(scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       (int)kScatterSmem);
+  // per call, not once per process: the attribute belongs to the current device's context
+  const cudaError_t attr = cudaFuncSetAttribute(scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)kScatterSmem);
   if (attr != cudaSuccess) return (int)attr;
   scatter_rows_kernel<<<w.nblk, kStoreThreads, kScatterSmem, s>>>(A, w.flags, w.block_base, w.totals, p);
   GSR_LAUNCHED();
