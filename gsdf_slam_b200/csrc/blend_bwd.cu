@@ -199,24 +199,31 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       }
       if (!__any_sync(0xffffffffu, any_cand)) continue;  // splat misses this warp's half tile
 
-      bool contributed = false;
+      // the four exp / alpha chains are evaluated together (4-way ILP, shared constants, no branches) like
+      // in the forward kernel; the chain of a pixel that is not a candidate computes a value nobody uses
+      float G[kSlots], alpha[kSlots];
+      bool live[kSlots];
 #pragma unroll
       for (int q = 0; q < kSlots; ++q) {
-        if (!cand[q]) continue;
-        const float G = exp(pw[q]);
-        const float alpha = min(0.99f, con_o.w * G);
-        if (alpha < 1.0f / 255.0f) continue;
-        contributed = true;
-        {
+        G[q] = exp(pw[q]);
+        alpha[q] = min(0.99f, con_o.w * G[q]);
+        live[q] = cand[q] && !(alpha[q] < 1.0f / 255.0f);
+      }
+      const bool contributed = live[0] || live[1] || live[2] || live[3];
+      if (!__any_sync(0xffffffffu, contributed)) continue;
+      {
+        const float4 col = sR[buf][3 * j + 2];
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) {
+          if (!live[q]) continue;
           const float2 d = {A.x - pxf[q & 1], A.y - pyf[q & 2]};
-          const float4 col = sR[buf][3 * j + 2];
-          const float one_m = 1.0f - alpha;
+          const float one_m = 1.0f - alpha[q];
           // 1 / (1 - alpha), 1 - alpha in [0.01, 1]: the hardware reciprocal (1 ulp) is enough for a
           // gradient term (parity bar 1e-4 rel-L2) and, unlike __frcp_rn / IEEE division, compiles to a
           // single MUFU.RCP without the range check + fix-up + slow-path call (10 instructions per pair)
           float inv;
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(one_m));
-          const float Ta = T[q] * alpha;
+          const float Ta = T[q] * alpha[q];
           const float cdl = col.x * dL[q][0] + col.y * dL[q][1] + col.z * dL[q][2];
           v[6] += Ta * dL[q][0];
           v[7] += Ta * dL[q][1];
@@ -225,7 +232,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
           const float dL_dalpha = T[q] * cdl + inv * S[q];
           T[q] *= one_m;
 
-          const float w = G * dL_dalpha;
+          const float w = G[q] * dL_dalpha;
           const float wdx = w * d.x;
           const float wdy = w * d.y;
           v[0] += wdx;
@@ -236,7 +243,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
           v[5] += w;
         }
       }
-      if (!__any_sync(0xffffffffu, contributed)) continue;
 
       float s8, s9;
       warp_reduce9_smem(v, lane, s_red[0], s8, s9);
