@@ -1,0 +1,80 @@
+"""Turns the two ncu artefacts of a round into the tracked summaries under profiles/:
+  python tools/ncu_summarize.py launches gpurun_out/launches_r1h.csv profiles/ncu_launches_r1_summary.md
+  python tools/ncu_summarize.py full gpurun_out/top_r1h.ncu-rep profiles/ncu_top_kernels_r1.json profiles/dram_traffic.json"""
+import csv, io, json, subprocess, sys
+
+STEP_KERNELS = ["preprocess_kernel", "tile_meta_kernel", "emit_kernel", "emit_large_kernel", "tile_sort_pack_small_kernel",
+                "tile_sort_pack_mid_kernel", "tile_sort_pack_long_kernel", "blend_fwd_kernel", "blend_bwd_kernel",
+                "preprocess_bwd_kernel", "adam_rows_all_kernel"]
+
+
+def short(name):
+    n = name.split("(")[0].split("::")[-1]
+    return n.replace("void ", "").strip()
+
+
+def launches(src, dst):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10]
+    h = rows[0]
+    ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+    seq = [(short(r[ki]), float(r[vi].replace(",", "")) / 1000.0) for r in rows[1:]]
+    # the last complete step: from the last preprocess_kernel that is followed by an adam kernel
+    starts = [i for i, (k, _) in enumerate(seq) if k == "preprocess_kernel"]
+    step = None
+    for s in reversed(starts):
+        tail = seq[s:]
+        names = [k for k, _ in tail]
+        if "adam_rows_all_kernel" in names:
+            step = tail[: names.index("adam_rows_all_kernel") + 1]
+            break
+    tot = sum(t for _, t in step)
+    out = ["# ncu launch list, round 1 (cfg2: 500k SH-3 Gaussians, 1200x680, one mapping step = fwd + bwd + masked Adam)", "",
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 1 "
+           "--no-cpu-baseline` (one steady-state step; cold-cache, serialised: compare SHARES with the live CUDA-event stage "
+           "times in `bench_r1_product.json`).", "", "| # | kernel | us | share |", "|---|---|---|---|"]
+    for i, (k, t) in enumerate(step):
+        out.append(f"| {i} | {k} | {t:.2f} | {100 * t / tot:.1f}% |")
+    out.append(f"| | total | {tot:.1f} | |")
+    open(dst, "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
+def full(rep, dst, traffic_dst):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    h, units = rows[0], rows[1]
+    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__inst_executed.sum", "sm__cycles_active.avg", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size"]
+    idx = {w: h.index(w) for w in want if w in h}
+    kernels, traffic = [], {}
+    for r in rows[2:]:
+        if len(r) < len(h):
+            continue
+        d = {w: r[i] for w, i in idx.items()}
+        d["Kernel Name"] = short(d["Kernel Name"])
+        kernels.append(d)
+
+        def to_bytes(key):
+            v, u = float(d[key].replace(",", "")), units[idx[key]].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        stage = d["Kernel Name"].replace("_kernel", "").replace("_small", "")
+        traffic[stage] = int(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
+    json.dump({"command": "ncu --set full --clock-control none --import-source on -k regex:... -s 24 -c 8 python bench.py "
+                          "--steps 2 --warmup 1 --no-cpu-baseline", "units": {w: units[i] for w, i in idx.items()},
+               "kernels": kernels}, open(dst, "w"), indent=1)
+    if traffic_dst:
+        old = json.load(open(traffic_dst)) if __import__("os").path.exists(traffic_dst) else {}
+        old.update(traffic)
+        json.dump(old, open(traffic_dst, "w"), indent=1)
+    for k in kernels:
+        print(k["Kernel Name"], k.get("gpu__time_duration.sum"), k.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+              k.get("sm__warps_active.avg.pct_of_peak_sustained_active"), k.get("launch__registers_per_thread"))
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
