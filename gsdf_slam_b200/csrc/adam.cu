@@ -62,9 +62,16 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
   const float m2 = __fmaf_rn(a.one_minus_beta1, g, m1);
   const float v1 = __fmul_rn(v, a.beta2);
   const float v2 = __fmaf_rn(a.one_minus_beta2, __fmul_rn(g, g), v1);  // a + alpha * (b * c)
-  const float d0 = __fmul_rn(__fsqrt_rn(v2), G.inv_sqrt_bc2);
+  // Rows that never received a gradient have m == v == 0: sqrt(0) and 0 / d take the slow paths of the
+  // IEEE routines (zero is a "special" operand for their range checks), which made this kernel issue-bound
+  // on maps where most rows are untouched.  The results of the guarded forms are the same bits.
+  float sq = v2;  // +0
+  if (v2 != 0.f) sq = __fsqrt_rn(v2);
+  const float d0 = __fmul_rn(sq, G.inv_sqrt_bc2);
   const float d = __fadd_rn(d0, a.eps);
-  p = __fmaf_rn(G.neg_step_size, __fdiv_rn(m2, d), p);
+  float q = m2;   // +-0 / d == +-0 for d > 0
+  if (m2 != 0.f || !(d > 0.f)) q = __fdiv_rn(m2, d);
+  p = __fmaf_rn(G.neg_step_size, q, p);
   m = m2;
   v = v2;
 }
@@ -172,8 +179,16 @@ __device__ __forceinline__ void adam_zero_grad_chunk(const AdamRowsParams& ar, i
   const long long end = min(G.numel, base + kAdamRowsChunk);
   const int* __restrict__ mask = ar.row_mask;
   // one wide division per chunk; everything below is 32-bit relative to the chunk's first row
-  const unsigned row_base = (unsigned)((unsigned long long)base / w);
-  const unsigned rem_base = (unsigned)((unsigned long long)base - (unsigned long long)row_base * w);
+  // (32-bit whenever the offset fits: the 64-bit division is ~100 instructions, a large part of a thread
+  // that handles a single float4)
+  unsigned row_base, rem_base;
+  if (base <= 0xffffffffLL) {
+    row_base = (unsigned)base / w;
+    rem_base = (unsigned)base - row_base * w;
+  } else {
+    row_base = (unsigned)((unsigned long long)base / w);
+    rem_base = (unsigned)((unsigned long long)base - (unsigned long long)row_base * w);
+  }
 
   if (G.vec_ok && end - base == kAdamRowsChunk) {
     unsigned mine[kAdamRowsVec];  // bit j set <=> element j of the float4 belongs to a row WITHOUT gradient

@@ -62,9 +62,14 @@ __device__ __forceinline__ void peer_adam_elem(float& p, float g, float& m, floa
   const float m2 = __fmaf_rn(a.one_minus_beta1, g, m1);
   const float v1 = __fmul_rn(v, a.beta2);
   const float v2 = __fmaf_rn(a.one_minus_beta2, __fmul_rn(g, g), v1);
-  const float d0 = __fmul_rn(__fsqrt_rn(v2), inv_sqrt_bc2);
+  // zero operands take the slow paths of the IEEE sqrt / division (see adam.cu: adam_elem); same bits
+  float sq = v2;
+  if (v2 != 0.f) sq = __fsqrt_rn(v2);
+  const float d0 = __fmul_rn(sq, inv_sqrt_bc2);
   const float d = __fadd_rn(d0, a.eps);
-  p = __fmaf_rn(neg_step_size, __fdiv_rn(m2, d), p);
+  float q = m2;
+  if (m2 != 0.f || !(d > 0.f)) q = __fdiv_rn(m2, d);
+  p = __fmaf_rn(neg_step_size, q, p);
   m = m2;
   v = v2;
 }
