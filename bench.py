@@ -407,9 +407,9 @@ def run_product(args, rank, world, dev):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.config}: {scene.name}, one keyframe per GPU per step, "
-                               + ("fwd + fused L1+SSIM loss + bwd + exchange + Adam; activations out of scope"
+                               + ("fwd + fused L1+SSIM loss + bwd + exchange + Adam; activated inputs (the drop-in API)"
                                   if args.with_loss else
-                                  "fwd+bwd+(exchange)+fused Adam; loss/activations out of scope"),
+                                  "fwd+bwd+(exchange)+fused Adam on activated inputs (the drop-in API); --with-loss adds the fused L1+SSIM loss"),
                    "P": counts["P"], "sh_degree": scene.degree, "image": [cam.W, cam.H],
                    "keyframes_per_step": world, "parallelism": f"dp{world} (keyframe batch)",
                    "exchange": ("none (single rank)" if world == 1 else
