@@ -654,15 +654,21 @@ tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 
 int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
                           BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
-                          const float4* splat_rec, float4* rec, cudaStream_t s) {
+                          const float4* splat_rec, float4* rec, bool do_mid, bool do_long, cudaStream_t s) {
   if (T == 0) return 0;
   tile_sort_pack_small_kernel<<<T, kSortSmallThreads, 0, s>>>(ranges, order, T, bin_hdr, capacity,
                                                                         items, splat_rec, rec);
   GSR_LAUNCHED();
-  // persistent: 2 CTAs of 16 warps per SM over the mid-length lists (exits at once if there are none)
-  tile_sort_pack_mid_kernel<<<148 * 2, kSortMidThreads, 0, s>>>(ranges, order, hdr, T, capacity, items, splat_rec,
-                                                               rec);
-  GSR_LAUNCHED();
+  // The kernels for mid-length and long lists are launched only when the caller expects such lists
+  // (gsr_forward: the previous frame's counts; it re-runs the stage if the guess was wrong): an empty
+  // launch costs 3 us each.
+  if (do_mid) {
+    // persistent: 2 CTAs of 16 warps per SM over the mid-length lists (exits at once if there are none)
+    tile_sort_pack_mid_kernel<<<148 * 2, kSortMidThreads, 0, s>>>(ranges, order, hdr, T, capacity, items, splat_rec,
+                                                                 rec);
+    GSR_LAUNCHED();
+  }
+  if (!do_long) return (int)cudaGetLastError();
   static bool attr_set = false;
   const int dyn = kLongWarps * 256 * (int)sizeof(uint32_t) + 2 * kSortLongSmemCap * (int)sizeof(uint64_t);
   if (!attr_set) {

@@ -174,7 +174,8 @@ int gsr_forward(const gsr_forward_args* a) {
   uint32_t* host_R = pinned_word();
   cudaEvent_t ev_R = readback_event();
   if (!host_R || !ev_R) return GSR_ERR_ALLOC;
-  GSR_CUDA(cudaMemcpyAsync(host_R, &g.hdr->num_dup, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  // R and the numbers of mid-length / long per-tile lists (header words 0 .. 5)
+  GSR_CUDA(cudaMemcpyAsync(host_R, &g.hdr->num_dup, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   GSR_CUDA(cudaEventRecord(ev_R, s));
 
   // The per-duplicate buffer is sized OPTIMISTICALLY from the previous call on this thread, so
@@ -183,16 +184,28 @@ int gsr_forward(const gsr_forward_args* a) {
   // it did not fit — or on the first call — the tail is (re)run with the exact size.
   static thread_local uint32_t cap_hint = 0;
   static thread_local int hint_P = -1, hint_W = -1, hint_H = -1;
-  if (hint_P != P || hint_W != W || hint_H != H) cap_hint = 0;  // a different scene / resolution
+  // the same optimism decides which of the per-tile sort kernels are launched: lists of 512+ (mid) and
+  // 4092+ (long) entries get their kernels only if the previous frame had such lists (-1: unknown)
+  // Both hints are sticky (a class seen once keeps its kernel for kHintFrames calls, the capacity decays
+  // by 1/64 per call) so that a mapper alternating between keyframes does not pay a re-run on every call.
+  constexpr int kHintFrames = 64;
+  static thread_local int hint_mid = -1, hint_long = -1;
+  if (hint_P != P || hint_W != W || hint_H != H) {  // a different scene / resolution
+    cap_hint = 0;
+    hint_mid = hint_long = -1;
+  }
   hint_P = P; hint_W = W; hint_H = H;
   uint32_t cap = cap_hint;
   uint32_t R = 0;
   bool have_R = false;
+  bool do_mid = hint_mid != 0, do_long = hint_long != 0;
   if (cap == 0) {
     GSR_CUDA(cudaEventSynchronize(ev_R));
-    R = *host_R;
+    R = host_R[0];
     have_R = true;
     cap = R;
+    do_mid = host_R[4] > host_R[5];
+    do_long = host_R[5] > 0;
   }
   BinView b;
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -208,19 +221,30 @@ int gsr_forward(const gsr_forward_args* a) {
                                    g.conic_opacity, a->radii, gx, gy, im.ranges, im.tile_fill, b.items, cap,
                                    &g.hdr->num_large, g.large_list, s));
       GSR_PROF("tile_sort_pack", launch_tile_sort_pack(P, T, im.ranges, im.tile_order, g.hdr, b.hdr, cap, b.items, b.scratch,
-                                                       g.splat_rec, b.rec, s));
+                                                       g.splat_rec, b.rec, do_mid, do_long, s));
     }
     GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
                             im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, s));
     if (!have_R) {
       GSR_CUDA(cudaEventSynchronize(ev_R));  // completed long ago: the GPU is several kernels further
-      R = *host_R;
+      R = host_R[0];
       have_R = true;
     }
-    if (R <= cap) break;
-    cap = R;  // the optimistic buffer was too small: redo the per-duplicate stages
+    const bool need_mid = host_R[4] > host_R[5], need_long = host_R[5] > 0;
+    const bool sort_ok = (do_mid || !need_mid) && (do_long || !need_long);
+    if (R <= cap && sort_ok) break;
+    // the optimistic buffer was too small, or a list length class appeared whose sort kernel was not
+    // launched: redo the per-duplicate stages with the exact answers
+    if (R > cap) cap = R;
+    do_mid = need_mid;
+    do_long = need_long;
   }
-  cap_hint = R + R / 8 + 4096;
+  {
+    const uint32_t want = R + R / 8 + 4096, decayed = cap_hint - cap_hint / 64;
+    cap_hint = want > decayed ? want : decayed;
+  }
+  hint_mid = host_R[4] > host_R[5] ? kHintFrames : (hint_mid > 0 ? hint_mid - 1 : 0);
+  hint_long = host_R[5] > 0 ? kHintFrames : (hint_long > 0 ? hint_long - 1 : 0);
   *a->num_rendered = (int)R;
   if (a->sample_resize) a->sample_resize(a->sample_user, 0);
   if (a->debug) {

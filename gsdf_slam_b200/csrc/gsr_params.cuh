@@ -84,7 +84,7 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
                 cudaStream_t s);
 int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
                           BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
-                          const float4* splat_rec, float4* rec, cudaStream_t s);
+                          const float4* splat_rec, float4* rec, bool do_mid, bool do_long, cudaStream_t s);
 int launch_export_binning(uint32_t T, const uint2* ranges, const uint64_t* items, uint64_t* keys,
                           uint32_t* point_list, cudaStream_t s);
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,
