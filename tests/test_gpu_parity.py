@@ -176,6 +176,35 @@ def test_optimistic_duplicate_buffer_is_regrown_when_the_next_frame_needs_more()
     _compare_forward(small, ts, f_again, run_reference(small, ts))
 
 
+def test_sort_kernel_hints_follow_alternating_list_lengths():
+    """gsr_forward launches the sort kernels for mid-length (512+) and long (4092+) per-tile lists only when
+    earlier frames with the same (P, W, H) had such lists, and verifies the guess after the frame.  Frames
+    that alternate between short lists and very long ones must match the reference every time — also the
+    first frame of each kind (wrong guess -> re-run) and the frames after it (sticky hint)."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref/libgsdf_ref.so not built")
+    P, W, H = 12_000, 208, 144
+    spread = scenes.tiny(seed=71, P=P, W=W, H=H, degree=1)
+    spread.scales = (spread.scales * 0.25).astype(np.float32)         # short lists everywhere
+    mid = scenes.tiny(seed=72, P=P, W=W, H=H, degree=1)                # lists of ~1000
+    mid.scales = (mid.scales * 1.5).astype(np.float32)
+    stacked = scenes.tiny(seed=73, P=P, W=W, H=H, degree=1)            # one pile: lists > 4092
+    stacked.means3D = (stacked.means3D * np.array([0.03, 0.03, 1.0], np.float32)).astype(np.float32)
+    frames = [spread, stacked, spread, mid, spread, spread, stacked, mid, spread]
+    longest = []
+    for sc in frames:
+        t = to_dev(sc)
+        fwd = run_product_forward(sc, t)
+        torch.cuda.synchronize()
+        ref = run_reference(sc, t)
+        _compare_forward(sc, t, fwd, ref)
+        _compare_grads(run_product_backward(sc, t, fwd), ref["grads"])
+        r = ref["ranges"].long()
+        longest.append(int((r[:, 1] - r[:, 0]).max()))
+    assert min(longest) < 512 and max(longest) >= 4092                 # all three kernels were needed
+    assert any(512 <= x < 4092 for x in longest)
+
+
 def test_sh0_empty_rest_drops_colour_gradient():
     """Reference quirk 14: a 0-element `sh` skips the whole SH backward (dL_ddc == 0)."""
     if not _ref_available():
