@@ -55,6 +55,7 @@ class BackwardArgs(C.Structure):
         ("dL_ddc", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p),
         ("debug", C.c_int), ("stream", C.c_void_p), ("raw_params", C.c_int), ("rendered_rows_only", C.c_int),
+        ("accumulate", C.c_int),
     ]
 
 

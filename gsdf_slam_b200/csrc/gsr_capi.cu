@@ -300,7 +300,9 @@ int gsr_backward(const gsr_backward_args* a) {
   bp.dL_dmean2D = a->dL_dmean2D; bp.dL_dconic = a->dL_dconic; bp.dL_dopacity = a->dL_dopacity;
   bp.dL_dcolor = a->dL_dcolor; bp.dL_dmean3D = a->dL_dmean3D; bp.dL_dcov3D = a->dL_dcov3D;
   bp.dL_ddc = a->dL_ddc; bp.dL_dsh = a->dL_dsh; bp.dL_dscale = a->dL_dscale; bp.dL_drot = a->dL_drot;
-  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible, a->rendered_rows_only == 0, s));
+  bp.accumulate = a->accumulate != 0;
+  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible,
+                                                   a->rendered_rows_only == 0 && a->accumulate == 0, s));
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));
     GSR_CUDA(cudaGetLastError());

@@ -41,6 +41,7 @@ struct PreprocessParams {
 struct PreBwdParams {
   int P, D, M;
   int activate;                 // gradients w.r.t. the RAW opacity / scale / rotation (row f-2)
+  int accumulate;               // add the parameter gradients to the rows' current values (keyframe batch)
   const float* opacities;       // raw opacities (needed only when activate)
   const float* means3D;
   const int* radii;

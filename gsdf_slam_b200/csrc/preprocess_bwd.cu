@@ -39,6 +39,11 @@ __device__ __forceinline__ float dotv(V3 a, V3 b) { return a.x * b.x + a.y * b.y
 __device__ __forceinline__ void store3(float* p, size_t i, V3 v) {
   p[3 * i + 0] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z;
 }
+// parameter gradients: overwrite, or add to the row (gsr_backward_args.accumulate)
+__device__ __forceinline__ void out3(float* p, size_t i, V3 v, bool acc) {
+  if (acc) { v.x += p[3 * i + 0]; v.y += p[3 * i + 1]; v.z += p[3 * i + 2]; }
+  store3(p, i, v);
+}
 
 // Per-Gaussian body.  `sh_row` is this Gaussian's dL/dsh row (3*M floats) in SHARED
 // memory, pre-zeroed; the CTA writes the rows out coalesced afterwards.
@@ -86,7 +91,10 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
   if (a.dL_dconic)
     reinterpret_cast<float4*>(a.dL_dconic)[i] = make_float4(dL_dconic.x, dL_dconic.y, 0.f, dL_dconic.z);
   // raw-parameter entry point: chain through sigmoid (sigma' = o (1 - o), o = the activated opacity)
-  a.dL_dopacity[i] = a.activate ? dopacity * cop.w * (1.0f - cop.w) : dopacity;
+  {
+    const float dop = a.activate ? dopacity * cop.w * (1.0f - cop.w) : dopacity;
+    a.dL_dopacity[i] = a.accumulate ? a.dL_dopacity[i] + dop : dop;
+  }
   store3(a.dL_dcolor, i, dL_dRGB);
 
   const float3 mean = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
@@ -324,8 +332,8 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
       dL_dmean_total += r;
     }
   }
-  store3(a.dL_ddc, i, out_ddc);
-  store3(a.dL_dmean3D, i, dL_dmean_total);
+  out3(a.dL_ddc, i, out_ddc, a.accumulate != 0);
+  out3(a.dL_dmean3D, i, dL_dmean_total, a.accumulate != 0);
 
   // ---- cov3D -> scale, rotation (reference computeCov3D backward, backward.cu:317-397)
   if (a.scales != nullptr) {
@@ -348,7 +356,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
     dscale.z = dot3(Rt[2], dL_dMt[2]);
     // raw-parameter entry point: d exp(s)/ds = exp(s) = the activated scale
     if (a.activate) dscale = {dscale.x * scale.x, dscale.y * scale.y, dscale.z * scale.z};
-    store3(a.dL_dscale, i, dscale);
+    out3(a.dL_dscale, i, dscale, a.accumulate != 0);
 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -371,8 +379,13 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
       dL_dq = {(dL_dq.x - q.x * qd) / q_norm, (dL_dq.y - q.y * qd) / q_norm, (dL_dq.z - q.z * qd) / q_norm,
                (dL_dq.w - q.w * qd) / q_norm};
     }
-    reinterpret_cast<float4*>(a.dL_drot)[i] = dL_dq;
-  } else {
+    if (a.accumulate) {
+      const float4 o = reinterpret_cast<const float4*>(a.dL_drot)[i];
+      reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(o.x + dL_dq.x, o.y + dL_dq.y, o.z + dL_dq.z, o.w + dL_dq.w);
+    } else {
+      reinterpret_cast<float4*>(a.dL_drot)[i] = dL_dq;
+    }
+  } else if (!a.accumulate) {
     store3(a.dL_dscale, i, {0.f, 0.f, 0.f});
     reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -460,8 +473,13 @@ preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
         if (g < 0) continue;
         float* dst = a.dL_dsh + (size_t)g * row;
         const float* srow = &s_dsh[warp][src * row];
-        if (lane < row) dst[lane] = srow[lane];
-        if (lane + 32 < row) dst[lane + 32] = srow[lane + 32];
+        if (a.accumulate) {
+          if (lane < row) dst[lane] += srow[lane];
+          if (lane + 32 < row) dst[lane + 32] += srow[lane + 32];
+        } else {
+          if (lane < row) dst[lane] = srow[lane];
+          if (lane + 32 < row) dst[lane + 32] = srow[lane + 32];
+        }
       }
     }
     __syncwarp();

@@ -194,17 +194,11 @@ class KeyframeBatchMapper:
         if len(keyframes) == 0:
             self.arena.zero_()
         for i, kf in enumerate(keyframes):
-            views = self.grad_views if i == 0 else None
-            if i > 0:
-                if self._scratch_arena is None:
-                    self._scratch_arena = torch.zeros_like(self.arena)
-                views = self._views(self._scratch_arena)
             # one keyframe per rank: rows this rank did not render are never read by the exchange (per-row
-            # rank bitmask), so the backward pass may skip the dense zero fill
-            _, radii, _ = self.render_backward(kf, views, on_forward=on_forward,
-                                               rendered_rows_only=(len(keyframes) == 1))
-            if i > 0:
-                self.arena.add_(self._scratch_arena)
+            # rank bitmask), so the backward pass may skip the dense zero fill.  Several keyframes: the
+            # first one writes the arena densely, the others add their rendered rows to it.
+            _, radii, _ = self.render_backward(kf, self.grad_views, on_forward=on_forward,
+                                               rendered_rows_only=(len(keyframes) == 1), accumulate=(i > 0))
             mask = radii if mask is None else torch.maximum(mask, radii)
         if mask is None:
             pe["radii"].zero_()
@@ -266,7 +260,7 @@ class KeyframeBatchMapper:
                                       radii_ready_event=radii_ready_event, raw_params=self.raw_params)
 
     def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor], fwd=None, on_forward=None,
-                        rendered_rows_only: bool = False):
+                        rendered_rows_only: bool = False, accumulate: bool = False):
         """fwd + bwd of one keyframe; parameter gradients are written into grad_views.
         ``on_forward(kf, fwd)`` runs between the two passes (e.g. to start reading the image back
         and to make the stream wait for the uploaded dL/d(image))."""
@@ -290,7 +284,7 @@ class KeyframeBatchMapper:
                                            e, kf.viewmatrix, kf.projmatrix, kf.tanfovx, kf.tanfovy,
                                            dL_dout, p["dc"], p["sh"], self.degree, kf.campos, geom, R,
                                            binning, img, B, sample, False, want_dcov3D=False, out=out,
-                                           rendered_rows_only=rendered_rows_only,
+                                           rendered_rows_only=rendered_rows_only, accumulate=accumulate,
                                            raw_opacity=p["opacity"] if self.raw_params else None)
         self.last_radii, self.last_color = radii, color
         return color, radii, g
@@ -301,12 +295,11 @@ class KeyframeBatchMapper:
         if len(keyframes) == 0:
             self.arena.zero_()
             return
-        self.render_backward(keyframes[0], self.grad_views, on_forward=on_forward)  # writes in place
+        self.render_backward(keyframes[0], self.grad_views, on_forward=on_forward)  # writes in place (dense)
         for kf in keyframes[1:]:
-            if self._scratch_arena is None:
-                self._scratch_arena = torch.zeros_like(self.arena)  # padding slots stay 0
-            self.render_backward(kf, self._views(self._scratch_arena), on_forward=on_forward)
-            self.arena.add_(self._scratch_arena)
+            # later keyframes add their rendered rows straight into the arena (gsr_backward accumulate): no
+            # scratch arena, no dense zero fill, no dense add
+            self.render_backward(kf, self.grad_views, on_forward=on_forward, accumulate=True)
 
     def allreduce(self) -> None:
         import torch.distributed as dist

@@ -120,7 +120,8 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                                    tan_fovy, dL_dout_color, dc, sh, degree, campos, geomBuffer, R,
                                    binningBuffer, imageBuffer, B, sampleBuffer, debug,
                                    want_dcov3D: bool = True, out: Optional[dict] = None,
-                                   rendered_rows_only: bool = False, raw_opacity: Optional[torch.Tensor] = None):
+                                   rendered_rows_only: bool = False, raw_opacity: Optional[torch.Tensor] = None,
+                                   accumulate: bool = False):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh,
     dL_dscales, dL_drotations)   (same order as src/rasterize_points.cu:204)
 
@@ -177,7 +178,8 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             dL_dcolor=_ptr(dL_dcolors), dL_dmean3D=_ptr(dL_dmeans3D), dL_dcov3D=_ptr(dL_dcov3D),
             dL_ddc=_ptr(dL_ddc), dL_dsh=_ptr(dL_dsh), dL_dscale=_ptr(dL_dscales),
             dL_drot=_ptr(dL_drotations), debug=int(bool(debug)), stream=_stream(dev),
-            raw_params=int(raw_opacity is not None), rendered_rows_only=int(bool(rendered_rows_only)))
+            raw_params=int(raw_opacity is not None), rendered_rows_only=int(bool(rendered_rows_only)),
+            accumulate=int(bool(accumulate)))
         with torch.cuda.device(dev):
             _lib.check(L.gsr_backward(C.byref(a)), "gsr_backward")
     if dL_dcov3D is None:

@@ -135,6 +135,12 @@ typedef struct gsr_backward_args {
                                   instead of zero-filling it — for callers that consume the gradients
                                   through the radii mask (gsr_adam_step_rows); saves the dense zero
                                   stream (276 B per Gaussian) */
+  int accumulate;              /* !=0 (implies rendered_rows_only): the six parameter gradients — dL_dmean3D,
+                                  dL_ddc, dL_dsh, dL_dopacity, dL_dscale, dL_drot — are ADDED to what the
+                                  rendered rows already hold, i.e. a second backward() without zero_grad
+                                  (the keyframe-batch sum of SURVEY.md §8e) without a scratch arena and a
+                                  dense add.  The per-view outputs (dL_dmean2D, dL_dconic, dL_dcolor,
+                                  dL_dcov3D) are overwritten as usual. */
 } gsr_backward_args;
 
 int gsr_forward(const gsr_forward_args* a);

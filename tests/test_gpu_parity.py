@@ -205,6 +205,34 @@ def test_sort_kernel_hints_follow_alternating_list_lengths():
     assert any(512 <= x < 4092 for x in longest)
 
 
+def test_backward_accumulate_adds_to_the_rendered_rows_only():
+    """gsr_backward_args.accumulate (keyframe batches): a second view's parameter gradients
+    are added to the rows it renders; every other row and the per-view outputs behave as without it."""
+    import gsdf_slam_b200 as gs
+    sc = scenes.tiny(seed=81, P=5000, W=208, H=144, degree=3)
+    t = to_dev(sc)
+    fwd = run_product_forward(sc, t)
+    g1 = run_product_backward(sc, t, fwd)
+    names = ["dL_dmeans3D", "dL_ddc", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    base = {n: torch.randn(g1[n].shape, device="cuda", generator=gen) for n in names}
+    out = {n: base[n].clone() for n in names}
+    cam, e = sc.cam, t["empty"]
+    R, B, color, radii, geom, binning, img, sample = fwd
+    g2 = gs.RasterizeGaussiansBackwardCUDA(t["bg"], t["means3D"], radii, e, t["scales"], t["rotations"], 1.0, e,
+                                           t["viewmatrix"], t["projmatrix"], cam.tanfovx, cam.tanfovy, t["dL_dout"],
+                                           t["dc"], t["sh"], sc.degree, t["campos"], geom, R, binning, img, B, sample,
+                                           False, out=out, accumulate=True)
+    torch.cuda.synchronize()
+    vis = radii > 0
+    assert 0 < int(vis.sum()) < sc.P
+    for n in names:
+        got, want = out[n], base[n] + g1[n]          # g1 is zero on the rows that were not rendered
+        assert torch.equal(got[~vis], base[n][~vis]), n                     # untouched
+        assert float((got[vis] - want[vis]).abs().max()) <= 1e-5 * max(1.0, float(want[vis].abs().max())), n
+    assert float((g2[0] - g1["dL_dmeans2D"]).abs().max()) <= 1e-6 * max(1.0, float(g1["dL_dmeans2D"].abs().max()))
+
+
 def test_sh0_empty_rest_drops_colour_gradient():
     """Reference quirk 14: a 0-element `sh` skips the whole SH backward (dL_ddc == 0)."""
     if not _ref_available():

@@ -52,11 +52,16 @@ def test_arena_layout_is_aligned_and_59_floats_per_gaussian():
 class _FakeMapper(KeyframeBatchMapper):
     """render_backward replaced by a deterministic function of (keyframe id, parameter)."""
 
-    def render_backward(self, kf, grad_views, fwd=None, on_forward=None):
+    def render_backward(self, kf, grad_views, fwd=None, on_forward=None, rendered_rows_only=False,
+                        accumulate=False):
         for i, name in enumerate(SEGMENTS):
             g = grad_views[name]
             if g.numel():
-                g.copy_(torch.sin(self.params[name] * (kf + 1) + i))
+                v = torch.sin(self.params[name] * (kf + 1) + i)
+                if accumulate:       # gsr_backward_args.accumulate: later keyframes add to the arena
+                    g.add_(v)
+                else:
+                    g.copy_(v)
         return None, None, None
 
     def _adam_ranges(self, ranges, steps, grad_scale):
