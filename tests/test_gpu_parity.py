@@ -229,8 +229,11 @@ def test_backward_accumulate_adds_to_the_rendered_rows_only():
     for n in names:
         got, want = out[n], base[n] + g1[n]          # g1 is zero on the rows that were not rendered
         assert torch.equal(got[~vis], base[n][~vis]), n                     # untouched
-        assert float((got[vis] - want[vis]).abs().max()) <= 1e-5 * max(1.0, float(want[vis].abs().max())), n
-    assert float((g2[0] - g1["dL_dmeans2D"]).abs().max()) <= 1e-6 * max(1.0, float(g1["dL_dmeans2D"].abs().max()))
+        # two backward passes sum their atomics in different orders: compare like the gradient gates do
+        assert rel_l2(got[vis] - base[n][vis], g1[n][vis]) <= 1e-5, n
+    # per-view outputs are overwritten for the rendered rows (the others are left untouched, like with
+    # rendered_rows_only: freshly allocated outputs hold garbage there)
+    assert rel_l2(g2[0][vis], g1["dL_dmeans2D"][vis]) <= 1e-5
 
 
 def test_sh0_empty_rest_drops_colour_gradient():
