@@ -109,9 +109,12 @@ __device__ __forceinline__ float sh_channel(int deg, float x, float y, float z, 
 
 constexpr int kPreThreads = 128;
 constexpr int kShFloats = 45;  // 15 coefficients x 3 channels
+// SH rows of the surviving Gaussians of a warp are staged kShGroup at a time (a mapping view keeps ~5 of
+// 32): 1.4 KB instead of 5.6 KB of shared memory per warp, which was what limited the resident CTAs
+constexpr int kShGroup = 8;
 
 #ifndef GSR_PRE_MINBLOCKS
-#define GSR_PRE_MINBLOCKS 6
+#define GSR_PRE_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_kernel(const PreprocessParams a) {
   // CTA-staged input rows
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
   __shared__ __align__(16) float s_scale[kPreThreads * 3];
   __shared__ __align__(16) float s_rot[kPreThreads * 4];
   __shared__ __align__(16) float s_dc[kPreThreads * 3];
-  __shared__ float s_sh[kPreThreads / 32][32 * kShFloats];  // per-warp SH rows (23 KB)
+  __shared__ float s_sh[kPreThreads / 32][kShGroup * kShFloats];  // per-warp SH rows, kShGroup at a time
   __shared__ uint32_t s_tiles[kPreThreads / 32][32];        // per-warp tile counters
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,31 +225,43 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
   if (a.colors_precomp == nullptr) {
     const int deg = (a.shs != nullptr) ? min(a.D, a.M >= 15 ? 3 : (a.M >= 8 ? 2 : (a.M >= 3 ? 1 : 0))) : 0;
     const unsigned vis_mask = __ballot_sync(0xffffffffu, visible);
-    if (deg > 0) {
-      const int ncoef = min(a.M, 15) * 3;
-      unsigned m = vis_mask;
-      while (m) {
-        // asynchronous copies: every visible row of the warp is in flight at once
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const float* row = a.shs + (size_t)(base + warp * 32 + src) * (size_t)a.M * 3;
-        float* dst = &s_sh[warp][src * kShFloats];
-        if (lane < ncoef) cp_async_f32(dst + lane, row + lane);
-        if (lane + 32 < ncoef) cp_async_f32(dst + lane + 32, row + lane + 32);
-      }
-      cp_async_wait_all();
-      __syncwarp();
-    }
+    const int my_rank = __popc(vis_mask & ((1u << lane) - 1u));  // position among the warp's survivors
+    const int n_vis = __popc(vis_mask);
+    float3 dir = {0.f, 0.f, 0.f};
     if (visible) {
-      float3 dir = {p_orig.x - a.campos[0], p_orig.y - a.campos[1], p_orig.z - a.campos[2]};
+      dir = {p_orig.x - a.campos[0], p_orig.y - a.campos[1], p_orig.z - a.campos[2]};
       const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
       dir = {dir.x / len, dir.y / len, dir.z / len};
-      const float* sh = &s_sh[warp][lane * kShFloats];
-      float r = sh_channel(deg, dir.x, dir.y, dir.z, s_dc[3 * tid + 0], sh + 0, 3);
-      float g = sh_channel(deg, dir.x, dir.y, dir.z, s_dc[3 * tid + 1], sh + 1, 3);
-      float b = sh_channel(deg, dir.x, dir.y, dir.z, s_dc[3 * tid + 2], sh + 2, 3);
-      clamp_bits = (r < 0 ? 1 : 0) | (g < 0 ? 2 : 0) | (b < 0 ? 4 : 0);
-      rgb = {fmaxf(r, 0.0f), fmaxf(g, 0.0f), fmaxf(b, 0.0f)};
+    }
+    for (int g0 = 0; g0 < (deg > 0 ? n_vis : 1); g0 += kShGroup) {
+      if (deg > 0) {
+        const int ncoef = min(a.M, 15) * 3;
+        // the survivors with rank g0 .. g0 + kShGroup - 1: asynchronous copies, all rows in flight at once
+        unsigned m = vis_mask;
+        int rank = 0;
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          if (rank >= g0 && rank < g0 + kShGroup) {
+            const float* row = a.shs + (size_t)(base + warp * 32 + src) * (size_t)a.M * 3;
+            float* dst = &s_sh[warp][(rank - g0) * kShFloats];
+            if (lane < ncoef) cp_async_f32(dst + lane, row + lane);
+            if (lane + 32 < ncoef) cp_async_f32(dst + lane + 32, row + lane + 32);
+          }
+          ++rank;
+        }
+        cp_async_wait_all();
+        __syncwarp();
+      }
+      if (visible && (deg == 0 || (my_rank >= g0 && my_rank < g0 + kShGroup))) {
+        const float* sh = &s_sh[warp][(deg > 0 ? my_rank - g0 : 0) * kShFloats];
+        float r = sh_channel(deg, dir.x, dir.y, dir.z, s_dc[3 * tid + 0], sh + 0, 3);
+        float g = sh_channel(deg, dir.x, dir.y, dir.z, s_dc[3 * tid + 1], sh + 1, 3);
+        float b = sh_channel(deg, dir.x, dir.y, dir.z, s_dc[3 * tid + 2], sh + 2, 3);
+        clamp_bits = (r < 0 ? 1 : 0) | (g < 0 ? 2 : 0) | (b < 0 ? 4 : 0);
+        rgb = {fmaxf(r, 0.0f), fmaxf(g, 0.0f), fmaxf(b, 0.0f)};
+      }
+      __syncwarp();  // the group's rows are overwritten by the next group
     }
   }
 
