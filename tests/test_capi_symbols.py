@@ -54,6 +54,36 @@ def test_argument_validation_without_device():
     assert int(L.gsr_sort_temp_bytes(1_000_000)) > 0
 
 
+def test_store_and_ingest_argument_validation_without_device():
+    """Rows f-3 / f-4: bad arguments are rejected before any CUDA call, empty inputs are fine."""
+    L = _lib.lib()
+    bad = -1
+    assert L.gsr_prune_points(None, None, None, None, None, None) == bad
+    assert L.gsr_densify_and_prune(None, None, None, None, None, None) == bad
+    st = _lib.GaussianStoreC()
+    st.rows, st.capacity, st.n_rest = 10, 5, 15                     # rows > capacity
+    assert L.gsr_prune_points(C.byref(st), C.byref(st), None, None, None, None) == bad
+    assert L.gsr_densification_postfix(C.byref(st), None, None, 1, None) == bad
+    assert L.gsr_add_densification_stats(-1, None, None, None, None, None, None) == bad
+    assert L.gsr_add_densification_stats(0, None, None, None, None, None, None) == 0
+    assert L.gsr_add_densification_stats(5, None, None, None, None, None, None) == bad
+    assert L.gsr_reset_opacity(0, None, None, None, 1.0, None) == 0
+    assert L.gsr_reset_opacity(3, None, None, None, 1.0, None) == bad
+    assert L.gsr_voxel_dedup(None, 0, None, 0, 0.05, None, None, None) == 0
+    assert L.gsr_voxel_dedup(None, 0, None, 4, 0.0, None, None, None) == bad      # voxel size must be > 0
+    assert L.gsr_voxel_dedup(None, 0, None, 4, 0.05, None, None, None) == bad     # missing buffers
+    assert L.gsr_select_rows(None, -1, 0, None, None, None, None, None) == bad
+    assert L.gsr_colorize_points(None, 0, None, None, None, None, 64, 48, None, None, None, None, None) == 0
+    assert L.gsr_colorize_points(None, 8, None, None, None, None, 64, 48, None, None, None, None, None) == bad
+    assert L.gsr_colorize_points(None, 8, None, None, None, None, 0, 48, None, None, None, None, None) == bad
+    assert L.gsr_ply_pack_rows(0, 15, None, None, None, None, None, None, None, None) == 0
+    assert L.gsr_ply_pack_rows(4, 15, None, None, None, None, None, None, None, None) == bad
+    assert L.gsr_peer_rank_mask_u8(None, 2, 10, None, None) == bad
+    assert int(L.gsr_store_workspace_bytes(1_000_000)) >= 1_000_000
+    assert int(L.gsr_voxel_dedup_workspace_bytes(1_000_000)) >= 16_000_000          # >= 2 slots of 8 bytes per key
+    assert int(L.gsr_colorize_workspace_bytes(1000)) > 5000
+
+
 def test_means3d_shape_error_matches_reference_message():
     import torch
     with pytest.raises(RuntimeError, match="means3D must have dimensions"):
