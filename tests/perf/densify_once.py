@@ -1,7 +1,7 @@
 """ncu target: one prunePoints + one densifyAndPrune at P rows (SH-3), steady state."""
 import os, sys, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "perf"))
 from oracle import densify_ref as R
 import time_densify as T
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000

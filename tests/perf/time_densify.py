@@ -4,7 +4,7 @@ P = 500k and 3M SH-3 Gaussians.  Prints one JSON line per operation with the alg
 (one read of every source row + one write of every destination row, 724 B per row: 59 floats x
 (param + 2 moments) + 4 statistics words) and the achieved fraction of the measured HBM peak."""
 import json, os, sys, numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 from gsdf_slam_b200.gaussian_model import GaussianModel
 from oracle import densify_ref as R   # baseline arm only
 

@@ -1,5 +1,5 @@
 import os, sys, numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 import gsdf_slam_b200 as gs
 from oracle import ref_binding as rb
 def t(fn, n=5):

@@ -12,7 +12,7 @@ changes every 10 iterations): the whole iteration of GaussianMapper::trainForOne
 Prints one JSON line.  The oracle modules are used here only as the timed baseline arm."""
 import json, os, sys, time
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 import gsdf_slam_b200 as gs
 from gsdf_slam_b200 import scenes
 from gsdf_slam_b200.gaussian_model import GaussianModel
