@@ -498,7 +498,7 @@ def run_reference(args, rank, world, dev):
     stage.update(cam_views)
     img_host = torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory()
     names = ("means3D", "dc", "sh", "opacity", "scales", "rotations")
-    from gsdf_slam_b200.loss import reference_loss
+    from oracle.loss_ref import reference_mapping_loss
     gname = dict(means3D="dL_dmeans3D", dc="dL_ddc", sh="dL_dsh", opacity="dL_dopacity",
                  scales="dL_dscales", rotations="dL_drotations")
     from gsdf_slam_b200.mapping import DEFAULT_LR
@@ -556,9 +556,7 @@ def run_reference(args, rank, world, dev):
             main.wait_event(ev_h2d)
         if args.with_loss:
             # the reference's loss: LibTorch op sequence + autograd (src/gaussian_mapper.cpp:414-431)
-            x = color.detach().requires_grad_(True)
-            reference_loss(x, dl, None, 0.2).backward()
-            dl = x.grad
+            dl = reference_mapping_loss(color, dl, None, 0.2)[3]   # the reference's own loss_utils.h + autograd
         g = rr.backward(src["bg"], p["means3D"], radii, e, p["scales"], p["rotations"], 1.0, e,
                         src["viewmatrix"], src["projmatrix"], cam.tanfovx, cam.tanfovy, dl,
                         p["dc"], p["sh"], scene.degree, src["campos"], debug=debug)

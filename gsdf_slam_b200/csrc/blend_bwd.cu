@@ -262,7 +262,7 @@ int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_ord
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  blend_bwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, max_contrib, rec, W, H, bg,
+  blend_bwd_kernel<<<2 * grid, kBlendThreads, blend_smem_pad(), s>>>(ranges, tile_order, max_contrib, rec, W, H, bg,
                                                   final_T, n_contrib, accum_c, dL_dpix, acc);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();

@@ -6,6 +6,7 @@
 // splat touches that block at all.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gsr_common.cuh"
 
@@ -28,6 +29,16 @@ __device__ __forceinline__ uint32_t slot_px(uint32_t tile_x, int lane, int q) {
 }
 __device__ __forceinline__ uint32_t slot_py(uint32_t tile_y, int warp, int lane, int q) {
   return tile_y * GSR_TILE_Y + warp * 8 + (q >> 1) * 4 + (lane >> 3);
+}
+
+// developer knob (tools/stage_times.py): extra dynamic shared memory per CTA, i.e. fewer resident CTAs per SM
+inline unsigned blend_smem_pad() {
+  static int pad = -1;
+  if (pad < 0) {
+    const char* e = getenv("GSR_BLEND_SMEM_PAD");
+    pad = e ? atoi(e) : 0;
+  }
+  return (unsigned)pad;
 }
 
 }  // namespace gsr

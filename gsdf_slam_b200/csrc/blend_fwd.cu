@@ -174,7 +174,7 @@ int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_ord
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, uint32_t capacity,
                      cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  blend_fwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec, W, H, bg, out_color,
+  blend_fwd_kernel<<<2 * grid, kBlendThreads, blend_smem_pad(), s>>>(ranges, tile_order, rec, W, H, bg, out_color,
                                                   final_T, n_contrib, accum_c, max_contrib, capacity);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();

@@ -20,5 +20,6 @@ for s in "${SRCS[@]}"; do
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 OBJS=(); for s in "${SRCS[@]}"; do OBJS+=("$OBJDIR/${s%.cu}.o"); done
-"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -gencode arch=compute_100a,code=sm_100a
+"$NVCC" -shared -o "$OUT.tmp" "${OBJS[@]}" -gencode arch=compute_100a,code=sm_100a
+mv -f "$OUT.tmp" "$OUT"   # atomic: a concurrent snapshot never sees a partial library
 echo "built $OUT"

@@ -202,6 +202,71 @@ __global__ void __launch_bounds__(256) peer_rank_mask_u8_kernel(const PeerFlagPa
   }
 }
 
+
+// ---- densification statistics across ranks ------------------------------------
+// The reference updates, per VIEW (src/gaussian_mapper.cpp:443-447, src/gaussian_model.cpp:667-681), for the
+// rows with radii > 0:  max_radii2D = max(max_radii2D, radii);  xyz_gradient_accum += |dL_dmean2D.xy|;
+// denom += 1.  The norm is non-linear, so it is taken per keyframe on the rank that rendered it
+// (peer_local_stats_kernel, into the rank's per-step delta arrays [accum | denom | max_radii], peer-mapped)
+// and the deltas of all ranks are combined afterwards (peer_stats_exchange_kernel): every rank pulls, for
+// each row, the deltas of the ranks that rendered it — in rank order, so the replicated statistics stay
+// bit-identical on all ranks — and applies sum / sum / max to its own replica.  The same kernel emits the
+// per-row rank bitmask gsr_adam_step_peer consumes (it replaces gsr_peer_rank_mask_u8 in that case).
+__global__ void __launch_bounds__(256)
+peer_local_stats_kernel(long long P, const int* __restrict__ radii, const float* __restrict__ dmean2D,
+                        float* __restrict__ stats /* [3][P] or null */, uint8_t* __restrict__ flags) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= P) return;
+  const int r = radii[i];
+  if (r <= 0) return;
+  flags[i] = 1;
+  if (stats == nullptr) return;
+  const float gx = dmean2D[3 * i], gy = dmean2D[3 * i + 1];
+  stats[i] = stats[i] + sqrtf(fmaf(gy, gy, gx * gx));   // same expression as densification_stats_kernel
+  stats[P + i] = stats[P + i] + 1.0f;
+  stats[2 * P + i] = fmaxf(stats[2 * P + i], (float)r);
+}
+
+struct PeerStatsParams {
+  const uint8_t* flags[GSR_MAX_PEERS];
+  const float* stats[GSR_MAX_PEERS];
+  int n_peers;
+};
+__global__ void __launch_bounds__(256)
+peer_stats_exchange_kernel(const PeerStatsParams a, long long P, int* __restrict__ mask_out,
+                           float* __restrict__ max_radii2D, float* __restrict__ accum, float* __restrict__ denom) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= P) return;
+  int m = 0;
+#pragma unroll
+  for (int k = 0; k < GSR_MAX_PEERS; ++k)
+    if (k < a.n_peers && a.flags[k][i]) m |= 1 << k;
+  mask_out[i] = m;
+  if (m == 0) return;
+  // all remote loads first (NVLink round trips overlap), then the combination in rank order
+  float da[GSR_MAX_PEERS], dd[GSR_MAX_PEERS], dr[GSR_MAX_PEERS];
+#pragma unroll
+  for (int k = 0; k < GSR_MAX_PEERS; ++k) {
+    if (k < a.n_peers && ((m >> k) & 1)) {
+      da[k] = a.stats[k][i];
+      dd[k] = a.stats[k][P + i];
+      dr[k] = a.stats[k][2 * P + i];
+    }
+  }
+  float sa = 0.f, sd = 0.f, mr = 0.f;
+#pragma unroll
+  for (int k = 0; k < GSR_MAX_PEERS; ++k) {
+    if (k < a.n_peers && ((m >> k) & 1)) {
+      sa += da[k];
+      sd += dd[k];
+      mr = fmaxf(mr, dr[k]);
+    }
+  }
+  accum[i] = accum[i] + sa;
+  denom[i] = denom[i] + sd;
+  max_radii2D[i] = fmaxf(max_radii2D[i], mr);
+}
+
 }  // namespace gsr
 
 using namespace gsr;
@@ -240,6 +305,36 @@ int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_
   const long long threads = (rows + 3) / 4;
   peer_rank_mask_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       a, rows, mask_out);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+int gsr_peer_local_stats(int64_t P, const int32_t* radii, const float* dL_dmeans2D, float* stats_local,
+                         uint8_t* flags, void* stream) {
+  if (P < 0) return GSR_ERR_BAD_ARG;
+  if (P == 0) return GSR_OK;
+  if (!radii || !flags || (stats_local && !dL_dmeans2D)) return GSR_ERR_BAD_ARG;
+  peer_local_stats_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      P, radii, dL_dmeans2D, stats_local, flags);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
+
+int gsr_peer_stats_exchange(const uint8_t* const* flags_peers, const float* const* stats_peers, int n_peers,
+                            int64_t P, int32_t* mask_out, float* max_radii2D, float* xyz_gradient_accum,
+                            float* denom, void* stream) {
+  if (n_peers < 1 || n_peers > GSR_MAX_PEERS || P < 0 || !flags_peers || !stats_peers) return GSR_ERR_BAD_ARG;
+  if (P == 0) return GSR_OK;
+  if (!mask_out || !max_radii2D || !xyz_gradient_accum || !denom) return GSR_ERR_BAD_ARG;
+  PeerStatsParams a;
+  a.n_peers = n_peers;
+  for (int k = 0; k < n_peers; ++k) {
+    if (!flags_peers[k] || !stats_peers[k]) return GSR_ERR_BAD_ARG;
+    a.flags[k] = flags_peers[k];
+    a.stats[k] = stats_peers[k];
+  }
+  peer_stats_exchange_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, P, mask_out, max_radii2D, xyz_gradient_accum, denom);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

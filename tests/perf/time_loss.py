@@ -1,7 +1,8 @@
 """Developer tool: fused L1+SSIM loss vs the reference's LibTorch op sequence (fwd+bwd), 1200x680."""
 import os, sys, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-from gsdf_slam_b200.loss import l1_ssim_loss, reference_loss
+from gsdf_slam_b200.loss import l1_ssim_loss
+from oracle.loss_ref import reference_loss
 H, W = 680, 1200
 gt = torch.rand((3, H, W), device="cuda"); img = (gt + 0.1 * torch.randn_like(gt)).clamp(0, 1)
 mask = torch.ones((H, W), device="cuda"); mask[:8] = 0

@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 import gsdf_slam_b200 as gs
 from gsdf_slam_b200 import scenes
 from gsdf_slam_b200.gaussian_model import GaussianModel
-from gsdf_slam_b200.loss import l1_ssim_loss, reference_loss
+from gsdf_slam_b200.loss import l1_ssim_loss
+from oracle.loss_ref import reference_loss
 from oracle import densify_ref as R
 from oracle import ref_binding as rb
 
