@@ -3,27 +3,34 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--config cfg2]
 
-Workload (BASELINE.json configs[1], "cfg2"): Replica-style keyframe, 500 k SH-3 Gaussians at
-1200x680, seeded synthetic scene (gsdf_slam_b200/scenes.py).  One STEP = one mapping iteration
-of the hot path on every rank: RasterizeGaussiansCUDA (forward) + RasterizeGaussiansBackwardCUDA
-(backward) of that rank's keyframe over the replicated Gaussian set, NCCL all-reduce of the
-59*P-float gradient arena when N > 1, and the fused Adam step.  The L1+SSIM loss and the
-activation functions are outside the path; dL/d(image) is a seeded tensor.
-Weak scaling: one keyframe per rank per step, value = keyframe iterations / s over all ranks.
+Headline workload (BASELINE.json configs[1], "cfg2"): Replica-style keyframe, 500 k SH-3 Gaussians at
+1200x680, seeded synthetic scene (gsdf_slam_b200/scenes.py).  One STEP = one mapping iteration of the hot
+path on every rank: RasterizeGaussiansCUDA (forward) + RasterizeGaussiansBackwardCUDA (backward) of that
+rank's keyframe over the replicated Gaussian set, the gradient exchange when N > 1 (fused peer-memory
+kernel) and the fused Adam step.  Weak scaling: one keyframe per rank per step, value = keyframe
+iterations / s over all ranks.  dL/d(image) is a seeded tensor (--with-loss puts the L1+SSIM loss inside).
 
 `value`  : inputs resident in HBM, K steps timed with CUDA events between barriers.
-`e2e`    : the same step through the public API with HOST buffers: every step copies the
-           keyframe inputs (camera matrices, background, dL/d(image)) from pinned host memory
-           (the image-sized upload double-buffered on a copy stream) and reads the rendered image
-           back to the host, waiting for it before the next step starts.
---impl reference : the UNMODIFIED reference CUDA rasterizer compiled for sm_100a
-           (oracle/_ref, see oracle/build_ref.sh) + LibTorch's Adam op sequence, same step,
-           measured like `e2e`.  (The reference has no CPU implementation; its CPU restatement
-           — the oracle port — is what `cpu_baseline` times.)
+`e2e`    : the same step through the public API with HOST buffers: every step copies the keyframe inputs
+           (camera block, dL/d(image)) from pinned host memory and reads the rendered image back into pinned
+           host memory; the copies run on a copy stream, double-buffered — the image of step k is waited for
+           before step k+2 is enqueued, so one rank's PCIe stall is not broadcast through the barriers.
+Further blocks of the same JSON line:
+`rasterizer_only` (N = 1): the metric's literal quantity — RasterizeGaussiansCUDA + RasterizeGaussiansBackwardCUDA
+           through the C++ drop-in shim (dense gradients, the reference's allocation pattern), it/s.
+`mapping_cfg5` : BASELINE.json configs[4]: 3 M Gaussians, K = 8 keyframes per optimiser step split over the N
+           ranks (STRONG scaling of a fixed batch): fwd + bwd of the local keyframes, densification statistics,
+           exchange, Adam; steps/s, per-rank breakdown, NVLink bytes of the exchange.
+`exchange_parity` (N > 1, untimed): the same steps three ways — fused peer exchange, NCCL all-reduce path, one
+           rank accumulating all keyframes sequentially — and the differences between them.
+--impl reference : the UNMODIFIED reference CUDA rasterizer compiled for sm_100a (oracle/_ref, see
+           oracle/build_ref.sh) + LibTorch's Adam op sequence, same step(s), rank 0 only.  (The reference has no
+           CPU implementation; its CPU restatement — the oracle port — is what `cpu_baseline` times.)
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -40,6 +47,7 @@ if ROOT not in sys.path:
 
 METRIC = "rasterizer fwd+bwd it/s @1200x680, 500k Gaussians; mapping it/s at 1/2/4/8 GPU"
 UNIT = "keyframe it/s (fwd+bwd+Adam)"
+CFG5_KEYFRAMES = 8
 
 
 def env_int(name, default):
@@ -110,6 +118,9 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NVLINK_PEER_GBS = 770.0   # measured peer-copy bandwidth per direction per GPU on this pool (B200_PROFILING.md)
+
+
 def make_scene(cfg: str, rank: int):
     from gsdf_slam_b200 import scenes
     if cfg == "cfg2":
@@ -129,6 +140,15 @@ def make_scene(cfg: str, rank: int):
     else:
         raise SystemExit(f"unknown --config {cfg}")
     return scene, cam
+
+
+def make_cfg5(small: bool):
+    from gsdf_slam_b200 import scenes
+    if small:   # CI-sized stand-in (--config small / --small-cfg5)
+        s = scenes.room_scene(120_000, 640, 360, 320.0, 320.0, seed=5, box=(16.0, 3.0, 12.0), name="cfg5_small")
+        s.extra_cams = scenes.ring_cameras(CFG5_KEYFRAMES, 640, 360, 320.0, 320.0, 1.0)
+        return s
+    return scenes.cfg5()
 
 
 def host_keyframe(scene, cam, with_loss=False):
@@ -158,36 +178,59 @@ def camera_block(hk, dev):
     return flat, d, views
 
 
+def dev_params(scene, dev):
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    return dict(means3D=t(scene.means3D), dc=t(scene.dc), sh=t(scene.sh), opacity=t(scene.opacity),
+                scales=t(scene.scales), rotations=t(scene.rotations))
+
+
 def workload_counts(scene, cam, params, dev):
-    """P, V, R, E ... of this rank's keyframe (computed once, outside the timed region)."""
+    """P, V, R, E, pair counts ... of this rank's keyframe (computed once, outside the timed region)."""
     import gsdf_slam_b200 as gs
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from gsdf_slam_b200 import _lib
     e = torch.empty(0, device=dev)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-    fwd = gs.RasterizeGaussiansCUDA(t(scene.bg), params["means3D"], e, params["opacity"], params["scales"],
+    bg = t(scene.bg)
+    fwd = gs.RasterizeGaussiansCUDA(bg, params["means3D"], e, params["opacity"], params["scales"],
                                     params["rotations"], 1.0, e, t(cam.viewmatrix), t(cam.projmatrix),
                                     cam.tanfovx, cam.tanfovy, cam.H, cam.W, params["dc"], params["sh"],
                                     scene.degree, t(cam.campos), False, False)
-    from gsdf_slam_b200 import _lib
-    import ctypes as C
+    L = _lib.lib()
     N = cam.W * cam.H
     T = ((cam.W + 15) // 16) * ((cam.H + 15) // 16)
     n_contrib = torch.zeros(N, dtype=torch.int32, device=dev)
     ranges = torch.zeros((T, 2), dtype=torch.int32, device=dev)
     maxc = torch.zeros(T, dtype=torch.int32, device=dev)
-    _lib.check(_lib.lib().gsr_export_image(C.c_void_p(fwd[6].data_ptr()), cam.W, cam.H, None,
-                                           C.c_void_p(n_contrib.data_ptr()), C.c_void_p(ranges.data_ptr()),
-                                           C.c_void_p(maxc.data_ptr()), None), "export_image")
+    _lib.check(L.gsr_export_image(C.c_void_p(fwd[6].data_ptr()), cam.W, cam.H, None,
+                                  C.c_void_p(n_contrib.data_ptr()), C.c_void_p(ranges.data_ptr()),
+                                  C.c_void_p(maxc.data_ptr()), None), "export_image")
+    pc = torch.zeros(3, dtype=torch.int64, device=dev)
+    scratch = torch.empty((3, cam.H, cam.W), dtype=torch.float32, device=dev)
+    if fwd[0] > 0:
+        _lib.check(L.gsr_export_pair_counts(C.c_void_p(fwd[5].data_ptr()), C.c_void_p(fwd[6].data_ptr()), int(fwd[0]),
+                                            cam.W, cam.H, C.c_void_p(bg.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                            C.c_void_p(pc.data_ptr()), None), "export_pair_counts")
     torch.cuda.synchronize()
     lens = (ranges[:, 1] - ranges[:, 0]).long()
+    pcs = [int(x) for x in pc.tolist()]
     return dict(P=scene.P, V=int((fwd[3] > 0).sum()), R=int(fwd[0]), T=T, N=N, M=int(params["sh"].size(1)),
                 E=int(n_contrib.long().sum()), max_tile_len=int(lens.max()),
-                sum_max_contrib=int(maxc.long().sum()))
+                sum_max_contrib=int(maxc.long().sum()),
+                pairs_visited=pcs[0], pairs_gated=pcs[1], pairs_blended=pcs[2])
 
 
-def stage_model(counts, tile_bits):
-    """Algorithmic bytes / flops per launch of each stage (SURVEY.md §8d, DESIGN.md §4)."""
-    P, V, R, N, T, M, E = (counts[k] for k in ("P", "V", "R", "N", "T", "M", "E"))
+# Algorithmic flops of the blend kernels, from COUNTED pairs (gsr_export_pair_counts), using the reference's own
+# per-pair arithmetic (forward.cu:422-448, backward.cu:597-637; an FMA counts 2):
+#   every visited pair  : d = xy - pix (2), power (5 mul + 2 fma = 9)                                  = 11
+#   every gated pair    : expf (8 + MUFU), alpha = min(.99, o*G) (2), test_T (2)                        = 12
+#   every blended pair  : fwd: 3 mul + 3 fma + T (10);  bwd: the gradient terms of backward.cu:609-637  = 10 / 49
+FLOP_VISIT, FLOP_GATE, FLOP_BLEND_FWD, FLOP_BLEND_BWD = 11, 12, 10, 49
+
+
+def stage_model(counts):
+    """Algorithmic bytes / flops per launch of each stage (SURVEY.md §8d, DESIGN.md §3)."""
+    P, V, R, N, T, M = (counts[k] for k in ("P", "V", "R", "N", "T", "M"))
+    smc = counts["sum_max_contrib"]
     b = {
         "preprocess": 12 * P + (44 + 12 * M) * V + 16 * P + 43 * V,
         "tile_meta": 4 * T + 16 * T,
@@ -195,8 +238,10 @@ def stage_model(counts, tile_bits):
         "emit": (8 + 4 + 8 + 16 + 4) * V + (8 + 8) * R,
         # per-tile sort + pack: items in/out, 48-byte record gathered and written per duplicate
         "tile_sort_pack": (16 + 48 + 48) * R,
-        "blend_fwd": 48 * R + 32 * N + 4 * T,
-        "blend_bwd": 48 * counts["sum_max_contrib"] + 32 * N + 72 * R,
+        # the blend kernels stop at the deepest contributor of a tile: 48 bytes per record up to there (each of
+        # the two half tiles reads them: the second read hits L2, HBM sees one)
+        "blend_fwd": 48 * min(R, smc) + 32 * N + 4 * T,
+        "blend_bwd": 48 * min(R, smc) + 32 * N + 72 * min(R, smc),
         "preprocess_bwd": (87 + 12 * M) * V + 48 * V + (52 + 12 * M) * V + 4 * V,  # rendered rows only
         "adam": 28 * (14 + 3 * M) * P,
         # visibility-split Adam: rows without gradient move 24 B/element (grad not read)
@@ -204,22 +249,280 @@ def stage_model(counts, tile_bits):
         "adam_rows_with_grad": 28 * (14 + 3 * M) * V,
         "adam_rows_all": (24 * P + 4 * V) * (14 + 3 * M),
     }
-    f = {"blend_fwd": 25 * E, "blend_bwd": 60 * E}
+    vis, gat, ble = counts["pairs_visited"], counts["pairs_gated"], counts["pairs_blended"]
+    f = {"blend_fwd": FLOP_VISIT * vis + FLOP_GATE * gat + FLOP_BLEND_FWD * ble,
+         "blend_bwd": FLOP_VISIT * vis + FLOP_GATE * gat + FLOP_BLEND_BWD * ble}
     return b, f
+
+
+def read_profile(L):
+    buf = C.create_string_buffer(8192)
+    L.gsr_profile_read(buf, 8192)
+    prof = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, tot = line.split()
+        prof[name] = (float(tot), int(cnt))
+    return prof
+
+
+def checksum(t: torch.Tensor) -> torch.Tensor:
+    """Order-independent 2x64-bit digest of a tensor's bit pattern (replica comparison across ranks)."""
+    v = t.contiguous().view(torch.int32).long()
+    return torch.stack([v.sum(), (v * v % 1000003).sum()])
+
+
+# --------------------------------------------------------------------------------------
+def timed_loop(fn, steps, warmup, world, dev, L):
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        fn()
+    barrier()
+    a = torch.cuda.Event(enable_timing=True)
+    b = torch.cuda.Event(enable_timing=True)
+    launches0 = L.gsr_launch_count()
+    t0 = time.time()
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    barrier()
+    t1 = time.time()
+    ms = a.elapsed_time(b)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    return ms, L.gsr_launch_count() - launches0, (t0, t1)
+
+
+def rank_breakdown_of(mapper, step_fn, world, dev, n_tr=10):
+    """Where the step time goes on every rank (render = fwd + bwd of this rank's views; wait = first barrier,
+    i.e. waiting for the slowest rank; exchange = rank mask / statistics + fused peer kernel + second barrier)."""
+    import torch.distributed as dist
+    acc = torch.zeros(6, device=dev, dtype=torch.float64)
+    for _ in range(n_tr):
+        mapper.trace = []
+        step_fn()
+        torch.cuda.synchronize()
+        ev = dict(mapper.trace)
+        acc[0] += ev["step_begin"].elapsed_time(ev["render_end"])
+        acc[1] += ev["render_end"].elapsed_time(ev["barrier1_end"])
+        acc[2] += ev["barrier1_end"].elapsed_time(ev["step_end"])
+        acc[3] += ev["barrier1_end"].elapsed_time(ev["mask_end"])
+        acc[4] += ev["mask_end"].elapsed_time(ev["peer_adam_end"])
+        acc[5] += ev["peer_adam_end"].elapsed_time(ev["step_end"])
+    mapper.trace = None
+    acc /= n_tr
+    allr = [torch.zeros_like(acc) for _ in range(world)]
+    dist.all_gather(allr, acc)
+    return [{"rank": r, "render_ms": round(float(x[0]), 4), "wait_ms": round(float(x[1]), 4),
+             "exchange_ms": round(float(x[2]), 4), "mask_stats_ms": round(float(x[3]), 4),
+             "peer_adam_ms": round(float(x[4]), 4), "barrier2_ms": round(float(x[5]), 4)}
+            for r, x in enumerate(allr)]
+
+
+def exchange_summary(mapper, breakdown):
+    """NVLink traffic model of the fused exchange next to its measured time, and the remaining loss named."""
+    xb = mapper.exchange_bytes()
+    if xb is None or not breakdown:
+        return None
+    adam_ms = float(np.mean([b["peer_adam_ms"] for b in breakdown]))
+    wait_ms = float(np.mean([b["wait_ms"] for b in breakdown]))
+    bar_ms = float(np.mean([b["barrier2_ms"] for b in breakdown]))
+    out = dict(xb)
+    out["param_in_gbs_upper_bound"] = round(xb["param_in_bytes"] / max(adam_ms, 1e-6) / 1e6, 1)
+    out["nvlink_peak_gbs"] = NVLINK_PEER_GBS
+    out["note"] = ("upper bound: assumes every parameter of the shard changed and was broadcast; rows whose update is "
+                   "the identity (zero moments, zero gradient) are not sent")
+    losses = {"peer kernel": adam_ms, "barrier wait (slowest view)": wait_ms, "second barrier": bar_ms}
+    out["largest_remaining_loss"] = max(losses, key=losses.get)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+def rasterizer_only_product(scene, cam, params, dev, steps, warmup):
+    """RasterizeGaussiansCUDA + RasterizeGaussiansBackwardCUDA through the C++ drop-in shim (dense gradients, the
+    reference's allocation pattern) — the metric's literal quantity."""
+    shim = os.path.join(ROOT, "gsdf_slam_b200", "libgsr_torch_shim.so")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    e = torch.empty(0, dtype=torch.float32, device=dev)
+    bg, view, proj, campos, dL = t(scene.bg), t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos), t(scene.dL_dout)
+    api = "C++ shim (libgsr_torch_shim.so: RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA)"
+    try:
+        torch.ops.load_library(shim)
+        ops = torch.ops.gsr_shim
+
+        def once():
+            r = ops.rasterize_forward(bg, params["means3D"], e, params["opacity"], params["scales"], params["rotations"],
+                                      1.0, e, view, proj, cam.tanfovx, cam.tanfovy, cam.H, cam.W, params["dc"],
+                                      params["sh"], scene.degree, campos, False, False)
+            ops.rasterize_backward(bg, params["means3D"], r[3], e, params["scales"], params["rotations"], 1.0, e, view,
+                                   proj, cam.tanfovx, cam.tanfovy, dL, params["dc"], params["sh"], scene.degree, campos,
+                                   r[4], r[0], r[5], r[6], r[1], r[7], False)
+        once()
+    except Exception as exc:  # noqa: BLE001
+        import gsdf_slam_b200 as gs
+        api = f"ctypes mirror (shim unavailable: {exc!r})"
+
+        def once():
+            r = gs.RasterizeGaussiansCUDA(bg, params["means3D"], e, params["opacity"], params["scales"],
+                                          params["rotations"], 1.0, e, view, proj, cam.tanfovx, cam.tanfovy, cam.H,
+                                          cam.W, params["dc"], params["sh"], scene.degree, campos, False, False)
+            gs.RasterizeGaussiansBackwardCUDA(bg, params["means3D"], r[3], e, params["scales"], params["rotations"],
+                                              1.0, e, view, proj, cam.tanfovx, cam.tanfovy, dL, params["dc"],
+                                              params["sh"], scene.degree, campos, r[4], r[0], r[5], r[6], r[1], r[7],
+                                              False)
+    for _ in range(warmup):
+        once()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        once()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"value": round(1000.0 / ms, 2), "unit": "rasterizer fwd+bwd it/s", "ms_per_iteration": round(ms, 4),
+            "api": api, "gradients": "dense [P, ...] tensors (zero rows for Gaussians that were not rendered)"}
+
+
+# --------------------------------------------------------------------------------------
+def cfg5_keyframes(scene5, dev, dL):
+    from gsdf_slam_b200.mapping import Keyframe
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    return [Keyframe(t(c.viewmatrix), t(c.projmatrix), t(c.campos), c.tanfovx, c.tanfovy, c.H, c.W, dL)
+            for c in scene5.extra_cams]
+
+
+def zero_stats(P, dev):
+    return {k: torch.zeros(P, dtype=torch.float32, device=dev)
+            for k in ("max_radii2D", "xyz_gradient_accum", "denom")}
+
+
+def run_cfg5(args, rank, world, dev, L, scene5, params5, kfs):
+    """BASELINE.json configs[4]: K = 8 keyframes per optimiser step over 3 M Gaussians, split over the ranks."""
+    from gsdf_slam_b200.mapping import KeyframeBatchMapper, partition_keyframes
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    local = [kfs[i] for i in partition_keyframes(len(kfs), world, rank)]
+    mapper = KeyframeBatchMapper(params5, scene5.degree, t(scene5.bg), freeze_render_inputs=True,
+                                 stats=zero_stats(scene5.P, dev))
+    steps, warmup = max(5, min(args.steps, 12)), 3
+
+    def step():
+        mapper.step(local)
+
+    ms, launches, _ = timed_loop(step, steps, warmup, world, dev, L)
+    ms_step = ms / steps
+    out = {"workload": f"{scene5.name}: {scene5.P} SH-{scene5.degree} Gaussians, {len(kfs)} keyframes "
+                       f"({scene5.extra_cams[0].W}x{scene5.extra_cams[0].H}) per optimiser step split over {world} "
+                       "rank(s): fwd + bwd of the local keyframes (rendered rows only, later keyframes add), "
+                       "densification statistics of every view, exchange, Adam",
+           "scaling": "strong (fixed batch of 8 keyframes)", "n_gpus": world, "keyframes_per_step": len(kfs),
+           "keyframes_per_rank": len(local), "steps": steps, "ms_per_step": round(ms_step, 4),
+           "value": round(1000.0 / ms_step, 2), "unit": "mapping it/s (optimiser steps of 8 keyframes)",
+           "keyframes_per_s": round(1000.0 * len(kfs) / ms_step, 1), "gpu_launches": int(launches),
+           "exchange": ("none (single rank): masked Adam over the rows some keyframe rendered" if world == 1 else
+                        "fused peer-memory kernel (gsr_adam_step_peer) + gsr_peer_stats_exchange"
+                        if mapper.peer is not None else "NCCL all-reduce fallback")}
+    n1 = os.path.join(ROOT, "profiles", "mapping_cfg5_n1.json")
+    if world > 1 and os.path.exists(n1) and not (args.small_cfg5 or args.config == "small"):
+        try:
+            ref = json.load(open(n1))
+            out["n1_ms_per_step_recorded"] = ref["ms_per_step"]
+            out["speedup_vs_recorded_n1"] = round(ref["ms_per_step"] / ms_step, 3)
+            out["n1_record"] = ("profiles/mapping_cfg5_n1.json (an earlier N=1 run of this block; the driver's own "
+                                "N=1 line is authoritative)")
+        except Exception:  # noqa: BLE001
+            pass
+    if world > 1 and mapper.peer is not None:
+        bd = rank_breakdown_of(mapper, step, world, dev, n_tr=5)
+        out["rank_breakdown"] = bd
+        out["nvlink"] = exchange_summary(mapper, bd)
+    del mapper
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_exchange_parity(rank, world, dev, scene5, params5, kfs, n_steps=2):
+    """Untimed: the same `n_steps` training steps (render inputs NOT frozen) three ways."""
+    import torch.distributed as dist
+    from gsdf_slam_b200.mapping import SEGMENTS, KeyframeBatchMapper, partition_keyframes
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    bg = t(scene5.bg)
+    local = [kfs[i] for i in partition_keyframes(len(kfs), world, rank)]
+    res = {}
+    for name, kw, batch in (("peer", dict(peer_exchange=True), local), ("nccl", dict(peer_exchange=False), local),
+                            ("sequential", dict(single_rank=True), kfs)):
+        if name == "sequential" and rank != 0:
+            continue
+        st = zero_stats(scene5.P, dev)
+        m = KeyframeBatchMapper({k: v.clone() for k, v in params5.items()}, scene5.degree, bg, stats=st, **kw)
+        if name == "peer" and m.peer is None:
+            res[name] = None
+            del m
+            continue
+        if name == "peer":
+            m.arena.fill_(float("nan"))      # rows nobody renders must never be read
+        for _ in range(n_steps):
+            m.step(batch)
+        torch.cuda.synchronize()
+        res[name] = ({k: m.opt_params[k].clone() for k in SEGMENTS}, {k: v.clone() for k, v in st.items()})
+        del m
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    out = {"steps": n_steps, "workload": f"{scene5.name}, {len(kfs)} keyframes per step over {world} ranks, "
+                                         "training steps with live parameters"}
+    if res.get("peer") is None:
+        out["peer_path"] = "unavailable (no symmetric memory)"
+        return out
+
+    def upd_rel(a, b):
+        worst = 0.0
+        for k in SEGMENTS:
+            d0 = (b[k] - params5[k]).double()
+            worst = max(worst, float((a[k].double() - b[k].double()).norm() / max(float(d0.norm()), 1e-30)))
+        return worst
+
+    pa, sa = res["peer"]
+    pb, sb = res["nccl"]
+    out["peer_vs_nccl_rel_l2"] = float(f"{upd_rel(pa, pb):.3e}")
+    digest = torch.cat([checksum(pa[k]) for k in SEGMENTS] + [checksum(sa[k]) for k in sa])
+    allg = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(allg, digest)
+    out["replicas_bit_identical"] = bool(all(torch.equal(allg[0], x) for x in allg))
+    out["finite"] = all(bool(torch.isfinite(pa[k]).all()) for k in SEGMENTS)
+    if rank == 0:
+        pc, sc = res["sequential"]
+        out["vs_sequential_rel_l2"] = float(f"{upd_rel(pa, pc):.3e}")
+        out["stats_denom_equal"] = bool(torch.equal(sa["denom"], sc["denom"]))
+        out["stats_max_radii_equal"] = bool(torch.equal(sa["max_radii2D"], sc["max_radii2D"]))
+        den = float(sc["xyz_gradient_accum"].double().norm())
+        num = float((sa["xyz_gradient_accum"].double() - sc["xyz_gradient_accum"].double()).norm())
+        out["stats_accum_rel_l2"] = float(f"{num / max(den, 1e-30):.3e}")
+        out["nccl_stats_denom_equal"] = bool(torch.equal(sb["denom"], sc["denom"]))
+        out["rows_with_statistics"] = int((sc["denom"] > 0).sum())
+        out["bar"] = ("rel-L2 of the parameter update <= 1e-5 (fp32 reduction order), replicas bit-identical, "
+                      "denom / max_radii exact")
+    return out
 
 
 # --------------------------------------------------------------------------------------
 def run_product(args, rank, world, dev):
     import torch.distributed as dist
-    import gsdf_slam_b200 as gs
     from gsdf_slam_b200 import _lib
     from gsdf_slam_b200.mapping import Keyframe, KeyframeBatchMapper
 
     L = _lib.lib()
     scene, cam = make_scene(args.config, rank)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-    params = dict(means3D=t(scene.means3D), dc=t(scene.dc), sh=t(scene.sh), opacity=t(scene.opacity),
-                  scales=t(scene.scales), rotations=t(scene.rotations))
+    params = dev_params(scene, dev)
     mapper = KeyframeBatchMapper(params, scene.degree, t(scene.bg), freeze_render_inputs=True)
     hk = host_keyframe(scene, cam, args.with_loss)
     big_dev = hk["dL_dout"].to(dev)
@@ -233,45 +536,43 @@ def run_product(args, rank, world, dev):
     counts = workload_counts(scene, cam, params, dev)
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def step_resident():
         mapper.step([kf_dev])
 
-    # device staging buffers for the e2e path + pinned result buffers
+    # device staging buffers for the e2e path + pinned result buffers (both double-buffered)
     stage = {k: torch.empty_like(v, device=dev) for k, v in hk.items()}
     cam_host, cam_dev, cam_views = camera_block(hk, dev)
     stage.update(cam_views)
-    img_host = torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory()
+    img_host = [torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory() for _ in range(2)]
     h2d_bytes = sum(v.numel() * 4 for v in hk.values())
-    d2h_bytes = img_host.numel() * 4
+    d2h_bytes = img_host[0].numel() * 4
     ev_h2d = torch.cuda.Event()
     ev_fwd = torch.cuda.Event()
     ev_step = [torch.cuda.Event(), torch.cuda.Event()]
-    for ev in ev_step:
+    ev_img = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in ev_step + ev_img:
         ev.record(torch.cuda.current_stream(dev))
     dl_stage = [stage["dL_dout"], torch.empty_like(stage["dL_dout"])]
     counter = [0]
 
     def step_e2e():
         main = torch.cuda.current_stream(dev)
+        slot = counter[0] & 1
+        counter[0] += 1
+        # the result of step k-2 (the rendered image in img_host[slot]) must have reached the host before its
+        # buffer is reused; the host never blocks on the step it has just enqueued
+        ev_img[slot].synchronize()
         # camera + background first (tiny), the image-sized gradient on the copy stream so it
         # overlaps the forward (a real mapper uploads the ground-truth image the same way)
         cam_dev.copy_(cam_host, non_blocking=True)
         # the image-sized upload is double-buffered: it may start while the previous step's
         # backward pass still reads the other buffer (two steps back is finished: ev_step[slot])
-        slot = counter[0] & 1
-        counter[0] += 1
         copy_stream.wait_event(ev_step[slot])
         with torch.cuda.stream(copy_stream):
             dl_stage[slot].copy_(hk["dL_dout"], non_blocking=True)
             ev_h2d.record(copy_stream)
         mapper.bg = stage["bg"]
         kf = make_kf(stage["viewmatrix"], stage["projmatrix"], stage["campos"], dl_stage[slot])
-        keep = {}
 
         def after_forward(_kf, fwd):
             # read the image back while the backward runs; the backward needs the uploaded dL_dout
@@ -279,100 +580,75 @@ def run_product(args, rank, world, dev):
             ev_fwd.record(main)
             copy_stream.wait_event(ev_fwd)
             with torch.cuda.stream(copy_stream):
-                img_host.copy_(color, non_blocking=True)
+                img_host[slot].copy_(color, non_blocking=True)
+                ev_img[slot].record(copy_stream)
             color.record_stream(copy_stream)
             main.wait_event(ev_h2d)
-            keep["color"] = color
 
         mapper.step([kf], on_forward=after_forward)
-        # the step's result (the rendered image) must have reached the host before the next step
-        # starts; the compute stream is NOT drained, so the host prepares step k+1 while the GPU
-        # finishes the backward pass and the optimiser of step k (like a real mapping loop)
         ev_step[slot].record(main)
-        copy_stream.synchronize()
-
-    def timed(fn, steps, warmup, sampler=None):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
-        launches0 = L.gsr_launch_count()
-        t0 = time.time()
-        a.record()
-        for _ in range(steps):
-            fn()
-        b.record()
-        barrier()
-        t1 = time.time()
-        ms = a.elapsed_time(b)
-        if world > 1:
-            tt = torch.tensor([ms], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
-        return ms, L.gsr_launch_count() - launches0, (t0, t1)
 
     sampler = ClockSampler(dev.index if dev.index is not None else 0)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms, launches, (t0, t1) = timed(step_resident, args.steps, args.warmup)
+    ms, launches, (t0, t1) = timed_loop(step_resident, args.steps, args.warmup, world, dev, L)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    e2e_ms, _, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    e2e_ms, _, _ = timed_loop(step_e2e, args.steps, max(3, args.warmup // 2), world, dev, L)
+    for ev in ev_img:
+        ev.synchronize()
 
     # per-stage durations with CUDA events on the launching stream (separate, untimed loop)
-    prof = {}
     L.gsr_profile_enable(1)
     mapper.serialize_side_stream = True   # per-stage times are taken without stream overlap
     for _ in range(max(5, min(args.steps, 20))):
         step_resident()
     torch.cuda.synchronize()
     mapper.serialize_side_stream = False
-    buf = (__import__("ctypes").create_string_buffer)(8192)
-    L.gsr_profile_read(buf, 8192)
+    prof = {k: tot / max(1, cnt) for k, (tot, cnt) in read_profile(L).items()}
     L.gsr_profile_enable(0)
-    for line in buf.value.decode().splitlines():
-        name, cnt, tot = line.split()
-        prof[name] = float(tot) / max(1, int(cnt))
 
-    # multi-rank: where the step time goes on every rank (render = fwd + bwd of this rank's view;
-    # wait = first barrier, i.e. waiting for the slowest rank's view; exchange = union mask + fused
-    # peer kernel + second barrier)
     rank_breakdown = None
     if world > 1 and mapper.peer is not None:
-        acc = torch.zeros(6, device=dev, dtype=torch.float64)
-        n_tr = 10
-        for _ in range(n_tr):
-            mapper.trace = []
-            step_resident()
-            torch.cuda.synchronize()
-            ev = dict(mapper.trace)
-            acc[0] += ev["step_begin"].elapsed_time(ev["render_end"])
-            acc[1] += ev["render_end"].elapsed_time(ev["barrier1_end"])
-            acc[2] += ev["barrier1_end"].elapsed_time(ev["step_end"])
-            acc[3] += ev["barrier1_end"].elapsed_time(ev["mask_end"])
-            acc[4] += ev["mask_end"].elapsed_time(ev["peer_adam_end"])
-            acc[5] += ev["peer_adam_end"].elapsed_time(ev["step_end"])
-        mapper.trace = None
-        acc /= n_tr
-        allr = [torch.zeros_like(acc) for _ in range(world)]
-        dist.all_gather(allr, acc)
-        rank_breakdown = [{"rank": r, "render_ms": round(float(x[0]), 4), "wait_ms": round(float(x[1]), 4),
-                           "exchange_ms": round(float(x[2]), 4), "mask_ms": round(float(x[3]), 4),
-                           "peer_adam_ms": round(float(x[4]), 4), "barrier2_ms": round(float(x[5]), 4)}
-                          for r, x in enumerate(allr)]
+        rank_breakdown = rank_breakdown_of(mapper, step_resident, world, dev)
+    nvlink = exchange_summary(mapper, rank_breakdown) if rank_breakdown else None
     if world > 1:
         lt = torch.tensor([launches], device=dev, dtype=torch.float64)
         dist.all_reduce(lt)
         launches = int(lt.item())
+    peer_active = mapper.peer is not None
+
+    # ---- the metric's literal quantity through the C++ drop-in shim (N = 1) ----
+    rast_only = None
+    if world == 1 and not args.no_shim:
+        rast_only = rasterizer_only_product(scene, cam, params, dev, max(10, min(args.steps, 30)), 5)
+    del mapper
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: 3 M Gaussians, 8 keyframes per step, strong scaling; N > 1: exchange parity ----
+    cfg5_block = parity_block = None
+    if not args.no_cfg5:
+        scene5 = make_cfg5(args.small_cfg5 or args.config == "small")
+        params5 = dev_params(scene5, dev)
+        kfs = cfg5_keyframes(scene5, dev, t(scene5.dL_dout))
+        cfg5_block = run_cfg5(args, rank, world, dev, L, scene5, params5, kfs)
+        if world > 1 and not args.no_parity:
+            parity_block = run_exchange_parity(rank, world, dev, scene5, params5, kfs)
+        del params5, kfs
+        torch.cuda.empty_cache()
     if rank != 0:
         return None
 
     hbm_peak, peak_src = load_peaks()
-    tb = max(1, int(np.ceil(np.log2(counts["T"]))))
-    bytes_model, flops_model = stage_model(counts, tb)
+    bytes_model, flops_model = stage_model(counts)
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    traffic = {}
+    if os.path.exists(traffic_file):
+        traffic = json.load(open(traffic_file)).get(args.config, {})
+        if not isinstance(traffic, dict):
+            traffic = {}
     stages = {}
     for name, ms_stage in sorted(prof.items(), key=lambda kv: -kv[1]):
         ent = {"ms": round(ms_stage, 5)}
@@ -384,6 +660,8 @@ def run_product(args, rank, world, dev):
             tf = flops_model[name] / (ms_stage * 1e-3) / 1e12
             ent.update(algorithmic_flops=int(flops_model[name]), achieved_tflops=round(tf, 3),
                        frac_of_fp32_peak=round(tf / fp32_peak_tflops, 4))
+        if name in traffic:
+            ent["dram_bytes_ncu"] = traffic[name]
         stages[name] = ent
     modelled = {k: v for k, v in prof.items() if k in bytes_model or k in flops_model}
     dom = max(modelled, key=modelled.get) if modelled else None
@@ -393,19 +671,19 @@ def run_product(args, rank, world, dev):
             ach = flops_model[dom] / (prof[dom] * 1e-3) / 1e12
             roofline = {"kernel": dom, "bound": "fp32", "achieved": round(ach, 3),
                         "peak": round(fp32_peak_tflops, 2), "unit": "TFLOP/s",
-                        "frac": round(ach / fp32_peak_tflops, 4), "traffic": None,
+                        "frac": round(ach / fp32_peak_tflops, 4), "traffic": traffic.get(dom),
                         "peak_source": f"148 SMs x 128 FP32 lanes x 2 x {sm_mhz:.0f} MHz (clock sampled "
                                        "during the run); no tensor-core work exists on this path",
+                        "flops_model": f"{FLOP_VISIT}*visited + {FLOP_GATE}*gated + "
+                                       f"{FLOP_BLEND_BWD if dom == 'blend_bwd' else FLOP_BLEND_FWD}*blended pairs, pairs "
+                                       "COUNTED by an instrumented replay (counts.pairs_*), the reference's per-pair arithmetic",
                         "hbm_achieved_gbs": stages[dom].get("achieved_gbs"),
                         "share_of_step": round(prof[dom] / sum(prof.values()), 3)}
         else:
             ach = bytes_model[dom] / (prof[dom] * 1e-3) / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak,
-                        "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
+                        "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": traffic.get(dom),
                         "peak_source": peak_src}
-    traffic_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if roofline and os.path.exists(traffic_file):
-        roofline["traffic"] = json.load(open(traffic_file)).get(roofline["kernel"])
 
     # largest HBM-bound stage, against the measured copy bandwidth
     hbm_stages = {k: v for k, v in stages.items() if k not in flops_model and "achieved_gbs" in v}
@@ -414,7 +692,7 @@ def run_product(args, rank, world, dev):
         k = max(hbm_stages, key=lambda n: hbm_stages[n]["algorithmic_bytes"])
         roofline_hbm = {"kernel": k, "bound": "hbm", "achieved": hbm_stages[k]["achieved_gbs"],
                         "peak": hbm_peak, "unit": "GB/s", "frac": hbm_stages[k]["frac_of_hbm_peak"],
-                        "peak_source": peak_src}
+                        "traffic": traffic.get(k), "peak_source": peak_src}
 
     ms_step = ms / args.steps
     e2e_step = e2e_ms / args.steps
@@ -431,7 +709,7 @@ def run_product(args, rank, world, dev):
                    "keyframes_per_step": world, "parallelism": f"dp{world} (keyframe batch)",
                    "exchange": ("none (single rank)" if world == 1 else
                                 "fused peer-memory kernel: gradient reduction + Adam on a 1/N shard + parameter "
-                                "broadcast over NVLink (gsr_adam_step_peer)" if mapper.peer is not None else
+                                "broadcast over NVLink (gsr_adam_step_peer)" if peer_active else
                                 "NCCL all-reduce of the gradient arena, pipelined with fused Adam"),
                    "l2_policy": "working set (params+grads+Adam state+scratch ~0.7 GB) exceeds the 126 MB L2",
                    "adam": ("fused, on a raw-parameter shadow copy (render inputs frozen); single rank: one "
@@ -439,15 +717,23 @@ def run_product(args, rank, world, dev):
                             "rendered rows, the backward pass skips the dense zero fill")},
         "counts": counts,
         "e2e": {"value": round(world * 1000.0 / e2e_step, 2), "unit": UNIT, "ms_per_step": round(e2e_step, 4),
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "pipelining": "copies double-buffered on a copy stream; the image of step k is awaited before step k+2"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "roofline_hbm": roofline_hbm,
         "stages": stages,
     }
+    if rast_only is not None:
+        line["rasterizer_only"] = rast_only
     if rank_breakdown is not None:
         line["rank_breakdown"] = rank_breakdown
+        line["nvlink"] = nvlink
+    if cfg5_block is not None:
+        line["mapping_cfg5"] = cfg5_block
+    if parity_block is not None:
+        line["exchange_parity"] = parity_block
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.config)
     return line
@@ -471,6 +757,35 @@ def cpu_baseline(cfg: str):
 
 
 # --------------------------------------------------------------------------------------
+class LibtorchAdam:
+    """torch::optim::Adam::step (single-tensor path) restated with the same ATen ops: the reference's optimizer."""
+
+    def __init__(self, p, names):
+        from gsdf_slam_b200.mapping import DEFAULT_LR
+        self.lr = DEFAULT_LR
+        self.names = names
+        self.shadow = {k: p[k].clone() for k in names}
+        self.m = {k: torch.zeros_like(p[k]) for k in names}
+        self.v = {k: torch.zeros_like(p[k]) for k in names}
+        self.step_count = 0
+
+    def step(self, grads, gname):
+        self.step_count += 1
+        s = self.step_count
+        bc1, bc2 = 1 - 0.9 ** s, 1 - 0.999 ** s
+        for k in self.names:
+            g = grads[gname[k]].view_as(self.shadow[k])
+            self.m[k].mul_(0.9).add_(g, alpha=0.1)
+            self.v[k].mul_(0.999).addcmul_(g, g, value=0.001)
+            denom = (self.v[k].sqrt() / np.sqrt(bc2)).add_(1e-15)
+            self.shadow[k].addcdiv_(self.m[k], denom, value=-(self.lr[k] / bc1))
+
+
+GRAD_OF = dict(means3D="dL_dmeans3D", dc="dL_ddc", sh="dL_dsh", opacity="dL_dopacity", scales="dL_dscales",
+               rotations="dL_drotations")
+PARAM_NAMES = ("means3D", "dc", "sh", "opacity", "scales", "rotations")
+
+
 def run_reference(args, rank, world, dev):
     """Reference arm: the unmodified reference CUDA rasterizer (oracle/_ref) + LibTorch's Adam
     op sequence, rank 0 only."""
@@ -487,56 +802,39 @@ def run_reference(args, rank, world, dev):
                 "data": "synthetic", "config": {"workload": args.config}, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     scene, cam = make_scene(args.config, 0)
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-    p = dict(means3D=t(scene.means3D), dc=t(scene.dc), sh=t(scene.sh), opacity=t(scene.opacity),
-             scales=t(scene.scales), rotations=t(scene.rotations))
+    p = dev_params(scene, dev)
     e = torch.empty(0, dtype=torch.float32, device=dev)
     rr = rb.RefRasterizer()
     hk = host_keyframe(scene, cam, args.with_loss)
     stage = {k: torch.empty_like(v, device=dev) for k, v in hk.items()}
     cam_host, cam_dev, cam_views = camera_block(hk, dev)   # same single camera copy per step as the product arm
     stage.update(cam_views)
-    img_host = torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory()
-    names = ("means3D", "dc", "sh", "opacity", "scales", "rotations")
+    img_host = [torch.empty((3, cam.H, cam.W), dtype=torch.float32).pin_memory() for _ in range(2)]
     from oracle.loss_ref import reference_mapping_loss
-    gname = dict(means3D="dL_dmeans3D", dc="dL_ddc", sh="dL_dsh", opacity="dL_dopacity",
-                 scales="dL_dscales", rotations="dL_drotations")
-    from gsdf_slam_b200.mapping import DEFAULT_LR
-    shadow = {k: p[k].clone() for k in names}
-    m = {k: torch.zeros_like(p[k]) for k in names}
-    v = {k: torch.zeros_like(p[k]) for k in names}
-    state = {"step": 0}
-
-    def adam(grads):  # torch::optim::Adam::step (single-tensor path), the reference's optimizer
-        state["step"] += 1
-        s = state["step"]
-        bc1, bc2 = 1 - 0.9 ** s, 1 - 0.999 ** s
-        for k in names:
-            g = grads[gname[k]].view_as(shadow[k])
-            m[k].mul_(0.9).add_(g, alpha=0.1)
-            v[k].mul_(0.999).addcmul_(g, g, value=0.001)
-            denom = (v[k].sqrt() / np.sqrt(bc2)).add_(1e-15)
-            shadow[k].addcdiv_(m[k], denom, value=-(DEFAULT_LR[k] / bc1))
+    opt = LibtorchAdam(p, PARAM_NAMES)
 
     copy_stream = torch.cuda.Stream(device=dev)
     ev_h2d, ev_fwd = torch.cuda.Event(), torch.cuda.Event()
     ev_step = [torch.cuda.Event(), torch.cuda.Event()]
-    for ev in ev_step:
+    ev_img = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in ev_step + ev_img:
         ev.record(torch.cuda.current_stream(dev))
     dl_stage = [stage["dL_dout"], torch.empty_like(stage["dL_dout"])]
     counter = [0]
 
-    def step(debug=False, host_io=True):
+    def step(debug=False, host_io=True, adam=True):
         # host I/O exactly like the product's e2e step: camera block on the compute stream, the
-        # image-sized gradient up and the rendered image down on a copy stream, only the image
-        # read is waited for at the end of the step
+        # image-sized gradient up and the rendered image down on a copy stream, double-buffered, the image of
+        # step k awaited before step k+2
         src = stage
         main = torch.cuda.current_stream(dev)
         dl = stage["dL_dout"]
+        slot = 0
         if host_io:
-            cam_dev.copy_(cam_host, non_blocking=True)
             slot = counter[0] & 1
             counter[0] += 1
+            ev_img[slot].synchronize()
+            cam_dev.copy_(cam_host, non_blocking=True)
             dl = dl_stage[slot]
             copy_stream.wait_event(ev_step[slot])
             with torch.cuda.stream(copy_stream):
@@ -551,19 +849,19 @@ def run_reference(args, rank, world, dev):
             ev_fwd.record(main)
             copy_stream.wait_event(ev_fwd)
             with torch.cuda.stream(copy_stream):
-                img_host.copy_(color, non_blocking=True)
+                img_host[slot].copy_(color, non_blocking=True)
+                ev_img[slot].record(copy_stream)
             color.record_stream(copy_stream)
             main.wait_event(ev_h2d)
         if args.with_loss:
-            # the reference's loss: LibTorch op sequence + autograd (src/gaussian_mapper.cpp:414-431)
             dl = reference_mapping_loss(color, dl, None, 0.2)[3]   # the reference's own loss_utils.h + autograd
         g = rr.backward(src["bg"], p["means3D"], radii, e, p["scales"], p["rotations"], 1.0, e,
                         src["viewmatrix"], src["projmatrix"], cam.tanfovx, cam.tanfovy, dl,
                         p["dc"], p["sh"], scene.degree, src["campos"], debug=debug)
-        adam(g)
+        if adam:
+            opt.step(g, GRAD_OF)
         if host_io:
             ev_step[slot].record(main)
-            copy_stream.synchronize()
 
     for k in hk:
         stage[k].copy_(hk[k])
@@ -585,25 +883,77 @@ def run_reference(args, rank, world, dev):
     ms_e2e = timed(lambda: step(False, True), args.steps, args.warmup)
     ms_res = timed(lambda: step(False, False), args.steps, 3)
     ms_dbg = timed(lambda: step(True, False), max(3, args.steps // 2), 2)
+    ms_rast = timed(lambda: step(False, False, adam=False), max(10, min(args.steps, 30)), 3)
     h2d = sum(x.numel() * 4 for x in hk.values())
-    d2h = img_host.numel() * 4
-    cb = None if args.no_cpu_baseline else cpu_baseline(args.config)
-    line = {"metric": METRIC, "impl": "reference", "value": round(1000.0 / ms_e2e, 2), "unit": UNIT,
-            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_e2e, 4),
+    d2h = img_host[0].numel() * 4
+    line = {"metric": METRIC, "impl": "reference", "value": round(1000.0 / ms_res, 2), "unit": UNIT,
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_res, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {scene.name}; UNMODIFIED reference CUDA rasterizer "
                                    "recompiled for sm_100a (oracle/_ref) + LibTorch Adam op sequence"
-                                   + (" + LibTorch L1+SSIM loss with autograd" if args.with_loss else "") + "; "
-                                   "host buffers copied every step like the product's e2e",
+                                   + (" + the reference's loss_utils.h L1+SSIM with autograd" if args.with_loss else "") + "; "
+                                   "`value` device-resident like the product's, `e2e` with the product's host I/O",
                        "reference_debug_flag": False},
-            "e2e": {"value": round(1000.0 / ms_e2e, 2), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "value_device_resident": round(1000.0 / ms_res, 2),
-            "value_device_resident_debug_true_as_shipped": round(1000.0 / ms_dbg, 2)}
-    if cb is not None:
-        line["cpu_baseline"] = cb
+            "e2e": {"value": round(1000.0 / ms_e2e, 2), "unit": UNIT, "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "value_device_resident_debug_true_as_shipped": round(1000.0 / ms_dbg, 2),
+            "rasterizer_only": {"value": round(1000.0 / ms_rast, 2), "unit": "rasterizer fwd+bwd it/s",
+                                "ms_per_iteration": round(ms_rast, 4),
+                                "api": "Rasterizer::forward / backward with the reference shim's zero-filled allocations"}}
+    del rr, opt
+    torch.cuda.empty_cache()
+    if not args.no_cfg5:
+        line["mapping_cfg5"] = reference_cfg5(args, dev)
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.config)
     return line
+
+
+def reference_cfg5(args, dev):
+    """configs[4] on the reference arm: ONE GPU, the 8 keyframes processed sequentially with gradient accumulation
+    (the reference has no multi-GPU mode), LibTorch Adam op sequence."""
+    from oracle import ref_binding as rb
+    scene5 = make_cfg5(args.small_cfg5 or args.config == "small")
+    p = dev_params(scene5, dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    e = torch.empty(0, dtype=torch.float32, device=dev)
+    bg, dL = t(scene5.bg), t(scene5.dL_dout)
+    cams = [(t(c.viewmatrix), t(c.projmatrix), t(c.campos), c) for c in scene5.extra_cams]
+    opt = LibtorchAdam(p, PARAM_NAMES)
+    rr = rb.RefRasterizer()
+
+    def step():
+        acc = None
+        for view, proj, campos, c in cams:
+            R, B, color, radii = rr.forward(bg, p["means3D"], e, p["opacity"], p["scales"], p["rotations"], 1.0, e,
+                                            view, proj, c.tanfovx, c.tanfovy, c.H, c.W, p["dc"], p["sh"],
+                                            scene5.degree, campos)
+            g = rr.backward(bg, p["means3D"], radii, e, p["scales"], p["rotations"], 1.0, e, view, proj, c.tanfovx,
+                            c.tanfovy, dL, p["dc"], p["sh"], scene5.degree, campos)
+            if acc is None:
+                acc = {GRAD_OF[k]: g[GRAD_OF[k]] for k in PARAM_NAMES}
+            else:
+                for k in PARAM_NAMES:          # .grad accumulation of K backward() calls without zero_grad
+                    acc[GRAD_OF[k]].add_(g[GRAD_OF[k]])
+        opt.step(acc, GRAD_OF)
+
+    steps = max(3, min(args.steps, 6))
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"workload": f"{scene5.name}: {scene5.P} Gaussians, {len(cams)} keyframes per optimiser step, ONE GPU, "
+                        "sequential with gradient accumulation (reference rasterizer + LibTorch Adam ops)",
+            "n_gpus": 1, "steps": steps, "ms_per_step": round(ms, 4), "value": round(1000.0 / ms, 2),
+            "unit": "mapping it/s (optimiser steps of 8 keyframes)",
+            "keyframes_per_s": round(1000.0 * len(cams) / ms, 1)}
 
 
 def main():
@@ -623,9 +973,13 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the mapping_cfg5 block (3 M Gaussians, 8 keyframes per step)")
+    ap.add_argument("--small-cfg5", action="store_true", help="CI-sized stand-in for the cfg5 scene")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed exchange_parity block (N > 1)")
+    ap.add_argument("--no-shim", action="store_true", help="skip the rasterizer_only block (C++ drop-in shim, N = 1)")
     ap.add_argument("--with-loss", action="store_true",
                     help="include the photometric L1+SSIM loss (SURVEY row f-1) in the step: fused kernels in "
-                         "the product arm, the reference's LibTorch op sequence + autograd in the reference arm; "
+                         "the product arm, the reference's own loss_utils.h + autograd in the reference arm; "
                          "the image-sized input is then the ground-truth image instead of dL/d(image)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

@@ -33,7 +33,7 @@ class ForwardArgs(C.Structure):
         ("sample_resize", RESIZE_FN), ("sample_user", C.c_void_p),
         ("stream", C.c_void_p),
         ("num_rendered", C.POINTER(C.c_int)), ("num_buckets", C.POINTER(C.c_int)),
-        ("raw_params", C.c_int), ("radii_ready_event", C.c_void_p),
+        ("raw_params", C.c_int), ("radii_ready_event", C.c_void_p), ("context", C.c_void_p),
     ]
 
 
@@ -55,7 +55,7 @@ class BackwardArgs(C.Structure):
         ("dL_ddc", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p),
         ("debug", C.c_int), ("stream", C.c_void_p), ("raw_params", C.c_int), ("rendered_rows_only", C.c_int),
-        ("accumulate", C.c_int),
+        ("accumulate", C.c_int), ("accumulate_rows", C.c_void_p),
     ]
 
 
@@ -84,6 +84,7 @@ class PeerAdamArgs(C.Structure):
         ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("union_mask", C.c_void_p),
         ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", C.c_float),
         ("step", C.c_int64), ("stream", C.c_void_p), ("shard_chunk", C.c_int64),
+        ("param_multicast", C.c_void_p),
     ]
 
 
@@ -118,11 +119,23 @@ EXPORTED_SYMBOLS = [
     "gsr_add_densification_stats", "gsr_reset_opacity", "gsr_voxel_dedup_workspace_bytes", "gsr_voxel_dedup",
     "gsr_select_rows", "gsr_increase_pcd_rows", "gsr_colorize_workspace_bytes", "gsr_colorize_points",
     "gsr_ply_pack_rows", "gsr_ply_unpack_rows",
-    "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_sort_temp_bytes",
+    "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_export_pair_counts", "gsr_sort_temp_bytes",
     "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
+    "gsr_context_create", "gsr_context_destroy",
 ]
 
 _lib = None
+
+
+class _Missing:
+    """Stand-in for a symbol an older developer build (GSR_LIB_PATH) does not export."""
+    argtypes = restype = None
+
+    def __init__(self, name):
+        self.name = name
+
+    def __call__(self, *a, **k):
+        raise RuntimeError(f"{LIB_PATH} does not export {self.name}")
 
 
 def build(verbose: bool = False) -> str:
@@ -148,6 +161,11 @@ def lib() -> C.CDLL:
             "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
             "There is no CPU fallback for the rasterizer hot path.")
     L = C.CDLL(LIB_PATH)
+    if "GSR_LIB_PATH" in os.environ:
+        # developer A/B builds (variants/*.so) may predate a symbol: calling it raises, loading does not
+        for name in EXPORTED_SYMBOLS:
+            if not hasattr(L, name):
+                setattr(L, name, _Missing(name))
     L.gsr_forward.argtypes = [C.POINTER(ForwardArgs)]
     L.gsr_forward.restype = C.c_int
     L.gsr_backward.argtypes = [C.POINTER(BackwardArgs)]
@@ -222,6 +240,9 @@ def lib() -> C.CDLL:
     L.gsr_export_geometry.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_export_geometry.restype = C.c_int
+    L.gsr_export_pair_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+    L.gsr_export_pair_counts.restype = C.c_int
     L.gsr_sort_temp_bytes.argtypes = [C.c_int64]
     L.gsr_sort_temp_bytes.restype = C.c_size_t
     L.gsr_sort_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
@@ -233,6 +254,10 @@ def lib() -> C.CDLL:
     L.gsr_profile_enable.restype = None
     L.gsr_profile_read.argtypes = [C.c_char_p, C.c_size_t]
     L.gsr_profile_read.restype = C.c_int
+    L.gsr_context_create.argtypes = []
+    L.gsr_context_create.restype = C.c_void_p
+    L.gsr_context_destroy.argtypes = [C.c_void_p]
+    L.gsr_context_destroy.restype = None
     L.gsr_version.argtypes = []
     L.gsr_version.restype = C.c_char_p
     _lib = L

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "gsr_capi.h"
 #include "gsr_common.cuh"
 #include "gsr_params.cuh"
@@ -210,8 +212,11 @@ emit_kernel(const uint64_t* __restrict__ vis_items, const uint32_t* __restrict__
   warp_walk_rects_flat(cnt != 0 && !large, co, xy, rect_min, rect_max, thr, depth_bits, g,
                        [&](int, int x, int y, uint32_t owner_depth, uint32_t owner_g) {
                          const uint32_t tile = (uint32_t)(y * grid_x + x);
-                         const uint32_t pos = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
-                         if (pos < capacity) items[pos] = ((uint64_t)owner_depth << 32) | owner_g;
+                         const uint2 rg = ranges[tile];
+                         const uint32_t pos = rg.x + atomicAdd(&tile_fill[tile], 1u);
+                         // pos < rg.y always holds (preprocess counted with the same test); the guard keeps a
+                         // mismatch from ever spilling into the neighbouring tile's list
+                         if (pos < rg.y && pos < capacity) items[pos] = ((uint64_t)owner_depth << 32) | owner_g;
                        });
 }
 
@@ -251,8 +256,9 @@ emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __re
         const int x = (int)rect_min.x + t - (t / w) * w;
         if (tile_min_power(co, xy, x, y) <= thr) {
           const uint32_t tile = (uint32_t)(y * grid_x + x);
-          const uint32_t pos = ranges[tile].x + atomicAdd(&tile_fill[tile], 1u);
-          if (pos < capacity) items[pos] = it;
+          const uint2 rg = ranges[tile];
+          const uint32_t pos = rg.x + atomicAdd(&tile_fill[tile], 1u);
+          if (pos < rg.y && pos < capacity) items[pos] = it;
         }
       }
     }
@@ -265,7 +271,7 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
                 uint64_t* items, uint32_t capacity, uint32_t* large_count, uint32_t* large_list,
                 cudaStream_t s) {
   if (P <= 0) return 0;
-  if (P >= (1 << 24)) return GSR_ERR_BAD_ARG;  // queue entries hold 24-bit list positions
+  if (P >= (1 << 24)) return GSR_ERR_BAD_ARG;  // queue entries hold 24-bit list positions (gsr_forward checks first)
   const uint32_t large_capacity = 2u * (uint32_t)P;
   // the grid covers all P list slots; warps past the *num_visible rendered ones leave at once
   const long long warps = ((long long)P + kEmitOwners - 1) / kEmitOwners;
@@ -286,7 +292,7 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
 // sorted order is unique) and the packed per-duplicate records
 //   {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}.
 // Lists shorter than kSortSmallCap entries are sorted in registers by the "small" launch (one
-// 2-warp CTA per tile, LPT order, bitonic network).  The "long" launch (persistent CTAs over the
+// 4-warp CTA per tile, LPT order, bitonic network).  The "long" launch (persistent CTAs over the
 // hdr->num_long_tiles longest tiles, which form a prefix of the LPT order) runs a stable LSD
 // radix sort per tile, in shared memory up to kSortLongSmemCap entries and through global
 // scratch beyond — any list length works.
@@ -669,13 +675,19 @@ int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t
     GSR_LAUNCHED();
   }
   if (!do_long) return (int)cudaGetLastError();
-  static bool attr_set = false;
   const int dyn = kLongWarps * 256 * (int)sizeof(uint32_t) + 2 * kSortLongSmemCap * (int)sizeof(uint64_t);
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tile_sort_pack_long_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+  {
+    // the attribute belongs to the (function, device) pair: set it once per device
+    constexpr int kMaxDev = 64;
+    static std::atomic<bool> attr_set[kMaxDev];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDev || !attr_set[dev].load(std::memory_order_acquire)) {
+      cudaError_t e = cudaFuncSetAttribute(tile_sort_pack_long_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+      if (e != cudaSuccess) return (int)e;
+      if (dev >= 0 && dev < kMaxDev) attr_set[dev].store(true, std::memory_order_release);
+    }
   }
   int idx_bits = 1;
   while (idx_bits < 32 && (1ull << idx_bits) < (unsigned long long)P) ++idx_bits;

@@ -5,17 +5,23 @@
 // preprocess_bwd.cu / adam.cu / knn.cu on the caller's stream.
 //
 // Forward pipeline (reference: Rasterizer::forward, rasterizer_impl.cu:366-538):
-//   preprocess -> onesweep sort of (depth|idx) over P -> chained scan of the exact
-//   tile counts in depth order -> [one 4-byte readback of R] -> emit (tile|idx)
-//   -> onesweep sort of the tile digits over R -> ranges + packed records ->
-//   blend.  One host synchronisation (the reference has two blocking copies plus,
-//   as shipped with debug=true, a device-wide sync after every kernel).
+//   memset(counters) -> preprocess (geometry, SH colours, EXACT per-tile splat counts) -> tile_meta
+//   (scan of the T counts: tile ranges, R, launch order) -> emit (every duplicate dropped into its
+//   tile's range) -> tile_sort_pack (per-tile depth sort + packed records) -> blend_fwd.
+//   No global sort, no scan over Gaussians, no mid-pipeline host synchronisation: the per-duplicate
+//   buffer is sized optimistically from the previous call of the same context and R (24 bytes, read
+//   back asynchronously) is only checked once everything has been enqueued (the reference has two
+//   blocking copies plus, as shipped with debug=true, a device-wide sync after every kernel).
+// Host-side state (read-back event, pinned words, sizing hints) lives in a gsr_context: caller-owned
+// (gsr_context_create) or, by default, one per (host thread, device) — never shared between threads
+// or devices.
 #include "gsr_capi.h"
 
 #include <cuda_runtime.h>
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -23,7 +29,7 @@
 #include "gsr_common.cuh"
 
 namespace gsr {
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 }  // namespace gsr
 
@@ -31,20 +37,44 @@ long long g_launch_count = 0;
 
 namespace gsr {
 
-static uint32_t* pinned_word() {
-  static thread_local uint32_t* p = nullptr;
-  if (!p) {
-    if (cudaHostAlloc(reinterpret_cast<void**>(&p), 64, cudaHostAllocPortable) != cudaSuccess) {
-      p = nullptr;
-    }
+}  // namespace gsr
+
+// Host-side state of gsr_forward: everything that used to be implicit per-thread state.  Bound to the
+// device that was current when it was created.
+struct gsr_context {
+  int device = -1;
+  uint32_t* pinned = nullptr;     // 64 bytes of pinned host memory: R and the list-length class counts
+  cudaEvent_t ev = nullptr;       // read-back complete
+  // the per-duplicate buffer is sized from the previous call with the same (P, W, H); 0 = unknown
+  uint32_t cap_hint = 0;
+  int hint_P = -1, hint_W = -1, hint_H = -1;
+  // per-tile sort kernels for mid-length (512+) / long (4092+) lists are launched only if recent frames
+  // had such lists (-1: unknown, n > 0: seen within the last n calls)
+  int hint_mid = -1, hint_long = -1;
+};
+
+namespace gsr {
+
+static gsr_context* context_new() {
+  gsr_context* c = new gsr_context();
+  if (cudaGetDevice(&c->device) != cudaSuccess ||
+      cudaHostAlloc(reinterpret_cast<void**>(&c->pinned), 64, cudaHostAllocPortable) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming) != cudaSuccess) {
+    if (c->pinned) cudaFreeHost(c->pinned);
+    delete c;
+    return nullptr;
   }
-  return p;
+  return c;
 }
 
-static cudaEvent_t readback_event() {
-  static thread_local cudaEvent_t ev = nullptr;
-  if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
-  return ev;
+// default context of the calling thread for the current device
+static gsr_context* default_context() {
+  static thread_local std::vector<gsr_context*> per_device;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return nullptr;
+  if ((size_t)dev >= per_device.size()) per_device.resize((size_t)dev + 1, nullptr);
+  if (!per_device[dev]) per_device[dev] = context_new();
+  return per_device[dev];
 }
 
 // ---- optional per-stage CUDA-event profiler (bench.py's live roofline measurement) ----
@@ -73,10 +103,12 @@ struct Profiler {
   }
 };
 static Profiler g_prof;
+static std::mutex g_prof_mutex;     // the profiler is a developer aid; when on, its bookkeeping is serialised
 struct ProfScope {
   cudaStream_t s; int slot = -1; cudaEvent_t a{}, b{};
   ProfScope(const char* name, cudaStream_t st) : s(st) {
     if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     slot = g_prof.slot_of(name);
     if (!g_prof.pool.empty()) { a = g_prof.pool.back().first; b = g_prof.pool.back().second; g_prof.pool.pop_back(); }
     else { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -84,6 +116,7 @@ struct ProfScope {
   }
   ~ProfScope() {
     if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     cudaEventRecord(b, s);
     g_prof.pending.push_back({slot, a, b});
   }
@@ -112,7 +145,15 @@ using namespace gsr;
 extern "C" {
 
 const char* gsr_version(void) { return "gsdf_slam_b200 0.1 (sm_100a)"; }
-int64_t gsr_launch_count(void) { return (int64_t)gsr::g_launch_count; }
+int64_t gsr_launch_count(void) { return (int64_t)gsr::g_launch_count.load(std::memory_order_relaxed); }
+
+gsr_context* gsr_context_create(void) { return gsr::context_new(); }
+void gsr_context_destroy(gsr_context* c) {
+  if (!c) return;
+  if (c->ev) cudaEventDestroy(c->ev);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  delete c;
+}
 
 int gsr_forward(const gsr_forward_args* a) {
   if (!a || a->P < 0 || a->W <= 0 || a->H <= 0 || !a->out_color || !a->num_rendered) return GSR_ERR_BAD_ARG;
@@ -131,6 +172,13 @@ int gsr_forward(const gsr_forward_args* a) {
     return GSR_ERR_BAD_ARG;
   if (!a->colors_precomp && !a->dc) return GSR_ERR_BAD_ARG;
   if (!a->cov3D_precomp && (!a->scales || !a->rotations)) return GSR_ERR_BAD_ARG;
+  if (P >= (1 << 24)) return GSR_ERR_BAD_ARG;  // work-queue entries of the emit stage hold 24-bit list positions
+  gsr_context* ctx = a->context ? static_cast<gsr_context*>(a->context) : default_context();
+  if (!ctx) return GSR_ERR_ALLOC;
+  {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != ctx->device) return GSR_ERR_BAD_ARG;  // context of another device
+  }
 
   const int gx = (W + GSR_TILE_X - 1) / GSR_TILE_X, gy = (H + GSR_TILE_Y - 1) / GSR_TILE_Y;
   const uint32_t T = (uint32_t)gx * gy;
@@ -142,7 +190,7 @@ int gsr_forward(const gsr_forward_args* a) {
   ImageView im = image_view(img_base, N, T);
 
   GSR_CUDA(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
-  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));  // tile_count | tile_fill
+  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));  // tile_count | tile_fill | cursors
 
   PreprocessParams pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -171,30 +219,29 @@ int gsr_forward(const gsr_forward_args* a) {
 
   // ranges, R and the per-tile launch order from the exact per-tile counts
   GSR_PROF("tile_meta", launch_tile_meta(im.tile_count, T, im.ranges, g.hdr, im.tile_order, im.max_contrib, s));
-  uint32_t* host_R = pinned_word();
-  cudaEvent_t ev_R = readback_event();
-  if (!host_R || !ev_R) return GSR_ERR_ALLOC;
+  uint32_t* host_R = ctx->pinned;
+  cudaEvent_t ev_R = ctx->ev;
   // R and the numbers of mid-length / long per-tile lists (header words 0 .. 5)
   GSR_CUDA(cudaMemcpyAsync(host_R, &g.hdr->num_dup, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   GSR_CUDA(cudaEventRecord(ev_R, s));
 
-  // The per-duplicate buffer is sized OPTIMISTICALLY from the previous call on this thread, so
+  // The per-duplicate buffer is sized OPTIMISTICALLY from the previous call of this context, so
   // the rest of the forward pass is enqueued without waiting for R (no kernel's grid depends on
   // it; every write is guarded by the capacity).  R is checked once everything is enqueued; if
   // it did not fit — or on the first call — the tail is (re)run with the exact size.
-  static thread_local uint32_t cap_hint = 0;
-  static thread_local int hint_P = -1, hint_W = -1, hint_H = -1;
-  // the same optimism decides which of the per-tile sort kernels are launched: lists of 512+ (mid) and
-  // 4092+ (long) entries get their kernels only if the previous frame had such lists (-1: unknown)
+  // The same optimism decides which of the per-tile sort kernels are launched: lists of 512+ (mid) and
+  // 4092+ (long) entries get their kernels only if recent frames had such lists.
   // Both hints are sticky (a class seen once keeps its kernel for kHintFrames calls, the capacity decays
   // by 1/64 per call) so that a mapper alternating between keyframes does not pay a re-run on every call.
   constexpr int kHintFrames = 64;
-  static thread_local int hint_mid = -1, hint_long = -1;
-  if (hint_P != P || hint_W != W || hint_H != H) {  // a different scene / resolution
+  uint32_t& cap_hint = ctx->cap_hint;
+  int& hint_mid = ctx->hint_mid;
+  int& hint_long = ctx->hint_long;
+  if (ctx->hint_P != P || ctx->hint_W != W || ctx->hint_H != H) {  // a different scene / resolution
     cap_hint = 0;
     hint_mid = hint_long = -1;
   }
-  hint_P = P; hint_W = W; hint_H = H;
+  ctx->hint_P = P; ctx->hint_W = W; ctx->hint_H = H;
   uint32_t cap = cap_hint;
   uint32_t R = 0;
   bool have_R = false;
@@ -213,7 +260,10 @@ int gsr_forward(const gsr_forward_args* a) {
     if (!bin_base) return GSR_ERR_ALLOC;
     b = bin_view(bin_base, (size_t)cap);
     if (attempt > 0) {
-      GSR_CUDA(cudaMemsetAsync(im.tile_fill, 0, (size_t)T * sizeof(uint32_t), s));
+      // tile_fill | cursors are contiguous; max_contrib may hold values of the aborted attempt (blend_fwd
+      // only ever raises it)
+      GSR_CUDA(cudaMemsetAsync(im.tile_fill, 0, (size_t)((char*)im.tile_count + im.zero_bytes - (char*)im.tile_fill), s));
+      GSR_CUDA(cudaMemsetAsync(im.max_contrib, 0, (size_t)T * sizeof(uint32_t), s));
       GSR_CUDA(cudaMemsetAsync(&g.hdr->num_large, 0, sizeof(uint32_t), s));
     }
     if (!have_R || R > 0) {
@@ -224,7 +274,7 @@ int gsr_forward(const gsr_forward_args* a) {
                                                        g.splat_rec, b.rec, do_mid, do_long, s));
     }
     GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
-                            im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, s));
+                            im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, im.cursors, nullptr, s));
     if (!have_R) {
       GSR_CUDA(cudaEventSynchronize(ev_R));  // completed long ago: the GPU is several kernels further
       R = host_R[0];
@@ -273,11 +323,12 @@ int gsr_backward(const gsr_backward_args* a) {
   GeomView g = geom_view(a->geom_buffer, (size_t)P);
   ImageView im = image_view(a->image_buffer, N, T);
 
-  GSR_CUDA(cudaMemsetAsync(g.acc, 0, (size_t)P * 12 * sizeof(float), s));
+  // work cursor of blend_bwd (128-byte header) + the moment sums behind it
+  GSR_CUDA(cudaMemsetAsync(g.bwd_hdr, 0, (size_t)((char*)(g.acc + (size_t)P * 12) - (char*)g.bwd_hdr), s));
   if (a->R > 0) {
     BinView b = bin_view(a->binning_buffer, (size_t)a->R);  // rec does not depend on the capacity
     GSR_PROF("blend_bwd", launch_blend_bwd(W, H, im.ranges, im.tile_order, im.max_contrib, b.rec,
-                            a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, s));
+                            a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, g.bwd_hdr, s));
   }
   PreBwdParams bp;
   std::memset(&bp, 0, sizeof(bp));
@@ -301,6 +352,7 @@ int gsr_backward(const gsr_backward_args* a) {
   bp.dL_dcolor = a->dL_dcolor; bp.dL_dmean3D = a->dL_dmean3D; bp.dL_dcov3D = a->dL_dcov3D;
   bp.dL_ddc = a->dL_ddc; bp.dL_dsh = a->dL_dsh; bp.dL_dscale = a->dL_dscale; bp.dL_drot = a->dL_drot;
   bp.accumulate = a->accumulate != 0;
+  bp.accumulate_rows = a->accumulate ? a->accumulate_rows : nullptr;
   GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible,
                                                    a->rendered_rows_only == 0 && a->accumulate == 0, s));
   if (a->debug) {
@@ -379,6 +431,25 @@ int gsr_export_image(const char* image_buffer, int W, int H, float* final_T, uin
   return GSR_OK;
 }
 
+int gsr_export_pair_counts(const char* binning_buffer, char* image_buffer, int R, int W, int H,
+                           const float* background, float* scratch_color, uint64_t* counts_out, void* stream) {
+  // replays blend_fwd on the buffers of a finished gsr_forward with the instrumented kernel; every output it
+  // rewrites (final_T, n_contrib, accum_c, max_contrib) receives the value it already holds
+  if (!image_buffer || !background || !scratch_color || !counts_out || W <= 0 || H <= 0) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  GSR_CUDA(cudaMemsetAsync(counts_out, 0, 3 * sizeof(uint64_t), s));
+  if (R <= 0) return GSR_OK;
+  if (!binning_buffer) return GSR_ERR_BAD_ARG;
+  const size_t N = (size_t)W * H;
+  const uint32_t T = (uint32_t)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
+  ImageView im = image_view(image_buffer, N, T);
+  BinView b = bin_view(const_cast<char*>(binning_buffer), (size_t)R);  // rec does not depend on the capacity
+  GSR_CUDA(cudaMemsetAsync(im.cursors, 0, 32 * sizeof(uint32_t), s));
+  return launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, background, scratch_color, im.final_T, im.n_contrib,
+                          im.accum_c, im.max_contrib, 0xffffffffu, im.cursors,
+                          reinterpret_cast<unsigned long long*>(counts_out), s);
+}
+
 int gsr_export_geometry(const char* geom_buffer, int P, float* depths, float* means2D,
                         float* conic_opacity, float* rgb, uint32_t* tiles_touched, uint8_t* clamped,
                         void* stream) {
@@ -397,6 +468,7 @@ int gsr_export_geometry(const char* geom_buffer, int P, float* depths, float* me
 }
 
 void gsr_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_prof.drain();
   g_prof.on = on != 0;
   if (on) {
@@ -407,6 +479,7 @@ void gsr_profile_enable(int on) {
 
 // Writes "name count total_ms\n" lines (NUL terminated) and returns the number of stages.
 int gsr_profile_read(char* out, size_t cap) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_prof.drain();
   size_t off = 0;
   int n = 0;

@@ -10,7 +10,9 @@
 //                                                        ranks: per-row rank bitmask, gsr_peer_union_mask)
 //   m, v   = shard-local Adam moments (only 1/N of the state exists on each rank)
 //   p      = Adam update of the local copy
-//   store p to the parameter arena of EVERY rank       (N-1 remote stores, skipped when p is unchanged)
+//   store p to the parameter arena of EVERY rank       (skipped when p is unchanged; ONE multicast store that the
+//                                                        NVSwitch replicates (multimem.st, NVLS) when the arena has
+//                                                        a multicast mapping, else N-1 remote stores + a local one)
 // so each rank reads ~ sum_k (fraction rank k rendered) / N * 236 B and writes (N-1)/N * 236 B per
 // Gaussian over NVLink, and touches only 1/N of the Adam state in HBM.  The caller brackets the
 // kernel with two cross-rank barriers (gradients visible / parameters landed).
@@ -42,6 +44,7 @@ struct PeerSegDev {
 struct PeerAdamParams {
   float* param[GSR_MAX_PEERS];
   const float* grad[GSR_MAX_PEERS];
+  float* param_mc;       // multicast mapping of the parameter arena (NVLS) or null
   int n_peers;
   int n_segs;
   PeerSegDev seg[GSR_PEER_MAX_SEGMENTS];
@@ -150,9 +153,16 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
   const bool changed = __float_as_uint(p.x) != __float_as_uint(p_old.x) || __float_as_uint(p.y) != __float_as_uint(p_old.y) ||
                        __float_as_uint(p.z) != __float_as_uint(p_old.z) || __float_as_uint(p.w) != __float_as_uint(p_old.w);
   if (changed) {
+    if (a.param_mc != nullptr) {
+      // one store; the NVSwitch replicates it into the arena of every rank (this one included)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.param_mc + e), "f"(p.x),
+                   "f"(p.y), "f"(p.z), "f"(p.w)
+                   : "memory");
+    } else {
 #pragma unroll
-    for (int k = 0; k < GSR_MAX_PEERS; ++k)
-      if (k < a.n_peers) *reinterpret_cast<float4*>(a.param[k] + e) = p;
+      for (int k = 0; k < GSR_MAX_PEERS; ++k)
+        if (k < a.n_peers) *reinterpret_cast<float4*>(a.param[k] + e) = p;
+    }
   }
 }
 
@@ -354,7 +364,8 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* in) {
     a.param[k] = in->param_peers[k];
     a.grad[k] = in->grad_peers[k];
   }
-  if (((uintptr_t)in->exp_avg | (uintptr_t)in->exp_avg_sq) & 15) return GSR_ERR_BAD_ARG;
+  if (((uintptr_t)in->exp_avg | (uintptr_t)in->exp_avg_sq | (uintptr_t)in->param_multicast) & 15) return GSR_ERR_BAD_ARG;
+  a.param_mc = in->param_multicast;
   const double bc1 = 1.0 - std::pow(in->beta1, (double)in->step);
   const double bc2 = 1.0 - std::pow(in->beta2, (double)in->step);
   a.n_segs = in->n_segments;

@@ -52,6 +52,9 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
                                                    const float* sh_in_row) {
   const size_t i = (size_t)idx;
   const int M = a.M;
+  // keyframe batches: add to the row's current parameter gradients instead of overwriting them — for every row,
+  // or (accumulate_rows) only for the rows an earlier keyframe of the batch has already written
+  const bool accm = a.accumulate != 0 && (a.accumulate_rows == nullptr || a.accumulate_rows[idx] > 0);
 
   if (!rendered) {
     // not rendered: all gradients are zero
@@ -93,7 +96,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
   // raw-parameter entry point: chain through sigmoid (sigma' = o (1 - o), o = the activated opacity)
   {
     const float dop = a.activate ? dopacity * cop.w * (1.0f - cop.w) : dopacity;
-    a.dL_dopacity[i] = a.accumulate ? a.dL_dopacity[i] + dop : dop;
+    a.dL_dopacity[i] = accm ? a.dL_dopacity[i] + dop : dop;
   }
   store3(a.dL_dcolor, i, dL_dRGB);
 
@@ -332,8 +335,8 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
       dL_dmean_total += r;
     }
   }
-  out3(a.dL_ddc, i, out_ddc, a.accumulate != 0);
-  out3(a.dL_dmean3D, i, dL_dmean_total, a.accumulate != 0);
+  out3(a.dL_ddc, i, out_ddc, accm);
+  out3(a.dL_dmean3D, i, dL_dmean_total, accm);
 
   // ---- cov3D -> scale, rotation (reference computeCov3D backward, backward.cu:317-397)
   if (a.scales != nullptr) {
@@ -356,7 +359,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
     dscale.z = dot3(Rt[2], dL_dMt[2]);
     // raw-parameter entry point: d exp(s)/ds = exp(s) = the activated scale
     if (a.activate) dscale = {dscale.x * scale.x, dscale.y * scale.y, dscale.z * scale.z};
-    out3(a.dL_dscale, i, dscale, a.accumulate != 0);
+    out3(a.dL_dscale, i, dscale, accm);
 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -379,13 +382,13 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
       dL_dq = {(dL_dq.x - q.x * qd) / q_norm, (dL_dq.y - q.y * qd) / q_norm, (dL_dq.z - q.z * qd) / q_norm,
                (dL_dq.w - q.w * qd) / q_norm};
     }
-    if (a.accumulate) {
+    if (accm) {
       const float4 o = reinterpret_cast<const float4*>(a.dL_drot)[i];
       reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(o.x + dL_dq.x, o.y + dL_dq.y, o.z + dL_dq.z, o.w + dL_dq.w);
     } else {
       reinterpret_cast<float4*>(a.dL_drot)[i] = dL_dq;
     }
-  } else if (!a.accumulate) {
+  } else if (!accm) {
     store3(a.dL_dscale, i, {0.f, 0.f, 0.f});
     reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -473,7 +476,7 @@ preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
         if (g < 0) continue;
         float* dst = a.dL_dsh + (size_t)g * row;
         const float* srow = &s_dsh[warp][src * row];
-        if (a.accumulate) {
+        if (a.accumulate && (a.accumulate_rows == nullptr || a.accumulate_rows[g] > 0)) {
           if (lane < row) dst[lane] += srow[lane];
           if (lane + 32 < row) dst[lane + 32] += srow[lane + 32];
         } else {

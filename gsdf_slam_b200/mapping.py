@@ -1,21 +1,36 @@
 """Keyframe-batch data-parallel mapping step.
 
 The reference trains on ONE keyframe per iteration on one GPU
-(/root/reference/src/gaussian_mapper.cpp:335-468: render -> loss -> backward -> Adam).  Here a
-batch of keyframes is split disjointly across ranks (one process per GPU); every rank renders
-and back-propagates its keyframes over a REPLICATED Gaussian set, the per-rank gradients are
-summed with ONE NCCL all-reduce over a flat gradient arena, and every rank applies the
-identical fused Adam step (gsr_adam_step) to its replica — no parameter broadcast is needed.
+(/root/reference/src/gaussian_mapper.cpp:335-468: render -> loss -> backward -> densification
+statistics -> Adam).  Here a batch of K keyframes is split disjointly across ranks (one process per
+GPU); every rank renders and back-propagates its keyframes over a REPLICATED Gaussian set, then the
+ranks exchange, and the semantics pinned by SURVEY.md §8e hold: batch gradient = SUM over the K
+keyframes (K sequential backward() calls without zero_grad), ONE Adam step per batch, and the
+per-view densification statistics (max_radii2D, xyz_gradient_accum, denom;
+src/gaussian_mapper.cpp:443-447, src/gaussian_model.cpp:667-681) of all K views.
 
-Gradient arena layout (fp32, each segment 16-byte aligned and itself a valid contiguous
-gradient tensor): [xyz 3P | f_dc 3P | opacity P | scaling 3P | rotation 4P | f_rest 3MP].
+Exchange, N > 1 ranks on one NVLink node (default): ONE fused kernel over peer memory
+(gsr_adam_step_peer): every rank owns an interleaved 1/N shard of the flat arena, sums the gradient
+arenas of the ranks that rendered each row (per-row rank bitmask), runs Adam on shard-local moments and
+stores the new parameters into all N replicas (one multicast store through the NVSwitch when the
+symmetric allocation has a multicast address, else N unicast stores).  A second small kernel
+(gsr_peer_stats_exchange) builds the rank bitmask and combines the densification statistics.
+Fallback (no symmetric memory, or GSR_PEER_EXCHANGE=0): NCCL all-reduce of the arena (chunked, pipelined
+with the fused Adam) and all-reduce sum / max of the statistics; every rank then applies the identical
+full-size update.  Single rank: the K backward passes write / add only the rows they render
+(gsr_backward_args.accumulate_rows) and ONE masked Adam pass reads the gradient only for those rows.
 
-A keyframe either carries dL/d(image) (the caller owns the loss) or a ground-truth image, in
-which case the fused L1 + SSIM loss of loss.py runs between the two passes.
-The activation functions are outside this path (f-2): the step works on activated parameters.
+Gradient arena layout (fp32, each segment 16-byte aligned and itself a valid contiguous gradient
+tensor): [xyz 3P | f_dc 3P | opacity P | scaling 3P | rotation 4P | f_rest 3MP].
+
+A keyframe either carries dL/d(image) (the caller owns the loss) or a ground-truth image, in which
+case the fused L1 + SSIM loss of loss.py (row f-1) runs between the two passes.  With ``raw_params`` the
+model's RAW opacity / scaling / rotation are the inputs and the activations run inside the preprocess
+kernels (row f-2).
 """
 from __future__ import annotations
 
+import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -30,6 +45,7 @@ GRAD_NAME = {"means3D": "dL_dmeans3D", "dc": "dL_ddc", "sh": "dL_dsh", "opacity"
 # the reference's per-group learning rates (cfg/gaussian_mapper/*/*.yaml, gaussian_model.cpp:325-345)
 DEFAULT_LR = {"means3D": 1.6e-4, "dc": 0.0025, "sh": 0.0025 / 20.0, "opacity": 0.05, "scales": 0.005,
               "rotations": 0.001}
+STATS = ("max_radii2D", "xyz_gradient_accum", "denom")
 
 
 def partition_keyframes(num_keyframes: int, world_size: int, rank: int) -> List[int]:
@@ -72,17 +88,26 @@ class Keyframe:
 
 
 class KeyframeBatchMapper:
-    """Replicated Gaussians + flat gradient arena + fused Adam; one instance per rank."""
+    """Replicated Gaussians + flat gradient arena + fused Adam; one instance per rank.
+
+    ``stats``: optional dict {"max_radii2D", "xyz_gradient_accum", "denom"} of float32 tensors with P elements
+    (the replicated densification statistics, e.g. GaussianModel's); updated with the statistics of all K
+    keyframes of every step, identically on every rank.
+    ``single_rank``: ignore the process group (sequential reference of the multi-rank step in tests / bench).
+    """
 
     def __init__(self, params: Dict[str, torch.Tensor], degree: int, bg: torch.Tensor,
                  lr: Optional[Dict[str, float]] = None, eps: float = 1e-15,
                  process_group=None, freeze_render_inputs: bool = False, overlap_adam: bool = False,
                  masked_single_view: bool = True, peer_exchange: Optional[bool] = None,
-                 lambda_dssim: float = 0.2, raw_params: bool = False):
+                 lambda_dssim: float = 0.2, raw_params: bool = False,
+                 stats: Optional[Dict[str, torch.Tensor]] = None, single_rank: bool = False,
+                 multicast: Optional[bool] = None):
         self.params = {k: params[k].contiguous() for k in SEGMENTS}
         self.degree = int(degree)
         self.bg = bg
         self.pg = process_group
+        self.single_rank = bool(single_rank)
         dev = self.params["means3D"].device
         self.P = int(self.params["means3D"].size(0))
         self.M = int(self.params["sh"].size(1)) if self.params["sh"].dim() >= 2 else 0
@@ -95,9 +120,15 @@ class KeyframeBatchMapper:
         # copies, so every step renders the same scene while doing the full optimiser work.
         self.opt_params = ({k: v.clone() for k, v in self.params.items()} if freeze_render_inputs
                            else self.params)
+        self.stats = None
+        if stats is not None:
+            self.stats = {}
+            for k in STATS:
+                t = stats[k]
+                if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.P:
+                    raise RuntimeError(f"stats[{k!r}] must be a contiguous float32 tensor with P elements")
+                self.stats[k] = t
         lr = dict(DEFAULT_LR, **(lr or {}))
-        self.optimizer = FusedAdam([{"params": [self.opt_params[k]], "lr": lr[k]} for k in SEGMENTS
-                                    if self.opt_params[k].numel() > 0], lr=0.0, eps=eps)
         self.last_radii: Optional[torch.Tensor] = None
         self.last_color: Optional[torch.Tensor] = None
         self.lambda_dssim = float(lambda_dssim)
@@ -112,17 +143,26 @@ class KeyframeBatchMapper:
         if peer_exchange is None:
             import os
             peer_exchange = os.environ.get("GSR_PEER_EXCHANGE", "1") != "0"
+        if multicast is None:
+            import os
+            multicast = os.environ.get("GSR_PEER_MULTICAST", "1") != "0"
         if peer_exchange and dev.type == "cuda" and self.world_size > 1:
-            self._setup_peer_exchange(lr, eps)
-        # visibility-split Adam (gsr_adam_step_rows): the zero-gradient rows are updated on a
-        # side stream while the blend / backward kernels run.  OFF by default: measured on B200
-        # (cfg2) the streaming sweep slows the co-running blend kernels by as much as it hides
-        # (step 1.08 ms vs 0.99 ms fused), so the fused single launch stays the default
+            self._setup_peer_exchange(eps, bool(multicast))
+        # the optimiser is built over the FINAL parameter tensors (the symmetric views on the peer path):
+        # learning rates / betas / eps are read from its param_groups on every step by every path
+        self.optimizer = FusedAdam([{"params": [self.opt_params[k]], "lr": lr[k], "name": k} for k in SEGMENTS
+                                    if self.opt_params[k].numel() > 0], lr=0.0, eps=eps)
+        # statistics deltas of this rank's keyframes for the NCCL fallback (the peer path keeps them in
+        # symmetric memory)
+        self._stats_local: Optional[torch.Tensor] = None
+        # visibility-split Adam (gsr_adam_step_rows) overlapped with the rasterizer on a side stream.  OFF by
+        # default: measured on B200 (cfg2) the streaming sweep slows the co-running blend kernels by as much
+        # as it hides
         self.overlap_adam = bool(overlap_adam) and dev.type == "cuda"
-        # single rank, one keyframe: the backward pass writes only the rendered rows (no dense
-        # zero fill) and ONE masked Adam pass reads the gradient only for those rows
-        # (gsr_adam_step_rows, GSR_ADAM_ROWS_ALL) — 276 + 59*4 bytes per non-rendered Gaussian less
-        # HBM traffic per iteration than zero-fill + dense Adam, bit-identical result
+        # single rank: the backward passes write only the rendered rows (no dense zero fill) and ONE masked
+        # Adam pass reads the gradient only for those rows (gsr_adam_step_rows, GSR_ADAM_ROWS_ALL) — 276 +
+        # 59*4 bytes per non-rendered Gaussian less HBM traffic per iteration than zero-fill + dense Adam,
+        # bit-identical result
         self.masked_single_view = bool(masked_single_view) and dev.type == "cuda"
         self.serialize_side_stream = False   # profiling aid: run the side-stream work on the main stream
         self.trace = None                    # profiling aid: list collecting (label, timing event) pairs
@@ -130,8 +170,39 @@ class KeyframeBatchMapper:
         self._ev_radii: Optional[torch.cuda.Event] = None
         self._ev_side: Optional[torch.cuda.Event] = None
 
+    # ---- small helpers ---------------------------------------------------------------------------
+    def _views(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
+        v = {}
+        for name in SEGMENTS:
+            off, n, shape = self.layout[name]
+            v[name] = arena[off:off + n].view(shape)
+        return v
+
+    @property
+    def world_size(self) -> int:
+        if self.single_rank:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _group(self, name: str) -> dict:
+        return next(g for g in self.optimizer.param_groups if g.get("name") == name)
+
+    def set_lr(self, name: str, lr: float) -> None:
+        """The reference's updateLearningRate (src/gaussian_model.cpp:354-396): takes effect on every path."""
+        self._group(name)["lr"] = float(lr)
+
+    def _stream_ptr(self):
+        return C.c_void_p(torch.cuda.current_stream(self.arena.device).cuda_stream)
+
+    def _mark(self, label: str, stream) -> None:
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.trace.append((label, ev))
+
     # ---- peer-memory exchange (N > 1) ------------------------------------------------------------
-    def _setup_peer_exchange(self, lr: Dict[str, float], eps: float) -> None:
+    def _setup_peer_exchange(self, eps: float, multicast: bool) -> None:
         """Moves the gradient arena and the optimised parameters into symmetric (peer-mapped)
         memory and shards the Adam state.  Falls back to the NCCL path (with a warning) when
         symmetric memory cannot be set up on this system."""
@@ -147,11 +218,16 @@ class KeyframeBatchMapper:
                 raise RuntimeError("more than GSR_MAX_PEERS ranks")
             g_arena = symm.empty(total, dtype=torch.float32, device=dev)
             p_arena = symm.empty(total, dtype=torch.float32, device=dev)
-            radii = symm.empty(max(self.P, 1) + 16, dtype=torch.uint8, device=dev)   # one "rendered" byte per row
-            g_arena.zero_(); p_arena.zero_(); radii.zero_()
+            flags = symm.empty(max(self.P, 1) + 16, dtype=torch.uint8, device=dev)   # one "rendered" byte per row
+            g_arena.zero_(); p_arena.zero_(); flags.zero_()
             hg = symm.rendezvous(g_arena, group)
             hp = symm.rendezvous(p_arena, group)
-            hr = symm.rendezvous(radii, group)
+            hf = symm.rendezvous(flags, group)
+            st_local, hs = None, None
+            if self.stats is not None:
+                st_local = symm.empty(3 * max(self.P, 1), dtype=torch.float32, device=dev)   # accum | denom | max_radii
+                st_local.zero_()
+                hs = symm.rendezvous(st_local, group)
         except Exception as exc:  # noqa: BLE001
             print(f"[gsdf_slam_b200] peer-memory exchange unavailable ({exc!r}); using the NCCL all-reduce path",
                   file=sys.stderr)
@@ -172,48 +248,80 @@ class KeyframeBatchMapper:
         chunk = 65536
         n_chunks = (total + chunk - 1) // chunk
         owned = (n_chunks - rank + world - 1) // world if n_chunks > rank else 0
-        lo, hi = 0, total
         n_mom = max(owned * chunk, 4)
-        self.peer = dict(world=world, rank=rank, hg=hg, hp=hp, hr=hr, g_arena=g_arena, p_arena=p_arena,
-                         radii=radii, lo=lo, hi=hi, step=0, eps=float(eps), lr=dict(lr),
-                         chunk=chunk, exp_avg=torch.zeros(n_mom, dtype=torch.float32, device=dev),
+        mc_ptr = 0
+        if multicast:
+            try:
+                mc_ptr = int(getattr(hp, "multicast_ptr", 0) or 0)
+            except Exception:  # noqa: BLE001
+                mc_ptr = 0
+        self.peer = dict(world=world, rank=rank, hg=hg, hp=hp, hf=hf, hs=hs, g_arena=g_arena, p_arena=p_arena,
+                         flags=flags, stats_local=st_local, lo=0, hi=total, step=0, eps=float(eps), chunk=chunk,
+                         mc_ptr=mc_ptr,
+                         exp_avg=torch.zeros(n_mom, dtype=torch.float32, device=dev),
                          exp_avg_sq=torch.zeros(n_mom, dtype=torch.float32, device=dev),
-                         union=torch.zeros(max(self.P, 1) + 4, dtype=torch.int32, device=dev),
-                         flag_tmp=torch.zeros(max(self.P, 1), dtype=torch.bool, device=dev))
+                         union=torch.zeros(max(self.P, 1) + 4, dtype=torch.int32, device=dev))
         torch.cuda.synchronize(dev)
         dist.barrier(group)
 
-    def _step_peer(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
-        import ctypes as C
+    def exchange_bytes(self) -> Optional[dict]:
+        """Model of the NVLink traffic of one peer exchange, per rank (bench.py prints it next to the measured
+        time): parameter broadcast = this rank's shard to N-1 peers (one multicast store if available)."""
+        if self.peer is None:
+            return None
+        pe = self.peer
+        total = self.layout["_total"][1]
+        shard = 4 * total / pe["world"]
+        return {"param_shard_bytes": int(shard), "param_out_bytes_unicast": int(shard * (pe["world"] - 1)),
+                "param_in_bytes": int(shard * (pe["world"] - 1)), "multicast": bool(pe["mc_ptr"])}
 
+    def _local_stats(self, radii: torch.Tensor, dL_dmeans2D: torch.Tensor, stats_local: Optional[torch.Tensor],
+                     flags: torch.Tensor) -> None:
+        from . import _lib
+        r = radii if radii.dtype == torch.int32 else radii.to(torch.int32)
+        _lib.check(_lib.lib().gsr_peer_local_stats(self.P, C.c_void_p(r.data_ptr()), C.c_void_p(dL_dmeans2D.data_ptr()),
+                                                   C.c_void_p(stats_local.data_ptr()) if stats_local is not None else None,
+                                                   C.c_void_p(flags.data_ptr()), self._stream_ptr()),
+                   "gsr_peer_local_stats")
+
+    def _step_peer(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
         from . import _lib
         pe = self.peer
         dev = self.arena.device
-        mask = None
-        self._mark("step_begin", torch.cuda.current_stream(dev))
-        if len(keyframes) == 0:
-            self.arena.zero_()
-        for i, kf in enumerate(keyframes):
-            # one keyframe per rank: rows this rank did not render are never read by the exchange (per-row
-            # rank bitmask), so the backward pass may skip the dense zero fill.  Several keyframes: the
-            # first one writes the arena densely, the others add their rendered rows to it.
-            _, radii, _ = self.render_backward(kf, self.grad_views, on_forward=on_forward,
-                                               rendered_rows_only=(len(keyframes) == 1), accumulate=(i > 0))
-            mask = radii if mask is None else torch.maximum(mask, radii)
-        if mask is None:
-            pe["radii"].zero_()
-        else:
-            torch.gt(mask, 0, out=pe["flag_tmp"])
-            pe["radii"][: self.P].copy_(pe["flag_tmp"])
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         L = _lib.lib()
-        self._mark("render_end", torch.cuda.current_stream(dev))
-        pe["hg"].barrier(channel=0)          # every rank's gradients and radii are written
-        self._mark("barrier1_end", torch.cuda.current_stream(dev))
-        rptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hr"].buffer_ptrs])
-        _lib.check(L.gsr_peer_rank_mask_u8(rptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
-                   "gsr_peer_rank_mask_u8")
-        self._mark("mask_end", torch.cuda.current_stream(dev))
+        main = torch.cuda.current_stream(dev)
+        self._mark("step_begin", main)
+        # this rank's "rendered" flags (and statistics deltas) of the step; the previous step's second barrier
+        # guarantees that no peer still reads them
+        pe["flags"].zero_()
+        if pe["stats_local"] is not None:
+            pe["stats_local"].zero_()
+        mask = None
+        for i, kf in enumerate(keyframes):
+            # rows this rank does not render are never read by the exchange (per-row rank bitmask), so no
+            # backward pass needs the dense zero fill: the first keyframe writes its rendered rows, the others
+            # add to the rows already written and overwrite the rest (gsr_backward_args.accumulate_rows)
+            _, radii, g = self.render_backward(kf, self.grad_views, on_forward=on_forward,
+                                               rendered_rows_only=True, accumulate=(i > 0), accumulate_rows=mask)
+            self._local_stats(radii, g[0], pe["stats_local"], pe["flags"])
+            if i + 1 < len(keyframes):
+                mask = radii.clone() if mask is None else torch.maximum(mask, radii, out=mask)
+        stream = self._stream_ptr()
+        self._mark("render_end", main)
+        pe["hg"].barrier(channel=0)          # every rank's gradients, flags and statistics are written
+        self._mark("barrier1_end", main)
+        fptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hf"].buffer_ptrs])
+        if pe["stats_local"] is not None:
+            sptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hs"].buffer_ptrs])
+            st = self.stats
+            _lib.check(L.gsr_peer_stats_exchange(fptrs, sptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()),
+                                                 C.c_void_p(st["max_radii2D"].data_ptr()),
+                                                 C.c_void_p(st["xyz_gradient_accum"].data_ptr()),
+                                                 C.c_void_p(st["denom"].data_ptr()), stream), "gsr_peer_stats_exchange")
+        else:
+            _lib.check(L.gsr_peer_rank_mask_u8(fptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
+                       "gsr_peer_rank_mask_u8")
+        self._mark("mask_end", main)
         pe["step"] += 1
         a = _lib.PeerAdamArgs()
         a.n_peers, a.rank = pe["world"], pe["rank"]
@@ -222,34 +330,30 @@ class KeyframeBatchMapper:
             a.grad_peers[k] = int(pe["hg"].buffer_ptrs[k])
         segs = [n for n in ARENA_ORDER if self.layout[n][1] > 0]
         a.n_segments = len(segs)
+        betas = eps = None
         for i, n in enumerate(segs):
             off, numel, _shape = self.layout[n]
+            grp = self._group(n)
+            if betas is None:
+                betas, eps = grp["betas"], grp["eps"]
+            elif (betas, eps) != (grp["betas"], grp["eps"]):
+                raise RuntimeError("gsr_adam_step_peer needs the same betas / eps in every parameter group")
             a.segments[i].start, a.segments[i].numel = off, numel
             a.segments[i].width = numel // self.P
-            a.segments[i].lr = float(pe["lr"][n])
+            a.segments[i].lr = float(grp["lr"])
         a.shard_lo, a.shard_hi, a.shard_chunk = pe["lo"], pe["hi"], pe["chunk"]
         a.exp_avg, a.exp_avg_sq = pe["exp_avg"].data_ptr(), pe["exp_avg_sq"].data_ptr()
         a.union_mask = pe["union"].data_ptr()
-        a.beta1, a.beta2, a.eps, a.grad_scale = 0.9, 0.999, pe["eps"], float(grad_scale)
+        a.beta1, a.beta2, a.eps, a.grad_scale = float(betas[0]), float(betas[1]), float(eps), float(grad_scale)
         a.step = pe["step"]
         a.stream = stream
+        a.param_multicast = pe["mc_ptr"]
         _lib.check(L.gsr_adam_step_peer(C.byref(a)), "gsr_adam_step_peer")
-        self._mark("peer_adam_end", torch.cuda.current_stream(dev))
+        self._mark("peer_adam_end", main)
         pe["hp"].barrier(channel=0)          # every rank's parameter stores have landed
-        self._mark("step_end", torch.cuda.current_stream(dev))
+        self._mark("step_end", main)
 
-    def _views(self, arena: torch.Tensor) -> Dict[str, torch.Tensor]:
-        v = {}
-        for name in SEGMENTS:
-            off, n, shape = self.layout[name]
-            v[name] = arena[off:off + n].view(shape)
-        return v
-
-    @property
-    def world_size(self) -> int:
-        import torch.distributed as dist
-        return dist.get_world_size(self.pg) if (dist.is_available() and dist.is_initialized()) else 1
-
+    # ---- rendering -------------------------------------------------------------------------------
     def render(self, kf: Keyframe, radii_ready_event=None):
         """Forward pass of one keyframe -> the reference's 8-tuple (rasterize_points.h:18-39)."""
         p = self.params
@@ -260,7 +364,8 @@ class KeyframeBatchMapper:
                                       radii_ready_event=radii_ready_event, raw_params=self.raw_params)
 
     def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor], fwd=None, on_forward=None,
-                        rendered_rows_only: bool = False, accumulate: bool = False):
+                        rendered_rows_only: bool = False, accumulate: bool = False,
+                        accumulate_rows: Optional[torch.Tensor] = None):
         """fwd + bwd of one keyframe; parameter gradients are written into grad_views.
         ``on_forward(kf, fwd)`` runs between the two passes (e.g. to start reading the image back
         and to make the stream wait for the uploaded dL/d(image))."""
@@ -285,26 +390,66 @@ class KeyframeBatchMapper:
                                            dL_dout, p["dc"], p["sh"], self.degree, kf.campos, geom, R,
                                            binning, img, B, sample, False, want_dcov3D=False, out=out,
                                            rendered_rows_only=rendered_rows_only, accumulate=accumulate,
+                                           accumulate_rows=accumulate_rows,
                                            raw_opacity=p["opacity"] if self.raw_params else None)
         self.last_radii, self.last_color = radii, color
         return color, radii, g
 
+    def _add_stats(self, radii: torch.Tensor, dL_dmeans2D: torch.Tensor) -> None:
+        """One view's densification statistics straight into the (single-rank) state: the reference's sequence
+        (src/gaussian_mapper.cpp:443-447 + GaussianModel::addDensificationStats)."""
+        if self.stats is None or self.P == 0:
+            return
+        from . import _lib
+        st = self.stats
+        r = radii if radii.dtype == torch.int32 else radii.to(torch.int32)
+        _lib.check(_lib.lib().gsr_add_densification_stats(self.P, C.c_void_p(r.data_ptr()),
+                                                          C.c_void_p(dL_dmeans2D.data_ptr()),
+                                                          C.c_void_p(st["max_radii2D"].data_ptr()),
+                                                          C.c_void_p(st["xyz_gradient_accum"].data_ptr()),
+                                                          C.c_void_p(st["denom"].data_ptr()), self._stream_ptr()),
+                   "gsr_add_densification_stats")
+
     def accumulate(self, keyframes: Sequence[Keyframe], on_forward=None) -> None:
-        """Sum of the local keyframes' gradients -> arena (== K sequential backward() calls
-        without zero_grad, the semantics pinned in SURVEY.md §8e)."""
+        """Sum of the local keyframes' gradients -> arena, DENSE (rows nobody rendered hold zeros): what an
+        all-reduce needs.  == K sequential backward() calls without zero_grad."""
+        multi = self.world_size > 1
+        if self.stats is not None and multi:
+            if self._stats_local is None:
+                self._stats_local = torch.zeros(3 * max(self.P, 1), dtype=torch.float32, device=self.arena.device)
+                self._flags_local = torch.zeros(max(self.P, 1), dtype=torch.uint8, device=self.arena.device)
+            self._stats_local.zero_()
         if len(keyframes) == 0:
             self.arena.zero_()
             return
-        self.render_backward(keyframes[0], self.grad_views, on_forward=on_forward)  # writes in place (dense)
-        for kf in keyframes[1:]:
-            # later keyframes add their rendered rows straight into the arena (gsr_backward accumulate): no
-            # scratch arena, no dense zero fill, no dense add
-            self.render_backward(kf, self.grad_views, on_forward=on_forward, accumulate=True)
+        for i, kf in enumerate(keyframes):
+            # the first keyframe writes in place (dense: zero fill + rendered rows); later keyframes add their
+            # rendered rows straight into the arena (gsr_backward accumulate): no scratch arena, no dense add
+            _, radii, g = self.render_backward(kf, self.grad_views, on_forward=on_forward, accumulate=(i > 0))
+            if self.stats is not None:
+                if multi:
+                    self._local_stats(radii, g[0], self._stats_local, self._flags_local)
+                else:
+                    self._add_stats(radii, g[0])
 
     def allreduce(self) -> None:
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1:
+        if self.world_size > 1:
             dist.all_reduce(self.arena, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _allreduce_stats(self) -> None:
+        """NCCL fallback of gsr_peer_stats_exchange: sum {accum, denom}, max {max_radii} over the ranks."""
+        import torch.distributed as dist
+        if self.stats is None or self.world_size <= 1 or self._stats_local is None:
+            return
+        P = self.P
+        sl = self._stats_local
+        dist.all_reduce(sl[: 2 * P], op=dist.ReduceOp.SUM, group=self.pg)
+        dist.all_reduce(sl[2 * P: 3 * P], op=dist.ReduceOp.MAX, group=self.pg)
+        st = self.stats
+        st["xyz_gradient_accum"].view(-1).add_(sl[:P])
+        st["denom"].view(-1).add_(sl[P: 2 * P])
+        torch.maximum(st["max_radii2D"].view(-1), sl[2 * P: 3 * P], out=st["max_radii2D"].view(-1))
 
     def adam_step(self, grad_scale: float = 1.0) -> None:
         grads = {self.opt_params[k]: self.grad_views[k] for k in SEGMENTS
@@ -332,8 +477,6 @@ class KeyframeBatchMapper:
 
     def _adam_ranges(self, ranges, steps, grad_scale: float) -> None:
         """One fused Adam launch over sub-ranges [(segment, lo, hi)] of the parameter tensors."""
-        import ctypes as C
-
         from . import _lib
         items = []
         betas = eps = None
@@ -341,17 +484,15 @@ class KeyframeBatchMapper:
             p = self.opt_params[name].view(-1)
             st = self.optimizer._state(self.opt_params[name])
             g = self.grad_views[name].view(-1)
-            grp = next(gr for gr in self.optimizer.param_groups if gr["params"][0] is self.opt_params[name])
+            grp = self._group(name)
             betas, eps = grp["betas"], grp["eps"]
             items.append(_lib.AdamGroup(param=p[lo:hi].data_ptr(), grad=g[lo:hi].data_ptr(),
                                         exp_avg=st["exp_avg"].view(-1)[lo:hi].data_ptr(),
                                         exp_avg_sq=st["exp_avg_sq"].view(-1)[lo:hi].data_ptr(),
                                         numel=hi - lo, lr=float(grp["lr"]), step=int(steps[name])))
         arr = (_lib.AdamGroup * len(items))(*items)
-        dev = self.arena.device
         _lib.check(_lib.lib().gsr_adam_step(arr, len(items), float(betas[0]), float(betas[1]), float(eps),
-                                            float(grad_scale),
-                                            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                                            float(grad_scale), self._stream_ptr()),
                    "gsr_adam_step")
 
     def exchange_and_update(self, grad_scale: float = 1.0) -> None:
@@ -359,8 +500,7 @@ class KeyframeBatchMapper:
         ~32 MB chunks on NCCL's stream and the fused Adam consumes each chunk as soon as it has
         landed, so most of the Adam pass (HBM-bound) hides behind the NVLink transfer."""
         import torch.distributed as dist
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.pg) > 1
-        if not multi:
+        if self.world_size <= 1:
             self.adam_step(grad_scale)
             return
         chunks = self._chunks()
@@ -377,6 +517,7 @@ class KeyframeBatchMapper:
         for (_, _, ranges), w in zip(chunks, works):
             w.wait()  # the compute stream waits for this chunk only
             self._adam_ranges(ranges, steps, grad_scale)
+        self._allreduce_stats()
 
     # ---- single-rank step with the visibility-split Adam overlapped with the rasterizer -----
     def _streams(self):
@@ -390,12 +531,6 @@ class KeyframeBatchMapper:
             self._ev_radii = torch.cuda.Event()
             self._ev_side = torch.cuda.Event()
         return torch.cuda.current_stream(dev), self._side
-
-    def _mark(self, label: str, stream) -> None:
-        if self.trace is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(stream)
-            self.trace.append((label, ev))
 
     def _step_overlapped(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
         """Rows that no local keyframe renders have a zero gradient: their Adam update only needs
@@ -429,16 +564,33 @@ class KeyframeBatchMapper:
                     self._mark("side_adam_end", side)
                     self._ev_side.record(side)
             if i == 0:
-                self.render_backward(kf, self.grad_views, fwd=fwd)
+                _, _, g = self.render_backward(kf, self.grad_views, fwd=fwd)
             else:
                 if self._scratch_arena is None:
                     self._scratch_arena = torch.zeros_like(self.arena)
-                self.render_backward(kf, self._views(self._scratch_arena), fwd=fwd)
+                _, _, g = self.render_backward(kf, self._views(self._scratch_arena), fwd=fwd)
                 self.arena.add_(self._scratch_arena)
+            self._add_stats(radii, g[0])
         self._mark("backward_end", main)
         opt.step_rows(mask, opt.ROWS_WITH_GRAD, grads=grads, grad_scale=grad_scale, new_step=False)
         self._mark("main_adam_end", main)
         main.wait_event(self._ev_side)  # later work on this stream sees the complete update
+
+    def _step_masked(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
+        """Single rank, K >= 1 keyframes: no backward pass zero-fills; the first writes its rendered rows, the
+        others add to the rows already written and overwrite the rest; ONE masked Adam pass reads the gradient
+        only for the rows some keyframe rendered.  Bit-identical to zero fill + dense sum + dense Adam."""
+        mask = None
+        for i, kf in enumerate(keyframes):
+            _, radii, g = self.render_backward(kf, self.grad_views, on_forward=on_forward, rendered_rows_only=True,
+                                               accumulate=(i > 0), accumulate_rows=mask)
+            self._add_stats(radii, g[0])
+            if len(keyframes) == 1:
+                mask = radii
+            else:
+                mask = radii.clone() if mask is None else torch.maximum(mask, radii, out=mask)
+        grads = {self.opt_params[k]: self.grad_views[k] for k in SEGMENTS if self.opt_params[k].numel() > 0}
+        self.optimizer.step_rows(mask, self.optimizer.ROWS_ALL, grads=grads, grad_scale=grad_scale, new_step=True)
 
     def step(self, keyframes: Sequence[Keyframe], grad_scale: float = 1.0, on_forward=None) -> None:
         """One mapping iteration over this rank's keyframes."""
@@ -448,12 +600,8 @@ class KeyframeBatchMapper:
         if self.overlap_adam and self.world_size == 1 and len(keyframes) > 0 and self.P > 0:
             self._step_overlapped(keyframes, grad_scale, on_forward)
             return
-        if self.masked_single_view and self.world_size == 1 and len(keyframes) == 1 and self.P > 0:
-            _, radii, _ = self.render_backward(keyframes[0], self.grad_views, on_forward=on_forward,
-                                               rendered_rows_only=True)
-            grads = {self.opt_params[k]: self.grad_views[k] for k in SEGMENTS if self.opt_params[k].numel() > 0}
-            self.optimizer.step_rows(radii, self.optimizer.ROWS_ALL, grads=grads, grad_scale=grad_scale,
-                                     new_step=True)
+        if self.masked_single_view and self.world_size == 1 and len(keyframes) >= 1 and self.P > 0:
+            self._step_masked(keyframes, grad_scale, on_forward)
             return
         self.accumulate(keyframes, on_forward)
         self.exchange_and_update(grad_scale)

@@ -121,7 +121,7 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                                    binningBuffer, imageBuffer, B, sampleBuffer, debug,
                                    want_dcov3D: bool = True, out: Optional[dict] = None,
                                    rendered_rows_only: bool = False, raw_opacity: Optional[torch.Tensor] = None,
-                                   accumulate: bool = False):
+                                   accumulate: bool = False, accumulate_rows: Optional[torch.Tensor] = None):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh,
     dL_dscales, dL_drotations)   (same order as src/rasterize_points.cu:204)
 
@@ -132,10 +132,16 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     (``FusedAdam.step_rows(..., ROWS_ALL)``).
     ``raw_opacity`` (extension, row f-2): the forward ran with ``raw_params``; ``scales`` /
     ``rotations`` are raw too and dL_dopacity / dL_dscales / dL_drotations come back w.r.t. the RAW
-    parameters (chain rule through sigmoid / exp / normalize inside the backward preprocess)."""
+    parameters (chain rule through sigmoid / exp / normalize inside the backward preprocess).
+    ``accumulate`` / ``accumulate_rows`` (extension, keyframe batches): add the parameter gradients to the rows'
+    current values — to every rendered row, or only to the rows marked (> 0) in the int32 ``accumulate_rows``
+    (the rows an earlier keyframe of the batch has written); see gsr_backward_args."""
     L = _lib.lib()
     dev = means3D.device
     P = int(means3D.size(0))
+    if accumulate_rows is not None and (accumulate_rows.dtype != torch.int32 or not accumulate_rows.is_contiguous()
+                                        or accumulate_rows.numel() != P):
+        raise RuntimeError("accumulate_rows must be a contiguous int32 tensor with one entry per Gaussian")
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
     M = int(sh.size(1)) if (sh is not None and sh.dim() >= 2 and sh.size(0) != 0) else 0
     opts = dict(dtype=torch.float32, device=dev)
@@ -179,7 +185,8 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             dL_ddc=_ptr(dL_ddc), dL_dsh=_ptr(dL_dsh), dL_dscale=_ptr(dL_dscales),
             dL_drot=_ptr(dL_drotations), debug=int(bool(debug)), stream=_stream(dev),
             raw_params=int(raw_opacity is not None), rendered_rows_only=int(bool(rendered_rows_only)),
-            accumulate=int(bool(accumulate)))
+            accumulate=int(bool(accumulate)),
+            accumulate_rows=_ptr(accumulate_rows) if accumulate_rows is not None else None)
         with torch.cuda.device(dev):
             _lib.check(L.gsr_backward(C.byref(a)), "gsr_backward")
     if dL_dcov3D is None:

@@ -32,9 +32,13 @@
  * All functions return 0 on success, a negative gsr error code or a positive
  * cudaError_t otherwise; nothing throws across this ABI.  All work is enqueued
  * on `stream` (a cudaStream_t).  gsr_forward sizes the per-duplicate buffer
- * optimistically from its previous call and only waits for the 4-byte count R
- * after everything is enqueued (first call on a thread: one blocking wait; see
- * DESIGN.md).
+ * optimistically from its previous call and only waits for the 24-byte count block
+ * after everything is enqueued (first call of a context: one blocking wait; see
+ * DESIGN.md).  That host-side state lives in a gsr_context (below): pass your own, or
+ * leave `context` NULL for a default one per (host thread, device).  There is no other
+ * hidden state between calls; gsr_forward / gsr_backward may be entered from several
+ * host threads (the reference's mapper and viewer threads) on different streams.
+ * Limits: P < 2^24 Gaussians per call (GSR_ERR_BAD_ARG beyond).
  */
 #ifndef GSR_CAPI_H_
 #define GSR_CAPI_H_
@@ -50,6 +54,12 @@ extern "C" {
 #define GSR_ERR_BAD_ARG (-1)
 #define GSR_ERR_ALLOC (-2)
 #define GSR_ERR_NO_DEVICE (-3)
+
+/* Host-side state of gsr_forward (read-back event, pinned words, buffer-size and sort-kernel hints),
+ * bound to the device that is current at creation.  One context must not be used by two threads at once. */
+typedef struct gsr_context gsr_context;
+gsr_context* gsr_context_create(void);
+void gsr_context_destroy(gsr_context* ctx);
 
 /* Resizes the caller-owned scratch buffer to `bytes` and returns its device address. */
 typedef char* (*gsr_resize_fn)(void* user, size_t bytes);
@@ -90,6 +100,7 @@ typedef struct gsr_forward_args {
   void* radii_ready_event;     /* optional cudaEvent_t, recorded on `stream` right after the kernel
                                   that writes `radii` (lets a side stream start gsr_adam_step_rows
                                   phase 0 while the rest of the forward pass runs); may be NULL */
+  void* context;               /* gsr_context* or NULL (default: one per host thread and device) */
 } gsr_forward_args;
 
 typedef struct gsr_backward_args {
@@ -141,6 +152,10 @@ typedef struct gsr_backward_args {
                                   (the keyframe-batch sum of SURVEY.md §8e) without a scratch arena and a
                                   dense add.  The per-view outputs (dL_dmean2D, dL_dconic, dL_dcolor,
                                   dL_dcov3D) are overwritten as usual. */
+  const int32_t* accumulate_rows; /* optional with accumulate, [P]: only the rows with a value > 0 (written by an
+                                  earlier keyframe of the batch, e.g. the running maximum of their radii) are
+                                  added to, the other rendered rows are overwritten — so NO keyframe of a
+                                  batch needs the dense zero fill; NULL = add to every rendered row */
 } gsr_backward_args;
 
 int gsr_forward(const gsr_forward_args* a);
@@ -240,6 +255,11 @@ typedef struct gsr_peer_adam_args {
    * chunks c with c % n_peers == r (shard_lo must be 0); exp_avg / exp_avg_sq hold the owned chunks back
    * to back.  Every rank then gets the same mix of narrow and wide parameter rows, i.e. the same work. */
   int64_t shard_chunk;
+  /* Optional MULTICAST address of the parameter arena (NVLS: one mapping that the NVSwitch replicates into the
+   * arena of every rank, e.g. torch symmetric memory's multicast_ptr).  When non-NULL the new parameters leave
+   * the SM as ONE multimem store per 16 bytes instead of n_peers unicast stores: 1/n_peers of the store
+   * instructions and of the NVLink egress.  NULL: unicast stores to param_peers[0..n_peers). */
+  float* param_multicast;
 } gsr_peer_adam_args;
 int gsr_adam_step_peer(const gsr_peer_adam_args* a);
 /* union_out[row] = bitmask of the ranks that rendered the row: bit k set <=> radii_peers[k][row] > 0
@@ -419,6 +439,11 @@ int gsr_export_binning(const char* geom_buffer, const char* binning_buffer,
 int gsr_export_image(const char* image_buffer, int W, int H, float* final_T,
                      uint32_t* n_contrib, uint32_t* ranges /*[T,2]*/,
                      uint32_t* max_contrib /*[T]*/, void* stream);
+/* Measurement aid (bench.py's roofline numerators): replays the forward blend of a finished gsr_forward with an
+ * instrumented kernel and returns counts_out[3] (device) = (splat, pixel) pairs {visited while the pixel was not
+ * done, passing the power gate (exp evaluated), blended}.  scratch_color: [3,H,W] floats, overwritten. */
+int gsr_export_pair_counts(const char* binning_buffer, char* image_buffer, int R, int W, int H,
+                           const float* background, float* scratch_color, uint64_t* counts_out, void* stream);
 int gsr_export_geometry(const char* geom_buffer, int P, float* depths,
                         float* means2D, float* conic_opacity, float* rgb,
                         uint32_t* tiles_touched, uint8_t* clamped, void* stream);
