@@ -88,6 +88,21 @@ class PeerAdamArgs(C.Structure):
     ]
 
 
+class MapperConfig(C.Structure):
+    """gsr_mapper_config (include/gsr_mapper.h)."""
+    _fields_ = [("P", C.c_int64), ("M", C.c_int), ("sh_degree", C.c_int), ("rank", C.c_int), ("world", C.c_int),
+                ("lr", C.c_double * 6), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("raw_params", C.c_int), ("with_stats", C.c_int), ("lambda_dssim", C.c_float)]
+
+
+class MapperKeyframe(C.Structure):
+    """gsr_mapper_keyframe (include/gsr_mapper.h)."""
+    _fields_ = [("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("W", C.c_int), ("H", C.c_int),
+                ("dL_dpix", C.c_void_p), ("gt_image", C.c_void_p), ("mask", C.c_void_p), ("out_color", C.c_void_p)]
+
+
+GSR_MAPPER_HANDLE_BYTES = 256
 GSR_STORE_GROUPS = 6
 
 
@@ -122,6 +137,9 @@ EXPORTED_SYMBOLS = [
     "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_export_pair_counts", "gsr_sort_temp_bytes",
     "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
     "gsr_context_create", "gsr_context_destroy",
+    # include/gsr_mapper.h
+    "gsr_mapper_create", "gsr_mapper_connect", "gsr_mapper_param", "gsr_mapper_stat", "gsr_mapper_set_lr",
+    "gsr_mapper_step", "gsr_mapper_steps_done", "gsr_mapper_destroy",
 ]
 
 _lib = None
@@ -258,6 +276,23 @@ def lib() -> C.CDLL:
     L.gsr_context_create.restype = C.c_void_p
     L.gsr_context_destroy.argtypes = [C.c_void_p]
     L.gsr_context_destroy.restype = None
+    L.gsr_mapper_create.argtypes = [C.POINTER(MapperConfig), C.c_void_p]
+    L.gsr_mapper_create.restype = C.c_void_p
+    L.gsr_mapper_connect.argtypes = [C.c_void_p, C.c_void_p]
+    L.gsr_mapper_connect.restype = C.c_int
+    L.gsr_mapper_param.argtypes = [C.c_void_p, C.c_int]
+    L.gsr_mapper_param.restype = C.c_void_p
+    L.gsr_mapper_stat.argtypes = [C.c_void_p, C.c_int]
+    L.gsr_mapper_stat.restype = C.c_void_p
+    L.gsr_mapper_set_lr.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.gsr_mapper_set_lr.restype = C.c_int
+    L.gsr_mapper_step.argtypes = [C.c_void_p, C.POINTER(MapperKeyframe), C.c_int, C.c_void_p, C.c_float, C.c_void_p,
+                                  C.c_void_p]
+    L.gsr_mapper_step.restype = C.c_int
+    L.gsr_mapper_steps_done.argtypes = [C.c_void_p]
+    L.gsr_mapper_steps_done.restype = C.c_int64
+    L.gsr_mapper_destroy.argtypes = [C.c_void_p]
+    L.gsr_mapper_destroy.restype = None
     L.gsr_version.argtypes = []
     L.gsr_version.restype = C.c_char_p
     _lib = L

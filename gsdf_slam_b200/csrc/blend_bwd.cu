@@ -1,8 +1,8 @@
 // Backward alpha-blend: per-splat sums of the pixel gradients.  Replaces the reference's
 // per-splat-bucket kernel BACKWARD::PerGaussianRenderCUDA (backward.cu:463-653).
 //
-// Design (B200-first, not the reference's): one warp per 16x8 half tile, four pixels per thread, persistent
-// 4-warp CTAs pulling half tiles from an atomic cursor (blend_common.cuh).  The tile's list is REPLAYED FRONT-TO-BACK exactly like the
+// Design (B200-first, not the reference's): one 64-thread CTA per tile, four pixels per
+// thread (blend_common.cuh).  The tile's list is REPLAYED FRONT-TO-BACK exactly like the
 // forward, so T and the accumulated-colour prefix are recomputed in registers (bit-identical
 // to the forward) and no checkpoint stream exists.  For each (splat, pixel) pair that blends,
 // the same quantities as the reference (backward.cu:597-637) are formed — alpha, T,
@@ -81,24 +81,27 @@ __device__ __forceinline__ void warp_reduce9_smem(const float (&v)[9], int lane,
   __syncwarp();  // rows are rewritten by the next reduction
 }
 
-__global__ void __launch_bounds__(kBlendCtaThreads, GSR_BLEND_BWD_MINBLOCKS)
+__global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_BWD_MINBLOCKS)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ max_contrib,
                  const float4* __restrict__ rec, int W, int H, const float* __restrict__ bg,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ accum_c, const float* __restrict__ dL_dpix,
-                 float* __restrict__ acc /* [P][12] */, uint32_t* __restrict__ cursor, uint32_t num_units) {
-  __shared__ __align__(128) float4 sR_all[kBlendWarps][2][3 * kBlendBatch];  // 48-byte records, one bulk copy per batch
-  __shared__ __align__(8) uint64_t s_full_all[kBlendWarps][2];
-  __shared__ __align__(16) float s_red_all[kBlendWarps][8 * kRedStride];
+                 float* __restrict__ acc /* [P][12] */) {
+  __shared__ __align__(128) float4 sR[2][3 * kBlendBatch];  // 48-byte records, one bulk copy per batch
+  __shared__ __align__(8) uint64_t s_full[2];
+  __shared__ __align__(16) float s_red[kBlendThreads / 32][8 * kRedStride];
 
-  const int lane = threadIdx.x & 31;
-  const int wid = threadIdx.x >> 5;
-  float4 (*sR)[3 * kBlendBatch] = sR_all[wid];
-  uint64_t* s_full = s_full_all[wid];
-  float* s_red = s_red_all[wid];
+  const int lane = threadIdx.x;
+  // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel); two CTAs per tile
+  const uint32_t tile_id = tile_order[blockIdx.x >> 1];
+  const int warp = blockIdx.x & 1;  // upper / lower half of the tile
   const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
+  const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
   const size_t N = (size_t)W * H;
-  const float bgc[3] = {bg[0], bg[1], bg[2]};
+
+  const uint2 range = ranges[tile_id];
+  // nothing behind the deepest contributor of the tile receives gradient
+  int total = min((int)(range.y - range.x), (int)max_contrib[tile_id]);
 
   if (lane == 0) {
     mbar_init(&s_full[0], 1);
@@ -106,21 +109,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     fence_mbar_init();
   }
   __syncwarp();
-  uint32_t phase = 0;  // bit b: parity the next wait on buffer b expects
-
-  for (;;) {
-  // next unit: half tile `unit & 1` of the tile at position `unit >> 1` of the longest-list-first order
-  uint32_t unit = 0;
-  if (lane == 0) unit = atomicAdd(cursor, 1u);
-  unit = __shfl_sync(0xffffffffu, unit, 0);
-  if (unit >= num_units) break;
-  const uint32_t tile_id = tile_order[unit >> 1];
-  const int warp = (int)(unit & 1u);  // upper / lower half of the tile
-  const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
-
-  const uint2 range = ranges[tile_id];
-  // nothing behind the deepest contributor of the tile receives gradient
-  int total = min((int)(range.y - range.x), (int)max_contrib[tile_id]);
 
   auto issue = [&](int round) {
     const int buf = round & 1;
@@ -141,6 +129,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   float pxf[kSlots], pyf[kSlots], T[kSlots], S[kSlots];
   uint32_t last[kSlots];
   float dL[kSlots][3];
+  const float bgc[3] = {bg[0], bg[1], bg[2]};
   uint32_t my_last = 0;
 #pragma unroll
   for (int q = 0; q < kSlots; ++q) {
@@ -178,8 +167,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
   for (int i = 0; i < rounds; ++i) {
     const int buf = i & 1;
-    mbar_wait(&s_full[buf], (phase >> buf) & 1u);
-    phase ^= 1u << buf;
+    mbar_wait(&s_full[buf], (uint32_t)((i >> 1) & 1));
     __syncwarp();  // previous batch fully consumed by every lane
     if (lane == 0 && i + 1 < rounds) issue(i + 1);
 
@@ -257,7 +245,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       }
 
       float s8, s9;
-      warp_reduce9_smem(v, lane, s_red, s8, s9);
+      warp_reduce9_smem(v, lane, s_red[0], s8, s9);
       const uint32_t g = __float_as_uint(B.w);
       if ((lane & 3) == 0) {
         if (s8 != 0.f) atomicAdd(&acc[(size_t)g * 12 + (lane >> 2)], s8);
@@ -266,20 +254,16 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
       }
     }
   }
-  __syncwarp();  // the staging buffers are refilled by the next unit
-  }  // persistent loop
 }
 
 int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_order,
                      const uint32_t* max_contrib,
                      const float4* rec, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
-                     const float* dL_dpix, float* acc, uint32_t* cursor, cudaStream_t s) {
-  const unsigned tiles = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  const unsigned units = 2 * tiles;
-  const unsigned grid = blend_persistent_grid(units, blend_bwd_kernel);
-  blend_bwd_kernel<<<grid, kBlendCtaThreads, 0, s>>>(ranges, tile_order, max_contrib, rec, W, H, bg,
-                                                   final_T, n_contrib, accum_c, dL_dpix, acc, cursor, units);
+                     const float* dL_dpix, float* acc, cudaStream_t s) {
+  const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
+  blend_bwd_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, max_contrib, rec, W, H, bg,
+                                                  final_T, n_contrib, accum_c, dL_dpix, acc);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

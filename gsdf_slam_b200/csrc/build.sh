@@ -8,7 +8,7 @@ OUT="${GSR_OUT:-$HERE/../libgsr.so}"
 OBJDIR="${GSR_OBJDIR:-$HERE/obj}"
 FLAGS=(-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC
        -I"$ROOT/include" -I"$HERE" ${GSR_EXTRA_NVCC_FLAGS:-})
-SRCS=(gsr_capi.cu densify.cu ingest.cu preprocess.cu radix_sort.cu binning.cu blend_fwd.cu blend_bwd.cu preprocess_bwd.cu adam.cu peer_adam.cu loss.cu knn.cu)
+SRCS=(gsr_capi.cu densify.cu ingest.cu preprocess.cu radix_sort.cu binning.cu blend_fwd.cu blend_bwd.cu preprocess_bwd.cu adam.cu peer_adam.cu loss.cu knn.cu mapper.cu)
 mkdir -p "$OBJDIR"
 pids=()
 for s in "${SRCS[@]}"; do

@@ -190,7 +190,29 @@ int gsr_forward(const gsr_forward_args* a) {
   ImageView im = image_view(img_base, N, T);
 
   GSR_CUDA(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
-  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));  // tile_count | tile_fill | cursors
+  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));  // tile_count | tile_fill
+
+  uint32_t* host_R = ctx->pinned;
+  cudaEvent_t ev_R = ctx->ev;
+
+  // The per-duplicate buffer is sized OPTIMISTICALLY from the previous call of this context, so
+  // the whole forward pass is enqueued without waiting for R (no kernel's grid depends on
+  // it; every write is guarded by the capacity).  R is checked once everything is enqueued; if
+  // it did not fit — or on the first call — the per-duplicate stages are (re)run with the exact size.
+  // The same optimism decides which of the per-tile sort kernels are launched: lists of 512+ (mid) and
+  // 4092+ (long) entries get their kernels only if recent frames had such lists.
+  // Both hints are sticky (a class seen once keeps its kernel for kHintFrames calls, the capacity decays
+  // by 1/64 per call) so that a mapper alternating between keyframes does not pay a re-run on every call.
+  constexpr int kHintFrames = 64;
+  uint32_t& cap_hint = ctx->cap_hint;
+  int& hint_mid = ctx->hint_mid;
+  int& hint_long = ctx->hint_long;
+  if (ctx->hint_P != P || ctx->hint_W != W || ctx->hint_H != H) {  // a different scene / resolution
+    cap_hint = 0;
+    hint_mid = hint_long = -1;
+  }
+  ctx->hint_P = P; ctx->hint_W = W; ctx->hint_H = H;
+  uint32_t cap = cap_hint;
 
   PreprocessParams pp;
   std::memset(&pp, 0, sizeof(pp));
@@ -219,30 +241,10 @@ int gsr_forward(const gsr_forward_args* a) {
 
   // ranges, R and the per-tile launch order from the exact per-tile counts
   GSR_PROF("tile_meta", launch_tile_meta(im.tile_count, T, im.ranges, g.hdr, im.tile_order, im.max_contrib, s));
-  uint32_t* host_R = ctx->pinned;
-  cudaEvent_t ev_R = ctx->ev;
   // R and the numbers of mid-length / long per-tile lists (header words 0 .. 5)
   GSR_CUDA(cudaMemcpyAsync(host_R, &g.hdr->num_dup, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   GSR_CUDA(cudaEventRecord(ev_R, s));
 
-  // The per-duplicate buffer is sized OPTIMISTICALLY from the previous call of this context, so
-  // the rest of the forward pass is enqueued without waiting for R (no kernel's grid depends on
-  // it; every write is guarded by the capacity).  R is checked once everything is enqueued; if
-  // it did not fit — or on the first call — the tail is (re)run with the exact size.
-  // The same optimism decides which of the per-tile sort kernels are launched: lists of 512+ (mid) and
-  // 4092+ (long) entries get their kernels only if recent frames had such lists.
-  // Both hints are sticky (a class seen once keeps its kernel for kHintFrames calls, the capacity decays
-  // by 1/64 per call) so that a mapper alternating between keyframes does not pay a re-run on every call.
-  constexpr int kHintFrames = 64;
-  uint32_t& cap_hint = ctx->cap_hint;
-  int& hint_mid = ctx->hint_mid;
-  int& hint_long = ctx->hint_long;
-  if (ctx->hint_P != P || ctx->hint_W != W || ctx->hint_H != H) {  // a different scene / resolution
-    cap_hint = 0;
-    hint_mid = hint_long = -1;
-  }
-  ctx->hint_P = P; ctx->hint_W = W; ctx->hint_H = H;
-  uint32_t cap = cap_hint;
   uint32_t R = 0;
   bool have_R = false;
   bool do_mid = hint_mid != 0, do_long = hint_long != 0;
@@ -260,9 +262,8 @@ int gsr_forward(const gsr_forward_args* a) {
     if (!bin_base) return GSR_ERR_ALLOC;
     b = bin_view(bin_base, (size_t)cap);
     if (attempt > 0) {
-      // tile_fill | cursors are contiguous; max_contrib may hold values of the aborted attempt (blend_fwd
-      // only ever raises it)
-      GSR_CUDA(cudaMemsetAsync(im.tile_fill, 0, (size_t)((char*)im.tile_count + im.zero_bytes - (char*)im.tile_fill), s));
+      // max_contrib may hold values of the aborted attempt (blend_fwd only ever raises it)
+      GSR_CUDA(cudaMemsetAsync(im.tile_fill, 0, (size_t)T * sizeof(uint32_t), s));
       GSR_CUDA(cudaMemsetAsync(im.max_contrib, 0, (size_t)T * sizeof(uint32_t), s));
       GSR_CUDA(cudaMemsetAsync(&g.hdr->num_large, 0, sizeof(uint32_t), s));
     }
@@ -274,7 +275,7 @@ int gsr_forward(const gsr_forward_args* a) {
                                                        g.splat_rec, b.rec, do_mid, do_long, s));
     }
     GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
-                            im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, im.cursors, nullptr, s));
+                            im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, nullptr, s));
     if (!have_R) {
       GSR_CUDA(cudaEventSynchronize(ev_R));  // completed long ago: the GPU is several kernels further
       R = host_R[0];
@@ -323,12 +324,11 @@ int gsr_backward(const gsr_backward_args* a) {
   GeomView g = geom_view(a->geom_buffer, (size_t)P);
   ImageView im = image_view(a->image_buffer, N, T);
 
-  // work cursor of blend_bwd (128-byte header) + the moment sums behind it
-  GSR_CUDA(cudaMemsetAsync(g.bwd_hdr, 0, (size_t)((char*)(g.acc + (size_t)P * 12) - (char*)g.bwd_hdr), s));
+  GSR_CUDA(cudaMemsetAsync(g.acc, 0, (size_t)P * 12 * sizeof(float), s));
   if (a->R > 0) {
     BinView b = bin_view(a->binning_buffer, (size_t)a->R);  // rec does not depend on the capacity
     GSR_PROF("blend_bwd", launch_blend_bwd(W, H, im.ranges, im.tile_order, im.max_contrib, b.rec,
-                            a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, g.bwd_hdr, s));
+                            a->background, im.final_T, im.n_contrib, im.accum_c, a->dL_dpix, g.acc, s));
   }
   PreBwdParams bp;
   std::memset(&bp, 0, sizeof(bp));
@@ -444,10 +444,8 @@ int gsr_export_pair_counts(const char* binning_buffer, char* image_buffer, int R
   const uint32_t T = (uint32_t)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
   ImageView im = image_view(image_buffer, N, T);
   BinView b = bin_view(const_cast<char*>(binning_buffer), (size_t)R);  // rec does not depend on the capacity
-  GSR_CUDA(cudaMemsetAsync(im.cursors, 0, 32 * sizeof(uint32_t), s));
   return launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, background, scratch_color, im.final_T, im.n_contrib,
-                          im.accum_c, im.max_contrib, 0xffffffffu, im.cursors,
-                          reinterpret_cast<unsigned long long*>(counts_out), s);
+                          im.accum_c, im.max_contrib, 0xffffffffu, reinterpret_cast<unsigned long long*>(counts_out), s);
 }
 
 int gsr_export_geometry(const char* geom_buffer, int P, float* depths, float* means2D,

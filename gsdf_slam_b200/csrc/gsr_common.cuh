@@ -47,7 +47,6 @@ struct GeomView {
   float* rgb;                // [3P]
   uint32_t* tiles_touched;   // [P] exact number of tiles passing the opacity-aware test
   uint8_t* clamped;          // [P] bit c set <=> channel c was clamped
-  uint32_t* bwd_hdr;         // [32] word 0: work cursor of blend_bwd; directly in front of `acc`, one memset clears both
   float* acc;                // [12P] backward moment sums {Mx,My,Mxx,Mxy,Myy,M0,r,g,b,-,-,-}
   uint64_t* vis_items;       // [P] compacted rendered Gaussians (depth_bits<<32 | idx), unordered
   float4* splat_rec;         // [P][3] packed splat record of every rendered Gaussian (copied per duplicate)
@@ -56,10 +55,9 @@ struct GeomView {
 
 constexpr int kTileHistPasses = 4;   // (kept for the stand-alone sort API)
 struct ImageView {
-  // tile_count | tile_fill | cursors are contiguous and zeroed by one memset before preprocess
+  // tile_count | tile_fill are contiguous and zeroed by one memset before preprocess
   uint32_t* tile_count;      // [T] exact number of splats per tile (accumulated by preprocess)
   uint32_t* tile_fill;       // [T] slots handed out so far by the emit stage
-  uint32_t* cursors;         // [32] word 0: work cursor of blend_fwd
   size_t zero_bytes;         // bytes to clear starting at tile_count
   float* final_T;            // [N]
   uint32_t* n_contrib;       // [N]
@@ -111,7 +109,6 @@ inline GeomView geom_view(char* base, size_t P) {
   g.rgb = carve<float>(p, 3 * P);
   g.tiles_touched = carve<uint32_t>(p, P);
   g.clamped = carve<uint8_t>(p, P);
-  g.bwd_hdr = carve<uint32_t>(p, 32);   // 128 bytes, so `acc` starts right behind it
   g.acc = carve<float>(p, 12 * P);
   g.vis_items = carve<uint64_t>(p, P);
   g.splat_rec = carve<float4>(p, 3 * P);
@@ -128,7 +125,6 @@ inline ImageView image_view(char* base, size_t N, size_t T) {
   char* p = base;
   v.tile_count = carve<uint32_t>(p, T);
   v.tile_fill = carve<uint32_t>(p, T);
-  v.cursors = carve<uint32_t>(p, 32);
   v.zero_bytes = (size_t)(p - reinterpret_cast<char*>(v.tile_count));
   v.final_T = carve<float>(p, N);
   v.n_contrib = carve<uint32_t>(p, N);

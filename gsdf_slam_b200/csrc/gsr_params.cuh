@@ -92,11 +92,11 @@ int launch_export_binning(uint32_t T, const uint2* ranges, const uint64_t* items
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,
                      const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, uint32_t capacity,
-                     uint32_t* cursor, unsigned long long* pair_counts, cudaStream_t s);
+                     unsigned long long* pair_counts, cudaStream_t s);
 int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_order,
                      const uint32_t* max_contrib, const float4* rec, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
-                     const float* dL_dpix, float* acc, uint32_t* cursor, cudaStream_t s);
+                     const float* dL_dpix, float* acc, cudaStream_t s);
 int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,
                           bool zero_fill, cudaStream_t s);
 int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,

@@ -11,6 +11,12 @@
 // loads into shared memory and each thread picks its own row from there; the
 // 180-byte SH rows are fetched only for Gaussians that survive culling, one
 // coalesced warp-wide read per surviving Gaussian.  Outputs are written SoA.
+// The stage is LATENCY-bound, not bandwidth-bound (measured, round 2): a variant that fetched
+// scale / rotation only for the z-cull survivors and compacted the survivors between its stages (256-Gaussian
+// CTAs, barrier-separated phases, each with its own dependent global loads) moved fewer bytes and ran dense
+// warps, but took 111 us instead of 59 us at cfg2 (410 vs 228 us at 3 M Gaussians); appending the
+// (Gaussian, tile) hits found here to a list, so that the emit stage only streams them, cost this kernel more
+// (+22 us) than it saved there (-16 us).  All input rows in flight at once is what matters here.
 #include <cuda_runtime.h>
 #include <stdint.h>
 

@@ -13,9 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    hdr = open(os.path.join(ROOT, "include", "gsr_capi.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    return sorted(set(re.findall(r"\b(gsr_[a-z0-9_]+)\s*\(", hdr)))
+    out = set()
+    for name in ("gsr_capi.h", "gsr_mapper.h"):
+        hdr = open(os.path.join(ROOT, "include", name)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        out |= set(re.findall(r"\b(gsr_[a-z0-9_]+)\s*\(", hdr))
+    return sorted(out)
 
 
 def test_header_symbols_are_exported():
@@ -23,7 +26,7 @@ def test_header_symbols_are_exported():
     declared = _declared_symbols()
     assert declared, "no declarations parsed"
     for name in declared:
-        assert hasattr(L, name), f"{name} declared in include/gsr_capi.h but not exported"
+        assert hasattr(L, name), f"{name} declared in include/*.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
     assert b"sm_100a" in L.gsr_version()
 

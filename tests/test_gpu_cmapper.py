@@ -1,0 +1,86 @@
+"""The C entry for the keyframe-batch mapping step (include/gsr_mapper.h, csrc/mapper.cu) against the Python mapper
+(gsdf_slam_b200/mapping.py) on one GPU: same keyframes, same steps -> same parameters and densification statistics
+(both sequence the same kernels; the float atomics of the backward blend make two runs differ in the last bits).
+The 2-GPU comparison (CUDA-IPC arenas, on-device barrier, fused peer exchange) is tools/check_cmapper.py under
+torchrun, run by the builder on a 2-GPU box (gpurun_out/ keeps its output)."""
+import numpy as np
+import pytest
+import torch
+
+from util import rel_l2, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(P=40_000):
+    from gsdf_slam_b200.mapping import Keyframe
+    scene = scenes.room_scene(P, 640, 368, 320.0, 320.0, seed=14, name="cmapper_room")
+    cams = scenes.ring_cameras(4, 640, 368, 320.0, 320.0, radius=0.3)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    params = dict(means3D=t(scene.means3D), dc=t(scene.dc), sh=t(scene.sh), opacity=t(scene.opacity),
+                  scales=t(scene.scales), rotations=t(scene.rotations))
+    dL = t(scene.dL_dout)
+    kfs = [Keyframe(t(c.viewmatrix), t(c.projmatrix), t(c.campos), c.tanfovx, c.tanfovy, c.H, c.W, dL) for c in cams]
+    return scene, params, kfs, t(scene.bg)
+
+
+def test_c_mapper_matches_python_mapper_on_one_gpu():
+    from gsdf_slam_b200.cmapper import CMapper
+    from gsdf_slam_b200.mapping import SEGMENTS, KeyframeBatchMapper
+    scene, params, kfs, bg = _setup()
+    P = scene.P
+    stats = {k: torch.zeros(P, device="cuda") for k in ("max_radii2D", "xyz_gradient_accum", "denom")}
+    py = KeyframeBatchMapper({k: v.clone() for k, v in params.items()}, scene.degree, bg, stats=stats)
+    cm = CMapper(params, scene.degree, bg)
+    for step in range(3):
+        if step == 2:
+            py.set_lr("means3D", 3.2e-4)
+            cm.set_lr("means3D", 3.2e-4)
+        batch = kfs[:3] if step != 1 else kfs[1:2]
+        py.step(batch)
+        cm.step(batch)
+    torch.cuda.synchronize()
+    got = cm.params()
+    for k in SEGMENTS:
+        upd = py.opt_params[k] - params[k]
+        assert float(upd.abs().max()) > 0
+        assert rel_l2(got[k] - params[k], upd) <= 1e-5, k
+    st = cm.stats()
+    assert torch.equal(st["denom"], stats["denom"]) and torch.equal(st["max_radii2D"], stats["max_radii2D"])
+    assert rel_l2(st["xyz_gradient_accum"], stats["xyz_gradient_accum"]) <= 1e-5
+    assert float(stats["denom"].max()) >= 3
+    cm.close()
+
+
+def test_c_mapper_fused_loss_keyframes_and_image_output():
+    from gsdf_slam_b200.cmapper import CMapper
+    from gsdf_slam_b200.mapping import Keyframe, KeyframeBatchMapper
+    scene, params, kfs, bg = _setup(20_000)
+    gt = torch.rand((3, kfs[0].H, kfs[0].W), device="cuda")
+    kf = Keyframe(kfs[0].viewmatrix, kfs[0].projmatrix, kfs[0].campos, kfs[0].tanfovx, kfs[0].tanfovy, kfs[0].H,
+                  kfs[0].W, gt_image=gt)
+    py = KeyframeBatchMapper({k: v.clone() for k, v in params.items()}, scene.degree, bg)
+    cm = CMapper(params, scene.degree, bg, with_stats=False)
+    img = torch.zeros_like(gt)
+    loss = torch.zeros(3, device="cuda")
+    py.step([kf])
+    cm.step([kf], out_colors=[img], loss_out=loss)
+    torch.cuda.synchronize()
+    assert torch.equal(img, py.last_color)
+    assert torch.allclose(loss, py.last_loss, rtol=1e-6, atol=1e-7)
+    got = cm.params()
+    assert rel_l2(got["means3D"] - params["means3D"], py.opt_params["means3D"] - params["means3D"]) <= 1e-5
+    cm.close()
+
+
+def test_c_mapper_rejects_bad_configs():
+    import ctypes as C
+    from gsdf_slam_b200 import _lib
+    L = _lib.lib()
+    assert not L.gsr_mapper_create(None, None)
+    cfg = _lib.MapperConfig()
+    cfg.P, cfg.M, cfg.world, cfg.rank = 100, 7, 1, 0          # M must be 0 or 15
+    assert not L.gsr_mapper_create(C.byref(cfg), None)
+    cfg.M, cfg.world = 15, 2                                   # world > 1 needs a handle buffer
+    assert not L.gsr_mapper_create(C.byref(cfg), None)
+    assert L.gsr_mapper_step(None, None, 0, None, 1.0, None, None) != 0
