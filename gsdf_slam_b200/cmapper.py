@@ -19,6 +19,18 @@ SEG = {"means3D": 0, "dc": 1, "opacity": 2, "scales": 3, "rotations": 4, "sh": 5
 STAT = {"max_radii2D": 0, "xyz_gradient_accum": 1, "denom": 2}                      # GSR_STAT_*
 
 
+class _DevArray:
+    """Zero-copy torch view of device memory owned by the C mapper (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def _view(ptr: int, n: int, device) -> torch.Tensor:
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DevArray(ptr, n), device=device)
+
+
 class CMapper:
     def __init__(self, params: Dict[str, torch.Tensor], degree: int, bg: torch.Tensor, rank: int = 0, world: int = 1,
                  process_group=None, lr: Optional[Dict[str, float]] = None, eps: float = 1e-15, raw_params: bool = False,
@@ -58,30 +70,26 @@ class CMapper:
                 continue
             ptr = L.gsr_mapper_param(C.c_void_p(self.h), k)
             self.param_ptr[name] = (ptr, n, tuple(params[name].shape))
-            src = params[name].contiguous().float()
-            with torch.cuda.device(dev):
-                torch.cuda.current_stream(dev).synchronize()
-                rc = torch.cuda.cudart().cudaMemcpy(ptr, src.data_ptr(), n * 4, 3)   # cudaMemcpyDeviceToDevice
-            if int(rc) != 0:
-                raise RuntimeError(f"cudaMemcpy of {name} failed: {rc}")
+            # the replica lives in the mapper's (peer-mapped) arena: views of it are ordinary tensors
+            _view(ptr, n, dev).view(params[name].shape).copy_(params[name])
         self.with_stats = bool(with_stats)
+        torch.cuda.synchronize(dev)
 
-    def _read(self, ptr: int, n: int, shape) -> torch.Tensor:
-        out = torch.empty(n, dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
-            torch.cuda.synchronize(self.device)
-            rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr, n * 4, 3)
-        if int(rc) != 0:
-            raise RuntimeError(f"cudaMemcpy failed: {rc}")
-        return out.view(shape)
+    def param_views(self) -> Dict[str, torch.Tensor]:
+        """LIVE zero-copy views of this rank's parameter replica (valid until close())."""
+        return {name: _view(ptr, n, self.device).view(shape) for name, (ptr, n, shape) in self.param_ptr.items()}
 
     def params(self) -> Dict[str, torch.Tensor]:
         """Copies of this rank's parameter replica."""
-        return {name: self._read(ptr, n, shape) for name, (ptr, n, shape) in self.param_ptr.items()}
+        torch.cuda.synchronize(self.device)
+        return {k: v.clone() for k, v in self.param_views().items()}
 
     def stats(self) -> Dict[str, torch.Tensor]:
-        return {name: self._read(self.L.gsr_mapper_stat(C.c_void_p(self.h), k), self.P, (self.P,))
-                for name, k in STAT.items()} if self.with_stats else {}
+        if not self.with_stats:
+            return {}
+        torch.cuda.synchronize(self.device)
+        return {name: _view(self.L.gsr_mapper_stat(C.c_void_p(self.h), k), self.P, self.device).clone()
+                for name, k in STAT.items()}
 
     def set_lr(self, name: str, lr: float) -> None:
         _lib.check(self.L.gsr_mapper_set_lr(C.c_void_p(self.h), SEG[name], float(lr)), "gsr_mapper_set_lr")
