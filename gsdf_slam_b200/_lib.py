@@ -132,7 +132,7 @@ EXPORTED_SYMBOLS = [
     "gsr_l1_ssim_loss", "gsr_l1_ssim_workspace_bytes",
     "gsr_store_workspace_bytes", "gsr_prune_points", "gsr_densify_and_prune", "gsr_densification_postfix",
     "gsr_add_densification_stats", "gsr_reset_opacity", "gsr_voxel_dedup_workspace_bytes", "gsr_voxel_dedup",
-    "gsr_select_rows", "gsr_increase_pcd_rows", "gsr_colorize_workspace_bytes", "gsr_colorize_points",
+    "gsr_select_rows", "gsr_increase_pcd_rows", "gsr_colorize_workspace_bytes", "gsr_colorize_points", "gsr_pack_xyz",
     "gsr_ply_pack_rows", "gsr_ply_unpack_rows",
     "gsr_export_binning", "gsr_export_image", "gsr_export_geometry", "gsr_export_pair_counts", "gsr_sort_temp_bytes",
     "gsr_sort_u64", "gsr_launch_count", "gsr_version", "gsr_profile_enable", "gsr_profile_read",
@@ -245,6 +245,8 @@ def lib() -> C.CDLL:
     L.gsr_colorize_points.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
     L.gsr_colorize_points.restype = C.c_int
+    L.gsr_pack_xyz.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    L.gsr_pack_xyz.restype = C.c_int
     L.gsr_ply_pack_rows.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 8
     L.gsr_ply_pack_rows.restype = C.c_int
     L.gsr_ply_unpack_rows.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 8

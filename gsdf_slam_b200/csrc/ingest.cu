@@ -68,9 +68,32 @@ colorize_gather_kernel(const float* __restrict__ points, const uint32_t* __restr
 }  // namespace
 }  // namespace gsr
 
+namespace gsr {
+namespace {
+// point records with a stride (KITTI .bin: x, y, z, intensity) -> dense [n,3]
+__global__ void __launch_bounds__(256)
+pack_xyz_kernel(const float* __restrict__ src, int64_t n, int stride, float* __restrict__ dst) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;   // one thread per output float: coalesced writes
+  if (e >= 3 * n) return;
+  const int64_t i = e / 3;
+  dst[e] = src[i * stride + (e - 3 * i)];
+}
+}  // namespace
+}  // namespace gsr
+
 using namespace gsr;
 
 extern "C" {
+
+int gsr_pack_xyz(const float* records, int64_t n, int stride_floats, float* xyz_out, void* stream) {
+  if (n < 0 || stride_floats < 3) return GSR_ERR_BAD_ARG;
+  if (n == 0) return GSR_OK;
+  if (!records || !xyz_out) return GSR_ERR_BAD_ARG;
+  pack_xyz_kernel<<<(unsigned)((3 * n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(records, n, stride_floats,
+                                                                                                 xyz_out);
+  GSR_LAUNCHED();
+  return (int)cudaGetLastError();
+}
 
 size_t gsr_colorize_workspace_bytes(int64_t n) {
   const size_t a = ((size_t)(n > 0 ? n : 0) + 255) / 256 * 256;  // flags

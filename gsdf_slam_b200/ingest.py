@@ -48,3 +48,30 @@ def colorize_launcher(points: torch.Tensor, colors: torch.Tensor, proj: torch.Te
                                              C.byref(count), _stream(dev)), "gsr_colorize_points")
     k = int(count.value)
     return out_p[:k], out_c[:k]
+
+
+def points_from_records(records, stride_floats: int = 4, device="cuda") -> torch.Tensor:
+    """The [n,3] point tensor of a LiDAR frame from its on-disk records (KITTI .bin: x, y, z, intensity -> stride 4;
+    anything buffer-like / numpy / a tensor).  Replaces the reference's per-element fill of a CUDA tensor
+    (submodules/data_loader/data_loader.cpp:172-179: 3 n device operations) with ONE pinned host-to-device copy and
+    one repack kernel (gsr_pack_xyz)."""
+    import numpy as np
+    L = _lib.lib()
+    dev = torch.device(device)
+    if isinstance(records, torch.Tensor):
+        flat = records.reshape(-1).to(torch.float32)
+    else:
+        flat = torch.from_numpy(np.ascontiguousarray(np.frombuffer(records, dtype=np.float32)
+                                                     if not isinstance(records, np.ndarray) else records,
+                                                     dtype=np.float32).reshape(-1).copy())
+    if flat.numel() % stride_floats != 0:
+        raise RuntimeError("points_from_records: the buffer is not a whole number of records")
+    n = flat.numel() // stride_floats
+    if not flat.is_cuda:
+        flat = flat.pin_memory().to(dev, non_blocking=True)
+    out = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            _lib.check(L.gsr_pack_xyz(C.c_void_p(flat.data_ptr()), n, int(stride_floats), C.c_void_p(out.data_ptr()),
+                                      _stream(dev)), "gsr_pack_xyz")
+    return out

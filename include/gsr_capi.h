@@ -425,6 +425,11 @@ int gsr_ply_unpack_rows(int64_t P, int n_rest, const float* rows, float* xyz, fl
  * COMPACTED survivors in input order: points_out / colors_out [count,3], both with room for n rows.
  * The count is waited for and stored in *count_out_host when that is non-NULL.
  * workspace: gsr_colorize_workspace_bytes(n). */
+/* The point tensor of a LiDAR frame (submodules/data_loader/data_loader.cpp:172-179: the reference fills a CUDA
+ * tensor with one `tensor[i][j] = value` assignment per coordinate, i.e. 3 n tiny device operations): `records` is
+ * the scan as read from disk and copied to the device in ONE transfer — n records of stride_floats floats whose
+ * first three are x, y, z (KITTI .bin: 4) — and xyz_out [n,3] the dense point tensor colorize consumes. */
+int gsr_pack_xyz(const float* records, int64_t n, int stride_floats, float* xyz_out, void* stream);
 size_t gsr_colorize_workspace_bytes(int64_t n);
 int gsr_colorize_points(const float* points, int64_t n, const float* lidar_pose, const float* proj_mat,
                         const float* Tr_velo_to_cam, const float* image, int img_width, int img_height,
