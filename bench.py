@@ -450,37 +450,33 @@ def run_cfg5(args, rank, world, dev, L, scene5, params5, kfs):
 
 
 def run_exchange_parity(rank, world, dev, scene5, params5, kfs, n_steps=2):
-    """Untimed: the same `n_steps` training steps (render inputs NOT frozen) three ways."""
+    """Untimed: the same `n_steps` training steps (render inputs NOT frozen) three ways — fused peer exchange, NCCL
+    all-reduce path, one rank accumulating all keyframes sequentially — twice:
+      * eps = 1 ("linear"): the Adam update is then proportional to the reduced gradient (denominator ~ 1), so the
+        differences measure the EXCHANGE itself (bar: 1e-5, fp32 reduction order);
+      * eps = 1e-15 (the reference's): Adam's first steps are ~ lr * sign(g), so the handful of elements whose summed
+        gradient is ~0 flip with the order of the float atomics of the backward pass — in ANY implementation; the
+        run-to-run difference of the single-rank path (`noise_floor`) is printed next to the cross-path numbers."""
     import torch.distributed as dist
     from gsdf_slam_b200.mapping import SEGMENTS, KeyframeBatchMapper, partition_keyframes
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     bg = t(scene5.bg)
     local = [kfs[i] for i in partition_keyframes(len(kfs), world, rank)]
-    res = {}
-    for name, kw, batch in (("peer", dict(peer_exchange=True), local), ("nccl", dict(peer_exchange=False), local),
-                            ("sequential", dict(single_rank=True), kfs)):
-        if name == "sequential" and rank != 0:
-            continue
+
+    def run(kw, batch, eps, poison=False):
         st = zero_stats(scene5.P, dev)
-        m = KeyframeBatchMapper({k: v.clone() for k, v in params5.items()}, scene5.degree, bg, stats=st, **kw)
-        if name == "peer" and m.peer is None:
-            res[name] = None
+        m = KeyframeBatchMapper({k: v.clone() for k, v in params5.items()}, scene5.degree, bg, stats=st, eps=eps, **kw)
+        if kw.get("peer_exchange") and m.peer is None:
             del m
-            continue
-        if name == "peer":
+            return None
+        if poison:
             m.arena.fill_(float("nan"))      # rows nobody renders must never be read
         for _ in range(n_steps):
             m.step(batch)
         torch.cuda.synchronize()
-        res[name] = ({k: m.opt_params[k].clone() for k in SEGMENTS}, {k: v.clone() for k, v in st.items()})
+        out = ({k: m.opt_params[k].clone() for k in SEGMENTS}, {k: v.clone() for k, v in st.items()})
         del m
         torch.cuda.empty_cache()
-    if world > 1:
-        dist.barrier()
-    out = {"steps": n_steps, "workload": f"{scene5.name}, {len(kfs)} keyframes per step over {world} ranks, "
-                                         "training steps with live parameters"}
-    if res.get("peer") is None:
-        out["peer_path"] = "unavailable (no symmetric memory)"
         return out
 
     def upd_rel(a, b):
@@ -488,28 +484,51 @@ def run_exchange_parity(rank, world, dev, scene5, params5, kfs, n_steps=2):
         for k in SEGMENTS:
             d0 = (b[k] - params5[k]).double()
             worst = max(worst, float((a[k].double() - b[k].double()).norm() / max(float(d0.norm()), 1e-30)))
-        return worst
+        return float(f"{worst:.3e}")
 
-    pa, sa = res["peer"]
-    pb, sb = res["nccl"]
-    out["peer_vs_nccl_rel_l2"] = float(f"{upd_rel(pa, pb):.3e}")
-    digest = torch.cat([checksum(pa[k]) for k in SEGMENTS] + [checksum(sa[k]) for k in sa])
-    allg = [torch.zeros_like(digest) for _ in range(world)]
-    dist.all_gather(allg, digest)
-    out["replicas_bit_identical"] = bool(all(torch.equal(allg[0], x) for x in allg))
-    out["finite"] = all(bool(torch.isfinite(pa[k]).all()) for k in SEGMENTS)
-    if rank == 0:
-        pc, sc = res["sequential"]
-        out["vs_sequential_rel_l2"] = float(f"{upd_rel(pa, pc):.3e}")
-        out["stats_denom_equal"] = bool(torch.equal(sa["denom"], sc["denom"]))
-        out["stats_max_radii_equal"] = bool(torch.equal(sa["max_radii2D"], sc["max_radii2D"]))
-        den = float(sc["xyz_gradient_accum"].double().norm())
-        num = float((sa["xyz_gradient_accum"].double() - sc["xyz_gradient_accum"].double()).norm())
-        out["stats_accum_rel_l2"] = float(f"{num / max(den, 1e-30):.3e}")
-        out["nccl_stats_denom_equal"] = bool(torch.equal(sb["denom"], sc["denom"]))
-        out["rows_with_statistics"] = int((sc["denom"] > 0).sum())
-        out["bar"] = ("rel-L2 of the parameter update <= 1e-5 (fp32 reduction order), replicas bit-identical, "
-                      "denom / max_radii exact")
+    out = {"steps": n_steps, "workload": f"{scene5.name}, {len(kfs)} keyframes per step over {world} ranks, "
+                                         "training steps with live parameters"}
+    for tag, eps in (("linear_eps1", 1.0), ("reference_eps1e-15", 1e-15)):
+        peer = run(dict(peer_exchange=True), local, eps, poison=True)
+        nccl = run(dict(peer_exchange=False), local, eps)
+        seq = run(dict(single_rank=True), kfs, eps) if rank == 0 else None
+        seq2 = run(dict(single_rank=True), kfs, eps) if (rank == 0 and eps < 1.0) else None
+        dist.barrier()
+        blk = {}
+        if peer is None:
+            out["peer_path"] = "unavailable (no symmetric memory)"
+            return out
+        pa, sa = peer
+        pb, sb = nccl
+        blk["peer_vs_nccl_rel_l2"] = upd_rel(pa, pb)
+        digest = torch.cat([checksum(pa[k]) for k in SEGMENTS] + [checksum(sa[k]) for k in sa])
+        allg = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(allg, digest)
+        blk["replicas_bit_identical"] = bool(all(torch.equal(allg[0], x) for x in allg))
+        blk["finite"] = all(bool(torch.isfinite(pa[k]).all()) for k in SEGMENTS)
+        if rank == 0:
+            pc, sc = seq
+            blk["vs_sequential_rel_l2"] = upd_rel(pa, pc)
+            blk["nccl_vs_sequential_rel_l2"] = upd_rel(pb, pc)
+            if seq2 is not None:
+                blk["noise_floor_sequential_vs_itself_rel_l2"] = upd_rel(seq2[0], pc)
+            blk["stats_denom_equal"] = bool(torch.equal(sa["denom"], sc["denom"]))
+            blk["stats_max_radii_equal"] = bool(torch.equal(sa["max_radii2D"], sc["max_radii2D"]))
+            den = float(sc["xyz_gradient_accum"].double().norm())
+            num = float((sa["xyz_gradient_accum"].double() - sc["xyz_gradient_accum"].double()).norm())
+            blk["stats_accum_rel_l2"] = float(f"{num / max(den, 1e-30):.3e}")
+            blk["nccl_stats_denom_equal"] = bool(torch.equal(sb["denom"], sc["denom"]))
+            blk["rows_with_statistics"] = int((sc["denom"] > 0).sum())
+        out[tag] = blk
+        del peer, nccl, seq, seq2
+        torch.cuda.empty_cache()
+    lin = out.get("linear_eps1", {})
+    out["peer_vs_nccl_rel_l2"] = lin.get("peer_vs_nccl_rel_l2")
+    out["vs_sequential_rel_l2"] = lin.get("vs_sequential_rel_l2")
+    out["replicas_bit_identical"] = bool(lin.get("replicas_bit_identical")) and \
+        bool(out.get("reference_eps1e-15", {}).get("replicas_bit_identical"))
+    out["bar"] = ("linear_eps1: rel-L2 of the parameter update <= 1e-5 (fp32 reduction order); replicas bit-identical; "
+                  "denom / max_radii exact; reference_eps1e-15: at its own noise floor")
     return out
 
 
