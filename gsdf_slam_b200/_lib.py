@@ -204,9 +204,9 @@ def lib() -> C.CDLL:
     L.gsr_peer_union_mask.restype = C.c_int
     L.gsr_peer_rank_mask_u8.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     L.gsr_peer_rank_mask_u8.restype = C.c_int
-    L.gsr_peer_local_stats.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsr_peer_local_stats.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.gsr_peer_local_stats.restype = C.c_int
-    L.gsr_peer_stats_exchange.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int64,
+    L.gsr_peer_stats_exchange.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.c_int, C.c_int64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_peer_stats_exchange.restype = C.c_int
     L.gsr_l1_ssim_workspace_bytes.argtypes = [C.c_int, C.c_int]

@@ -68,23 +68,10 @@ static_assert(sizeof(HandleBlob) <= GSR_MAPPER_HANDLE_BYTES, "handle blob too la
 // Cross-GPU barrier on signal pads in peer memory: thread k posts `epoch` to slot [rank] of peer k's pad (release,
 // system scope) and then waits until slot [k] of the own pad has reached `epoch`.  Stream order puts it behind the
 // kernels whose writes it publishes; one rank per GPU, so the waiting kernels always run concurrently.
-__global__ void peer_barrier_kernel(uint32_t* const* pads, int rank, int world, uint32_t epoch) {
-  const int k = threadIdx.x;
-  if (k >= world) return;
-  __threadfence_system();
-  uint32_t* remote = pads[k] + rank;
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
-  const uint32_t* mine = pads[rank] + k;
-  uint32_t v;
-  do {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-  } while ((int32_t)(v - epoch) < 0);
-}
-
 struct PadPtrs {
   uint32_t* p[GSR_MAPPER_MAX_RANKS];
 };
-__global__ void peer_barrier_kernel_v(PadPtrs pads, int rank, int world, uint32_t epoch) {
+__global__ void peer_barrier_kernel(PadPtrs pads, int rank, int world, uint32_t epoch) {
   const int k = threadIdx.x;
   if (k >= world) return;
   __threadfence_system();
@@ -111,6 +98,7 @@ struct gsr_mapper {
   int widths[kSegs] = {3, 3, 1, 3, 4, 0};
   int64_t seg_off[kSegs] = {0}, seg_n[kSegs] = {0};
   int64_t total = 0;          // floats per arena
+  int64_t stats_stride = 0;   // floats between the three per-rank statistics delta arrays
   double lr[kSegs];
   // symmetric block of this rank: [param arena | gradient arena | stats deltas 3P | flags P+16 | signal pad]
   char* sym = nullptr;
@@ -146,7 +134,7 @@ static int mapper_barrier(gsr_mapper* m, cudaStream_t s) {
   PadPtrs pads;
   for (int k = 0; k < m->cfg.world; ++k) pads.p[k] = m->pad_ptr(k);
   m->epoch += 1;
-  peer_barrier_kernel_v<<<1, 32, 0, s>>>(pads, m->cfg.rank, m->cfg.world, m->epoch);
+  peer_barrier_kernel<<<1, 32, 0, s>>>(pads, m->cfg.rank, m->cfg.world, m->epoch);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }
@@ -188,7 +176,8 @@ gsr_mapper* gsr_mapper_create(const gsr_mapper_config* cfg, void* handle_out) {
   auto carve_off = [&](size_t bytes) { const size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
   m->off_param = carve_off((size_t)m->total * 4);
   m->off_grad = carve_off((size_t)m->total * 4);
-  m->off_stats = carve_off((size_t)3 * m->P * 4);
+  m->stats_stride = (m->P + 3) / 4 * 4;
+  m->off_stats = carve_off((size_t)3 * m->stats_stride * 4);
   m->off_flags = carve_off((size_t)m->P + 16);
   m->off_pad = carve_off(256);
   m->sym_bytes = o;
@@ -288,7 +277,7 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
     // this rank's "rendered" flags and statistics deltas of the step (the previous step's second barrier
     // guarantees that no peer still reads them)
     MAP_CUDA(cudaMemsetAsync(m->flags_ptr(rank), 0, (size_t)P + 16, s));
-    if (m->stats) MAP_CUDA(cudaMemsetAsync(m->stats_local_ptr(rank), 0, (size_t)3 * P * 4, s));
+    if (m->stats) MAP_CUDA(cudaMemsetAsync(m->stats_local_ptr(rank), 0, (size_t)3 * m->stats_stride * 4, s));
   }
   for (int i = 0; i < n; ++i) {
     const gsr_mapper_keyframe& kf = kfs[i];
@@ -350,7 +339,7 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
 
     if (world > 1) {
       MAP_RC(gsr_peer_local_stats(P, m->radii, m->dmean2D, m->stats ? m->stats_local_ptr(rank) : nullptr,
-                                  m->flags_ptr(rank), s));
+                                  m->stats_stride, m->flags_ptr(rank), s));
     } else if (m->stats) {
       MAP_RC(gsr_add_densification_stats(P, m->radii, m->dmean2D, stat_maxr, stat_accum, stat_denom, s));
     }
@@ -390,7 +379,7 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
     sl[k] = m->stats_local_ptr(k);
   }
   if (m->stats)
-    MAP_RC(gsr_peer_stats_exchange(fl, sl, world, P, m->union_mask, stat_maxr, stat_accum, stat_denom, s));
+    MAP_RC(gsr_peer_stats_exchange(fl, sl, m->stats_stride, world, P, m->union_mask, stat_maxr, stat_accum, stat_denom, s));
   else
     MAP_RC(gsr_peer_rank_mask_u8(fl, world, P, m->union_mask, s));
   gsr_peer_adam_args a;

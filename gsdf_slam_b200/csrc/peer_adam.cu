@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(256) peer_rank_mask_u8_kernel(const PeerFlagPa
 // bit-identical on all ranks — and applies sum / sum / max to its own replica.  The same kernel emits the
 // per-row rank bitmask gsr_adam_step_peer consumes (it replaces gsr_peer_rank_mask_u8 in that case).
 __global__ void __launch_bounds__(256)
-peer_local_stats_kernel(long long P, const int* __restrict__ radii, const float* __restrict__ dmean2D,
-                        float* __restrict__ stats /* [3][P] or null */, uint8_t* __restrict__ flags) {
+peer_local_stats_kernel(long long P, long long stride, const int* __restrict__ radii, const float* __restrict__ dmean2D,
+                        float* __restrict__ stats /* [3][stride] or null */, uint8_t* __restrict__ flags) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= P) return;
   const int r = radii[i];
@@ -233,8 +233,8 @@ peer_local_stats_kernel(long long P, const int* __restrict__ radii, const float*
   if (stats == nullptr) return;
   const float gx = dmean2D[3 * i], gy = dmean2D[3 * i + 1];
   stats[i] = stats[i] + sqrtf(fmaf(gy, gy, gx * gx));   // same expression as densification_stats_kernel
-  stats[P + i] = stats[P + i] + 1.0f;
-  stats[2 * P + i] = fmaxf(stats[2 * P + i], (float)r);
+  stats[stride + i] = stats[stride + i] + 1.0f;
+  stats[2 * stride + i] = fmaxf(stats[2 * stride + i], (float)r);
 }
 
 struct PeerStatsParams {
@@ -242,39 +242,72 @@ struct PeerStatsParams {
   const float* stats[GSR_MAX_PEERS];
   int n_peers;
 };
+// Four rows per thread: one 4-byte flag word per peer (a quarter of the NVLink requests of a byte per row) and
+// 16-byte statistics loads from the ranks that rendered any of the four rows.
 __global__ void __launch_bounds__(256)
-peer_stats_exchange_kernel(const PeerStatsParams a, long long P, int* __restrict__ mask_out,
+peer_stats_exchange_kernel(const PeerStatsParams a, long long P, long long stride, int* __restrict__ mask_out,
                            float* __restrict__ max_radii2D, float* __restrict__ accum, float* __restrict__ denom) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long i = 4 * ((long long)blockIdx.x * 256 + threadIdx.x);
   if (i >= P) return;
-  int m = 0;
+  const int nrow = (int)min(4LL, P - i);
+  uint32_t w[GSR_MAX_PEERS];
+  unsigned any = 0;   // bit k: rank k rendered one of the rows
 #pragma unroll
-  for (int k = 0; k < GSR_MAX_PEERS; ++k)
-    if (k < a.n_peers && a.flags[k][i]) m |= 1 << k;
-  mask_out[i] = m;
-  if (m == 0) return;
+  for (int k = 0; k < GSR_MAX_PEERS; ++k) {
+    if (k < a.n_peers) {
+      w[k] = *reinterpret_cast<const uint32_t*>(a.flags[k] + i);   // the flag buffers are padded by 16 bytes
+      if (nrow < 4) w[k] &= (1u << (8 * nrow)) - 1u;
+      any |= w[k] ? (1u << k) : 0u;
+    }
+  }
+  int m[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < GSR_MAX_PEERS; ++k) {
+    if (k < a.n_peers) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] |= ((w[k] >> (8 * j)) & 0xffu) ? (1 << k) : 0;
+    }
+  }
+  if (nrow == 4) {
+    *reinterpret_cast<int4*>(mask_out + i) = make_int4(m[0], m[1], m[2], m[3]);
+  } else {
+    for (int j = 0; j < nrow; ++j) mask_out[i + j] = m[j];
+  }
+  if (any == 0) return;
   // all remote loads first (NVLink round trips overlap), then the combination in rank order
-  float da[GSR_MAX_PEERS], dd[GSR_MAX_PEERS], dr[GSR_MAX_PEERS];
+  float4 da[GSR_MAX_PEERS], dd[GSR_MAX_PEERS], dr[GSR_MAX_PEERS];
 #pragma unroll
   for (int k = 0; k < GSR_MAX_PEERS; ++k) {
-    if (k < a.n_peers && ((m >> k) & 1)) {
-      da[k] = a.stats[k][i];
-      dd[k] = a.stats[k][P + i];
-      dr[k] = a.stats[k][2 * P + i];
+    if (k < a.n_peers && ((any >> k) & 1u)) {
+      // stride is a multiple of 4 and the peer arrays are 16-byte aligned: the 4-row group never straddles
+      da[k] = *reinterpret_cast<const float4*>(a.stats[k] + i);
+      dd[k] = *reinterpret_cast<const float4*>(a.stats[k] + stride + i);
+      dr[k] = *reinterpret_cast<const float4*>(a.stats[k] + 2 * stride + i);
     }
   }
-  float sa = 0.f, sd = 0.f, mr = 0.f;
+  float sa[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f}, mr[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < GSR_MAX_PEERS; ++k) {
-    if (k < a.n_peers && ((m >> k) & 1)) {
-      sa += da[k];
-      sd += dd[k];
-      mr = fmaxf(mr, dr[k]);
+    if (k < a.n_peers && ((any >> k) & 1u)) {
+      const float xa[4] = {da[k].x, da[k].y, da[k].z, da[k].w};
+      const float xd[4] = {dd[k].x, dd[k].y, dd[k].z, dd[k].w};
+      const float xr[4] = {dr[k].x, dr[k].y, dr[k].z, dr[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((m[j] >> k) & 1) {     // only the ranks that rendered THIS row (others hold 0 there anyway)
+          sa[j] += xa[j];
+          sd[j] += xd[j];
+          mr[j] = fmaxf(mr[j], xr[j]);
+        }
+      }
     }
   }
-  accum[i] = accum[i] + sa;
-  denom[i] = denom[i] + sd;
-  max_radii2D[i] = fmaxf(max_radii2D[i], mr);
+  for (int j = 0; j < nrow; ++j) {
+    if (m[j] == 0) continue;
+    accum[i + j] = accum[i + j] + sa[j];
+    denom[i + j] = denom[i + j] + sd[j];
+    max_radii2D[i + j] = fmaxf(max_radii2D[i + j], mr[j]);
+  }
 }
 
 }  // namespace gsr
@@ -320,31 +353,35 @@ int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_
 }
 
 int gsr_peer_local_stats(int64_t P, const int32_t* radii, const float* dL_dmeans2D, float* stats_local,
-                         uint8_t* flags, void* stream) {
+                         int64_t stats_stride, uint8_t* flags, void* stream) {
   if (P < 0) return GSR_ERR_BAD_ARG;
   if (P == 0) return GSR_OK;
-  if (!radii || !flags || (stats_local && !dL_dmeans2D)) return GSR_ERR_BAD_ARG;
+  if (!radii || !flags || (stats_local && (!dL_dmeans2D || stats_stride < P))) return GSR_ERR_BAD_ARG;
   peer_local_stats_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      P, radii, dL_dmeans2D, stats_local, flags);
+      P, stats_stride, radii, dL_dmeans2D, stats_local, flags);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }
 
-int gsr_peer_stats_exchange(const uint8_t* const* flags_peers, const float* const* stats_peers, int n_peers,
-                            int64_t P, int32_t* mask_out, float* max_radii2D, float* xyz_gradient_accum,
+int gsr_peer_stats_exchange(const uint8_t* const* flags_peers, const float* const* stats_peers, int64_t stats_stride,
+                            int n_peers, int64_t P, int32_t* mask_out, float* max_radii2D, float* xyz_gradient_accum,
                             float* denom, void* stream) {
   if (n_peers < 1 || n_peers > GSR_MAX_PEERS || P < 0 || !flags_peers || !stats_peers) return GSR_ERR_BAD_ARG;
   if (P == 0) return GSR_OK;
-  if (!mask_out || !max_radii2D || !xyz_gradient_accum || !denom) return GSR_ERR_BAD_ARG;
+  if (!mask_out || !max_radii2D || !xyz_gradient_accum || !denom || stats_stride < P || (stats_stride & 3) ||
+      ((uintptr_t)mask_out & 15))
+    return GSR_ERR_BAD_ARG;
   PeerStatsParams a;
   a.n_peers = n_peers;
   for (int k = 0; k < n_peers; ++k) {
-    if (!flags_peers[k] || !stats_peers[k]) return GSR_ERR_BAD_ARG;
+    if (!flags_peers[k] || !stats_peers[k] || ((uintptr_t)flags_peers[k] & 3) || ((uintptr_t)stats_peers[k] & 15))
+      return GSR_ERR_BAD_ARG;
     a.flags[k] = flags_peers[k];
     a.stats[k] = stats_peers[k];
   }
-  peer_stats_exchange_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      a, P, mask_out, max_radii2D, xyz_gradient_accum, denom);
+  const long long threads = (P + 3) / 4;
+  peer_stats_exchange_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, P, stats_stride, mask_out, max_radii2D, xyz_gradient_accum, denom);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -120,6 +120,7 @@ class KeyframeBatchMapper:
         # copies, so every step renders the same scene while doing the full optimiser work.
         self.opt_params = ({k: v.clone() for k, v in self.params.items()} if freeze_render_inputs
                            else self.params)
+        self._stats_stride = (max(self.P, 1) + 3) // 4 * 4     # floats between the three per-rank delta arrays
         self.stats = None
         if stats is not None:
             self.stats = {}
@@ -225,7 +226,7 @@ class KeyframeBatchMapper:
             hf = symm.rendezvous(flags, group)
             st_local, hs = None, None
             if self.stats is not None:
-                st_local = symm.empty(3 * max(self.P, 1), dtype=torch.float32, device=dev)   # accum | denom | max_radii
+                st_local = symm.empty(3 * self._stats_stride, dtype=torch.float32, device=dev)   # accum | denom | max_radii
                 st_local.zero_()
                 hs = symm.rendezvous(st_local, group)
         except Exception as exc:  # noqa: BLE001
@@ -281,7 +282,7 @@ class KeyframeBatchMapper:
         r = radii if radii.dtype == torch.int32 else radii.to(torch.int32)
         _lib.check(_lib.lib().gsr_peer_local_stats(self.P, C.c_void_p(r.data_ptr()), C.c_void_p(dL_dmeans2D.data_ptr()),
                                                    C.c_void_p(stats_local.data_ptr()) if stats_local is not None else None,
-                                                   C.c_void_p(flags.data_ptr()), self._stream_ptr()),
+                                                   self._stats_stride, C.c_void_p(flags.data_ptr()), self._stream_ptr()),
                    "gsr_peer_local_stats")
 
     def _step_peer(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
@@ -314,7 +315,8 @@ class KeyframeBatchMapper:
         if pe["stats_local"] is not None:
             sptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hs"].buffer_ptrs])
             st = self.stats
-            _lib.check(L.gsr_peer_stats_exchange(fptrs, sptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()),
+            _lib.check(L.gsr_peer_stats_exchange(fptrs, sptrs, self._stats_stride, pe["world"], self.P,
+                                                 C.c_void_p(pe["union"].data_ptr()),
                                                  C.c_void_p(st["max_radii2D"].data_ptr()),
                                                  C.c_void_p(st["xyz_gradient_accum"].data_ptr()),
                                                  C.c_void_p(st["denom"].data_ptr()), stream), "gsr_peer_stats_exchange")
@@ -416,7 +418,7 @@ class KeyframeBatchMapper:
         multi = self.world_size > 1
         if self.stats is not None and multi:
             if self._stats_local is None:
-                self._stats_local = torch.zeros(3 * max(self.P, 1), dtype=torch.float32, device=self.arena.device)
+                self._stats_local = torch.zeros(3 * self._stats_stride, dtype=torch.float32, device=self.arena.device)
                 self._flags_local = torch.zeros(max(self.P, 1), dtype=torch.uint8, device=self.arena.device)
             self._stats_local.zero_()
         if len(keyframes) == 0:
@@ -442,14 +444,14 @@ class KeyframeBatchMapper:
         import torch.distributed as dist
         if self.stats is None or self.world_size <= 1 or self._stats_local is None:
             return
-        P = self.P
+        P, S = self.P, self._stats_stride
         sl = self._stats_local
-        dist.all_reduce(sl[: 2 * P], op=dist.ReduceOp.SUM, group=self.pg)
-        dist.all_reduce(sl[2 * P: 3 * P], op=dist.ReduceOp.MAX, group=self.pg)
+        dist.all_reduce(sl[: 2 * S], op=dist.ReduceOp.SUM, group=self.pg)
+        dist.all_reduce(sl[2 * S: 3 * S], op=dist.ReduceOp.MAX, group=self.pg)
         st = self.stats
         st["xyz_gradient_accum"].view(-1).add_(sl[:P])
-        st["denom"].view(-1).add_(sl[P: 2 * P])
-        torch.maximum(st["max_radii2D"].view(-1), sl[2 * P: 3 * P], out=st["max_radii2D"].view(-1))
+        st["denom"].view(-1).add_(sl[S: S + P])
+        torch.maximum(st["max_radii2D"].view(-1), sl[2 * S: 2 * S + P], out=st["max_radii2D"].view(-1))
 
     def adam_step(self, grad_scale: float = 1.0) -> None:
         grads = {self.opt_params[k]: self.grad_views[k] for k in SEGMENTS

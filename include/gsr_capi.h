@@ -277,16 +277,17 @@ int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_
  * GaussianModel::addDensificationStats, src/gaussian_model.cpp:667-681).
  * gsr_peer_local_stats: after each LOCAL keyframe's backward pass; for the rows with radii > 0 it sets
  *   flags[row] = 1 and, when stats_local != NULL, adds that view's terms to the rank's per-step deltas
- *   stats_local = [accum P | denom P | max_radii P] (floats; the caller zeroes flags and stats_local at the
- *   start of the step; both live in peer-mapped memory).
+ *   stats_local = [accum | denom | max_radii], three arrays of stats_stride >= P floats each (stats_stride a
+ *   multiple of 4, base 16-byte aligned; the caller zeroes flags — P + 16 bytes, 4-byte aligned — and stats_local
+ *   at the start of the step; both live in peer-mapped memory).
  * gsr_peer_stats_exchange: after the cross-rank barrier; mask_out[row] = bitmask of the ranks whose flag is
  *   set (what gsr_adam_step_peer consumes), and the replicated statistics of THIS rank receive
  *   xyz_gradient_accum += sum_k accum_k, denom += sum_k denom_k, max_radii2D = max(max_radii2D, max_k ...)
  *   over the ranks that rendered the row, in rank order (bit-identical replicas). */
 int gsr_peer_local_stats(int64_t P, const int32_t* radii, const float* dL_dmeans2D, float* stats_local,
-                         uint8_t* flags, void* stream);
-int gsr_peer_stats_exchange(const uint8_t* const* flags_peers, const float* const* stats_peers, int n_peers,
-                            int64_t P, int32_t* mask_out, float* max_radii2D, float* xyz_gradient_accum,
+                         int64_t stats_stride, uint8_t* flags, void* stream);
+int gsr_peer_stats_exchange(const uint8_t* const* flags_peers, const float* const* stats_peers, int64_t stats_stride,
+                            int n_peers, int64_t P, int32_t* mask_out, float* max_radii2D, float* xyz_gradient_accum,
                             float* denom, void* stream);
 
 /* ---- Gaussian-store surgery: densify / prune / increasePcd ----

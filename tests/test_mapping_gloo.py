@@ -73,11 +73,11 @@ class _FakeMapper(KeyframeBatchMapper):
         vis = radii > 0
         flags[: self.P][vis] = 1
         if stats_local is not None:
-            P = self.P
+            P, S = self.P, self._stats_stride
             norm = torch.sqrt(dL_dmeans2D[:, 0] ** 2 + dL_dmeans2D[:, 1] ** 2)
             stats_local[:P][vis] += norm[vis]
-            stats_local[P:2 * P][vis] += 1.0
-            stats_local[2 * P:3 * P][vis] = torch.maximum(stats_local[2 * P:3 * P][vis], radii[vis].float())
+            stats_local[S:S + P][vis] += 1.0
+            stats_local[2 * S:2 * S + P][vis] = torch.maximum(stats_local[2 * S:2 * S + P][vis], radii[vis].float())
 
     def _add_stats(self, radii, dL_dmeans2D):       # single rank: the reference's per-view sequence
         if self.stats is None:
