@@ -8,6 +8,11 @@
 // 4-warp CTAs (+5 % / +12 % time: the compiler loses the knowledge that the CTA is ONE warp, which keeps the
 // per-tile address arithmetic on the uniform datapath) and with single-warp CTAs (+2 %) — and fewer resident CTAs
 // per SM (24: +10 %, 16: +28 %).  The hardware's CTA scheduler over the longest-list-first order stays.
+// Also measured: the per-pixel arithmetic of pixel PAIRS issued as packed fp32x2 instructions (FFMA2 / FMUL2,
+// sm_100; bit-identical results incl. a packed restatement of expf): 17 % / 12 % fewer SASS instructions per
+// loop iteration, but forward 180 vs 179 us and backward 285 vs 265 us at cfg2 — the selects that replace the
+// per-pixel branches load the half-rate ALU pipe and FFMA2 occupies the FMA pipe for two cycles
+// (tools/microbench/issue_bench.cu) — so the scalar kernels stay.
 #pragma once
 #include <stdint.h>
 

@@ -18,16 +18,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include <stdlib.h>
-
 #include "blend_common.cuh"
-#include "f32x2.cuh"
 #include "gsr_common.cuh"
 #include "tma.cuh"
-
-#ifndef GSR_BLEND_PACKED_DEFAULT
-#define GSR_BLEND_PACKED_DEFAULT 0
-#endif
 
 namespace gsr {
 
@@ -191,175 +184,6 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Packed variant: the same kernel with the per-pixel floating-point work of a pixel PAIR issued as fp32x2
-// instructions (f32x2.cuh: FFMA2 / FMUL2, sm_100 only).  The kernel is bound by instruction issue, not by the FMA
-// pipe, so halving the issue slots of the exp chains (5 of their 8 steps have a packed form) and of the blend
-// update pays even though the pipe needs two cycles per packed instruction.  Every operation is the one the
-// scalar kernel performs, on the same operands, with the same rounding: results are bit-identical.
-// A pixel of a pair that does not take part in a step blends with alpha = 0, which leaves its state untouched
-// bit for bit (C + T*0*c = C) — that replaces the per-pixel branches.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_FWD_MINBLOCKS)
-blend_fwd_packed_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
-                        const float4* __restrict__ rec, int W, int H, const float* __restrict__ bg,
-                        float* __restrict__ out_color, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                        float* __restrict__ accum_c, uint32_t* __restrict__ max_contrib, uint32_t capacity) {
-  __shared__ __align__(128) float4 sR[2][3 * kBlendBatch];
-  __shared__ __align__(8) uint64_t s_full[2];
-
-  const int lane = threadIdx.x;
-  const uint32_t tile_id = tile_order[blockIdx.x >> 1];
-  const int warp = blockIdx.x & 1;  // upper / lower half of the tile
-  const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
-  const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
-
-  float pxf[kSlots], pyf[kSlots];
-  uint32_t pix_id[kSlots];
-  bool inside[kSlots];
-#pragma unroll
-  for (int q = 0; q < kSlots; ++q) {
-    const uint32_t px = slot_px(tile_x, lane, q);
-    const uint32_t py = slot_py(tile_y, warp, lane, q);
-    inside[q] = px < (uint32_t)W && py < (uint32_t)H;
-    pix_id[q] = (uint32_t)W * py + px;
-    pxf[q] = (float)px;
-    pyf[q] = (float)py;
-  }
-
-  const uint2 range = ranges[tile_id];
-  const int total = range.y <= capacity ? (int)(range.y - range.x) : 0;
-  const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
-
-  if (lane == 0) {
-    mbar_init(&s_full[0], 1);
-    mbar_init(&s_full[1], 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
-
-  auto issue = [&](int round) {
-    const int buf = round & 1;
-    const int start = range.x + round * kBlendBatch;
-    const int cnt = min(kBlendBatch, total - round * kBlendBatch);
-    const uint32_t bytes = (uint32_t)cnt * 48u;
-    mbar_expect_tx(&s_full[buf], bytes);
-    bulk_g2s(&sR[buf][0], rec + 3 * (size_t)start, bytes, &s_full[buf]);
-  };
-  if (lane == 0 && rounds > 0) issue(0);
-
-  // pair p = pixels (2p, 2p+1): same row of the half tile, 8 pixels apart; {lo, hi} of every packed register.
-  // hi[q]: largest power a splat may have at pixel q and still be evaluated: 0 while the pixel is live (the
-  // reference skips power > 0), -inf once it is finished or lies outside the image — a finished pixel costs no flag
-  float hi[kSlots];
-  uint32_t last_contributor[kSlots];
-  float T[kSlots], C[kSlots][3];   // pair p = slots (2p, 2p+1)
-  const f32x2 kOne2 = 0x3f8000003f800000ull;
-#pragma unroll
-  for (int q = 0; q < kSlots; ++q) {
-    hi[q] = inside[q] ? 0.0f : -INFINITY;
-    T[q] = 1.0f;
-    C[q][0] = C[q][1] = C[q][2] = 0.f;
-    last_contributor[q] = 0;
-  }
-  bool all_done = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3])) < 0.0f;
-
-  for (int i = 0; i < rounds; ++i) {
-    const int buf = i & 1;
-    mbar_wait(&s_full[buf], (uint32_t)((i >> 1) & 1));
-    if (__all_sync(0xffffffffu, all_done)) break;
-    if (lane == 0 && i + 1 < rounds) issue(i + 1);
-
-    const int cnt = min(kBlendBatch, total - i * kBlendBatch);
-    const uint32_t pos0 = (uint32_t)i * kBlendBatch;
-    for (int j = 0; !all_done && j < cnt; j++) {
-      const float4 A = sR[buf][3 * j];
-      const float4 B = sR[buf][3 * j + 1];
-      const float2 xy = {A.x, A.y};
-      const float4 con_o = {A.z, A.w, B.x, B.y};
-      // gate of all four pixels (scalar: the four powers share most of their sub-expressions)
-      float pw[kSlots];
-      bool cand[kSlots];
-      bool any_cand = false;
-#pragma unroll
-      for (int q = 0; q < kSlots; ++q) {
-        float2 d = {xy.x - pxf[q & 1], xy.y - pyf[q & 2]};
-        float power = -0.5f * (con_o.x * d.x * d.x + con_o.z * d.y * d.y) - con_o.y * d.x * d.y;
-        pw[q] = power;
-        cand[q] = !(power > hi[q]) && !(power < B.z);
-        any_cand = any_cand || cand[q];
-      }
-      if (!any_cand) continue;
-      // one pair at a time: exp / alpha = min(0.99, opacity * exp(power)), then the blend update; a pixel of the
-      // pair that does not take part blends with alpha = 0 — the identity, bit for bit
-      bool any_fin = false;
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        const int q0 = 2 * p, q1 = 2 * p + 1;
-        if (!(cand[q0] || cand[q1])) continue;
-        const f32x2 a2 = mul2(bc2(con_o.w), expf2(pk2(pw[q0], pw[q1])));
-        float a_lo, a_hi;
-        unpk2(a2, a_lo, a_hi);
-        a_lo = min(0.99f, a_lo);
-        a_hi = min(0.99f, a_hi);
-        const bool l0 = cand[q0] && !(a_lo < 1.0f / 255.0f), l1 = cand[q1] && !(a_hi < 1.0f / 255.0f);
-        if (!(l0 || l1)) continue;
-        const float4 col = sR[buf][3 * j + 2];
-        // test_T = T * (1 - alpha)
-        const f32x2 Tp = pk2(T[q0], T[q1]);
-        const f32x2 test2 = mul2(Tp, rsub2(pk2(l0 ? a_lo : 0.0f, l1 ? a_hi : 0.0f), kOne2));
-        float t_lo, t_hi;
-        unpk2(test2, t_lo, t_hi);
-        const bool fin0 = l0 && t_lo < 0.0001f, fin1 = l1 && t_hi < 0.0001f;
-        const bool ok0 = l0 && !fin0, ok1 = l1 && !fin1;
-        hi[q0] = fin0 ? -INFINITY : hi[q0];
-        hi[q1] = fin1 ? -INFINITY : hi[q1];
-        any_fin = any_fin || fin0 || fin1;
-        // C += colour * alpha * T;  T *= (1 - alpha)
-        const f32x2 am = pk2(ok0 ? a_lo : 0.0f, ok1 ? a_hi : 0.0f);
-        fma2_acc(C[q0][0], C[q1][0], Tp, mul2(bc2(col.x), am));
-        fma2_acc(C[q0][1], C[q1][1], Tp, mul2(bc2(col.y), am));
-        fma2_acc(C[q0][2], C[q1][2], Tp, mul2(bc2(col.z), am));
-        mul2_by(T[q0], T[q1], rsub2(am, kOne2));
-        last_contributor[q0] = ok0 ? pos0 + j + 1 : last_contributor[q0];
-        last_contributor[q1] = ok1 ? pos0 + j + 1 : last_contributor[q1];
-      }
-      if (any_fin) all_done = fmaxf(fmaxf(hi[0], hi[1]), fmaxf(hi[2], hi[3])) < 0.0f;
-    }
-  }
-
-  const size_t N = (size_t)W * H;
-  uint32_t my_max = 0;
-#pragma unroll
-  for (int q = 0; q < kSlots; ++q) {
-    const float Tq = T[q];
-    const float* Cq = C[q];
-    if (inside[q]) {
-      final_T[pix_id[q]] = Tq;
-      n_contrib[pix_id[q]] = last_contributor[q];
-      out_color[0 * N + pix_id[q]] = Cq[0] + Tq * bg[0];
-      out_color[1 * N + pix_id[q]] = Cq[1] + Tq * bg[1];
-      out_color[2 * N + pix_id[q]] = Cq[2] + Tq * bg[2];
-      accum_c[0 * N + pix_id[q]] = Cq[0];
-      accum_c[1 * N + pix_id[q]] = Cq[1];
-      accum_c[2 * N + pix_id[q]] = Cq[2];
-    }
-    my_max = max(my_max, last_contributor[q]);
-  }
-  const uint32_t wmax = __reduce_max_sync(0xffffffffu, my_max);
-  if (lane == 0) atomicMax(&max_contrib[tile_id], wmax);
-}
-
-// developer knob: GSR_BLEND_PACKED=0/1 selects the scalar / packed kernels at run time (A/B in one binary)
-static bool blend_fwd_use_packed() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("GSR_BLEND_PACKED");
-    v = e ? (atoi(e) != 0) : GSR_BLEND_PACKED_DEFAULT;
-  }
-  return v != 0;
-}
-
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,
                      const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, uint32_t capacity,
@@ -368,9 +192,6 @@ int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_ord
   if (pair_counts != nullptr)
     blend_fwd_kernel<true><<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec, W, H, bg, out_color, final_T,
                                                             n_contrib, accum_c, max_contrib, capacity, pair_counts);
-  else if (blend_fwd_use_packed())
-    blend_fwd_packed_kernel<<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec, W, H, bg, out_color, final_T,
-                                                             n_contrib, accum_c, max_contrib, capacity);
   else
     blend_fwd_kernel<false><<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec, W, H, bg, out_color, final_T,
                                                              n_contrib, accum_c, max_contrib, capacity, nullptr);
