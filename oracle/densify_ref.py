@@ -7,9 +7,13 @@ hand-derived expectations, tests/test_densify_oracle.py) and on CUDA tensors (th
 tests compare the product's kernels with it on identical inputs).  Only tests/ may import this
 module; nothing under gsdf_slam_b200/ does.
 
-Parity status: the reference has no tests or golden vectors for these functions, so the pin is
-(a) the hand-derived tiny case and (b) ATen itself — "parity unpinned" in the strict sense of a
-reference-produced vector, like the Adam oracle.
+Parity status: PINNED.  The reference has no tests or golden vectors for these functions, but its own code
+is compiled here: oracle/build_ref_densify.py extracts the bodies of GaussianModel::{prunePoints,
+densificationPostfix, densifyAndSplit, densifyAndClone, densifyAndPrune, resetOpacity, addDensificationStats, ...}
+from /root/reference/src/gaussian_model.cpp at build time and compiles them (oracle/_ref/gsdf_ref_densify.so,
+`ref_module()` / `reference_*` below).  tests/test_densify_oracle.py checks this restatement against that module on
+CPU tensors, tests/test_gpu_densify.py checks the product's kernels against it on the GPU.  (increasePcd /
+createFromPcd need the whole GaussianModel class and stay restated.)
 
 The model state is a dict of tensors with the reference's member names and shapes:
   xyz_ [P,3], features_dc_ [P,1,3], features_rest_ [P,M,3], opacity_ [P,1], scaling_ [P,3],
@@ -19,7 +23,85 @@ The model state is a dict of tensors with the reference's member names and shape
 """
 from __future__ import annotations
 
+import importlib.util
+import os
+
 import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "gsdf_ref_densify.so")
+_mod = None
+
+
+def ref_module():
+    """The reference's own densification code, compiled (None when oracle/_ref/gsdf_ref_densify.so is absent)."""
+    global _mod
+    if _mod is None and os.path.exists(_SO):
+        spec = importlib.util.spec_from_file_location("gsdf_ref_densify", _SO)
+        _mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_mod)
+    return _mod
+
+
+def _flat(st):
+    return ([st[n] for n in PARAMS], list(st["exp_avg"]), list(st["exp_avg_sq"]), st["exist_since_iter_"],
+            st["xyz_gradient_accum_"], st["denom_"], st["max_radii2D_"])
+
+
+def _unflat(out):
+    st = {n: out[g] for g, n in enumerate(PARAMS)}
+    st["exp_avg"] = list(out[6:12])
+    st["exp_avg_sq"] = list(out[12:18])
+    st["exist_since_iter_"], st["xyz_gradient_accum_"], st["denom_"], st["max_radii2D_"] = out[18:22]
+    return st
+
+
+def reference_densify_and_prune(st, max_grad, min_opacity, extent, max_screen_size, percent_dense, seed, step=7):
+    """The compiled reference's densifyAndPrune on a copy of `st`.  Returns (new_state, noise): `noise` is the
+    standard-normal tensor its at::normal(means, stds) call drew (at::normal(Tensor, Tensor) fills the output with
+    N(0,1) from the default generator, then multiplies by stds and adds means), reproduced by re-seeding."""
+    m = ref_module()
+    dev = st["xyz_"].device
+    torch.manual_seed(seed)
+    out = m.densify_and_prune(*_flat(st), float(max_grad), float(min_opacity), float(extent), int(max_screen_size),
+                              float(percent_dense), int(step))
+    # number of rows densifyAndSplit selected == rows at::normal drew for (N = 2 copies each)
+    grads = st["xyz_gradient_accum_"] / st["denom_"]
+    grads[grads.isnan()] = 0.0
+    f32 = lambda v: float(torch.tensor(v, dtype=torch.float32))  # noqa: E731
+    n_clone = int((torch.logical_and(torch.linalg.vector_norm(grads, dim=-1) >= f32(max_grad),
+                                     torch.exp(st["scaling_"]).max(dim=1).values <= f32(percent_dense) * f32(extent))).sum())
+    padded = torch.zeros(st["xyz_"].shape[0] + n_clone, device=dev)
+    padded[: grads.shape[0]] = grads.squeeze()
+    scal = torch.cat([st["scaling_"], st["scaling_"][:0]])   # clones are appended: recompute on the grown state below
+    st2, _ = densify_and_clone(clone_state(st), grads, f32(max_grad), f32(extent), f32(percent_dense))
+    sel = torch.logical_and(padded >= f32(max_grad),
+                            torch.exp(st2["scaling_"]).max(dim=1).values > f32(percent_dense) * f32(extent))
+    rows = 2 * int(sel.sum())
+    torch.manual_seed(seed)
+    noise = torch.normal(torch.zeros((rows, 3), device=dev), torch.ones((rows, 3), device=dev))
+    del scal
+    return _unflat(out), noise
+
+
+def reference_densify_and_clone(st, max_grad, extent, percent_dense, step=7):
+    """densifyAndClone of the compiled reference (runs on CPU too; densifyAndSplit needs CUDA: the reference's
+    build_rotation allocates on torch::kCUDA, include/general_utils.h:46)."""
+    return _unflat(ref_module().densify_and_clone(*_flat(st), float(max_grad), float(extent), float(percent_dense),
+                                                  int(step)))
+
+
+def reference_prune_points(st, mask, step=7):
+    return _unflat(ref_module().prune_points(*_flat(st), mask, int(step)))
+
+
+def reference_reset_opacity(st, step=7):
+    return _unflat(ref_module().reset_opacity(*_flat(st), int(step)))
+
+
+def reference_add_densification_stats(st, viewspace_grad, update_filter):
+    """GaussianModel::addDensificationStats alone (the max_radii2D line lives in the mapper)."""
+    return ref_module().add_densification_stats(st["xyz_gradient_accum_"], st["denom_"], viewspace_grad, update_filter)
 
 PARAMS = ("xyz_", "features_dc_", "features_rest_", "opacity_", "scaling_", "rotation_")
 C0 = 0.28209479177387814  # include/sh_utils.h:33 (a float constant there)

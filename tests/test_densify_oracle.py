@@ -3,9 +3,12 @@ host-side mirror's argument handling.  The reference has no tests for these func
 the expectations below are derived by hand from src/gaussian_model.cpp:431-665 and :207-317."""
 import math
 
+import pytest
+
 import torch
 
 from oracle import densify_ref as R
+from oracle import densify_ref as dr
 
 
 def _tiny():
@@ -104,3 +107,47 @@ def test_store_struct_layout_matches_header():
     # int64, int64, int32 (+pad), 18 pointers, 4 pointers
     assert C.sizeof(_lib.GaussianStoreC) == 8 + 8 + 8 + 18 * 8 + 4 * 8
     assert C.sizeof(_lib.DensifyArgs) == 4 * 4 + 2 * 4 + 8 + 8 + 8
+
+
+# ---- the restatement against the reference's OWN code, compiled (oracle/build_ref_densify.py) -----------------
+def _same_state(a, b, tol=0.0):
+    for name in dr.PARAMS + ("exist_since_iter_", "xyz_gradient_accum_", "denom_", "max_radii2D_"):
+        assert a[name].shape == b[name].shape, name
+        if tol == 0.0 or a[name].dtype != torch.float32:
+            assert torch.equal(a[name], b[name]), name
+        else:
+            assert torch.allclose(a[name], b[name], rtol=tol, atol=tol), name
+    for key in ("exp_avg", "exp_avg_sq"):
+        for g in range(6):
+            assert torch.equal(a[key][g].reshape(b[key][g].shape), b[key][g]), (key, g)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_restatement_matches_the_compiled_reference_densify_and_clone(seed):
+    """densifyAndClone + densificationPostfix (the whole densifyAndPrune needs CUDA in the reference — its
+    build_rotation allocates on torch::kCUDA — and is compared on the GPU box: tests/test_gpu_densify.py)."""
+    if dr.ref_module() is None:
+        pytest.skip("oracle/_ref/gsdf_ref_densify.so not built")
+    st = dr.random_state(1500, 15, seed=seed)
+    ref_st = dr.reference_densify_and_clone(dr.clone_state(st), 0.0002, 4.0, 0.01)
+    grads = st["xyz_gradient_accum_"] / st["denom_"]
+    grads[grads.isnan()] = 0.0
+    f32 = lambda v: float(torch.tensor(v, dtype=torch.float32))  # noqa: E731
+    mine, n_clone = dr.densify_and_clone(dr.clone_state(st), grads, f32(0.0002), f32(4.0), f32(0.01))
+    assert n_clone > 0 and mine["xyz_"].shape[0] == st["xyz_"].shape[0] + n_clone
+    _same_state(mine, ref_st)
+
+
+def test_restatement_matches_the_compiled_reference_prune_reset_and_stats():
+    if dr.ref_module() is None:
+        pytest.skip("oracle/_ref/gsdf_ref_densify.so not built")
+    st = dr.random_state(800, 15, seed=9)
+    g = torch.Generator().manual_seed(4)
+    mask = torch.rand(800, generator=g) < 0.3
+    _same_state(dr.prune_points(dr.clone_state(st), mask), dr.reference_prune_points(dr.clone_state(st), mask))
+    _same_state(dr.reset_opacity(dr.clone_state(st)), dr.reference_reset_opacity(dr.clone_state(st)))
+    radii = torch.where(torch.rand(800, generator=g) < 0.6, torch.rand(800, generator=g) * 30, torch.zeros(800))
+    grad = torch.randn(800, 3, generator=g)
+    mine = dr.add_densification_stats(dr.clone_state(st), grad, radii)
+    accum, denom = dr.reference_add_densification_stats(dr.clone_state(st), grad, radii > 0)
+    assert torch.equal(mine["xyz_gradient_accum_"], accum) and torch.equal(mine["denom_"], denom)

@@ -264,3 +264,58 @@ def test_mapping_loop_with_varying_row_count_stays_in_lockstep():
         _assert_equal_states(_model_state(m), ref)
         sizes.append(m.P)
     assert len(set(sizes)) == len(sizes)           # the row count really changed every round
+
+
+# ---- against the reference's OWN code, compiled (oracle/build_ref_densify.py -> oracle/_ref/gsdf_ref_densify.so) -----
+@pytest.mark.parametrize("P,M,screen", [(120_000, 15, 20), (30_001, 3, 0)])
+def test_densify_and_prune_against_the_compiled_reference(P, M, screen):
+    """densifyAndPrune of src/gaussian_model.cpp:644-665 itself (clone, split with at::normal + build_rotation + bmm,
+    the two prunes, the Adam-state surgery keyed by TensorImpl): (a) pins the ATen restatement oracle/densify_ref.py on
+    the GPU, bit for bit; (b) the product's fused kernel against it with the bars of this file."""
+    if R.ref_module() is None:
+        pytest.skip("oracle/_ref/gsdf_ref_densify.so not built")
+    st = R.random_state(P, M, seed=17 + P % 7, device="cuda")
+    ref, noise = R.reference_densify_and_prune(R.clone_state(st), 0.0002, 0.005, 4.0, screen, 0.01, seed=1234 + P)
+    mine, rc = R.densify_and_prune(R.clone_state(st), 0.0002, 0.005, 4.0, screen, 0.01, noise=noise)
+    assert rc["cloned"] > P // 50 and rc["split"] > P // 50 and noise.shape[0] == 2 * rc["split"]
+    _assert_equal_states(mine, ref)                               # (a) restatement == reference code, sampled rows too
+    m = _model(st, M)
+    pad = torch.zeros((2 * P, 3), device="cuda")
+    pad[: noise.shape[0]] = noise
+    counts = m.densifyAndPrune(0.0002, 0.005, 4.0, screen, noise=pad)
+    got = _model_state(m)
+    assert counts["rows"] == ref["xyz_"].shape[0] and counts["split"] == rc["split"]
+    _assert_equal_states(got, ref, skip=("xyz_", "scaling_"))     # (b) product == reference code
+    n_copy = counts["kept"] + counts["cloned"]
+    assert torch.equal(got["xyz_"][:n_copy], ref["xyz_"][:n_copy])
+    assert torch.equal(got["scaling_"][:n_copy], ref["scaling_"][:n_copy])
+    assert torch.allclose(got["scaling_"][n_copy:], ref["scaling_"][n_copy:], rtol=2e-7, atol=2e-7)
+    d = (got["xyz_"][n_copy:] - ref["xyz_"][n_copy:]).abs()
+    assert float((d / ref["xyz_"][n_copy:].abs().clamp_min(1.0)).max()) <= 1e-6
+
+
+def test_prune_reset_and_statistics_against_the_compiled_reference():
+    if R.ref_module() is None:
+        pytest.skip("oracle/_ref/gsdf_ref_densify.so not built")
+    P, M = 60_000, 15
+    st = R.random_state(P, M, seed=5, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(8)
+    mask = torch.rand(P, device="cuda", generator=g) < 0.25
+    m = _model(st, M)
+    m.prunePoints(mask)
+    _assert_equal_states(_model_state(m), R.reference_prune_points(R.clone_state(st), mask))
+    m = _model(st, M)
+    m.resetOpacity()
+    ref = R.reference_reset_opacity(R.clone_state(st))
+    got = _model_state(m)
+    assert torch.allclose(got["opacity_"], ref["opacity_"], rtol=1e-6, atol=1e-6)
+    assert float(got["exp_avg"][3].abs().max()) == 0.0 and float(ref["exp_avg"][3].abs().max()) == 0.0
+    radii = torch.where(torch.rand(P, device="cuda", generator=g) < 0.6,
+                        torch.randint(1, 40, (P,), device="cuda", generator=g), torch.zeros(P, device="cuda", dtype=torch.int64))
+    grad = torch.randn(P, 3, device="cuda", generator=g)
+    m = _model(st, M)
+    m.addDensificationStats(grad, radii.to(torch.int32))
+    accum, denom = R.reference_add_densification_stats(R.clone_state(st), grad, radii > 0)
+    got = _model_state(m)
+    assert torch.equal(got["denom_"], denom)
+    assert torch.allclose(got["xyz_gradient_accum_"], accum, rtol=1e-6, atol=1e-9)

@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gsdf_slam_b200", "libgsr.so")
 out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "sass_digest.txt")
-WATCH = ["UBLKCP", "SYNCS", "LDGSTS", "RED", "ATOMG", "ATOMS", "MUFU", "FFMA2", "REDUX", "SHFL", "VOTE", "MATCH", "LDS", "STS",
+WATCH = ["UBLKCP", "SYNCS", "LDGSTS", "RED", "REDG", "ATOMG", "ATOMS", "MUFU", "FFMA2", "REDUX", "SHFL", "VOTE", "MATCH", "LDS", "STS",
          "LDG", "STG", "BAR", "UTMALDG", "HMMA", "UTCHMMA"]
 
 res = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout
