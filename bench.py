@@ -327,20 +327,37 @@ def rank_breakdown_of(mapper, step_fn, world, dev, n_tr=10):
             for r, x in enumerate(allr)]
 
 
-def exchange_summary(mapper, breakdown):
-    """NVLink traffic model of the fused exchange next to its measured time, and the remaining loss named."""
-    xb = mapper.exchange_bytes()
-    if xb is None or not breakdown:
+def exchange_summary(mapper, breakdown, step_fn, world, dev):
+    """MEASURED NVLink traffic of the fused exchange (one extra, untimed step through the counting variant of the
+    peer kernel) next to its measured time, and the remaining loss named."""
+    import torch.distributed as dist
+    if mapper.peer is None or not breakdown:
         return None
-    adam_ms = float(np.mean([b["peer_adam_ms"] for b in breakdown]))
+    tr = mapper.measure_exchange_traffic(step_fn)
+    mine = torch.tensor([tr["grad_in_bytes"], tr["param_changed_bytes"]], device=dev, dtype=torch.float64)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    grad_in = np.array([float(x[0]) for x in allr])
+    changed = np.array([float(x[1]) for x in allr])
+    param_in = changed.sum() - changed                       # every other rank's changed groups land here
+    bytes_in = grad_in + param_in
+    adam_ms = np.array([b["peer_adam_ms"] for b in breakdown])
     wait_ms = float(np.mean([b["wait_ms"] for b in breakdown]))
     bar_ms = float(np.mean([b["barrier2_ms"] for b in breakdown]))
-    out = dict(xb)
-    out["param_in_gbs_upper_bound"] = round(xb["param_in_bytes"] / max(adam_ms, 1e-6) / 1e6, 1)
-    out["nvlink_peak_gbs"] = NVLINK_PEER_GBS
-    out["note"] = ("upper bound: assumes every parameter of the shard changed and was broadcast; rows whose update is "
-                   "the identity (zero moments, zero gradient) are not sent")
-    losses = {"peer kernel": adam_ms, "barrier wait (slowest view)": wait_ms, "second barrier": bar_ms}
+    mc = bool(mapper.peer["mc_ptr"])
+    out = {"arena_bytes": int(4 * mapper.layout["_total"][1]), "multicast": mc,
+           "grad_in_bytes_per_rank": [int(x) for x in grad_in],
+           "param_changed_bytes_per_rank": [int(x) for x in changed],
+           "bytes_in_per_rank_mean": int(bytes_in.mean()),
+           "bytes_out_per_rank_mean": int((changed * (1 if mc else world - 1)).mean() + grad_in.mean()),
+           "achieved_in_gbs": round(float((bytes_in / np.maximum(adam_ms, 1e-6)).mean()) / 1e6, 1),
+           "nvlink_peak_gbs": NVLINK_PEER_GBS,
+           "frac_of_nvlink_peak": round(float((bytes_in / np.maximum(adam_ms, 1e-6)).mean()) / 1e6 / NVLINK_PEER_GBS, 3),
+           "note": ("counted in the kernel: 16-byte gradient groups loaded from other ranks (responses arrive on this "
+                    "rank's ingress; the same amount leaves it on average as served loads) and 16-byte parameter groups "
+                    "whose value changed; unchanged groups (zero moments and zero gradient) are not sent; bytes_in / "
+                    "peer_adam_ms per rank, averaged")}
+    losses = {"peer kernel": float(adam_ms.mean()), "barrier wait (slowest view)": wait_ms, "second barrier": bar_ms}
     out["largest_remaining_loss"] = max(losses, key=losses.get)
     return out
 
@@ -443,7 +460,7 @@ def run_cfg5(args, rank, world, dev, L, scene5, params5, kfs):
     if world > 1 and mapper.peer is not None:
         bd = rank_breakdown_of(mapper, step, world, dev, n_tr=5)
         out["rank_breakdown"] = bd
-        out["nvlink"] = exchange_summary(mapper, bd)
+        out["nvlink"] = exchange_summary(mapper, bd, step, world, dev)
     del mapper
     torch.cuda.empty_cache()
     return out
@@ -632,7 +649,7 @@ def run_product(args, rank, world, dev):
     rank_breakdown = None
     if world > 1 and mapper.peer is not None:
         rank_breakdown = rank_breakdown_of(mapper, step_resident, world, dev)
-    nvlink = exchange_summary(mapper, rank_breakdown) if rank_breakdown else None
+    nvlink = exchange_summary(mapper, rank_breakdown, step_resident, world, dev) if rank_breakdown else None
     if world > 1:
         lt = torch.tensor([launches], device=dev, dtype=torch.float64)
         dist.all_reduce(lt)

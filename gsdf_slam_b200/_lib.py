@@ -84,7 +84,7 @@ class PeerAdamArgs(C.Structure):
         ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("union_mask", C.c_void_p),
         ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("grad_scale", C.c_float),
         ("step", C.c_int64), ("stream", C.c_void_p), ("shard_chunk", C.c_int64),
-        ("param_multicast", C.c_void_p),
+        ("param_multicast", C.c_void_p), ("traffic_counters", C.c_void_p),
     ]
 
 

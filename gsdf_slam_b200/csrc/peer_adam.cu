@@ -56,6 +56,7 @@ struct PeerAdamParams {
   const int* union_mask; // [rows] > 0 <=> some rank rendered the row
   float beta1, one_minus_beta1, beta2, one_minus_beta2, eps, grad_scale;
   int use_scale;
+  unsigned long long* traffic;  // kCount only: [0] remote 16-byte gradient loads, [1] changed 16-byte parameter groups
 };
 
 __device__ __forceinline__ void peer_adam_elem(float& p, float g, float& m, float& v, const PeerAdamParams& a,
@@ -77,6 +78,7 @@ __device__ __forceinline__ void peer_adam_elem(float& p, float g, float& m, floa
   v = v2;
 }
 
+template <bool kCount>
 __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamParams a, int my_rank) {
   // element handled by this thread and its slot in the shard-local moment arrays
   long long e, mo;
@@ -131,6 +133,10 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
 #pragma unroll
     for (int k = 0; k < GSR_MAX_PEERS; ++k)
       if (k < a.n_peers && ((want >> k) & 1u)) x[k] = __ldcs(reinterpret_cast<const float4*>(a.grad[k] + e));
+    if (kCount) {
+      const int remote = __popc(want & ((1u << a.n_peers) - 1u) & ~(1u << my_rank));
+      if (remote) atomicAdd(a.traffic, (unsigned long long)remote);
+    }
 #pragma unroll
     for (int k = 0; k < GSR_MAX_PEERS; ++k) {
       if (k < a.n_peers && ((want >> k) & 1u)) {
@@ -153,6 +159,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
   const bool changed = __float_as_uint(p.x) != __float_as_uint(p_old.x) || __float_as_uint(p.y) != __float_as_uint(p_old.y) ||
                        __float_as_uint(p.z) != __float_as_uint(p_old.z) || __float_as_uint(p.w) != __float_as_uint(p_old.w);
   if (changed) {
+    if (kCount) atomicAdd(a.traffic + 1, 1ull);
     if (a.param_mc != nullptr) {
       // one store; the NVSwitch replicates it into the arena of every rank (this one included)
       asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.param_mc + e), "f"(p.x),
@@ -442,7 +449,11 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* in) {
     ctas = owned * a.ctas_per_chunk;
     if (ctas == 0) return GSR_OK;
   }
-  peer_adam_kernel<<<(unsigned)ctas, kPeerThreads, 0, static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
+  a.traffic = in->traffic_counters;
+  if (a.traffic != nullptr)
+    peer_adam_kernel<true><<<(unsigned)ctas, kPeerThreads, 0, static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
+  else
+    peer_adam_kernel<false><<<(unsigned)ctas, kPeerThreads, 0, static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

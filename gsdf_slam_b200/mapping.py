@@ -141,6 +141,7 @@ class KeyframeBatchMapper:
         # N > 1 ranks on one NVLink node: gradient reduction + Adam + parameter broadcast fused in
         # one kernel over peer memory (gsr_adam_step_peer) instead of NCCL all-reduce + full Adam
         self.peer = None
+        self.traffic_counters = None   # set by measure_exchange_traffic only
         if peer_exchange is None:
             import os
             peer_exchange = os.environ.get("GSR_PEER_EXCHANGE", "1") != "0"
@@ -265,6 +266,22 @@ class KeyframeBatchMapper:
         torch.cuda.synchronize(dev)
         dist.barrier(group)
 
+    def measure_exchange_traffic(self, step_fn) -> Optional[dict]:
+        """Runs `step_fn` (one optimiser step) with the counting variant of the peer kernel and returns this rank's
+        NVLink traffic of that step in bytes: gradient rows pulled from other ranks and parameter groups pushed."""
+        if self.peer is None:
+            return None
+        self.traffic_counters = torch.zeros(2, dtype=torch.int64, device=self.arena.device)
+        try:
+            step_fn()
+            torch.cuda.synchronize(self.arena.device)
+            loads, changed = (int(x) for x in self.traffic_counters.tolist())
+        finally:
+            self.traffic_counters = None
+        n = self.peer["world"]
+        return {"grad_in_bytes": 16 * loads, "param_changed_bytes": 16 * changed,
+                "param_out_bytes": 16 * changed * (1 if self.peer["mc_ptr"] else n - 1)}
+
     def exchange_bytes(self) -> Optional[dict]:
         """Model of the NVLink traffic of one peer exchange, per rank (bench.py prints it next to the measured
         time): parameter broadcast = this rank's shard to N-1 peers (one multicast store if available)."""
@@ -350,6 +367,8 @@ class KeyframeBatchMapper:
         a.step = pe["step"]
         a.stream = stream
         a.param_multicast = pe["mc_ptr"]
+        if self.traffic_counters is not None:   # measurement only (bench.py): counted variant of the kernel
+            a.traffic_counters = self.traffic_counters.data_ptr()
         _lib.check(L.gsr_adam_step_peer(C.byref(a)), "gsr_adam_step_peer")
         self._mark("peer_adam_end", main)
         pe["hp"].barrier(channel=0)          # every rank's parameter stores have landed

@@ -260,6 +260,10 @@ typedef struct gsr_peer_adam_args {
    * the SM as ONE multimem store per 16 bytes instead of n_peers unicast stores: 1/n_peers of the store
    * instructions and of the NVLink egress.  NULL: unicast stores to param_peers[0..n_peers). */
   float* param_multicast;
+  /* Optional (device, two uint64 the caller zeroes): measurement of the kernel's NVLink traffic.  [0] += 16-byte
+   * gradient loads issued to OTHER ranks' arenas, [1] += 16-byte parameter groups that changed and were stored
+   * (each leaves as n_peers - 1 remote stores, or one multicast store).  NULL: nothing is counted (the timed path). */
+  unsigned long long* traffic_counters;
 } gsr_peer_adam_args;
 int gsr_adam_step_peer(const gsr_peer_adam_args* a);
 /* union_out[row] = bitmask of the ranks that rendered the row: bit k set <=> radii_peers[k][row] > 0
