@@ -457,6 +457,17 @@ def run_cfg5(args, rank, world, dev, L, scene5, params5, kfs):
                                 "N=1 line is authoritative)")
         except Exception:  # noqa: BLE001
             pass
+    # per-stage CUDA-event times of this rank's part of the step (untimed extra steps, rank 0's numbers)
+    L.gsr_profile_enable(1)
+    read_profile(L)
+    mapper.serialize_side_stream = True
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    mapper.serialize_side_stream = False
+    out["stages_ms_per_step_rank0"] = {k: round(tot / 3.0, 4) for k, (tot, cnt) in sorted(
+        read_profile(L).items(), key=lambda kv: -kv[1][0])}
+    L.gsr_profile_enable(0)
     if world > 1 and mapper.peer is not None:
         bd = rank_breakdown_of(mapper, step, world, dev, n_tr=5)
         out["rank_breakdown"] = bd

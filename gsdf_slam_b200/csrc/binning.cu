@@ -122,6 +122,7 @@ tile_meta_kernel(const uint32_t* __restrict__ tile_count, uint32_t T, uint2* __r
     hdr->max_tile_len = s_max;
     hdr->num_long_tiles = s_long;
     hdr->num_huge_tiles = s_huge;
+    hdr->num_large = 0;   // the preprocess stage's work queue is consumed; the emit stage builds its own
   }
 
   // exclusive scan of the 1024 bucket counts, then place the tiles

@@ -235,7 +235,11 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.radii = a->radii; pp.depths = g.depths; pp.means2D = g.means2D;
   pp.conic_opacity = g.conic_opacity; pp.rgb = g.rgb; pp.clamped = g.clamped;
   pp.tiles_touched = g.tiles_touched; pp.splat_rec = g.splat_rec; pp.vis_items = g.vis_items; pp.num_visible = &g.hdr->num_visible;
+  // the candidate list of the cull lives in the backward pass's moment sums (unused until gsr_backward zeroes them)
+  pp.cand = reinterpret_cast<uint32_t*>(g.acc); pp.num_cand = &g.hdr->num_cand;
+  pp.large_list = g.large_list; pp.large_count = &g.hdr->num_large; pp.large_capacity = 2u * (uint32_t)P;
   pp.tile_count = im.tile_count;
+  GSR_PROF("precull", launch_precull(pp, s));
   GSR_PROF("preprocess", launch_preprocess(pp, s));
   if (a->radii_ready_event) GSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->radii_ready_event), s));
 

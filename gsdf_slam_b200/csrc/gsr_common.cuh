@@ -36,7 +36,8 @@ struct GeomHeader {          // lives at the start of the geometry buffer (256 B
   uint32_t num_large;        // length of the large-rectangle work queue (binning.cu)
   uint32_t num_long_tiles;   // tiles with >= kSortSmallCap entries (mid + huge)
   uint32_t num_huge_tiles;   // tiles with >= kSortMidCap entries
-  uint32_t pad[58];
+  uint32_t num_cand;         // Gaussians that passed the conservative cull (preprocess.cu, stage 1)
+  uint32_t pad[57];
 };
 
 struct GeomView {
@@ -375,6 +376,8 @@ __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, 
   const int total = __shfl_sync(full, incl, 31);
   const int excl = incl - area;
   const float rcp_x = __frcp_rn(15 * 15 * co.x), rcp_z = __frcp_rn(15 * 15 * co.z);  // per Gaussian
+  // t / w by multiplication: ceil(2^32 / w) is exact for t, w < 2^16 (w == 1: the quotient is t)
+  const uint32_t w_magic = w_own > 1 ? 0xffffffffu / (uint32_t)w_own + 1u : 0u;
   for (int f0 = 0; f0 < total; f0 += 32) {
     const int f = f0 + lane;
     // owner = number of lanes whose inclusive prefix is <= f (prefix is non-decreasing)
@@ -401,12 +404,79 @@ __device__ __forceinline__ void warp_walk_rects_flat(bool has, const float4 co, 
     const uint32_t q1 = __shfl_sync(full, pay1, owner);
     const float rx = __shfl_sync(full, rcp_x, owner);
     const float rz = __shfl_sync(full, rcp_z, owner);
+    const uint32_t wm = __shfl_sync(full, w_magic, owner);
     if (f < total) {
-      const int y = y0 + t / w;
-      const int x = x0 + t - (t / w) * w;
+      const int q = w > 1 ? (int)__umulhi((uint32_t)t, wm) : t;
+      const int y = y0 + q;
+      const int x = x0 + t - q * w;
       if (tile_min_power_pre(c, p, x, y, rx, rz) <= th) on_hit(owner, x, y, q0, q1);
     }
   }
+}
+
+// The counting twin of warp_walk_rects_flat (preprocess.cu): +1 on tile_count[tile] for every (Gaussian, tile) pair
+// that passes the test, and the number of passing tiles of each lane's own rectangle as the return value — from the
+// hit ballots of the steps its rectangle spans (no shared-memory atomics).
+__device__ __forceinline__ uint32_t warp_count_rects_flat(bool has, const float4 co, const float2 xy,
+                                                          const uint2 rect_min, const uint2 rect_max, float thr,
+                                                          uint32_t* __restrict__ tile_count, int grid_x) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int w_own = has ? (int)(rect_max.x - rect_min.x) : 0;
+  const int area = has ? w_own * (int)(rect_max.y - rect_min.y) : 0;
+  int incl = area;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(full, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(full, incl, 31);
+  const int excl = incl - area;
+  const float rcp_x = __frcp_rn(15 * 15 * co.x), rcp_z = __frcp_rn(15 * 15 * co.z);  // per Gaussian
+  // t / w by multiplication: ceil(2^32 / w) is exact for t, w < 2^16 (w == 1: the quotient is t)
+  const uint32_t w_magic = w_own > 1 ? 0xffffffffu / (uint32_t)w_own + 1u : 0u;
+  uint32_t mine = 0;
+  for (int f0 = 0; f0 < total; f0 += 32) {
+    const int f = f0 + lane;
+    int owner = 0;
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const int v = __shfl_sync(full, incl, owner + step - 1);
+      if (v <= f) owner += step;
+    }
+    float4 c;
+    c.x = __shfl_sync(full, co.x, owner);
+    c.y = __shfl_sync(full, co.y, owner);
+    c.z = __shfl_sync(full, co.z, owner);
+    c.w = __shfl_sync(full, co.w, owner);
+    float2 p;
+    p.x = __shfl_sync(full, xy.x, owner);
+    p.y = __shfl_sync(full, xy.y, owner);
+    const int x0 = __shfl_sync(full, (int)rect_min.x, owner);
+    const int y0 = __shfl_sync(full, (int)rect_min.y, owner);
+    const int w = __shfl_sync(full, w_own, owner);
+    const float th = __shfl_sync(full, thr, owner);
+    const int t = f - __shfl_sync(full, excl, owner);
+    const float rx = __shfl_sync(full, rcp_x, owner);
+    const float rz = __shfl_sync(full, rcp_z, owner);
+    const uint32_t wm = __shfl_sync(full, w_magic, owner);
+    bool hit = false;
+    if (f < total) {
+      const int q = w > 1 ? (int)__umulhi((uint32_t)t, wm) : t;
+      const int y = y0 + q;
+      const int x = x0 + t - q * w;
+      hit = tile_min_power_pre(c, p, x, y, rx, rz) <= th;
+      if (hit) atomicAdd(&tile_count[y * grid_x + x], 1u);
+    }
+    const unsigned hits = __ballot_sync(full, hit);
+    // the part of this step that belongs to my own rectangle: flat positions [excl, incl) ∩ [f0, f0 + 32)
+    const int lo = max(excl - f0, 0), hi = min(incl - f0, 32);
+    if (hi > lo) {
+      const unsigned below_hi = hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u);
+      mine += (uint32_t)__popc(hits & below_hi & ~((1u << lo) - 1u));
+    }
+  }
+  return mine;
 }
 
 // ---- launch helpers implemented across the .cu files ------------------------

@@ -36,6 +36,11 @@ struct PreprocessParams {
   float4* splat_rec;      // [P][3] {x, y, conic.x, conic.y | conic.z, opacity, reject_power, idx | r, g, b, 0}
   uint64_t* vis_items;    // compacted (depth_bits<<32 | idx) of the rendered Gaussians
   uint32_t* num_visible;  // its length (zeroed by the caller)
+  uint32_t* cand;         // [P] scratch: Gaussians that pass the conservative cull (preprocess.cu, stage 1)
+  uint32_t* num_cand;     // its length (zeroed by the caller)
+  uint32_t* large_list;   // work queue of the large rectangles: (chunk << 24 | position in vis_items)
+  uint32_t* large_count;  // its length (zeroed by the caller; tile_meta_kernel zeroes it again for the emit stage)
+  uint32_t large_capacity;
   uint32_t* tile_count;   // [T] += 1 per (Gaussian, tile) that passes the exact test (zeroed by the caller)
 };
 struct PreBwdParams {
@@ -72,6 +77,7 @@ struct PreBwdParams {
   float* dL_drot;
 };
 
+int launch_precull(const PreprocessParams& p, cudaStream_t s);
 int launch_preprocess(const PreprocessParams& p, cudaStream_t s);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present,
                         cudaStream_t s);
