@@ -39,49 +39,73 @@ __device__ __forceinline__ float dotv(V3 a, V3 b) { return a.x * b.x + a.y * b.y
 __device__ __forceinline__ void store3(float* p, size_t i, V3 v) {
   p[3 * i + 0] = v.x; p[3 * i + 1] = v.y; p[3 * i + 2] = v.z;
 }
-// parameter gradients: overwrite, or add to the row (gsr_backward_args.accumulate)
-__device__ __forceinline__ void out3(float* p, size_t i, V3 v, bool acc) {
-  if (acc) { v.x += p[3 * i + 0]; v.y += p[3 * i + 1]; v.z += p[3 * i + 2]; }
+
+// Everything a Gaussian's backward pass reads from global memory, fetched up front: the loads are in flight
+// together with the SH-row gather instead of one dependent round trip after the other (the kernel is bound by
+// that latency chain).  With `accm` that includes the row's current parameter gradients (keyframe batches).
+struct PreBwdIn {
+  float4 acc0, acc1, acc2, cop, q;
+  float3 mean, scale;
+  uint8_t cl;
+  float old_op;
+  V3 old_dc, old_mean, old_scale;
+  float4 old_rot;
+};
+__device__ __forceinline__ void preprocess_bwd_load(const PreBwdParams& a, const int idx, const bool accm, PreBwdIn& in) {
+  const size_t i = (size_t)idx;
+  in.acc0 = reinterpret_cast<const float4*>(a.acc)[3 * i + 0];
+  in.acc1 = reinterpret_cast<const float4*>(a.acc)[3 * i + 1];
+  in.acc2 = reinterpret_cast<const float4*>(a.acc)[3 * i + 2];
+  in.cop = a.conic_opacity[i];
+  in.mean = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
+  in.scale = {0.f, 0.f, 0.f};
+  in.q = {0.f, 0.f, 0.f, 0.f};
+  if (a.scales != nullptr) {
+    in.scale = {a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2]};
+    in.q = reinterpret_cast<const float4*>(a.rotations)[i];
+  }
+  in.cl = (a.shs != nullptr) ? a.clamped[idx] : (uint8_t)0;
+  in.old_op = 0.f;
+  in.old_dc = in.old_mean = in.old_scale = {0.f, 0.f, 0.f};
+  in.old_rot = {0.f, 0.f, 0.f, 0.f};
+  if (accm) {
+    in.old_op = a.dL_dopacity[i];
+    in.old_dc = {a.dL_ddc[3 * i], a.dL_ddc[3 * i + 1], a.dL_ddc[3 * i + 2]};
+    in.old_mean = {a.dL_dmean3D[3 * i], a.dL_dmean3D[3 * i + 1], a.dL_dmean3D[3 * i + 2]};
+    if (a.scales != nullptr) {
+      in.old_scale = {a.dL_dscale[3 * i], a.dL_dscale[3 * i + 1], a.dL_dscale[3 * i + 2]};
+      in.old_rot = reinterpret_cast<const float4*>(a.dL_drot)[i];
+    }
+  }
+}
+// parameter gradients: overwrite, or add to the row's previous value (fetched by preprocess_bwd_load)
+__device__ __forceinline__ void out3(float* p, size_t i, V3 v, bool acc, V3 old) {
+  if (acc) { v.x += old.x; v.y += old.y; v.z += old.z; }
   store3(p, i, v);
 }
+// dL/dsh element in the shared row: preloaded with the row's previous value when accumulating
+__device__ __forceinline__ void sh_put(V3* p, V3 v, bool acc) {
+  if (acc) { v.x = __fadd_rn(p->x, v.x); v.y = __fadd_rn(p->y, v.y); v.z = __fadd_rn(p->z, v.z); }
+  *p = v;
+}
 
-// Per-Gaussian body.  `sh_row` is this Gaussian's dL/dsh row (3*M floats) in SHARED
-// memory, pre-zeroed; the CTA writes the rows out coalesced afterwards.
-__device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const int idx,
-                                                   const bool rendered, float* sh_row,
-                                                   const float* sh_in_row) {
+// Per-Gaussian body.  `sh_row` is this Gaussian's dL/dsh row (3*M floats) in SHARED memory — zeros, or with `accm`
+// the row's current values; the warp writes the rows out afterwards.  `accm` (keyframe batches): add to the row's
+// current parameter gradients instead of overwriting them — for every row, or (accumulate_rows) only for the rows
+// an earlier keyframe of the batch has already written.
+__device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const int idx, const bool accm,
+                                                   const PreBwdIn& in, float* sh_row, const float* sh_in_row) {
   const size_t i = (size_t)idx;
   const int M = a.M;
-  // keyframe batches: add to the row's current parameter gradients instead of overwriting them — for every row,
-  // or (accumulate_rows) only for the rows an earlier keyframe of the batch has already written
-  const bool accm = a.accumulate != 0 && (a.accumulate_rows == nullptr || a.accumulate_rows[idx] > 0);
-
-  if (!rendered) {
-    // not rendered: all gradients are zero
-    store3(a.dL_dmean2D, i, {0.f, 0.f, 0.f});
-    if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    a.dL_dopacity[i] = 0.f;
-    store3(a.dL_dcolor, i, {0.f, 0.f, 0.f});
-    store3(a.dL_dmean3D, i, {0.f, 0.f, 0.f});
-    if (a.dL_dcov3D)
-      for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * i + k] = 0.f;
-    store3(a.dL_ddc, i, {0.f, 0.f, 0.f});
-    store3(a.dL_dscale, i, {0.f, 0.f, 0.f});
-    reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
-  }
-
   // ---- accumulated 2D gradients ------------------------------------------------
-  const float4 acc0 = reinterpret_cast<const float4*>(a.acc)[3 * i + 0];
-  const float4 acc1 = reinterpret_cast<const float4*>(a.acc)[3 * i + 1];
-  const float4 acc2 = reinterpret_cast<const float4*>(a.acc)[3 * i + 2];
+  const float4 acc0 = in.acc0, acc1 = in.acc1, acc2 = in.acc2;
   // blend_bwd.cu accumulated, over every (pixel, this splat) pair with w = G*dL/dalpha and
   // d = mean2D - pixel:  Mx = sum w*dx, My, Mxx = sum w*dx^2, Mxy, Myy, M0 = sum w, colour sums.
   // The reference's per-pair terms (backward.cu:622-637) are linear in these moments:
   //   dL/dmean2D.x = sum dL_dG*(-G*(a*dx+b*dy))*0.5W = -op*0.5W*(a*Mx + b*My)     (dL_dG = op*dL/dalpha)
   //   dL/dconic.x  = sum -0.5*G*dx*dx*dL_dG          = -0.5*op*Mxx   (same for xy, yy)
   //   dL/dopacity  = sum G*dL/dalpha                 = M0
-  const float4 cop = a.conic_opacity[i];
+  const float4 cop = in.cop;
   const float Mx = acc0.x, My = acc0.y, Mxx = acc0.z, Mxy = acc0.w, Myy = acc1.x, M0 = acc1.y;
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
   const float dmean2D_x = -cop.w * ddelx_dx * (cop.x * Mx + cop.y * My);
@@ -96,11 +120,11 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
   // raw-parameter entry point: chain through sigmoid (sigma' = o (1 - o), o = the activated opacity)
   {
     const float dop = a.activate ? dopacity * cop.w * (1.0f - cop.w) : dopacity;
-    a.dL_dopacity[i] = accm ? a.dL_dopacity[i] + dop : dop;
+    a.dL_dopacity[i] = accm ? in.old_op + dop : dop;
   }
   store3(a.dL_dcolor, i, dL_dRGB);
 
-  const float3 mean = {a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]};
+  const float3 mean = in.mean;
 
   // ---- 3D covariance (recomputed rather than stored by the forward) -------------
   float cov3D[6];
@@ -109,8 +133,8 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
   float q_norm = 1.0f;
   M3 R, Mm;
   if (a.scales != nullptr) {
-    scale = {a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2]};
-    q = reinterpret_cast<const float4*>(a.rotations)[i];
+    scale = in.scale;
+    q = in.q;
     if (a.activate) {
       q_norm = quat_norm(q);
       scale = act_exp3(scale);
@@ -245,7 +269,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
     const V3* sh = reinterpret_cast<const V3*>(sh_in_row);  // this Gaussian's SH row (staged)
     V3* dL_dsh = reinterpret_cast<V3*>(sh_row);
 
-    const uint8_t cl = a.clamped[idx];
+    const uint8_t cl = in.cl;
     dL_dRGB.x *= (cl & 1) ? 0 : 1;
     dL_dRGB.y *= (cl & 2) ? 0 : 1;
     dL_dRGB.z *= (cl & 4) ? 0 : 1;
@@ -260,9 +284,9 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
       float dRGBdsh1 = -SH_C1 * y;
       float dRGBdsh2 = SH_C1 * z;
       float dRGBdsh3 = -SH_C1 * x;
-      dL_dsh[0] = dRGBdsh1 * dL_dRGB;
-      dL_dsh[1] = dRGBdsh2 * dL_dRGB;
-      dL_dsh[2] = dRGBdsh3 * dL_dRGB;
+      sh_put(&dL_dsh[0], dRGBdsh1 * dL_dRGB, accm);
+      sh_put(&dL_dsh[1], dRGBdsh2 * dL_dRGB, accm);
+      sh_put(&dL_dsh[2], dRGBdsh3 * dL_dRGB, accm);
       written = 3;
       dRGBdx = -SH_C1 * sh[2];
       dRGBdy = -SH_C1 * sh[0];
@@ -276,11 +300,11 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
         float dRGBdsh6 = SH_C2[2] * (2.f * zz - xx - yy);
         float dRGBdsh7 = SH_C2[3] * xz;
         float dRGBdsh8 = SH_C2[4] * (xx - yy);
-        dL_dsh[3] = dRGBdsh4 * dL_dRGB;
-        dL_dsh[4] = dRGBdsh5 * dL_dRGB;
-        dL_dsh[5] = dRGBdsh6 * dL_dRGB;
-        dL_dsh[6] = dRGBdsh7 * dL_dRGB;
-        dL_dsh[7] = dRGBdsh8 * dL_dRGB;
+        sh_put(&dL_dsh[3], dRGBdsh4 * dL_dRGB, accm);
+        sh_put(&dL_dsh[4], dRGBdsh5 * dL_dRGB, accm);
+        sh_put(&dL_dsh[5], dRGBdsh6 * dL_dRGB, accm);
+        sh_put(&dL_dsh[6], dRGBdsh7 * dL_dRGB, accm);
+        sh_put(&dL_dsh[7], dRGBdsh8 * dL_dRGB, accm);
         written = 8;
 
         dRGBdx += SH_C2[0] * y * sh[3] + SH_C2[2] * 2.f * -x * sh[5] + SH_C2[3] * z * sh[6] +
@@ -297,13 +321,13 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
           float dRGBdsh13 = SH_C3[4] * x * (4.f * zz - xx - yy);
           float dRGBdsh14 = SH_C3[5] * z * (xx - yy);
           float dRGBdsh15 = SH_C3[6] * x * (xx - 3.f * yy);
-          dL_dsh[8] = dRGBdsh9 * dL_dRGB;
-          dL_dsh[9] = dRGBdsh10 * dL_dRGB;
-          dL_dsh[10] = dRGBdsh11 * dL_dRGB;
-          dL_dsh[11] = dRGBdsh12 * dL_dRGB;
-          dL_dsh[12] = dRGBdsh13 * dL_dRGB;
-          dL_dsh[13] = dRGBdsh14 * dL_dRGB;
-          dL_dsh[14] = dRGBdsh15 * dL_dRGB;
+          sh_put(&dL_dsh[8], dRGBdsh9 * dL_dRGB, accm);
+          sh_put(&dL_dsh[9], dRGBdsh10 * dL_dRGB, accm);
+          sh_put(&dL_dsh[10], dRGBdsh11 * dL_dRGB, accm);
+          sh_put(&dL_dsh[11], dRGBdsh12 * dL_dRGB, accm);
+          sh_put(&dL_dsh[12], dRGBdsh13 * dL_dRGB, accm);
+          sh_put(&dL_dsh[13], dRGBdsh14 * dL_dRGB, accm);
+          sh_put(&dL_dsh[14], dRGBdsh15 * dL_dRGB, accm);
           written = 15;
 
           dRGBdx += (SH_C3[0] * sh[8] * 3.f * 2.f * xy + SH_C3[1] * sh[9] * yz +
@@ -335,8 +359,8 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
       dL_dmean_total += r;
     }
   }
-  out3(a.dL_ddc, i, out_ddc, accm);
-  out3(a.dL_dmean3D, i, dL_dmean_total, accm);
+  out3(a.dL_ddc, i, out_ddc, accm, in.old_dc);
+  out3(a.dL_dmean3D, i, dL_dmean_total, accm, in.old_mean);
 
   // ---- cov3D -> scale, rotation (reference computeCov3D backward, backward.cu:317-397)
   if (a.scales != nullptr) {
@@ -359,7 +383,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
     dscale.z = dot3(Rt[2], dL_dMt[2]);
     // raw-parameter entry point: d exp(s)/ds = exp(s) = the activated scale
     if (a.activate) dscale = {dscale.x * scale.x, dscale.y * scale.y, dscale.z * scale.z};
-    out3(a.dL_dscale, i, dscale, accm);
+    out3(a.dL_dscale, i, dscale, accm, in.old_scale);
 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -383,7 +407,7 @@ __device__ __forceinline__ void preprocess_bwd_one(const PreBwdParams& a, const 
                (dL_dq.w - q.w * qd) / q_norm};
     }
     if (accm) {
-      const float4 o = reinterpret_cast<const float4*>(a.dL_drot)[i];
+      const float4 o = in.old_rot;
       reinterpret_cast<float4*>(a.dL_drot)[i] = make_float4(o.x + dL_dq.x, o.y + dL_dq.y, o.z + dL_dq.z, o.w + dL_dq.w);
     } else {
       reinterpret_cast<float4*>(a.dL_drot)[i] = dL_dq;
@@ -433,8 +457,9 @@ __global__ void __launch_bounds__(kZeroThreads) zero_fill_kernel(const ZeroParam
 // ---- pass 2: the rendered Gaussians, taken from the depth-sorted list of the forward ------
 // sorted[0 .. *num_valid) are exactly the Gaussians that own at least one tile; every other
 // Gaussian received no gradient from the blend stage, so all of its outputs are zero.
+// 4 CTAs per SM = at most 128 registers (162 without the bound: 3 CTAs, measured slower on dense views)
 #ifndef GSR_PREBWD_MINBLOCKS
-#define GSR_PREBWD_MINBLOCKS 1
+#define GSR_PREBWD_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(kPreBwdThreads, GSR_PREBWD_MINBLOCKS)
 preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
@@ -452,37 +477,49 @@ preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
     const uint32_t t = r * stride + blockIdx.x * kPreBwdThreads + tid;
     const bool act = t < nv;
     const int idx = act ? (int)(uint32_t)(sorted[t] & 0xffffffffu) : -1;
-    if (has_sh) {
-      // gather the 32 SH rows with asynchronous copies: all of them are in flight together
-      for (int src = 0; src < 32; ++src) {
-        const int g = __shfl_sync(0xffffffffu, idx, src);
-        if (g < 0) continue;
+    const bool accm = act && a.accumulate != 0 && (a.accumulate_rows == nullptr || a.accumulate_rows[idx] > 0);
+    PreBwdIn in;
+    if (act) preprocess_bwd_load(a, idx, accm, in);
+    const unsigned accm_mask = __ballot_sync(0xffffffffu, accm);
+    const unsigned act_mask = __ballot_sync(0xffffffffu, act);
+    // (the grid is sized for the whole map while a view renders a fraction of it: three quarters of the warps have
+    // nothing to do, and walking 32 empty sources twice was a third of the kernel's instructions)
+    if (act_mask == 0) continue;
+    // gather the SH rows — and, for the rows that accumulate, their current dL/dsh rows — with asynchronous
+    // copies: all of them are in flight together (and together with the loads above)
+    for (unsigned todo = act_mask; todo; todo &= todo - 1) {
+      const int src = __ffs(todo) - 1;
+      const int g = __shfl_sync(0xffffffffu, idx, src);
+      if (has_sh) {
         const float* grow = a.shs + (size_t)g * (size_t)a.M * 3;
         float* dst = &s_sh[warp][src * row];
         if (lane < row) cp_async_f32(dst + lane, grow + lane);
         if (lane + 32 < row) cp_async_f32(dst + lane + 32, grow + lane + 32);
       }
-      cp_async_wait_all();
+      float* drow = &s_dsh[warp][src * row];
+      if (((accm_mask >> src) & 1u) && a.dL_dsh != nullptr) {
+        const float* old = a.dL_dsh + (size_t)g * row;
+        if (lane < row) cp_async_f32(drow + lane, old + lane);
+        if (lane + 32 < row) cp_async_f32(drow + lane + 32, old + lane + 32);
+      } else {
+        if (lane < row) drow[lane] = 0.f;
+        if (lane + 32 < row) drow[lane + 32] = 0.f;
+      }
     }
-    float* my_row = &s_dsh[warp][lane * row];
-    for (int k = 0; k < row; ++k) my_row[k] = 0.f;
+    cp_async_wait_all();
     __syncwarp();
-    if (act) preprocess_bwd_one(a, idx, true, my_row, &s_sh[warp][lane * row]);
+    float* my_row = &s_dsh[warp][lane * row];
+    if (act) preprocess_bwd_one(a, idx, accm, in, my_row, &s_sh[warp][lane * row]);
     __syncwarp();
     if (a.dL_dsh != nullptr && row > 0) {
-      // each rendered row leaves as one contiguous 12*M-byte segment
-      for (int src = 0; src < 32; ++src) {
+      // each rendered row leaves as one contiguous 12*M-byte segment (sums included: plain stores)
+      for (unsigned todo = act_mask; todo; todo &= todo - 1) {
+        const int src = __ffs(todo) - 1;
         const int g = __shfl_sync(0xffffffffu, idx, src);
-        if (g < 0) continue;
         float* dst = a.dL_dsh + (size_t)g * row;
         const float* srow = &s_dsh[warp][src * row];
-        if (a.accumulate && (a.accumulate_rows == nullptr || a.accumulate_rows[g] > 0)) {
-          if (lane < row) dst[lane] += srow[lane];
-          if (lane + 32 < row) dst[lane + 32] += srow[lane + 32];
-        } else {
-          if (lane < row) dst[lane] = srow[lane];
-          if (lane + 32 < row) dst[lane + 32] = srow[lane + 32];
-        }
+        if (lane < row) dst[lane] = srow[lane];
+        if (lane + 32 < row) dst[lane + 32] = srow[lane + 32];
       }
     }
     __syncwarp();

@@ -24,27 +24,40 @@ def _setup(P=40_000):
     return scene, params, kfs, t(scene.bg)
 
 
-def test_c_mapper_matches_python_mapper_on_one_gpu():
+def _three_steps(m, kfs):
+    for step in range(3):
+        if step == 2:
+            m.set_lr("means3D", 3.2e-4)
+        m.step(kfs[:3] if step != 1 else kfs[1:2])
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("eps", [1.0, 1e-15])
+def test_c_mapper_matches_python_mapper_on_one_gpu(eps):
+    """Both hosts sequence the same kernels; what differs between ANY two runs is the order of the backward blend's
+    float atomics.  So the bar is relative to the run-to-run difference of the Python mapper itself, measured here:
+    rel-L2 of the update <= max(5e-5, 4 x that) (measured: 4e-6 .. 1.2e-5 between two Python runs, 1.9e-5 .. 2.3e-5
+    between the two hosts for the SH group, whose gradient is a sum of ~10^3 atomically added colour terms).  eps = 1: the Adam update is proportional to the accumulated gradient
+    (differences ~1e-5); eps = 1e-15 (the reference's): the first Adam steps are ~ lr * sign(g), so elements whose
+    summed gradient is ~ 0 flip sign with the atomics' order (differences up to ~1e-3)."""
     from gsdf_slam_b200.cmapper import CMapper
     from gsdf_slam_b200.mapping import SEGMENTS, KeyframeBatchMapper
     scene, params, kfs, bg = _setup()
     P = scene.P
-    stats = {k: torch.zeros(P, device="cuda") for k in ("max_radii2D", "xyz_gradient_accum", "denom")}
-    py = KeyframeBatchMapper({k: v.clone() for k, v in params.items()}, scene.degree, bg, stats=stats)
-    cm = CMapper(params, scene.degree, bg)
-    for step in range(3):
-        if step == 2:
-            py.set_lr("means3D", 3.2e-4)
-            cm.set_lr("means3D", 3.2e-4)
-        batch = kfs[:3] if step != 1 else kfs[1:2]
-        py.step(batch)
-        cm.step(batch)
-    torch.cuda.synchronize()
+    zeros = lambda: {k: torch.zeros(P, device="cuda") for k in ("max_radii2D", "xyz_gradient_accum", "denom")}  # noqa: E731
+    stats, stats2 = zeros(), zeros()
+    py = KeyframeBatchMapper({k: v.clone() for k, v in params.items()}, scene.degree, bg, stats=stats, eps=eps)
+    py2 = KeyframeBatchMapper({k: v.clone() for k, v in params.items()}, scene.degree, bg, stats=stats2, eps=eps)
+    cm = CMapper(params, scene.degree, bg, eps=eps)
+    for m in (py, py2, cm):
+        _three_steps(m, kfs)
     got = cm.params()
     for k in SEGMENTS:
         upd = py.opt_params[k] - params[k]
         assert float(upd.abs().max()) > 0
-        assert rel_l2(got[k] - params[k], upd) <= 1e-5, k
+        noise = rel_l2(py2.opt_params[k] - params[k], upd)
+        bar = max(5e-5, 4.0 * noise)
+        assert rel_l2(got[k] - params[k], upd) <= bar, (k, noise)
     st = cm.stats()
     assert torch.equal(st["denom"], stats["denom"]) and torch.equal(st["max_radii2D"], stats["max_radii2D"])
     assert rel_l2(st["xyz_gradient_accum"], stats["xyz_gradient_accum"]) <= 1e-5
