@@ -55,7 +55,7 @@ class BackwardArgs(C.Structure):
         ("dL_ddc", C.c_void_p), ("dL_dsh", C.c_void_p), ("dL_dscale", C.c_void_p),
         ("dL_drot", C.c_void_p),
         ("debug", C.c_int), ("stream", C.c_void_p), ("raw_params", C.c_int), ("rendered_rows_only", C.c_int),
-        ("accumulate", C.c_int), ("accumulate_rows", C.c_void_p),
+        ("accumulate", C.c_int), ("accumulate_rows", C.c_void_p), ("grad_rows", C.c_void_p),
     ]
 
 
@@ -204,7 +204,8 @@ def lib() -> C.CDLL:
     L.gsr_peer_union_mask.restype = C.c_int
     L.gsr_peer_rank_mask_u8.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     L.gsr_peer_rank_mask_u8.restype = C.c_int
-    L.gsr_peer_local_stats.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    L.gsr_peer_local_stats.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
     L.gsr_peer_local_stats.restype = C.c_int
     L.gsr_peer_stats_exchange.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64, C.c_int, C.c_int64,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

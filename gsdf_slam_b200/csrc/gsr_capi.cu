@@ -357,7 +357,11 @@ int gsr_backward(const gsr_backward_args* a) {
   bp.dL_ddc = a->dL_ddc; bp.dL_dsh = a->dL_dsh; bp.dL_dscale = a->dL_dscale; bp.dL_drot = a->dL_drot;
   bp.accumulate = a->accumulate != 0;
   bp.accumulate_rows = a->accumulate ? a->accumulate_rows : nullptr;
-  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible,
+  bp.grad_rows = a->grad_rows;
+  bp.dense_zeroed = a->rendered_rows_only == 0 && a->accumulate == 0;
+  // the list of the Gaussians that received a gradient reuses the emit stage's work-queue storage and counter
+  GSR_CUDA(cudaMemsetAsync(&g.hdr->num_large, 0, sizeof(uint32_t), s));
+  GSR_PROF("preprocess_bwd", launch_preprocess_bwd(bp, g.vis_items, &g.hdr->num_visible, g.large_list, &g.hdr->num_large,
                                                    a->rendered_rows_only == 0 && a->accumulate == 0, s));
   if (a->debug) {
     GSR_CUDA(cudaStreamSynchronize(s));

@@ -48,6 +48,8 @@ struct PreBwdParams {
   int activate;                 // gradients w.r.t. the RAW opacity / scale / rotation (row f-2)
   int accumulate;               // add the parameter gradients to the rows' current values (keyframe batch)
   const int* accumulate_rows;   // optional with accumulate: only rows with a value > 0 are added to, the rest overwritten
+  int* grad_rows;               // optional in/out row mask kept by the kernel (gsr_backward_args.grad_rows)
+  int dense_zeroed;             // the outputs were zero-filled before this kernel (dense API): rows may be skipped
   const float* opacities;       // raw opacities (needed only when activate)
   const float* means3D;
   const int* radii;
@@ -103,8 +105,8 @@ int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_ord
                      const uint32_t* max_contrib, const float4* rec, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
                      const float* dL_dpix, float* acc, cudaStream_t s);
-int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,
-                          bool zero_fill, cudaStream_t s);
+int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* vis_items, const uint32_t* num_visible,
+                          uint32_t* list, uint32_t* num_list, bool zero_fill, cudaStream_t s);
 int launch_adam(const gsr_adam_group* groups, int n_groups, double beta1, double beta2, double eps,
                 float grad_scale, cudaStream_t s);
 size_t knn_temp_bytes(int64_t P);

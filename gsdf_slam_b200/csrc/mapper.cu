@@ -84,11 +84,6 @@ __global__ void peer_barrier_kernel(PadPtrs pads, int rank, int world, uint32_t 
   } while ((int32_t)(v - epoch) < 0);
 }
 
-__global__ void max_i32_kernel(int64_t n, const int* __restrict__ a, int* __restrict__ acc) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) acc[i] = max(acc[i], a[i]);
-}
-
 }  // namespace
 
 struct gsr_mapper {
@@ -113,7 +108,7 @@ struct gsr_mapper {
   int32_t* union_mask = nullptr;   // [P + 4]
   float* stats = nullptr;          // [3P] replicated statistics (max_radii2D | accum | denom)
   int32_t* radii = nullptr;        // [P] of the current keyframe
-  int32_t* mask = nullptr;         // [P] running maximum of the radii of the batch
+  int32_t* mask = nullptr;         // [P] rows of the batch that received a gradient (gsr_backward_args.grad_rows)
   float* dmean2D = nullptr;        // [3P] per-view output
   float* dcolor = nullptr;         // [3P] per-view output
   float* dL = nullptr;             // [3HW] dL/d(image) from the fused loss
@@ -279,6 +274,8 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
     MAP_CUDA(cudaMemsetAsync(m->flags_ptr(rank), 0, (size_t)P + 16, s));
     if (m->stats) MAP_CUDA(cudaMemsetAsync(m->stats_local_ptr(rank), 0, (size_t)3 * m->stats_stride * 4, s));
   }
+  // the batch's row mask: kept by gsr_backward itself (rows that received a gradient so far)
+  MAP_CUDA(cudaMemsetAsync(m->mask, 0, (size_t)P * 4, s));
   for (int i = 0; i < n; ++i) {
     const gsr_mapper_keyframe& kf = kfs[i];
     if (!kf.viewmatrix || !kf.projmatrix || !kf.campos || kf.W <= 0 || kf.H <= 0 || (!kf.dL_dpix && !kf.gt_image))
@@ -330,27 +327,20 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
     ba.dL_drot = seg(grads, GSR_SEG_ROTATION);
     ba.stream = s;
     ba.raw_params = m->cfg.raw_params;
-    // no keyframe zero-fills: the first writes its rendered rows, the others add to the rows already written
-    // (mask = running maximum of the radii) and overwrite the rest
+    // no keyframe zero-fills: the first writes the rows that received a gradient, the others add to the rows
+    // already written (grad_rows) and overwrite the rest; rows without gradient are never touched
     ba.rendered_rows_only = 1;
     ba.accumulate = i > 0;
-    ba.accumulate_rows = i > 0 ? m->mask : nullptr;
+    ba.grad_rows = m->mask;
     MAP_RC(gsr_backward(&ba));
 
     if (world > 1) {
       MAP_RC(gsr_peer_local_stats(P, m->radii, m->dmean2D, m->stats ? m->stats_local_ptr(rank) : nullptr,
-                                  m->stats_stride, m->flags_ptr(rank), s));
+                                  m->stats_stride, m->flags_ptr(rank), m->mask, s));
     } else if (m->stats) {
       MAP_RC(gsr_add_densification_stats(P, m->radii, m->dmean2D, stat_maxr, stat_accum, stat_denom, s));
     }
-    if (i == 0) {
-      MAP_CUDA(cudaMemcpyAsync(m->mask, m->radii, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
-    } else {
-      max_i32_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(P, m->radii, m->mask);
-      GSR_LAUNCHED();
-    }
   }
-  if (n == 0) MAP_CUDA(cudaMemsetAsync(m->mask, 0, (size_t)P * 4, s));
 
   m->adam_step += 1;
   if (world == 1) {

@@ -206,14 +206,14 @@ __global__ void __launch_bounds__(256) peer_rank_mask_u8_kernel(const PeerFlagPa
     for (int k = 0; k < GSR_MAX_PEERS; ++k) {
       if (k < a.n_peers) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] |= ((w[k] >> (8 * j)) & 0xffu) ? (1 << k) : 0;
+        for (int j = 0; j < 4; ++j) m[j] |= ((w[k] >> (8 * j)) & 0x02u) ? (1 << k) : 0;   // bit 1: gradient row valid
       }
     }
     *reinterpret_cast<int4*>(mask_out + i) = make_int4(m[0], m[1], m[2], m[3]);
   } else {
     for (int j = 0; i + j < rows; ++j) {
       int mm = 0;
-      for (int k = 0; k < a.n_peers; ++k) mm |= a.flags[k][i + j] ? (1 << k) : 0;
+      for (int k = 0; k < a.n_peers; ++k) mm |= (a.flags[k][i + j] & 2u) ? (1 << k) : 0;
       mask_out[i + j] = mm;
     }
   }
@@ -231,12 +231,14 @@ __global__ void __launch_bounds__(256) peer_rank_mask_u8_kernel(const PeerFlagPa
 // per-row rank bitmask gsr_adam_step_peer consumes (it replaces gsr_peer_rank_mask_u8 in that case).
 __global__ void __launch_bounds__(256)
 peer_local_stats_kernel(long long P, long long stride, const int* __restrict__ radii, const float* __restrict__ dmean2D,
-                        float* __restrict__ stats /* [3][stride] or null */, uint8_t* __restrict__ flags) {
+                        float* __restrict__ stats /* [3][stride] or null */, uint8_t* __restrict__ flags,
+                        const int* __restrict__ grad_rows /* or null: every rendered row's gradient is valid */) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= P) return;
   const int r = radii[i];
   if (r <= 0) return;
-  flags[i] = 1;
+  // bit 0: this rank rendered the row (statistics); bit 1: its gradient row is valid (gsr_backward_args.grad_rows)
+  flags[i] = (uint8_t)(1u | ((grad_rows == nullptr || grad_rows[i] > 0) ? 2u : 0u));
   if (stats == nullptr) return;
   const float gx = dmean2D[3 * i], gy = dmean2D[3 * i + 1];
   stats[i] = stats[i] + sqrtf(fmaf(gy, gy, gx * gx));   // same expression as densification_stats_kernel
@@ -267,18 +269,22 @@ peer_stats_exchange_kernel(const PeerStatsParams a, long long P, long long strid
       any |= w[k] ? (1u << k) : 0u;
     }
   }
-  int m[4] = {0, 0, 0, 0};
+  int m[4] = {0, 0, 0, 0};    // ranks that RENDERED the row (flag bit 0): whose statistics count
+  int mg[4] = {0, 0, 0, 0};   // ranks whose GRADIENT row is valid (flag bit 1): what gsr_adam_step_peer pulls
 #pragma unroll
   for (int k = 0; k < GSR_MAX_PEERS; ++k) {
     if (k < a.n_peers) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) m[j] |= ((w[k] >> (8 * j)) & 0xffu) ? (1 << k) : 0;
+      for (int j = 0; j < 4; ++j) {
+        m[j] |= ((w[k] >> (8 * j)) & 0xffu) ? (1 << k) : 0;
+        mg[j] |= ((w[k] >> (8 * j)) & 0x02u) ? (1 << k) : 0;
+      }
     }
   }
   if (nrow == 4) {
-    *reinterpret_cast<int4*>(mask_out + i) = make_int4(m[0], m[1], m[2], m[3]);
+    *reinterpret_cast<int4*>(mask_out + i) = make_int4(mg[0], mg[1], mg[2], mg[3]);
   } else {
-    for (int j = 0; j < nrow; ++j) mask_out[i + j] = m[j];
+    for (int j = 0; j < nrow; ++j) mask_out[i + j] = mg[j];
   }
   if (any == 0) return;
   // all remote loads first (NVLink round trips overlap), then the combination in rank order
@@ -360,12 +366,12 @@ int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_
 }
 
 int gsr_peer_local_stats(int64_t P, const int32_t* radii, const float* dL_dmeans2D, float* stats_local,
-                         int64_t stats_stride, uint8_t* flags, void* stream) {
+                         int64_t stats_stride, uint8_t* flags, const int32_t* grad_rows, void* stream) {
   if (P < 0) return GSR_ERR_BAD_ARG;
   if (P == 0) return GSR_OK;
   if (!radii || !flags || (stats_local && (!dL_dmeans2D || stats_stride < P))) return GSR_ERR_BAD_ARG;
   peer_local_stats_kernel<<<(unsigned)((P + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      P, stats_stride, radii, dL_dmeans2D, stats_local, flags);
+      P, stats_stride, radii, dL_dmeans2D, stats_local, flags, grad_rows);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -454,6 +454,65 @@ __global__ void __launch_bounds__(kZeroThreads) zero_fill_kernel(const ZeroParam
   }
 }
 
+// ---- pass 1b: which rendered Gaussians received a gradient -----------------------------------------------
+// A rendered Gaussian that no pixel blended (hidden behind opaque ones, or beyond the point where its tiles'
+// pixels saturated) has all-zero moment sums, hence all-zero gradients: nothing to compute — 85 % of the rendered
+// rows of a 3 M-Gaussian room view.  One thread per entry of the forward's list reads the 48-byte moment row and
+// appends the Gaussians with a gradient to a second list (one atomic per CTA); pass 2 runs on that list with
+// dense warps.  A row without gradient still gets its per-view outputs (zeros) unless the outputs were
+// zero-filled, and is kept in the list when nobody else would define its parameter-gradient rows (rendered_rows_only
+// without grad_rows, first writer).
+constexpr int kSelThreads = 256;
+__global__ void __launch_bounds__(kSelThreads)
+select_grad_rows_kernel(const PreBwdParams a, const uint64_t* __restrict__ vis_items, const uint32_t* __restrict__ num_visible,
+                        uint32_t* __restrict__ list, uint32_t* __restrict__ num_list) {
+  __shared__ uint32_t s_off[kSelThreads / 32];
+  __shared__ uint32_t s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nv = *num_visible;
+  for (uint32_t t0 = blockIdx.x * kSelThreads; t0 < nv; t0 += gridDim.x * kSelThreads) {   // uniform per CTA
+    const uint32_t t = t0 + threadIdx.x;
+    bool keep = false;
+    uint32_t idx = 0;
+    if (t < nv) {
+      idx = (uint32_t)(vis_items[t] & 0xffffffffu);
+      const float4 m0 = reinterpret_cast<const float4*>(a.acc)[3 * (size_t)idx + 0];
+      const float4 m1 = reinterpret_cast<const float4*>(a.acc)[3 * (size_t)idx + 1];
+      const float m2 = a.acc[12 * (size_t)idx + 8];
+      const bool has_grad = m0.x != 0.f || m0.y != 0.f || m0.z != 0.f || m0.w != 0.f || m1.x != 0.f || m1.y != 0.f ||
+                            m1.z != 0.f || m1.w != 0.f || m2 != 0.f;
+      bool accm = false;
+      if (a.accumulate != 0)
+        accm = a.grad_rows != nullptr ? a.grad_rows[idx] > 0 : (a.accumulate_rows == nullptr || a.accumulate_rows[idx] > 0);
+      keep = has_grad || !(a.dense_zeroed || a.grad_rows != nullptr || accm);
+      if (!keep && !a.dense_zeroed) {   // the per-view outputs of a rendered row are always defined
+        store3(a.dL_dmean2D, (size_t)idx, {0.f, 0.f, 0.f});
+        if (a.dL_dconic) reinterpret_cast<float4*>(a.dL_dconic)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        store3(a.dL_dcolor, (size_t)idx, {0.f, 0.f, 0.f});
+        if (a.dL_dcov3D)
+          for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * (size_t)idx + k] = 0.f;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_off[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t c = lane < kSelThreads / 32 ? s_off[lane] : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (lane < kSelThreads / 32) s_off[lane] = incl - c;
+      if (lane == 31 && incl) s_base = atomicAdd(num_list, incl);
+    }
+    __syncthreads();
+    if (keep) list[s_base + s_off[warp] + __popc(m & ((1u << lane) - 1u))] = idx;
+    __syncthreads();   // s_off / s_base are reused by the next round
+  }
+}
+
 // ---- pass 2: the rendered Gaussians, taken from the depth-sorted list of the forward ------
 // sorted[0 .. *num_valid) are exactly the Gaussians that own at least one tile; every other
 // Gaussian received no gradient from the blend stage, so all of its outputs are zero.
@@ -462,7 +521,7 @@ __global__ void __launch_bounds__(kZeroThreads) zero_fill_kernel(const ZeroParam
 #define GSR_PREBWD_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(kPreBwdThreads, GSR_PREBWD_MINBLOCKS)
-preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
+preprocess_bwd_kernel(const PreBwdParams a, const uint32_t* __restrict__ list,
                       const uint32_t* __restrict__ num_valid) {
   // per-warp staging: SH rows in (coalesced 180 B reads), dL/dsh rows out (coalesced writes)
   __shared__ float s_sh[kPreBwdThreads / 32][32 * 45];
@@ -476,10 +535,17 @@ preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
   for (uint32_t r = 0; r < rounds; ++r) {
     const uint32_t t = r * stride + blockIdx.x * kPreBwdThreads + tid;
     const bool act = t < nv;
-    const int idx = act ? (int)(uint32_t)(sorted[t] & 0xffffffffu) : -1;
-    const bool accm = act && a.accumulate != 0 && (a.accumulate_rows == nullptr || a.accumulate_rows[idx] > 0);
+    const int idx = act ? (int)list[t] : -1;
+    // keyframe batches: add to the row's current parameter gradients — for every row, or only for the rows an
+    // earlier keyframe of the batch has written (grad_rows, kept by these kernels; or the caller's accumulate_rows)
+    bool accm = false;
+    if (act && a.accumulate != 0)
+      accm = a.grad_rows != nullptr ? a.grad_rows[idx] > 0 : (a.accumulate_rows == nullptr || a.accumulate_rows[idx] > 0);
     PreBwdIn in;
-    if (act) preprocess_bwd_load(a, idx, accm, in);
+    if (act) {
+      preprocess_bwd_load(a, idx, accm, in);
+      if (a.grad_rows != nullptr && !accm) a.grad_rows[idx] = 1;
+    }
     const unsigned accm_mask = __ballot_sync(0xffffffffu, accm);
     const unsigned act_mask = __ballot_sync(0xffffffffu, act);
     // (the grid is sized for the whole map while a view renders a fraction of it: three quarters of the warps have
@@ -526,8 +592,8 @@ preprocess_bwd_kernel(const PreBwdParams a, const uint64_t* __restrict__ sorted,
   }
 }
 
-int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const uint32_t* num_valid,
-                          bool zero_fill, cudaStream_t s) {
+int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* vis_items, const uint32_t* num_visible,
+                          uint32_t* list, uint32_t* num_list, bool zero_fill, cudaStream_t s) {
   if (p.P <= 0) return 0;
   if (p.M > 15) return GSR_ERR_BAD_ARG;
   const long long P = p.P;
@@ -550,9 +616,14 @@ int launch_preprocess_bwd(const PreBwdParams& p, const uint64_t* sorted, const u
     zero_fill_kernel<<<blocks, kZeroThreads, 0, s>>>(z);
     GSR_LAUNCHED();
   }
-  // enough CTAs for one round in the common case (V <= 300 k); grid-stride beyond
+  // the Gaussians that received a gradient (*num_list, zeroed by the caller) ...
+  const int want_sel = (p.P + kSelThreads - 1) / kSelThreads;
+  select_grad_rows_kernel<<<want_sel < 148 * 8 ? want_sel : 148 * 8, kSelThreads, 0, s>>>(p, vis_items, num_visible, list,
+                                                                                         num_list);
+  GSR_LAUNCHED();
+  // ... and their gradients: enough CTAs for one round in the common case (<= 300 k rows); grid-stride beyond
   const int want = (p.P + kPreBwdThreads - 1) / kPreBwdThreads;
-  preprocess_bwd_kernel<<<want < 148 * 16 ? want : 148 * 16, kPreBwdThreads, 0, s>>>(p, sorted, num_valid);
+  preprocess_bwd_kernel<<<want < 148 * 16 ? want : 148 * 16, kPreBwdThreads, 0, s>>>(p, list, num_list);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -142,6 +142,7 @@ class KeyframeBatchMapper:
         # one kernel over peer memory (gsr_adam_step_peer) instead of NCCL all-reduce + full Adam
         self.peer = None
         self.traffic_counters = None   # set by measure_exchange_traffic only
+        self._grad_rows: Optional[torch.Tensor] = None
         if peer_exchange is None:
             import os
             peer_exchange = os.environ.get("GSR_PEER_EXCHANGE", "1") != "0"
@@ -282,6 +283,14 @@ class KeyframeBatchMapper:
         return {"grad_in_bytes": 16 * loads, "param_changed_bytes": 16 * changed,
                 "param_out_bytes": 16 * changed * (1 if self.peer["mc_ptr"] else n - 1)}
 
+    def _grad_rows_mask(self) -> torch.Tensor:
+        """The batch's row mask (int32 [P], zeroed): gsr_backward marks the rows that received a gradient."""
+        if self._grad_rows is None:
+            self._grad_rows = torch.zeros(self.P, dtype=torch.int32, device=self.arena.device)
+        else:
+            self._grad_rows.zero_()
+        return self._grad_rows
+
     def exchange_bytes(self) -> Optional[dict]:
         """Model of the NVLink traffic of one peer exchange, per rank (bench.py prints it next to the measured
         time): parameter broadcast = this rank's shard to N-1 peers (one multicast store if available)."""
@@ -294,12 +303,14 @@ class KeyframeBatchMapper:
                 "param_in_bytes": int(shard * (pe["world"] - 1)), "multicast": bool(pe["mc_ptr"])}
 
     def _local_stats(self, radii: torch.Tensor, dL_dmeans2D: torch.Tensor, stats_local: Optional[torch.Tensor],
-                     flags: torch.Tensor) -> None:
+                     flags: torch.Tensor, grad_rows: Optional[torch.Tensor] = None) -> None:
         from . import _lib
         r = radii if radii.dtype == torch.int32 else radii.to(torch.int32)
         _lib.check(_lib.lib().gsr_peer_local_stats(self.P, C.c_void_p(r.data_ptr()), C.c_void_p(dL_dmeans2D.data_ptr()),
                                                    C.c_void_p(stats_local.data_ptr()) if stats_local is not None else None,
-                                                   self._stats_stride, C.c_void_p(flags.data_ptr()), self._stream_ptr()),
+                                                   self._stats_stride, C.c_void_p(flags.data_ptr()),
+                                                   C.c_void_p(grad_rows.data_ptr()) if grad_rows is not None else None,
+                                                   self._stream_ptr()),
                    "gsr_peer_local_stats")
 
     def _step_peer(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
@@ -314,16 +325,15 @@ class KeyframeBatchMapper:
         pe["flags"].zero_()
         if pe["stats_local"] is not None:
             pe["stats_local"].zero_()
-        mask = None
+        rows = self._grad_rows_mask()
         for i, kf in enumerate(keyframes):
-            # rows this rank does not render are never read by the exchange (per-row rank bitmask), so no
-            # backward pass needs the dense zero fill: the first keyframe writes its rendered rows, the others
-            # add to the rows already written and overwrite the rest (gsr_backward_args.accumulate_rows)
+            # rows without a valid gradient on this rank are never read by the exchange (per-row rank bitmask), so
+            # no backward pass needs the dense zero fill: the first keyframe writes the rows that received a
+            # gradient, the others add to the rows already written and overwrite the rest; rendered rows that no
+            # pixel blended are not touched at all (gsr_backward_args.grad_rows, kept by the kernel)
             _, radii, g = self.render_backward(kf, self.grad_views, on_forward=on_forward,
-                                               rendered_rows_only=True, accumulate=(i > 0), accumulate_rows=mask)
-            self._local_stats(radii, g[0], pe["stats_local"], pe["flags"])
-            if i + 1 < len(keyframes):
-                mask = radii.clone() if mask is None else torch.maximum(mask, radii, out=mask)
+                                               rendered_rows_only=True, accumulate=(i > 0), grad_rows=rows)
+            self._local_stats(radii, g[0], pe["stats_local"], pe["flags"], rows)
         stream = self._stream_ptr()
         self._mark("render_end", main)
         pe["hg"].barrier(channel=0)          # every rank's gradients, flags and statistics are written
@@ -386,7 +396,7 @@ class KeyframeBatchMapper:
 
     def render_backward(self, kf: Keyframe, grad_views: Dict[str, torch.Tensor], fwd=None, on_forward=None,
                         rendered_rows_only: bool = False, accumulate: bool = False,
-                        accumulate_rows: Optional[torch.Tensor] = None):
+                        accumulate_rows: Optional[torch.Tensor] = None, grad_rows: Optional[torch.Tensor] = None):
         """fwd + bwd of one keyframe; parameter gradients are written into grad_views.
         ``on_forward(kf, fwd)`` runs between the two passes (e.g. to start reading the image back
         and to make the stream wait for the uploaded dL/d(image))."""
@@ -411,7 +421,7 @@ class KeyframeBatchMapper:
                                            dL_dout, p["dc"], p["sh"], self.degree, kf.campos, geom, R,
                                            binning, img, B, sample, False, want_dcov3D=False, out=out,
                                            rendered_rows_only=rendered_rows_only, accumulate=accumulate,
-                                           accumulate_rows=accumulate_rows,
+                                           accumulate_rows=accumulate_rows, grad_rows=grad_rows,
                                            raw_opacity=p["opacity"] if self.raw_params else None)
         self.last_radii, self.last_color = radii, color
         return color, radii, g
@@ -598,18 +608,15 @@ class KeyframeBatchMapper:
         main.wait_event(self._ev_side)  # later work on this stream sees the complete update
 
     def _step_masked(self, keyframes: Sequence[Keyframe], grad_scale: float, on_forward=None) -> None:
-        """Single rank, K >= 1 keyframes: no backward pass zero-fills; the first writes its rendered rows, the
-        others add to the rows already written and overwrite the rest; ONE masked Adam pass reads the gradient
-        only for the rows some keyframe rendered.  Bit-identical to zero fill + dense sum + dense Adam."""
-        mask = None
+        """Single rank, K >= 1 keyframes: no backward pass zero-fills; the first writes the rows that received a
+        gradient, the others add to the rows already written and overwrite the rest (gsr_backward_args.grad_rows);
+        ONE masked Adam pass reads the gradient only for those rows.  Same result as zero fill + dense sum + dense
+        Adam (rows without gradient contribute exact zeros there)."""
+        mask = self._grad_rows_mask()
         for i, kf in enumerate(keyframes):
             _, radii, g = self.render_backward(kf, self.grad_views, on_forward=on_forward, rendered_rows_only=True,
-                                               accumulate=(i > 0), accumulate_rows=mask)
+                                               accumulate=(i > 0), grad_rows=mask)
             self._add_stats(radii, g[0])
-            if len(keyframes) == 1:
-                mask = radii
-            else:
-                mask = radii.clone() if mask is None else torch.maximum(mask, radii, out=mask)
         grads = {self.opt_params[k]: self.grad_views[k] for k in SEGMENTS if self.opt_params[k].numel() > 0}
         self.optimizer.step_rows(mask, self.optimizer.ROWS_ALL, grads=grads, grad_scale=grad_scale, new_step=True)
 

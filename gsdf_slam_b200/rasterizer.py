@@ -121,7 +121,8 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
                                    binningBuffer, imageBuffer, B, sampleBuffer, debug,
                                    want_dcov3D: bool = True, out: Optional[dict] = None,
                                    rendered_rows_only: bool = False, raw_opacity: Optional[torch.Tensor] = None,
-                                   accumulate: bool = False, accumulate_rows: Optional[torch.Tensor] = None):
+                                   accumulate: bool = False, accumulate_rows: Optional[torch.Tensor] = None,
+                                   grad_rows: Optional[torch.Tensor] = None):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_ddc, dL_dsh,
     dL_dscales, dL_drotations)   (same order as src/rasterize_points.cu:204)
 
@@ -135,13 +136,17 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     parameters (chain rule through sigmoid / exp / normalize inside the backward preprocess).
     ``accumulate`` / ``accumulate_rows`` (extension, keyframe batches): add the parameter gradients to the rows'
     current values — to every rendered row, or only to the rows marked (> 0) in the int32 ``accumulate_rows``
-    (the rows an earlier keyframe of the batch has written); see gsr_backward_args."""
+    (the rows an earlier keyframe of the batch has written); see gsr_backward_args.
+    ``grad_rows`` (extension): int32 [P] in/out row mask kept by the callee — rows with a value > 0 are added to
+    (with ``accumulate``), and every rendered row that received a gradient is set to 1; rendered rows that no pixel
+    blended are neither flagged nor (with ``rendered_rows_only``) written.  Zero it at the start of a batch and hand it
+    to ``FusedAdam.step_rows`` as the row mask."""
     L = _lib.lib()
     dev = means3D.device
     P = int(means3D.size(0))
-    if accumulate_rows is not None and (accumulate_rows.dtype != torch.int32 or not accumulate_rows.is_contiguous()
-                                        or accumulate_rows.numel() != P):
-        raise RuntimeError("accumulate_rows must be a contiguous int32 tensor with one entry per Gaussian")
+    for name, rows in (("accumulate_rows", accumulate_rows), ("grad_rows", grad_rows)):
+        if rows is not None and (rows.dtype != torch.int32 or not rows.is_contiguous() or rows.numel() != P):
+            raise RuntimeError(f"{name} must be a contiguous int32 tensor with one entry per Gaussian")
     H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
     M = int(sh.size(1)) if (sh is not None and sh.dim() >= 2 and sh.size(0) != 0) else 0
     opts = dict(dtype=torch.float32, device=dev)
@@ -186,7 +191,8 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
             dL_drot=_ptr(dL_drotations), debug=int(bool(debug)), stream=_stream(dev),
             raw_params=int(raw_opacity is not None), rendered_rows_only=int(bool(rendered_rows_only)),
             accumulate=int(bool(accumulate)),
-            accumulate_rows=_ptr(accumulate_rows) if accumulate_rows is not None else None)
+            accumulate_rows=_ptr(accumulate_rows) if accumulate_rows is not None else None,
+            grad_rows=_ptr(grad_rows) if grad_rows is not None else None)
         with torch.cuda.device(dev):
             _lib.check(L.gsr_backward(C.byref(a)), "gsr_backward")
     if dL_dcov3D is None:

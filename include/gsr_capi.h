@@ -156,6 +156,19 @@ typedef struct gsr_backward_args {
                                   earlier keyframe of the batch, e.g. the running maximum of their radii) are
                                   added to, the other rendered rows are overwritten — so NO keyframe of a
                                   batch needs the dense zero fill; NULL = add to every rendered row */
+  int32_t* grad_rows;          /* optional, [P], in/out — the row mask of a keyframe batch kept by the callee
+                                  itself (the caller zeroes it at the start of the batch):
+                                    in : with `accumulate`, the rows with grad_rows > 0 are added to and the other
+                                         rendered rows overwritten (takes precedence over accumulate_rows);
+                                    out: grad_rows[row] = 1 for every rendered row that RECEIVED a gradient (some
+                                         pixel blended it).  A rendered row that received none (a splat hidden
+                                         behind opaque ones: all of its gradients are exactly zero — 85 % of the
+                                         rendered rows of a 3 M-Gaussian room view) is not flagged, and with
+                                         rendered_rows_only its six PARAMETER gradient rows are not written at all
+                                         (the per-view outputs dL_dmean2D / dL_dconic / dL_dcolor are, as zeros).
+                                  Consumers that go through this mask — gsr_adam_step_rows(row_mask = grad_rows),
+                                  gsr_peer_local_stats(..., grad_rows) -> gsr_adam_step_peer — treat every other row
+                                  as zero gradient, which is what it is. */
 } gsr_backward_args;
 
 int gsr_forward(const gsr_forward_args* a);
@@ -280,7 +293,8 @@ int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_
  * per-view update is GaussianMapper::trainForOneIteration, src/gaussian_mapper.cpp:443-447, and
  * GaussianModel::addDensificationStats, src/gaussian_model.cpp:667-681).
  * gsr_peer_local_stats: after each LOCAL keyframe's backward pass; for the rows with radii > 0 it sets
- *   flags[row] = 1 and, when stats_local != NULL, adds that view's terms to the rank's per-step deltas
+ *   flags[row] = 1 (rendered) | 2 (its gradient row is valid: grad_rows[row] > 0, or grad_rows == NULL — see
+ *   gsr_backward_args.grad_rows; only those rows are pulled over NVLink by gsr_adam_step_peer) and, when stats_local != NULL, adds that view's terms to the rank's per-step deltas
  *   stats_local = [accum | denom | max_radii], three arrays of stats_stride >= P floats each (stats_stride a
  *   multiple of 4, base 16-byte aligned; the caller zeroes flags — P + 16 bytes, 4-byte aligned — and stats_local
  *   at the start of the step; both live in peer-mapped memory).
@@ -289,7 +303,7 @@ int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_
  *   xyz_gradient_accum += sum_k accum_k, denom += sum_k denom_k, max_radii2D = max(max_radii2D, max_k ...)
  *   over the ranks that rendered the row, in rank order (bit-identical replicas). */
 int gsr_peer_local_stats(int64_t P, const int32_t* radii, const float* dL_dmeans2D, float* stats_local,
-                         int64_t stats_stride, uint8_t* flags, void* stream);
+                         int64_t stats_stride, uint8_t* flags, const int32_t* grad_rows, void* stream);
 int gsr_peer_stats_exchange(const uint8_t* const* flags_peers, const float* const* stats_peers, int64_t stats_stride,
                             int n_peers, int64_t P, int32_t* mask_out, float* max_radii2D, float* xyz_gradient_accum,
                             float* denom, void* stream);

@@ -236,6 +236,54 @@ def test_backward_accumulate_adds_to_the_rendered_rows_only():
     assert rel_l2(g2[0][vis], g1["dL_dmeans2D"][vis]) <= 1e-5
 
 
+def test_grad_rows_mask_skips_the_rows_no_pixel_blended():
+    """gsr_backward_args.grad_rows: the callee keeps the batch's row mask.  A rendered Gaussian that no pixel
+    blended (hidden behind opaque ones) has exactly zero gradients in the dense API; with grad_rows it is neither
+    flagged nor written, the flagged rows hold what the dense API returns, and a second keyframe adds to them."""
+    import gsdf_slam_b200 as gs
+    sc = scenes.room_scene(400_000, 320, 192, 160.0, 160.0, seed=33, name="occluded_room")   # long, opaque lists
+    t = to_dev(sc)
+    fwd = run_product_forward(sc, t)
+    dense = run_product_backward(sc, t, fwd)                         # reference API: every row defined
+    names = ["dL_dmeans3D", "dL_ddc", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"]
+    R, B, color, radii, geom, binning, img, sample = fwd
+    cam, e = sc.cam, t["empty"]
+    vis = radii > 0
+    nonzero = torch.zeros(sc.P, dtype=torch.bool, device="cuda")
+    for n in names:
+        nonzero |= (dense[n].reshape(sc.P, -1) != 0).any(1)
+
+    def backward(out, rows, accumulate):
+        return gs.RasterizeGaussiansBackwardCUDA(t["bg"], t["means3D"], radii, e, t["scales"], t["rotations"], 1.0, e,
+                                                 t["viewmatrix"], t["projmatrix"], cam.tanfovx, cam.tanfovy,
+                                                 t["dL_dout"], t["dc"], t["sh"], sc.degree, t["campos"], geom, R,
+                                                 binning, img, B, sample, False, out=out, rendered_rows_only=True,
+                                                 accumulate=accumulate, grad_rows=rows)
+
+    out = {n: torch.full_like(dense[n], float("nan")) for n in names}
+    rows = torch.zeros(sc.P, dtype=torch.int32, device="cuda")
+    g = backward(out, rows, False)
+    torch.cuda.synchronize()
+    flagged = rows > 0
+    hidden = vis & ~flagged
+    assert int(hidden.sum()) > sc.P // 50 and int(flagged.sum()) > sc.P // 200    # the scene does hide splats
+    assert not bool((flagged & ~vis).any())
+    assert not bool((nonzero & ~flagged).any())              # every row with a non-zero dense gradient is flagged
+    for n in names:
+        assert bool(torch.isnan(out[n][~flagged]).all()), n                      # never written
+        assert rel_l2(out[n][flagged], dense[n][flagged]) <= 1e-5, n
+        assert float(dense[n][hidden].abs().max()) == 0.0, n                     # ... and rightly so
+    assert float(g[0][hidden].abs().max()) == 0.0                                # per-view outputs are defined
+    assert rel_l2(g[0][flagged], dense["dL_dmeans2D"][flagged]) <= 1e-5
+    # a second keyframe of the batch (the same view): flagged rows are added to, nothing else is touched
+    backward(out, rows, True)
+    torch.cuda.synchronize()
+    assert torch.equal(rows > 0, flagged)
+    for n in names:
+        assert bool(torch.isnan(out[n][~flagged]).all()), n
+        assert rel_l2(out[n][flagged], 2.0 * dense[n][flagged]) <= 1e-5, n
+
+
 def test_sh0_empty_rest_drops_colour_gradient():
     """Reference quirk 14: a 0-element `sh` skips the whole SH backward (dL_ddc == 0)."""
     if not _ref_available():

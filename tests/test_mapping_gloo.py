@@ -54,7 +54,7 @@ class _FakeMapper(KeyframeBatchMapper):
     (gsr_peer_local_stats) by the same arithmetic in torch."""
 
     def render_backward(self, kf, grad_views, fwd=None, on_forward=None, rendered_rows_only=False,
-                        accumulate=False, accumulate_rows=None):
+                        accumulate=False, accumulate_rows=None, grad_rows=None):
         for i, name in enumerate(SEGMENTS):
             g = grad_views[name]
             if g.numel():
@@ -69,7 +69,7 @@ class _FakeMapper(KeyframeBatchMapper):
         dmean2D = torch.stack([torch.cos(rows * 0.1 + kf), torch.sin(rows * 0.2 - kf), torch.zeros(self.P)], 1).float()
         return None, radii, (dmean2D,)
 
-    def _local_stats(self, radii, dL_dmeans2D, stats_local, flags):
+    def _local_stats(self, radii, dL_dmeans2D, stats_local, flags, grad_rows=None):
         vis = radii > 0
         flags[: self.P][vis] = 1
         if stats_local is not None:
