@@ -266,7 +266,7 @@ def test_grad_rows_mask_skips_the_rows_no_pixel_blended():
     torch.cuda.synchronize()
     flagged = rows > 0
     hidden = vis & ~flagged
-    assert int(hidden.sum()) > sc.P // 50 and int(flagged.sum()) > sc.P // 200    # the scene does hide splats
+    assert int(hidden.sum()) > 2000 and int(flagged.sum()) > 2000    # the scene does hide splats
     assert not bool((flagged & ~vis).any())
     assert not bool((nonzero & ~flagged).any())              # every row with a non-zero dense gradient is flagged
     for n in names:

@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
-# GPU call r2z (2 GPUs): C mapper vs NCCL vs sequential, Python peer path, bench at N=2 (small, then full)
-O=gpurun_out/r2z; mkdir -p $O
+# GPU call r3c (2 GPUs): C mapper vs NCCL vs sequential, Python peer path, bench at N=2 (small, then full)
+O=gpurun_out/r3c; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
 nvidia-smi topo -m > $O/topo.txt 2>&1
 $TR tools/check_cmapper.py > $O/check_cmapper.json 2> $O/check_cmapper.err; echo "check_cmapper rc=$?"; cat $O/check_cmapper.json; tail -3 $O/check_cmapper.err
@@ -11,3 +11,4 @@ import json; d=json.load(open('$O/bench2_small.json')); print(json.dumps({k:d.ge
 $TR bench.py --gpus 2 --steps 30 --warmup 5 > $O/bench2.json 2> $O/bench2.err; echo "bench rc=$?"; tail -3 $O/bench2.err
 python -c "
 import json; d=json.load(open('$O/bench2.json')); print(json.dumps({k:d.get(k) for k in ('value','ms_per_step','e2e','exchange_parity','nvlink','rank_breakdown')})[:2500]); print(json.dumps(d['mapping_cfg5'])[:2500])"
+python -m pytest tests/test_gpu_parity.py -x -q -k "grad_rows or accumulate" 2>&1 | tail -3
