@@ -68,11 +68,11 @@ class AdamGroup(C.Structure):
 
 
 GSR_MAX_PEERS = 8
-GSR_PEER_MAX_SEGMENTS = 8
+GSR_PEER_MAX_SEGMENTS = 12
 
 
 class PeerSegment(C.Structure):
-    _fields_ = [("start", C.c_int64), ("numel", C.c_int64), ("width", C.c_int32), ("lr", C.c_double)]
+    _fields_ = [("start", C.c_int64), ("numel", C.c_int64), ("width", C.c_int32), ("rule", C.c_int32), ("lr", C.c_double)]
 
 
 class PeerAdamArgs(C.Structure):
@@ -102,6 +102,7 @@ class MapperKeyframe(C.Structure):
                 ("dL_dpix", C.c_void_p), ("gt_image", C.c_void_p), ("mask", C.c_void_p), ("out_color", C.c_void_p)]
 
 
+GSR_PEER_RULE_ADAM, GSR_PEER_RULE_SUM, GSR_PEER_RULE_MAX = 0, 1, 2
 GSR_MAPPER_HANDLE_BYTES = 256
 GSR_STORE_GROUPS = 6
 

@@ -92,13 +92,15 @@ struct gsr_mapper {
   int64_t P = 0;
   int widths[kSegs] = {3, 3, 1, 3, 4, 0};
   int64_t seg_off[kSegs] = {0}, seg_n[kSegs] = {0};
-  int64_t total = 0;          // floats per arena
-  int64_t stats_stride = 0;   // floats between the three per-rank statistics delta arrays
+  int64_t total = 0;          // floats of the six parameter segments
+  int64_t arena = 0;          // floats per arena: total + the three statistics segments [accum | denom | max_radii]
+  int64_t stats_stride = 0;   // floats between the statistics segments
   double lr[kSegs];
-  // symmetric block of this rank: [param arena | gradient arena | stats deltas 3P | flags P+16 | signal pad]
+  // symmetric block of this rank: [param arena (+ replicated statistics) | gradient arena (+ this rank's statistics
+  // deltas of the step) | flags P+16 | signal pad]
   char* sym = nullptr;
   size_t sym_bytes = 0;
-  size_t off_param = 0, off_grad = 0, off_stats = 0, off_flags = 0, off_pad = 0;
+  size_t off_param = 0, off_grad = 0, off_flags = 0, off_pad = 0;
   char* peer[GSR_MAPPER_MAX_RANKS] = {nullptr};   // base of every rank's block as mapped here (own: sym)
   bool connected = false;
   uint32_t epoch = 0;
@@ -106,7 +108,7 @@ struct gsr_mapper {
   float* exp_avg = nullptr;     // world > 1: the owned chunks; world == 1: the whole arena
   float* exp_avg_sq = nullptr;
   int32_t* union_mask = nullptr;   // [P + 4]
-  float* stats = nullptr;          // [3P] replicated statistics (max_radii2D | accum | denom)
+  bool stats = false;              // densification statistics kept (in the tail of the parameter arena)
   int32_t* radii = nullptr;        // [P] of the current keyframe
   int32_t* mask = nullptr;         // [P] rows of the batch that received a gradient (gsr_backward_args.grad_rows)
   float* dmean2D = nullptr;        // [3P] per-view output
@@ -120,7 +122,8 @@ struct gsr_mapper {
 
   float* param_ptr(int k) const { return reinterpret_cast<float*>(peer[k] + off_param); }
   float* grad_ptr(int k) const { return reinterpret_cast<float*>(peer[k] + off_grad); }
-  float* stats_local_ptr(int k) const { return reinterpret_cast<float*>(peer[k] + off_stats); }
+  float* stats_local_ptr(int k) const { return grad_ptr(k) + total; }                 // [accum | denom | max_radii]
+  float* stat_ptr(int j) const { return param_ptr(cfg.rank) + total + j * stats_stride; }   // j: 0 accum, 1 denom, 2 max
   uint8_t* flags_ptr(int k) const { return reinterpret_cast<uint8_t*>(peer[k] + off_flags); }
   uint32_t* pad_ptr(int k) const { return reinterpret_cast<uint32_t*>(peer[k] + off_pad); }
 };
@@ -165,18 +168,19 @@ gsr_mapper* gsr_mapper_create(const gsr_mapper_config* cfg, void* handle_out) {
     m->lr[k] = cfg->lr[k];
   }
   m->total = off;
+  m->stats_stride = (m->P + 3) / 4 * 4;
+  m->stats = cfg->with_stats != 0;
+  m->arena = m->total + (m->stats ? 3 * m->stats_stride : 0);
   bool ok = cudaGetDevice(&m->device) == cudaSuccess;
   // one allocation for everything the peers touch, so one IPC handle describes it
   size_t o = 0;
   auto carve_off = [&](size_t bytes) { const size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
-  m->off_param = carve_off((size_t)m->total * 4);
-  m->off_grad = carve_off((size_t)m->total * 4);
-  m->stats_stride = (m->P + 3) / 4 * 4;
-  m->off_stats = carve_off((size_t)3 * m->stats_stride * 4);
+  m->off_param = carve_off((size_t)m->arena * 4);
+  m->off_grad = carve_off((size_t)m->arena * 4);
   m->off_flags = carve_off((size_t)m->P + 16);
   m->off_pad = carve_off(256);
   m->sym_bytes = o;
-  const int64_t n_chunks = (m->total + kShardChunk - 1) / kShardChunk;
+  const int64_t n_chunks = (m->arena + kShardChunk - 1) / kShardChunk;
   const int64_t owned = n_chunks > cfg->rank ? (n_chunks - cfg->rank + cfg->world - 1) / cfg->world : 0;
   const size_t n_mom = cfg->world > 1 ? (size_t)(owned > 0 ? owned : 1) * kShardChunk : (size_t)m->total;
   ok = ok && cudaMalloc(reinterpret_cast<void**>(&m->sym), m->sym_bytes) == cudaSuccess &&
@@ -189,9 +193,6 @@ gsr_mapper* gsr_mapper_create(const gsr_mapper_config* cfg, void* handle_out) {
        cudaMalloc(reinterpret_cast<void**>(&m->mask), (size_t)m->P * 4) == cudaSuccess &&
        cudaMalloc(reinterpret_cast<void**>(&m->dmean2D), (size_t)m->P * 12) == cudaSuccess &&
        cudaMalloc(reinterpret_cast<void**>(&m->dcolor), (size_t)m->P * 12) == cudaSuccess;
-  if (ok && cfg->with_stats)
-    ok = cudaMalloc(reinterpret_cast<void**>(&m->stats), (size_t)3 * m->P * 4) == cudaSuccess &&
-         cudaMemset(m->stats, 0, (size_t)3 * m->P * 4) == cudaSuccess;
   if (ok) {
     m->ctx = gsr_context_create();
     ok = m->ctx != nullptr;
@@ -244,7 +245,8 @@ float* gsr_mapper_param(gsr_mapper* m, int segment) {
 
 float* gsr_mapper_stat(gsr_mapper* m, int which) {
   if (!m || !m->stats || which < 0 || which > 2) return nullptr;
-  return m->stats + (size_t)which * m->P;
+  static const int tail[3] = {2, 0, 1};   // API order: max_radii2D, xyz_gradient_accum, denom
+  return m->stat_ptr(tail[which]);
 }
 
 int gsr_mapper_set_lr(gsr_mapper* m, int segment, double lr) {
@@ -264,9 +266,9 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
   float* params = m->param_ptr(rank);
   float* grads = m->grad_ptr(rank);
   auto seg = [&](float* base, int k) { return m->seg_n[k] ? base + m->seg_off[k] : nullptr; };
-  float* stat_maxr = m->stats;
-  float* stat_accum = m->stats ? m->stats + (size_t)P : nullptr;
-  float* stat_denom = m->stats ? m->stats + 2 * (size_t)P : nullptr;
+  float* stat_accum = m->stats ? m->stat_ptr(0) : nullptr;
+  float* stat_denom = m->stats ? m->stat_ptr(1) : nullptr;
+  float* stat_maxr = m->stats ? m->stat_ptr(2) : nullptr;
 
   if (world > 1) {
     // this rank's "rendered" flags and statistics deltas of the step (the previous step's second barrier
@@ -363,15 +365,8 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
 
   MAP_RC(mapper_barrier(m, s));   // every rank's gradients, flags and statistics deltas are written
   const uint8_t* fl[GSR_MAPPER_MAX_RANKS];
-  const float* sl[GSR_MAPPER_MAX_RANKS];
-  for (int k = 0; k < world; ++k) {
-    fl[k] = m->flags_ptr(k);
-    sl[k] = m->stats_local_ptr(k);
-  }
-  if (m->stats)
-    MAP_RC(gsr_peer_stats_exchange(fl, sl, m->stats_stride, world, P, m->union_mask, stat_maxr, stat_accum, stat_denom, s));
-  else
-    MAP_RC(gsr_peer_rank_mask_u8(fl, world, P, m->union_mask, s));
+  for (int k = 0; k < world; ++k) fl[k] = m->flags_ptr(k);
+  MAP_RC(gsr_peer_rank_mask_u8(fl, world, P, m->union_mask, s));   // per row: who holds a gradient, who rendered it
   gsr_peer_adam_args a;
   std::memset(&a, 0, sizeof(a));
   a.n_peers = world;
@@ -389,9 +384,18 @@ int gsr_mapper_step(gsr_mapper* m, const gsr_mapper_keyframe* kfs, int n, const 
     a.segments[ns].lr = m->lr[k];
     ++ns;
   }
+  if (m->stats) {   // the statistics ride along: accum, denom summed over the ranks, max_radii their maximum
+    static const int rules[3] = {GSR_PEER_RULE_SUM, GSR_PEER_RULE_SUM, GSR_PEER_RULE_MAX};
+    for (int j = 0; j < 3; ++j, ++ns) {
+      a.segments[ns].start = m->total + j * m->stats_stride;
+      a.segments[ns].numel = P;
+      a.segments[ns].width = 1;
+      a.segments[ns].rule = rules[j];
+    }
+  }
   a.n_segments = ns;
   a.shard_lo = 0;
-  a.shard_hi = m->total;
+  a.shard_hi = m->arena;
   a.shard_chunk = kShardChunk;
   a.exp_avg = m->exp_avg;
   a.exp_avg_sq = m->exp_avg_sq;
@@ -410,7 +414,7 @@ void gsr_mapper_destroy(gsr_mapper* m) {
   cudaDeviceSynchronize();
   for (int k = 0; k < m->cfg.world; ++k)
     if (k != m->cfg.rank && m->peer[k]) cudaIpcCloseMemHandle(m->peer[k]);
-  void* bufs[] = {m->sym, m->exp_avg, m->exp_avg_sq, m->union_mask, m->stats, m->radii, m->mask,
+  void* bufs[] = {m->sym, m->exp_avg, m->exp_avg_sq, m->union_mask, m->radii, m->mask,
                   m->dmean2D, m->dcolor, m->dL, m->color};
   for (void* b : bufs)
     if (b) cudaFree(b);

@@ -37,7 +37,7 @@ struct PeerSegDev {
   long long start;       // first arena element of the segment
   long long numel;
   unsigned width;        // elements per row
-  unsigned magic;        // ceil(2^32 / width)
+  unsigned rule;         // GSR_PEER_RULE_*
   float neg_step_size;
   float inv_sqrt_bc2;
 };
@@ -78,8 +78,15 @@ __device__ __forceinline__ void peer_adam_elem(float& p, float g, float& m, floa
   v = v2;
 }
 
-template <bool kCount>
-__global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamParams a, int my_rank) {
+// (4 CTAs per SM = at most 64 registers: the statistics rules pushed the kernel to 72 registers and 3 CTAs, which
+// cost 15 % — it is bound by instruction issue and latency at this occupancy, not by HBM)
+#ifndef GSR_PEER_MINBLOCKS
+#define GSR_PEER_MINBLOCKS 4
+#endif
+// kPeers: n_peers rounded up to 1 / 2 / 4 / 8 — the loops over the peers are unrolled (all remote loads in flight
+// together), and the kernel is issue-bound, so two ranks should not execute the predicated code of eight
+template <bool kCount, int kPeers>
+__global__ void __launch_bounds__(kPeerThreads, GSR_PEER_MINBLOCKS) peer_adam_kernel(const PeerAdamParams a, int my_rank) {
   // element handled by this thread and its slot in the shard-local moment arrays
   long long e, mo;
   if (a.chunk > 0) {
@@ -93,16 +100,21 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
     mo = e - a.lo;
   }
   if (e >= a.hi) return;
-  // local state first: these HBM reads overlap the NVLink round trips below
+  // local state first: these HBM reads overlap the index arithmetic and the NVLink round trips below (the
+  // statistics segments have no moments; their slots of the moment arrays exist and are simply not written)
   const float4 p_old = *reinterpret_cast<const float4*>(a.param[my_rank] + e);
   float4 m = __ldcs(reinterpret_cast<const float4*>(a.exp_avg + mo));
   float4 v = __ldcs(reinterpret_cast<const float4*>(a.exp_avg_sq + mo));
-  // segment of this float4 (segments start on 4-element boundaries, so it lies in exactly one)
+  // segment of this float4 (segments start on 4-element boundaries, so it lies in exactly one; elements between
+  // two segments belong to none)
   int si = 0;
 #pragma unroll 1
   for (int k = 1; k < a.n_segs; ++k)
     if (e >= a.seg[k].start) si = k;
   const PeerSegDev S = a.seg[si];
+  const long long seg_end = S.start + S.numel;
+  if (e >= seg_end) return;
+  const bool adam = S.rule == GSR_PEER_RULE_ADAM;
   // rows of the four elements: one wide division per thread, then small offsets
   const unsigned long long off = (unsigned long long)(e - S.start);
   unsigned r0, rem;
@@ -113,47 +125,73 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
     r0 = (unsigned)(off / S.width);
     rem = (unsigned)(off - (unsigned long long)r0 * S.width);
   }
-  const long long seg_end = S.start + S.numel;
-  // per element: which ranks rendered its row (bit k of the row's mask, gsr_peer_union_mask)
+  // per element: which ranks hold a valid gradient row (mask bits 0..7) — or, for the statistics segments, which
+  // ranks rendered the row (bits 8..15)
+  const unsigned shift = adam ? 0u : 8u;
   unsigned who[4], want = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const unsigned rr = rem + j;
     const unsigned row = r0 + (rr >= S.width) + (rr >= 2 * S.width) + (rr >= 3 * S.width);
-    who[j] = (e + j < seg_end) ? (unsigned)__ldg(a.union_mask + row) : 0u;
+    who[j] = (e + j < seg_end) ? (((unsigned)__ldg(a.union_mask + row) >> shift) & 0xffu) : 0u;
     want |= who[j];
   }
   float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (want) {
-    // Only the arenas of the ranks that rendered one of these rows are read (a view sees a fraction of the
-    // map, so most of the N-1 remote loads disappear, and the ranks need not zero-fill the rows they did
-    // not render).  All loads are issued before the first sum (NVLink round trips overlap); the additions
-    // run in rank order on the one rank that owns the element, so every replica receives the same value.
-    float4 x[GSR_MAX_PEERS];
+    // Only the arenas of the ranks with a valid row are read (a view sees a fraction of the map, so most of the
+    // N-1 remote loads disappear, and the ranks need not zero-fill the rows they did not write).  All loads are
+    // issued before the first sum (NVLink round trips overlap); the additions run in rank order on the one rank
+    // that owns the element, so every replica receives the same value.
+    float4 x[kPeers];
 #pragma unroll
-    for (int k = 0; k < GSR_MAX_PEERS; ++k)
+    for (int k = 0; k < kPeers; ++k)
       if (k < a.n_peers && ((want >> k) & 1u)) x[k] = __ldcs(reinterpret_cast<const float4*>(a.grad[k] + e));
     if (kCount) {
       const int remote = __popc(want & ((1u << a.n_peers) - 1u) & ~(1u << my_rank));
       if (remote) atomicAdd(a.traffic, (unsigned long long)remote);
     }
+    if (S.rule != GSR_PEER_RULE_MAX) {   // (warp-uniform except where a warp straddles two segments)
 #pragma unroll
-    for (int k = 0; k < GSR_MAX_PEERS; ++k) {
-      if (k < a.n_peers && ((want >> k) & 1u)) {
-        if ((who[0] >> k) & 1u) g.x += x[k].x;
-        if ((who[1] >> k) & 1u) g.y += x[k].y;
-        if ((who[2] >> k) & 1u) g.z += x[k].z;
-        if ((who[3] >> k) & 1u) g.w += x[k].w;
+      for (int k = 0; k < kPeers; ++k) {
+        if (k < a.n_peers && ((want >> k) & 1u)) {
+          if ((who[0] >> k) & 1u) g.x += x[k].x;
+          if ((who[1] >> k) & 1u) g.y += x[k].y;
+          if ((who[2] >> k) & 1u) g.z += x[k].z;
+          if ((who[3] >> k) & 1u) g.w += x[k].w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kPeers; ++k) {
+        if (k < a.n_peers && ((want >> k) & 1u)) {
+          if ((who[0] >> k) & 1u) g.x = fmaxf(g.x, x[k].x);
+          if ((who[1] >> k) & 1u) g.y = fmaxf(g.y, x[k].y);
+          if ((who[2] >> k) & 1u) g.z = fmaxf(g.z, x[k].z);
+          if ((who[3] >> k) & 1u) g.w = fmaxf(g.w, x[k].w);
+        }
       }
     }
   }
   float4 p = p_old;
-  peer_adam_elem(p.x, g.x, m.x, v.x, a, S.neg_step_size, S.inv_sqrt_bc2);
-  peer_adam_elem(p.y, g.y, m.y, v.y, a, S.neg_step_size, S.inv_sqrt_bc2);
-  peer_adam_elem(p.z, g.z, m.z, v.z, a, S.neg_step_size, S.inv_sqrt_bc2);
-  peer_adam_elem(p.w, g.w, m.w, v.w, a, S.neg_step_size, S.inv_sqrt_bc2);
-  __stcs(reinterpret_cast<float4*>(a.exp_avg + mo), m);
-  __stcs(reinterpret_cast<float4*>(a.exp_avg_sq + mo), v);
+  if (adam) {
+    peer_adam_elem(p.x, g.x, m.x, v.x, a, S.neg_step_size, S.inv_sqrt_bc2);
+    peer_adam_elem(p.y, g.y, m.y, v.y, a, S.neg_step_size, S.inv_sqrt_bc2);
+    peer_adam_elem(p.z, g.z, m.z, v.z, a, S.neg_step_size, S.inv_sqrt_bc2);
+    peer_adam_elem(p.w, g.w, m.w, v.w, a, S.neg_step_size, S.inv_sqrt_bc2);
+    __stcs(reinterpret_cast<float4*>(a.exp_avg + mo), m);
+    __stcs(reinterpret_cast<float4*>(a.exp_avg_sq + mo), v);
+  } else if (S.rule == GSR_PEER_RULE_SUM) {
+    // (elements whose row nobody rendered keep their bits: no "+ 0")
+    if (who[0]) p.x = p.x + g.x;
+    if (who[1]) p.y = p.y + g.y;
+    if (who[2]) p.z = p.z + g.z;
+    if (who[3]) p.w = p.w + g.w;
+  } else {
+    if (who[0]) p.x = fmaxf(p.x, g.x);
+    if (who[1]) p.y = fmaxf(p.y, g.y);
+    if (who[2]) p.z = fmaxf(p.z, g.z);
+    if (who[3]) p.w = fmaxf(p.w, g.w);
+  }
   // every replica holds p_old already: values that did not change (rows whose moments and gradient are
   // all zero) need not travel
   const bool changed = __float_as_uint(p.x) != __float_as_uint(p_old.x) || __float_as_uint(p.y) != __float_as_uint(p_old.y) ||
@@ -167,7 +205,7 @@ __global__ void __launch_bounds__(kPeerThreads) peer_adam_kernel(const PeerAdamP
                    : "memory");
     } else {
 #pragma unroll
-      for (int k = 0; k < GSR_MAX_PEERS; ++k)
+      for (int k = 0; k < kPeers; ++k)
         if (k < a.n_peers) *reinterpret_cast<float4*>(a.param[k] + e) = p;
     }
   }
@@ -183,7 +221,7 @@ __global__ void __launch_bounds__(256) peer_union_mask_kernel(const PeerMaskPara
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   int m = 0;
-  for (int k = 0; k < a.n_peers; ++k) m |= (a.radii[k][i] > 0) ? (1 << k) : 0;
+  for (int k = 0; k < a.n_peers; ++k) m |= (a.radii[k][i] > 0) ? (0x101 << k) : 0;
   union_out[i] = m;
 }
 
@@ -206,14 +244,20 @@ __global__ void __launch_bounds__(256) peer_rank_mask_u8_kernel(const PeerFlagPa
     for (int k = 0; k < GSR_MAX_PEERS; ++k) {
       if (k < a.n_peers) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] |= ((w[k] >> (8 * j)) & 0x02u) ? (1 << k) : 0;   // bit 1: gradient row valid
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t b = (w[k] >> (8 * j)) & 0xffu;   // bit 0: rendered, bit 1: gradient row valid
+          m[j] |= ((b & 2u) ? (1 << k) : 0) | ((b & 1u) ? (0x100 << k) : 0);
+        }
       }
     }
     *reinterpret_cast<int4*>(mask_out + i) = make_int4(m[0], m[1], m[2], m[3]);
   } else {
     for (int j = 0; i + j < rows; ++j) {
       int mm = 0;
-      for (int k = 0; k < a.n_peers; ++k) mm |= (a.flags[k][i + j] & 2u) ? (1 << k) : 0;
+      for (int k = 0; k < a.n_peers; ++k) {
+        const uint32_t b = a.flags[k][i + j];
+        mm |= ((b & 2u) ? (1 << k) : 0) | ((b & 1u) ? (0x100 << k) : 0);
+      }
       mask_out[i + j] = mm;
     }
   }
@@ -426,7 +470,8 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* in) {
     a.seg[k].start = s.start;
     a.seg[k].numel = s.numel;
     a.seg[k].width = (unsigned)s.width;
-    a.seg[k].magic = 0;
+    if (s.rule < GSR_PEER_RULE_ADAM || s.rule > GSR_PEER_RULE_MAX) return GSR_ERR_BAD_ARG;
+    a.seg[k].rule = (unsigned)s.rule;
     a.seg[k].neg_step_size = (float)(-(s.lr / bc1));
     a.seg[k].inv_sqrt_bc2 = (float)(1.0 / std::sqrt(bc2));
     prev_end = s.start + s.numel;
@@ -456,10 +501,17 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* in) {
     if (ctas == 0) return GSR_OK;
   }
   a.traffic = in->traffic_counters;
-  if (a.traffic != nullptr)
-    peer_adam_kernel<true><<<(unsigned)ctas, kPeerThreads, 0, static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
-  else
-    peer_adam_kernel<false><<<(unsigned)ctas, kPeerThreads, 0, static_cast<cudaStream_t>(in->stream)>>>(a, in->rank);
+  cudaStream_t st = static_cast<cudaStream_t>(in->stream);
+#define GSR_PEER_LAUNCH(N)                                                                              \
+  do {                                                                                                  \
+    if (a.traffic != nullptr) peer_adam_kernel<true, N><<<(unsigned)ctas, kPeerThreads, 0, st>>>(a, in->rank);  \
+    else peer_adam_kernel<false, N><<<(unsigned)ctas, kPeerThreads, 0, st>>>(a, in->rank);               \
+  } while (0)
+  if (in->n_peers <= 1) GSR_PEER_LAUNCH(1);
+  else if (in->n_peers <= 2) GSR_PEER_LAUNCH(2);
+  else if (in->n_peers <= 4) GSR_PEER_LAUNCH(4);
+  else GSR_PEER_LAUNCH(8);
+#undef GSR_PEER_LAUNCH
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -122,6 +122,7 @@ class KeyframeBatchMapper:
                            else self.params)
         self._stats_stride = (max(self.P, 1) + 3) // 4 * 4     # floats between the three per-rank delta arrays
         self.stats = None
+        self._stats_user = stats     # with the peer exchange the statistics move into the arena: both dicts get the views
         if stats is not None:
             self.stats = {}
             for k in STATS:
@@ -219,18 +220,19 @@ class KeyframeBatchMapper:
             world, rank = dist.get_world_size(group), dist.get_rank(group)
             if world > 8:
                 raise RuntimeError("more than GSR_MAX_PEERS ranks")
-            g_arena = symm.empty(total, dtype=torch.float32, device=dev)
-            p_arena = symm.empty(total, dtype=torch.float32, device=dev)
-            flags = symm.empty(max(self.P, 1) + 16, dtype=torch.uint8, device=dev)   # one "rendered" byte per row
+            # with densification statistics the arenas grow by three one-float segments [accum | denom | max_radii]:
+            # gradient arena = this rank's per-step deltas, parameter arena = the replicated statistics, so the
+            # fused kernel reduces and broadcasts them with everything else (GSR_PEER_RULE_SUM / _MAX)
+            stat_off = (total + 3) // 4 * 4
+            arena_len = stat_off + 3 * self._stats_stride if self.stats is not None else total
+            g_arena = symm.empty(arena_len, dtype=torch.float32, device=dev)
+            p_arena = symm.empty(arena_len, dtype=torch.float32, device=dev)
+            flags = symm.empty(max(self.P, 1) + 16, dtype=torch.uint8, device=dev)   # per row: rendered | gradient valid
             g_arena.zero_(); p_arena.zero_(); flags.zero_()
             hg = symm.rendezvous(g_arena, group)
             hp = symm.rendezvous(p_arena, group)
             hf = symm.rendezvous(flags, group)
-            st_local, hs = None, None
-            if self.stats is not None:
-                st_local = symm.empty(3 * self._stats_stride, dtype=torch.float32, device=dev)   # accum | denom | max_radii
-                st_local.zero_()
-                hs = symm.rendezvous(st_local, group)
+            st_local = g_arena[stat_off:stat_off + 3 * self._stats_stride] if self.stats is not None else None
         except Exception as exc:  # noqa: BLE001
             print(f"[gsdf_slam_b200] peer-memory exchange unavailable ({exc!r}); using the NCCL all-reduce path",
                   file=sys.stderr)
@@ -245,6 +247,15 @@ class KeyframeBatchMapper:
             self.params = p_views
         self.arena = g_arena
         self.grad_views = self._views(g_arena)
+        if self.stats is not None:
+            # the caller's statistics move into the parameter arena; the dict it handed over now holds the views
+            order = ("xyz_gradient_accum", "denom", "max_radii2D")
+            for j, name in enumerate(order):
+                view = p_arena[stat_off + j * self._stats_stride: stat_off + j * self._stats_stride + self.P]
+                view.copy_(self.stats[name])
+                self.stats[name] = view
+                self._stats_user[name] = view
+            total = arena_len
         # interleaved sharding: rank r owns every world-th 64 Ki-element chunk of the arena, so every rank
         # gets the same mix of narrow (xyz, opacity, ...) and wide (sh) rows — a contiguous 1/N range gave
         # the ranks holding the narrow segments 30 % more parameter stores (measured at N = 8)
@@ -258,8 +269,9 @@ class KeyframeBatchMapper:
                 mc_ptr = int(getattr(hp, "multicast_ptr", 0) or 0)
             except Exception:  # noqa: BLE001
                 mc_ptr = 0
-        self.peer = dict(world=world, rank=rank, hg=hg, hp=hp, hf=hf, hs=hs, g_arena=g_arena, p_arena=p_arena,
-                         flags=flags, stats_local=st_local, lo=0, hi=total, step=0, eps=float(eps), chunk=chunk,
+        self.peer = dict(world=world, rank=rank, hg=hg, hp=hp, hf=hf, g_arena=g_arena, p_arena=p_arena,
+                         flags=flags, stats_local=st_local, stat_off=stat_off, lo=0, hi=total, step=0, eps=float(eps),
+                         chunk=chunk,
                          mc_ptr=mc_ptr,
                          exp_avg=torch.zeros(n_mom, dtype=torch.float32, device=dev),
                          exp_avg_sq=torch.zeros(n_mom, dtype=torch.float32, device=dev),
@@ -339,17 +351,8 @@ class KeyframeBatchMapper:
         pe["hg"].barrier(channel=0)          # every rank's gradients, flags and statistics are written
         self._mark("barrier1_end", main)
         fptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hf"].buffer_ptrs])
-        if pe["stats_local"] is not None:
-            sptrs = (C.c_void_p * pe["world"])(*[int(x) for x in pe["hs"].buffer_ptrs])
-            st = self.stats
-            _lib.check(L.gsr_peer_stats_exchange(fptrs, sptrs, self._stats_stride, pe["world"], self.P,
-                                                 C.c_void_p(pe["union"].data_ptr()),
-                                                 C.c_void_p(st["max_radii2D"].data_ptr()),
-                                                 C.c_void_p(st["xyz_gradient_accum"].data_ptr()),
-                                                 C.c_void_p(st["denom"].data_ptr()), stream), "gsr_peer_stats_exchange")
-        else:
-            _lib.check(L.gsr_peer_rank_mask_u8(fptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
-                       "gsr_peer_rank_mask_u8")
+        _lib.check(L.gsr_peer_rank_mask_u8(fptrs, pe["world"], self.P, C.c_void_p(pe["union"].data_ptr()), stream),
+                   "gsr_peer_rank_mask_u8")
         self._mark("mask_end", main)
         pe["step"] += 1
         a = _lib.PeerAdamArgs()
@@ -370,6 +373,12 @@ class KeyframeBatchMapper:
             a.segments[i].start, a.segments[i].numel = off, numel
             a.segments[i].width = numel // self.P
             a.segments[i].lr = float(grp["lr"])
+        if pe["stats_local"] is not None:   # accum, denom: summed over the ranks; max_radii: their maximum
+            for j, rule in enumerate((_lib.GSR_PEER_RULE_SUM, _lib.GSR_PEER_RULE_SUM, _lib.GSR_PEER_RULE_MAX)):
+                sg = a.segments[len(segs) + j]
+                sg.start, sg.numel = pe["stat_off"] + j * self._stats_stride, self.P
+                sg.width, sg.rule, sg.lr = 1, rule, 0.0
+            a.n_segments = len(segs) + 3
         a.shard_lo, a.shard_hi, a.shard_chunk = pe["lo"], pe["hi"], pe["chunk"]
         a.exp_avg, a.exp_avg_sq = pe["exp_avg"].data_ptr(), pe["exp_avg_sq"].data_ptr()
         a.union_mask = pe["union"].data_ptr()

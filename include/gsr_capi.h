@@ -242,11 +242,17 @@ int gsr_l1_ssim_loss(const float* image, const float* gt, const float* mask, int
  * Replaces torch::optim::Adam::step + the gradient all-reduce a multi-GPU port of
  * src/gaussian_mapper.cpp:465 would need. */
 #define GSR_MAX_PEERS 8
-#define GSR_PEER_MAX_SEGMENTS 8
+#define GSR_PEER_MAX_SEGMENTS 12
+#define GSR_PEER_RULE_ADAM 0   /* param <- Adam(param, sum over ranks of grad), the row's GRADIENT mask bits */
+#define GSR_PEER_RULE_SUM 1    /* param <- param + sum over ranks of grad (rank order), the row's RENDERED mask bits */
+#define GSR_PEER_RULE_MAX 2    /* param <- max(param, max over ranks of grad),           the row's RENDERED mask bits */
 typedef struct gsr_peer_segment {
   int64_t start;   /* first arena element */
   int64_t numel;
   int32_t width;   /* elements per row */
+  int32_t rule;    /* GSR_PEER_RULE_*: SUM / MAX carry the densification statistics of a keyframe batch through the
+                      same kernel as three one-float segments — "param" arena = the replicated statistic, "grad" arena
+                      = this rank's per-step delta (gsr_peer_local_stats); they have no Adam moments */
   double lr;
 } gsr_peer_segment;
 typedef struct gsr_peer_adam_args {
@@ -258,7 +264,8 @@ typedef struct gsr_peer_adam_args {
   int64_t shard_lo, shard_hi;   /* multiples of 4 elements */
   float* exp_avg;               /* [shard_hi - shard_lo], local */
   float* exp_avg_sq;
-  const int32_t* union_mask;    /* [rows]: bit k <=> rank k rendered the row (gsr_peer_union_mask) */
+  const int32_t* union_mask;    /* [rows]: bit k <=> rank k holds a valid GRADIENT row, bit 8 + k <=> rank k RENDERED
+                                   the row (gsr_peer_rank_mask_u8; gsr_peer_union_mask sets both alike) */
   double beta1, beta2, eps;
   float grad_scale;
   int64_t step;                 /* step count AFTER this update (>= 1) */
@@ -284,8 +291,9 @@ int gsr_adam_step_peer(const gsr_peer_adam_args* a);
  * set, so a rank may leave the rows it did not render unwritten (gsr_backward rendered_rows_only). */
 int gsr_peer_union_mask(const int32_t* const* radii_peers, int n_peers, int64_t rows,
                         int32_t* union_out, void* stream);
-/* The same mask from one-byte flags (flags_peers[k][row] != 0 <=> rank k rendered the row; 4-byte aligned
- * peer-mapped buffers, mask_out 16-byte aligned): a quarter of the NVLink traffic of the radii version. */
+/* The same mask from one-byte flags (flags_peers[k][row]: bit 0 <=> rank k rendered the row, bit 1 <=> its gradient
+ * row is valid — gsr_peer_local_stats; 4-byte aligned peer-mapped buffers, mask_out 16-byte aligned): a quarter of the
+ * NVLink traffic of the radii version.  mask_out[row] = gradient bits | rendered bits << 8. */
 int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_t rows,
                           int32_t* mask_out, void* stream);
 
