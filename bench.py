@@ -232,7 +232,11 @@ def stage_model(counts):
     P, V, R, N, T, M = (counts[k] for k in ("P", "V", "R", "N", "T", "M"))
     smc = counts["sum_max_contrib"]
     b = {
-        "preprocess": 12 * P + (44 + 12 * M) * V + 16 * P + 43 * V,
+        # stage 1 (cull): xyz + scale + rotation rows of every Gaussian, radii / tiles_touched zeros of the culled ones
+        "precull": 40 * P + 8 * P,
+        # stage 2 (the reference's arithmetic on the candidates, ~ the rendered ones): candidate id + input rows +
+        # SH row in, per-Gaussian outputs + list entry + 48-byte record out
+        "preprocess": (4 + 56 + 12 * M) * V + 99 * V,
         "tile_meta": 4 * T + 16 * T,
         # emit: list entry + rect inputs per visible Gaussian, one slot atomic (RMW) + one item per duplicate
         "emit": (8 + 4 + 8 + 16 + 4) * V + (8 + 8) * R,
@@ -242,7 +246,9 @@ def stage_model(counts):
         # the two half tiles reads them: the second read hits L2, HBM sees one)
         "blend_fwd": 48 * min(R, smc) + 32 * N + 4 * T,
         "blend_bwd": 48 * min(R, smc) + 32 * N + 72 * min(R, smc),
-        "preprocess_bwd": (87 + 12 * M) * V + 48 * V + (52 + 12 * M) * V + 4 * V,  # rendered rows only
+        # moment rows of every rendered Gaussian (selection) + the full row traffic as if every rendered Gaussian
+        # had a gradient (an upper bound: hidden splats are skipped)
+        "preprocess_bwd": 56 * V + (87 + 12 * M) * V + 48 * V + (52 + 12 * M) * V + 4 * V,
         "adam": 28 * (14 + 3 * M) * P,
         # visibility-split Adam: rows without gradient move 24 B/element (grad not read)
         "adam_rows_zero_grad": 24 * (14 + 3 * M) * (P - V),

@@ -326,9 +326,10 @@ peer_stats_exchange_kernel(const PeerStatsParams a, long long P, long long strid
     }
   }
   if (nrow == 4) {
-    *reinterpret_cast<int4*>(mask_out + i) = make_int4(mg[0], mg[1], mg[2], mg[3]);
+    *reinterpret_cast<int4*>(mask_out + i) = make_int4(mg[0] | (m[0] << 8), mg[1] | (m[1] << 8), mg[2] | (m[2] << 8),
+                                                       mg[3] | (m[3] << 8));
   } else {
-    for (int j = 0; j < nrow; ++j) mask_out[i + j] = mg[j];
+    for (int j = 0; j < nrow; ++j) mask_out[i + j] = mg[j] | (m[j] << 8);
   }
   if (any == 0) return;
   // all remote loads first (NVLink round trips overlap), then the combination in rank order

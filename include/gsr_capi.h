@@ -306,10 +306,15 @@ int gsr_peer_rank_mask_u8(const uint8_t* const* flags_peers, int n_peers, int64_
  *   stats_local = [accum | denom | max_radii], three arrays of stats_stride >= P floats each (stats_stride a
  *   multiple of 4, base 16-byte aligned; the caller zeroes flags — P + 16 bytes, 4-byte aligned — and stats_local
  *   at the start of the step; both live in peer-mapped memory).
- * gsr_peer_stats_exchange: after the cross-rank barrier; mask_out[row] = bitmask of the ranks whose flag is
- *   set (what gsr_adam_step_peer consumes), and the replicated statistics of THIS rank receive
- *   xyz_gradient_accum += sum_k accum_k, denom += sum_k denom_k, max_radii2D = max(max_radii2D, max_k ...)
- *   over the ranks that rendered the row, in rank order (bit-identical replicas). */
+ * The mappers of this repository then carry the statistics THROUGH gsr_adam_step_peer: stats_local is the tail of
+ *   the rank's gradient arena, the replicated statistics the tail of its parameter arena, described by three
+ *   one-float segments with GSR_PEER_RULE_SUM / _SUM / _MAX — each owner reduces its rows and broadcasts the result
+ *   (rank order, bit-identical replicas), 1/n_peers of the traffic of every rank pulling every rank's deltas.
+ * gsr_peer_stats_exchange is that all-pull alternative for callers that keep the statistics outside the arenas:
+ *   after the cross-rank barrier, mask_out[row] = gradient bits | rendered bits << 8 (what gsr_adam_step_peer
+ *   consumes) and the replicated statistics of THIS rank receive xyz_gradient_accum += sum_k accum_k,
+ *   denom += sum_k denom_k, max_radii2D = max(max_radii2D, max_k ...) over the ranks that rendered the row, in
+ *   rank order.  (Measured at 3 M Gaussians: 0.10 ms at 2 ranks, 0.41 ms at 8; the fused form costs 0.05 ms.) */
 int gsr_peer_local_stats(int64_t P, const int32_t* radii, const float* dL_dmeans2D, float* stats_local,
                          int64_t stats_stride, uint8_t* flags, const int32_t* grad_rows, void* stream);
 int gsr_peer_stats_exchange(const uint8_t* const* flags_peers, const float* const* stats_peers, int64_t stats_stride,

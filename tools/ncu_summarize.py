@@ -11,7 +11,7 @@ import os
 import subprocess
 import sys
 
-STEP_KERNELS = ["preprocess_kernel", "tile_meta_kernel", "emit_kernel", "emit_large_kernel", "tile_sort_pack_small_kernel",
+STEP_KERNELS = ["precull_kernel", "preprocess_kernel", "count_large_kernel", "select_grad_rows_kernel", "tile_meta_kernel", "emit_kernel", "emit_large_kernel", "tile_sort_pack_small_kernel",
                 "tile_sort_pack_mid_kernel", "tile_sort_pack_long_kernel", "blend_fwd_kernel", "blend_fwd_packed_kernel",
                 "blend_bwd_kernel", "blend_bwd_packed_kernel", "preprocess_bwd_kernel", "adam_rows_all_kernel"]
 
@@ -27,8 +27,9 @@ def launches(src, dst, tag):
     h = rows[0]
     ki, vi = h.index("Kernel Name"), h.index("Metric Value")
     seq = [(short(r[ki]), float(r[vi].replace(",", "")) / 1000.0) for r in rows[1:]]
-    # the last complete step: from the last preprocess_kernel that is followed by an adam kernel
-    starts = [i for i, (k, _) in enumerate(seq) if k == "preprocess_kernel"]
+    # the last complete step: from the last cull kernel (the first launch of a forward pass) that is followed by an adam kernel
+    first = "precull_kernel" if any(k == "precull_kernel" for k, _ in seq) else "preprocess_kernel"
+    starts = [i for i, (k, _) in enumerate(seq) if k == first]
     step = None
     for s in reversed(starts):
         tail = seq[s:]
@@ -38,7 +39,7 @@ def launches(src, dst, tag):
             break
     tot = sum(t for _, t in step)
     out = [f"# ncu launch list, round {tag} (cfg2: 500k SH-3 Gaussians, 1200x680, one mapping step = fwd + bwd + masked Adam)", "",
-           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 1 "
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv python bench.py --steps 2 --warmup 1 "
            "--no-cpu-baseline --no-cfg5 --no-shim` (one steady-state step; cold-cache, serialised: compare SHARES with the live "
            "CUDA-event stage times of the bench line).", "", "| # | kernel | us | share |", "|---|---|---|---|"]
     for i, (k, t) in enumerate(step):
@@ -81,7 +82,7 @@ def full(rep, dst, traffic_dst, cfg):
             v, u = float(d[key].replace(",", "")), units[idx[key]].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         stage = d["Kernel Name"].replace("_kernel", "").replace("_small", "").replace("_packed", "")
-        traffic[stage] = int(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
+        traffic[stage] = traffic.get(stage, 0) if False else int(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
     json.dump({"command": "ncu --set full --clock-control none --import-source on -k regex:... python bench.py --steps 2 --warmup 1 "
                           "--no-cpu-baseline --no-cfg5 --no-shim --config " + cfg,
                "units": {w: units[i] for w, i in idx.items()}, "kernels": kernels}, open(dst, "w"), indent=1)
@@ -95,8 +96,32 @@ def full(rep, dst, traffic_dst, cfg):
               k.get("smsp__thread_inst_executed_per_inst_executed.ratio"))
 
 
+def dram(src, traffic_dst, cfg):
+    """metrics-only pass (gpu__time_duration, dram__bytes_read / _write per launch) -> per-kernel DRAM bytes of `cfg`"""
+    rows = [r for r in csv.reader(open(src)) if len(r) > 10]
+    h = rows[0]
+    ki, mi, ui, vi = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Unit"), h.index("Metric Value")
+    ii = h.index("ID")
+    per = {}
+    for r in rows[1:]:
+        if not r[mi].startswith("dram__bytes"):
+            continue
+        v = float(r[vi].replace(",", "")) * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(r[ui].lower(), 1)
+        per.setdefault((r[ii], short(r[ki])), 0.0)
+        per[(r[ii], short(r[ki]))] += v
+    traffic = {}
+    for (_id, k), v in per.items():       # last launch of each kernel wins (steady state)
+        traffic[k.replace("_kernel", "").replace("_small", "")] = int(v)
+    old = json.load(open(traffic_dst)) if os.path.exists(traffic_dst) else {}
+    old[cfg] = traffic
+    json.dump(old, open(traffic_dst, "w"), indent=1)
+    print(cfg, traffic)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "dram":
+        dram(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "2")
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None, sys.argv[5] if len(sys.argv) > 5 else "cfg2")
