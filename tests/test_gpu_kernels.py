@@ -290,6 +290,114 @@ def test_peer_exchange_matches_nccl_path_on_two_gpus():
     assert res.returncode == 0 and "peer exchange OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_peer_exchange_with_all_ranks_emulated_on_one_gpu(world):
+    """The whole multi-rank exchange on ONE device (the driver's -m gpu box has one GPU): every "rank" owns its own
+    gradient / parameter arena and flag buffer in ordinary device memory, the kernels run once per rank — rank masks
+    from the flag bytes (rendered | gradient valid), then gsr_adam_step_peer on that rank's interleaved shard with
+    shard-local moments, reading all ranks' gradient arenas and storing into all ranks' parameter arenas (unicast).
+    Checked against the definition: Adam (LibTorch op sequence, moments bit-exact) on the rank-ordered sum of the
+    gradients of the ranks whose gradient bit is set; the statistics segments sum / sum / max the deltas of the ranks
+    whose RENDERED bit is set; all replicas end bit-identical; rows nobody flags are never read (NaN poison)."""
+    import ctypes as C
+    from gsdf_slam_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    gen = torch.Generator(device=dev).manual_seed(100 + world)
+    P = 70_001                                   # not a multiple of 4: segment padding and partial float4 groups
+    widths = [3, 3, 45, 1, 3, 4]
+    lrs = [1.6e-4, 0.0025, 0.0025 / 20, 0.05, 0.005, 0.001]
+    starts, off = [], 0
+    for w in widths:
+        starts.append(off)
+        off += (w * P + 3) // 4 * 4
+    stride = (P + 3) // 4 * 4
+    stat_off, arena_len = off, off + 3 * stride
+    chunk = 65536
+    rendered = torch.rand((world, P), device=dev, generator=gen) < 0.3          # rank k rendered the row
+    has_grad = rendered & (torch.rand((world, P), device=dev, generator=gen) < 0.6)   # ... and got a gradient
+    flags = [torch.zeros(P + 16, dtype=torch.uint8, device=dev) for _ in range(world)]
+    for k in range(world):
+        flags[k][:P] = rendered[k].to(torch.uint8) + 2 * has_grad[k].to(torch.uint8)
+    grads = [torch.full((arena_len,), float("nan"), device=dev) for _ in range(world)]
+    p0 = torch.zeros(arena_len, device=dev)
+    ref_g = []
+    for s, w in zip(starts, widths):
+        p0[s:s + w * P] = torch.randn(w * P, device=dev, generator=gen)
+        tot = torch.zeros((P, w), device=dev)
+        for k in range(world):                                        # rank order, like the kernel
+            gk = torch.randn((P, w), device=dev, generator=gen) * 1e-2
+            grads[k][s:s + w * P].view(P, w)[has_grad[k]] = gk[has_grad[k]]
+            tot = torch.where(has_grad[k][:, None], tot + gk, tot)
+        ref_g.append(tot)
+    # statistics: accumulated values in the parameter arena, this step's deltas in the gradient arenas
+    stat0 = torch.rand((3, P), device=dev, generator=gen)
+    ref_stat = stat0.clone()
+    sums = torch.zeros((2, P), device=dev)
+    mx = torch.zeros(P, device=dev)
+    for j in range(3):
+        p0[stat_off + j * stride: stat_off + j * stride + P] = stat0[j]
+    for k in range(world):
+        d = torch.rand((3, P), device=dev, generator=gen) * 5.0
+        for j in range(3):
+            grads[k][stat_off + j * stride: stat_off + j * stride + P][rendered[k]] = d[j][rendered[k]]
+        sums = torch.where(rendered[k][None, :], sums + d[:2], sums)
+        mx = torch.where(rendered[k], torch.maximum(mx, d[2]), mx)
+    anyr = rendered.any(0)
+    ref_stat[0] = torch.where(anyr, stat0[0] + sums[0], stat0[0])
+    ref_stat[1] = torch.where(anyr, stat0[1] + sums[1], stat0[1])
+    ref_stat[2] = torch.where(anyr, torch.maximum(stat0[2], mx), stat0[2])
+    params = [p0.clone() for _ in range(world)]
+    n_chunks = (arena_len + chunk - 1) // chunk
+    moments = []
+    for r in range(world):
+        owned = (n_chunks - r + world - 1) // world if n_chunks > r else 0
+        moments.append((torch.zeros(max(owned, 1) * chunk, device=dev), torch.zeros(max(owned, 1) * chunk, device=dev)))
+    masks = torch.zeros(P + 4, dtype=torch.int32, device=dev)
+    fptrs = (C.c_void_p * world)(*[f.data_ptr() for f in flags])
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.gsr_peer_rank_mask_u8(fptrs, world, P, C.c_void_p(masks.data_ptr()), stream), "rank_mask")
+    want_mask = torch.zeros(P, dtype=torch.int32, device=dev)
+    for k in range(world):
+        want_mask |= has_grad[k].int() << k
+        want_mask |= rendered[k].int() << (8 + k)
+    assert torch.equal(masks[:P], want_mask)
+    for step in (1, 2):
+        for r in range(world):
+            a = _lib.PeerAdamArgs()
+            a.n_peers, a.rank = world, r
+            for k in range(world):
+                a.param_peers[k], a.grad_peers[k] = params[k].data_ptr(), grads[k].data_ptr()
+            for i, (s0, w, lr) in enumerate(zip(starts, widths, lrs)):
+                a.segments[i].start, a.segments[i].numel, a.segments[i].width, a.segments[i].lr = s0, w * P, w, lr
+            for j, rule in enumerate((_lib.GSR_PEER_RULE_SUM, _lib.GSR_PEER_RULE_SUM, _lib.GSR_PEER_RULE_MAX)):
+                sg = a.segments[6 + j]
+                sg.start, sg.numel, sg.width, sg.rule = stat_off + j * stride, P, 1, rule
+            a.n_segments = 9
+            a.shard_lo, a.shard_hi, a.shard_chunk = 0, arena_len, chunk
+            a.exp_avg, a.exp_avg_sq = moments[r][0].data_ptr(), moments[r][1].data_ptr()
+            a.union_mask = masks.data_ptr()
+            a.beta1, a.beta2, a.eps, a.grad_scale, a.step = 0.9, 0.999, 1e-15, 1.0, step
+            a.stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(L.gsr_adam_step_peer(C.byref(a)), "gsr_adam_step_peer")
+        if step == 1:   # the statistics after ONE exchange
+            torch.cuda.synchronize()
+            for j in range(3):
+                got = params[0][stat_off + j * stride: stat_off + j * stride + P]
+                assert torch.equal(got, ref_stat[j]), j
+    torch.cuda.synchronize()
+    for k in range(1, world):
+        assert torch.equal(params[0].view(torch.int32), params[k].view(torch.int32))     # replicas bit-identical
+    assert bool(torch.isfinite(params[0]).all())
+    for s, w, lr, g in zip(starts, widths, lrs, ref_g):
+        p = p0[s:s + w * P].view(P, w).clone()
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for step in (1, 2):
+            _libtorch_adam_reference(p, g, m, v, lr, step)
+        got = params[0][s:s + w * P].view(P, w)
+        assert float((got - p).abs().max()) <= 2e-7 * max(1.0, float(p.abs().max())), w     # <= 2 ulp, like gsr_adam_step
+
+
 def _brute_knn(pts: torch.Tensor) -> torch.Tensor:
     out = torch.empty(pts.size(0), device=pts.device)
     for s in range(0, pts.size(0), 2048):
