@@ -290,6 +290,30 @@ def test_peer_exchange_matches_nccl_path_on_two_gpus():
     assert res.returncode == 0 and "peer exchange OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
+def test_two_devices_in_one_process_and_thread():
+    """One host thread driving two GPUs (round-1 advisor finding): the read-back event, the pinned word and the
+    capacity hints live in a per-device gsr_context, kernel attributes are set per device — the second device must
+    render the same image and gradients as the first, including a scene with long per-tile lists (the kernel that
+    needs the 80 KB dynamic shared-memory attribute)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from util import run_product_backward, run_product_forward
+    for sc in (scenes.tiny(seed=3, P=6000), scenes.cfg4(1_200_000)):      # cfg4 at 1.2 M: per-tile lists beyond 4092
+        outs = []
+        for dev in ("cuda:0", "cuda:1", "cuda:0"):
+            with torch.cuda.device(dev):
+                t = to_dev(sc, dev)
+                fwd = run_product_forward(sc, t)
+                g = run_product_backward(sc, t, fwd)
+                torch.cuda.synchronize(dev)
+                outs.append((fwd[0], fwd[2].cpu(), fwd[3].cpu(), g["dL_dmeans3D"].cpu()))
+        for o in outs[1:]:
+            assert o[0] == outs[0][0]
+            assert torch.equal(o[2], outs[0][2])                                   # radii
+            assert float((o[1] - outs[0][1]).abs().max()) <= 1e-6                  # image (atomics-free: exact)
+            assert rel_l2(o[3], outs[0][3]) <= 1e-5
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_peer_exchange_with_all_ranks_emulated_on_one_gpu(world):
     """The whole multi-rank exchange on ONE device (the driver's -m gpu box has one GPU): every "rank" owns its own
