@@ -51,6 +51,8 @@ struct gsr_context {
   // per-tile sort kernels for mid-length (512+) / long (4092+) lists are launched only if recent frames
   // had such lists (-1: unknown, n > 0: seen within the last n calls)
   int hint_mid = -1, hint_long = -1;
+  // the previous call rendered more than half of the map: the conservative cull has nothing to remove, skip it
+  int hint_dense = 0;
 };
 
 namespace gsr {
@@ -210,6 +212,7 @@ int gsr_forward(const gsr_forward_args* a) {
   if (ctx->hint_P != P || ctx->hint_W != W || ctx->hint_H != H) {  // a different scene / resolution
     cap_hint = 0;
     hint_mid = hint_long = -1;
+    ctx->hint_dense = 0;
   }
   ctx->hint_P = P; ctx->hint_W = W; ctx->hint_H = H;
   uint32_t cap = cap_hint;
@@ -239,7 +242,8 @@ int gsr_forward(const gsr_forward_args* a) {
   pp.cand = reinterpret_cast<uint32_t*>(g.acc); pp.num_cand = &g.hdr->num_cand;
   pp.large_list = g.large_list; pp.large_count = &g.hdr->num_large; pp.large_capacity = 2u * (uint32_t)P;
   pp.tile_count = im.tile_count;
-  GSR_PROF("precull", launch_precull(pp, s));
+  if (ctx->hint_dense > 0) pp.cand = nullptr;   // every Gaussian is a candidate (stage 2 repeats the z test anyway)
+  else GSR_PROF("precull", launch_precull(pp, s));
   GSR_PROF("preprocess", launch_preprocess(pp, s));
   if (a->radii_ready_event) GSR_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->radii_ready_event), s));
 
@@ -298,6 +302,7 @@ int gsr_forward(const gsr_forward_args* a) {
     const uint32_t want = R + R / 8 + 4096, decayed = cap_hint - cap_hint / 64;
     cap_hint = want > decayed ? want : decayed;
   }
+  ctx->hint_dense = host_R[2] > (uint32_t)P / 2 ? 1 : 0;   // header word 2: rendered Gaussians
   hint_mid = host_R[4] > host_R[5] ? kHintFrames : (hint_mid > 0 ? hint_mid - 1 : 0);
   hint_long = host_R[5] > 0 ? kHintFrames : (hint_long > 0 ? hint_long - 1 : 0);
   *a->num_rendered = (int)R;

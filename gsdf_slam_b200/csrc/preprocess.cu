@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
   __shared__ __align__(8) uint64_t s_bar[kPreThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t n_cand = *a.num_cand;
+  const uint32_t n_cand = a.cand != nullptr ? *a.num_cand : (uint32_t)a.P;   // no list: every Gaussian (cull skipped)
   uint32_t sh_phase = 0;   // parity of the warp's mbarrier
   if (lane == 0) {
     mbar_init(&s_bar[warp], 1);
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
   for (uint32_t chunk = blockIdx.x + gridDim.x * warp; chunk < n_chunks; chunk += gridDim.x * (kPreThreads / 32)) {
   const uint32_t w0 = chunk * (uint32_t)kCandPerWarp;
   const bool in_range = lane < kCandPerWarp && w0 + lane < n_cand;
-  const int idx = in_range ? (int)a.cand[w0 + lane] : 0;
+  const int idx = in_range ? (a.cand != nullptr ? (int)a.cand[w0 + lane] : (int)(w0 + lane)) : 0;
 
   // ---- this thread's input rows, all loads in flight at once --------------------------------------------
   float3 p_orig = {0.f, 0.f, 0.f}, sc = {0.f, 0.f, 0.f}, dc = {0.f, 0.f, 0.f};
@@ -342,7 +342,12 @@ __global__ void __launch_bounds__(kPreThreads, GSR_PRE_MINBLOCKS) preprocess_ker
 
   if (in_range) {
     p_view = xform_4x3(p_orig, a.view);
-    if (p_view.z > 0.2f) {   // (the z test and the `prefiltered` trap are stage 1's)
+    if (p_view.z <= 0.2f) {   // only without stage 1 (its candidates all pass)
+      if (a.prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+      }
+    } else {
       float4 p_hom = xform_4x4(p_orig, a.proj);
       float p_w = 1.0f / (p_hom.w + 0.0000001f);
       float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};

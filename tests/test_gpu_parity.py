@@ -236,6 +236,28 @@ def test_backward_accumulate_adds_to_the_rendered_rows_only():
     assert rel_l2(g2[0][vis], g1["dL_dmeans2D"][vis]) <= 1e-5
 
 
+def test_repeated_calls_skip_the_cull_when_most_of_the_map_is_rendered():
+    """The context remembers that the previous call rendered more than half of the map and skips the conservative
+    cull (stage 1 of the preprocess): the second and third call must pass the same bit-exact gates as the first."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built")
+    sc = scenes.frustum_scene(30_000, 320, 240, 300.0, 300.0, seed=71, degree=3, sh_coeffs=15, zmin=0.5, zmax=6.0,
+                              log_scale=0.03, log_sigma=0.5, name="dense_view")
+    t = to_dev(sc)
+    ref = run_reference(sc, t)
+    assert float((ref["radii"] > 0).float().mean()) > 0.6
+    first = None
+    for call in range(3):
+        fwd = run_product_forward(sc, t)
+        torch.cuda.synchronize()
+        _compare_forward(sc, t, fwd, ref)
+        _compare_grads(run_product_backward(sc, t, fwd), ref["grads"])
+        if first is None:
+            first = (fwd[0], fwd[2].clone(), fwd[3].clone())
+        else:
+            assert fwd[0] == first[0] and torch.equal(fwd[2], first[1]) and torch.equal(fwd[3], first[2])
+
+
 def test_grad_rows_mask_skips_the_rows_no_pixel_blended():
     """gsr_backward_args.grad_rows: the callee keeps the batch's row mask.  A rendered Gaussian that no pixel
     blended (hidden behind opaque ones) has exactly zero gradients in the dense API; with grad_rows it is neither
