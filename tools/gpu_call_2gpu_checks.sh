@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
-# GPU call r3f (2 GPUs): C mapper vs NCCL vs sequential, Python peer path, bench at N=2 (small, then full)
-O=gpurun_out/r3f; mkdir -p $O
+# GPU call (2 GPUs): C mapper vs NCCL vs sequential, Python peer path, bench at N=2 (small, then full)
+O=gpurun_out/checks2; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
 nvidia-smi topo -m > $O/topo.txt 2>&1
 $TR tools/check_cmapper.py > $O/check_cmapper.json 2> $O/check_cmapper.err; echo "check_cmapper rc=$?"; cat $O/check_cmapper.json; tail -3 $O/check_cmapper.err
