@@ -423,18 +423,132 @@ __device__ __forceinline__ void cta_sort_pack_tile(uint32_t n, uint32_t start, u
 __global__ void __launch_bounds__(kSortSmallThreads)
 tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, uint32_t T,
                             BinHeader* __restrict__ bin_hdr, uint32_t capacity, uint64_t* __restrict__ items,
+                            uint64_t* __restrict__ scratch, const uint32_t* __restrict__ sorted_len,
                             const float4* __restrict__ splat_rec, float4* __restrict__ rec) {
   __shared__ uint64_t s_x[kSortSmallCap];  // 4 KB: cross-warp exchange, then the sorted ids
   if (blockIdx.x == 0 && threadIdx.x == 0) bin_hdr->capacity = capacity;  // read by gsr_export_binning
-  const uint2 range = ranges[order[blockIdx.x]];
-  const uint32_t n = range.y - range.x;
-  if (n == 0 || n >= (uint32_t)kSortSmallCap || range.y > capacity) return;  // long lists: other launch
+  const uint32_t tile = order[blockIdx.x];
+  const uint2 range = ranges[tile];
+  uint32_t n = range.y - range.x;
+  if (n == 0 || range.y > capacity) return;
+  uint64_t* src = items;
+  if (n >= (uint32_t)kSortSmallCap) {
+    // a longer list: its nearest sorted_len entries were selected into `scratch` (tile_select_kernel); they are
+    // ordered and packed here, the list itself stays as emitted (the full sort, if ever needed, starts from it)
+    if (sorted_len == nullptr) return;
+    n = sorted_len[tile];
+    if (n == 0 || n >= (uint32_t)kSortSmallCap) return;
+    src = scratch;
+  }
   constexpr int kT = kSortSmallThreads;
   static_assert(kT * 8 >= kSortSmallCap, "the largest instantiation must hold kSortSmallCap entries");
-  if (n <= kT) cta_sort_pack_tile<1, kT>(n, range.x, items, splat_rec, rec, s_x);
-  else if (n <= 2 * kT) cta_sort_pack_tile<2, kT>(n, range.x, items, splat_rec, rec, s_x);
-  else if (n <= 4 * kT || kT * 4 >= kSortSmallCap) cta_sort_pack_tile<4, kT>(n, range.x, items, splat_rec, rec, s_x);
-  else cta_sort_pack_tile<8, kT>(n, range.x, items, splat_rec, rec, s_x);
+  if (n <= kT) cta_sort_pack_tile<1, kT>(n, range.x, src, splat_rec, rec, s_x);
+  else if (n <= 2 * kT) cta_sort_pack_tile<2, kT>(n, range.x, src, splat_rec, rec, s_x);
+  else if (n <= 4 * kT || kT * 4 >= kSortSmallCap) cta_sort_pack_tile<4, kT>(n, range.x, src, splat_rec, rec, s_x);
+  else cta_sort_pack_tile<8, kT>(n, range.x, src, splat_rec, rec, s_x);
+}
+
+// ---- lists of kSortSmallCap or more entries: select the nearest < kSortSmallCap -----------------------------
+// The blend kernels stop at the deepest contributor of a tile — at most a few hundred list positions in an opaque
+// scene (measured: 1 - 20 % of lists of 800 - 13 000 entries) — so ordering and packing the whole list is wasted.
+// Per tile: min / max of the depth words, a 256-bucket histogram of the (monotone) linear map onto that range, the
+// longest run of whole buckets holding fewer than kSortSmallCap entries -> those entries are the list's m nearest
+// (equal depths share a bucket, so the cut never splits a tie) and are copied to `scratch`; the small kernel sorts
+// and packs them.  blend_fwd reads the prefix only; a tile whose pixels are not saturated at its end — or whose
+// prefix would be too short to be worth it — is flagged, fully sorted by the mid / long kernels below and blended
+// again (rare: 1 tile in 3000 at cfg5, none at cfg1 / cfg4).
+constexpr int kSelThreadsSort = 512;
+constexpr uint32_t kSelMinPrefix = 256;   // fewer selectable entries: take the full sort straight away
+__device__ __forceinline__ void flag_redo(uint32_t tile, uint32_t* redo_flag, uint32_t* redo_list, uint32_t* redo_count) {
+  if (atomicExch(&redo_flag[tile], 1u) == 0u) redo_list[atomicAdd(redo_count, 1u)] = tile;
+}
+__global__ void __launch_bounds__(kSelThreadsSort)
+tile_select_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const GeomHeader* __restrict__ hdr,
+                   uint32_t T, uint32_t capacity, const uint64_t* __restrict__ items, uint64_t* __restrict__ scratch,
+                   uint32_t* __restrict__ sorted_len, uint32_t* __restrict__ redo_flag, uint32_t* __restrict__ redo_list,
+                   uint32_t* __restrict__ redo_count) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_red[2][kSelThreadsSort / 32];
+  __shared__ uint32_t s_slot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // lists of kSortSmallCap or more entries are the first num_long_tiles entries of the LPT order
+  const uint32_t limit = min(T, hdr->num_long_tiles);
+  for (uint32_t k = blockIdx.x; k < limit; k += gridDim.x) {
+    const uint32_t tile = order[k];
+    const uint2 range = ranges[tile];
+    const uint32_t n = range.y - range.x, start = range.x;
+    if (n < (uint32_t)kSortSmallCap || range.y > capacity) continue;
+    // depth range of the list
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    for (uint32_t i = tid; i < n; i += kSelThreadsSort) {
+      const uint32_t d = (uint32_t)(items[start + i] >> 32);
+      lo = min(lo, d);
+      hi = max(hi, d);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { s_red[0][warp] = lo; s_red[1][warp] = hi; }
+    if (tid < 256) s_hist[tid] = 0;
+    if (tid == 0) s_slot = 0;
+    __syncthreads();
+    lo = s_red[0][lane & (kSelThreadsSort / 32 - 1)];
+    hi = s_red[1][lane & (kSelThreadsSort / 32 - 1)];
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    // bucket = floor((d - lo) * 256 / (hi - lo + 1)) in float arithmetic: every step is monotone in d
+    const float scale = 256.0f / ((float)(hi - lo) + 1.0f);
+    auto bucket = [lo, scale](uint32_t d) { return min(255u, (uint32_t)((float)(d - lo) * scale)); };
+    for (uint32_t i = tid; i < n; i += kSelThreadsSort) atomicAdd(&s_hist[bucket((uint32_t)(items[start + i] >> 32))], 1u);
+    __syncthreads();
+    // inclusive scan of the 256 buckets by the first 8 warps; the cut = the buckets whose cumulative count stays
+    // below kSortSmallCap (cumulative counts are non-decreasing, so these form a prefix of the buckets)
+    uint32_t incl = 0;
+    if (tid < 256) {
+      incl = s_hist[tid];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += x;
+      }
+      if (lane == 31) s_red[0][warp] = incl;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t base = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+        if (w < warp) base += s_red[0][w];
+      incl += base;
+      const bool in = incl < (uint32_t)kSortSmallCap;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) s_red[1][warp] = (uint32_t)__popc(bal);
+      // the entries inside the cut = the largest cumulative count still below the cap
+      const uint32_t mine = in ? incl : 0u;
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, mine);
+      if (lane == 0) s_red[0][8 + warp] = wmax;
+    }
+    __syncthreads();
+    uint32_t cut = 0, m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      cut += s_red[1][w];
+      m = max(m, s_red[0][8 + w]);
+    }
+    if (m < min(kSelMinPrefix, n)) {
+      if (tid == 0) {
+        sorted_len[tile] = 0;
+        flag_redo(tile, redo_flag, redo_list, redo_count);
+      }
+      __syncthreads();
+      continue;
+    }
+    for (uint32_t i = tid; i < n; i += kSelThreadsSort) {
+      const uint64_t it = items[start + i];
+      if (bucket((uint32_t)(it >> 32)) < cut) scratch[start + atomicAdd(&s_slot, 1u)] = it;
+    }
+    if (tid == 0) sorted_len[tile] = m;
+    __syncthreads();   // shared state is reused by the next tile of this CTA
+  }
 }
 
 // ---- lists of kSortSmallCap .. kSortMidCap-1 entries: the same network on a 512-thread CTA --------
@@ -446,13 +560,16 @@ __global__ void __launch_bounds__(kSortMidThreads)
 tile_sort_pack_mid_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
                           const GeomHeader* __restrict__ hdr, uint32_t T, uint32_t capacity,
                           uint64_t* __restrict__ items, const float4* __restrict__ splat_rec,
-                          float4* __restrict__ rec) {
+                          float4* __restrict__ rec, const uint32_t* __restrict__ redo_list,
+                          const uint32_t* __restrict__ redo_count) {
   __shared__ uint64_t s_x[kSortMidThreads * 8];  // 32 KB
-  // In the LPT order the lists of >= kSortMidCap entries come first, then those of
-  // kSortSmallCap .. kSortMidCap-1 entries (both caps are bucket boundaries of that order).
-  const uint32_t first = min(T, hdr->num_huge_tiles), limit = min(T, hdr->num_long_tiles);
+  // The FULL sort of a list: for the tiles of redo_list (flagged by tile_select_kernel / blend_fwd), or — without a
+  // list (test export) — for every list of this length class.  In the LPT order the lists of >= kSortMidCap entries
+  // come first, then those of kSortSmallCap .. kSortMidCap-1 entries (both caps are bucket boundaries of that order).
+  const uint32_t first = redo_list ? 0u : min(T, hdr->num_huge_tiles);
+  const uint32_t limit = redo_list ? min(T, *redo_count) : min(T, hdr->num_long_tiles);
   for (uint32_t k = first + blockIdx.x; k < limit; k += gridDim.x) {
-    const uint2 range = ranges[order[k]];
+    const uint2 range = ranges[redo_list ? redo_list[k] : order[k]];
     const uint32_t n = range.y - range.x;
     if (n < (uint32_t)kSortSmallCap || n >= (uint32_t)kSortMidCap || range.y > capacity) continue;
     if (n <= 2 * kSortMidThreads) cta_sort_pack_tile<2, kSortMidThreads>(n, range.x, items, splat_rec, rec, s_x);
@@ -571,7 +688,8 @@ __global__ void __launch_bounds__(kSortLargeThreads)
 tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order,
                            const GeomHeader* __restrict__ hdr, uint32_t T, uint32_t capacity, int idx_passes,
                            uint64_t* __restrict__ items, uint64_t* __restrict__ scratch,
-                           const float4* __restrict__ splat_rec, float4* __restrict__ rec) {
+                           const float4* __restrict__ splat_rec, float4* __restrict__ rec,
+                           const uint32_t* __restrict__ redo_list, const uint32_t* __restrict__ redo_count) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   uint32_t (*s_hist)[256] = reinterpret_cast<uint32_t (*)[256]>(s_raw);
   uint64_t* s_a = reinterpret_cast<uint64_t*>(s_raw + kLongWarps * 256 * sizeof(uint32_t));
@@ -580,9 +698,9 @@ tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
   const int tid = threadIdx.x;
   // The lists of kSortMidCap or more entries are exactly the first num_huge_tiles entries of
   // the LPT order (kSortMidCap is the lower edge of its last bucket).
-  const uint32_t limit = min(T, hdr->num_huge_tiles);
+  const uint32_t limit = redo_list ? min(T, *redo_count) : min(T, hdr->num_huge_tiles);
   for (uint32_t k = blockIdx.x; k < limit; k += gridDim.x) {
-    const uint2 range = ranges[order[k]];
+    const uint2 range = ranges[redo_list ? redo_list[k] : order[k]];
     const uint32_t n = range.y - range.x, start = range.x;
     if (n < (uint32_t)kSortMidCap || range.y > capacity) continue;
     const bool in_smem = n <= (uint32_t)kSortLongSmemCap;
@@ -661,20 +779,38 @@ tile_sort_pack_long_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
   }
 }
 
+// select (lists of kSortSmallCap+ entries, when expected) + sort / pack of the short lists and of the selected prefixes
 int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
                           BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
-                          const float4* splat_rec, float4* rec, bool do_mid, bool do_long, cudaStream_t s) {
+                          const float4* splat_rec, float4* rec, bool do_mid, bool do_long, uint32_t* sorted_len,
+                          uint32_t* redo_flag, uint32_t* redo_list, uint32_t* redo_count, cudaStream_t s) {
+  (void)P;
   if (T == 0) return 0;
-  tile_sort_pack_small_kernel<<<T, kSortSmallThreads, 0, s>>>(ranges, order, T, bin_hdr, capacity,
-                                                                        items, splat_rec, rec);
+  // The kernels for lists of 512+ entries are launched only when the caller expects such lists (gsr_forward: the
+  // previous frames' counts; it re-runs the stage if the guess was wrong): an empty launch costs 3 us.
+  const bool longer = do_mid || do_long;
+  if (longer) {
+    tile_select_kernel<<<148 * 2, kSelThreadsSort, 0, s>>>(ranges, order, hdr, T, capacity, items, scratch, sorted_len,
+                                                           redo_flag, redo_list, redo_count);
+    GSR_LAUNCHED();
+  }
+  tile_sort_pack_small_kernel<<<T, kSortSmallThreads, 0, s>>>(ranges, order, T, bin_hdr, capacity, items, scratch,
+                                                                        longer ? sorted_len : nullptr, splat_rec, rec);
   GSR_LAUNCHED();
-  // The kernels for mid-length and long lists are launched only when the caller expects such lists
-  // (gsr_forward: the previous frame's counts; it re-runs the stage if the guess was wrong): an empty
-  // launch costs 3 us each.
+  return (int)cudaGetLastError();
+}
+
+// The FULL sort + pack of lists of kSortSmallCap+ entries: of the tiles in redo_list (production: the few tiles whose
+// sorted prefix did not suffice), or of every such list (redo_list == nullptr: the test export).
+int launch_tile_sort_full(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
+                          uint32_t capacity, uint64_t* items, uint64_t* scratch, const float4* splat_rec, float4* rec,
+                          bool do_mid, bool do_long, const uint32_t* redo_list, const uint32_t* redo_count,
+                          cudaStream_t s) {
+  if (T == 0) return 0;
   if (do_mid) {
-    // persistent: 2 CTAs of 16 warps per SM over the mid-length lists (exits at once if there are none)
+    // persistent: 2 CTAs of 16 warps per SM (exits at once if there is nothing to do)
     tile_sort_pack_mid_kernel<<<148 * 2, kSortMidThreads, 0, s>>>(ranges, order, hdr, T, capacity, items, splat_rec,
-                                                                 rec);
+                                                                 rec, redo_list, redo_count);
     GSR_LAUNCHED();
   }
   if (!do_long) return (int)cudaGetLastError();
@@ -697,7 +833,7 @@ int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t
   const int idx_passes = (idx_bits + 7) / 8;
   // two CTAs per SM (80 KB of shared memory each)
   tile_sort_pack_long_kernel<<<148 * 2, kSortLargeThreads, dyn, s>>>(ranges, order, hdr, T, capacity, idx_passes,
-                                                                     items, scratch, splat_rec, rec);
+                                                                     items, scratch, splat_rec, rec, redo_list, redo_count);
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -26,20 +26,23 @@ namespace gsr {
 
 // kCount: instrumented instantiation behind gsr_export_pair_counts (bench.py's roofline numerators): counts the
 // (splat, pixel) pairs visited / passing the power gate / blended.  The production instantiation carries none of it.
-template <bool kCount>
+// kRedo: the grid runs over the tiles of redo_list (fully sorted by then) instead of all tiles.
+template <bool kCount, bool kRedo>
 __global__ void __launch_bounds__(kBlendThreads, GSR_BLEND_FWD_MINBLOCKS)
 blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, const float4* __restrict__ rec,
                  int W, int H,
                  const float* __restrict__ bg, float* __restrict__ out_color,
                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
                  float* __restrict__ accum_c, uint32_t* __restrict__ max_contrib, uint32_t capacity,
-                 unsigned long long* __restrict__ pair_counts) {
+                 unsigned long long* __restrict__ pair_counts, const uint32_t* __restrict__ sorted_len,
+                 uint32_t* __restrict__ redo_flag, uint32_t* __restrict__ redo_list, uint32_t* __restrict__ redo_count) {
   __shared__ __align__(128) float4 sR[2][3 * kBlendBatch];  // 48-byte records, one bulk copy per batch
   __shared__ __align__(8) uint64_t s_full[2];
 
   const int lane = threadIdx.x;
+  if (kRedo && (blockIdx.x >> 1) >= *redo_count) return;
   // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel); two CTAs per tile
-  const uint32_t tile_id = tile_order[blockIdx.x >> 1];
+  const uint32_t tile_id = kRedo ? redo_list[blockIdx.x >> 1] : tile_order[blockIdx.x >> 1];
   const int warp = blockIdx.x & 1;  // upper / lower half of the tile
   const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
   const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
@@ -60,7 +63,12 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const uint2 range = ranges[tile_id];
   // capacity: records the (optimistically sized) buffer holds; a list that did not fit is not
   // touched — gsr_forward re-runs the stage with the exact size in that case
-  const int total = range.y <= capacity ? (int)(range.y - range.x) : 0;
+  const int full = range.y <= capacity ? (int)(range.y - range.x) : 0;
+  // lists of kSortSmallCap+ entries are sorted and packed only up to sorted_len[tile] (binning.cu: tile_select_kernel)
+  // unless the tile has been through the full sort (kRedo; the instrumented replay: flagged tiles)
+  int total = full;
+  if (!kRedo && sorted_len != nullptr && full >= kSortSmallCap && !(kCount && redo_flag[tile_id] != 0))
+    total = min(full, (int)sorted_len[tile_id]);
   const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
 
   if (lane == 0) {
@@ -158,6 +166,17 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     }
   }
 
+  if (!kRedo && !kCount && total < full) {
+    // the sorted prefix ended before every pixel was saturated: the tile takes the full sort and is blended again
+    bool all_done = true;
+#pragma unroll
+    for (int q = 0; q < kSlots; ++q) all_done = all_done && done[q];
+    if (!__all_sync(0xffffffffu, all_done)) {
+      if (lane == 0 && atomicExch(&redo_flag[tile_id], 1u) == 0u) redo_list[atomicAdd(redo_count, 1u)] = tile_id;
+      return;   // (the outputs of this half tile are written by the second pass)
+    }
+  }
+
   const size_t N = (size_t)W * H;
   uint32_t my_max = 0;
 #pragma unroll
@@ -187,14 +206,19 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,
                      const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, uint32_t capacity,
-                     unsigned long long* pair_counts, cudaStream_t s) {
+                     unsigned long long* pair_counts, const uint32_t* sorted_len, uint32_t* redo_flag,
+                     uint32_t* redo_list, uint32_t* redo_count, bool redo, cudaStream_t s) {
   const unsigned grid = (unsigned)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
-  if (pair_counts != nullptr)
-    blend_fwd_kernel<true><<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec, W, H, bg, out_color, final_T,
-                                                            n_contrib, accum_c, max_contrib, capacity, pair_counts);
+#define GSR_BLEND_FWD_ARGS                                                                                          \
+  ranges, tile_order, rec, W, H, bg, out_color, final_T, n_contrib, accum_c, max_contrib, capacity, pair_counts,   \
+      sorted_len, redo_flag, redo_list, redo_count
+  if (redo)   // (the number of flagged tiles is only known on the device: CTAs beyond it leave at once)
+    blend_fwd_kernel<false, true><<<2 * grid, kBlendThreads, 0, s>>>(GSR_BLEND_FWD_ARGS);
+  else if (pair_counts != nullptr)
+    blend_fwd_kernel<true, false><<<2 * grid, kBlendThreads, 0, s>>>(GSR_BLEND_FWD_ARGS);
   else
-    blend_fwd_kernel<false><<<2 * grid, kBlendThreads, 0, s>>>(ranges, tile_order, rec, W, H, bg, out_color, final_T,
-                                                             n_contrib, accum_c, max_contrib, capacity, nullptr);
+    blend_fwd_kernel<false, false><<<2 * grid, kBlendThreads, 0, s>>>(GSR_BLEND_FWD_ARGS);
+#undef GSR_BLEND_FWD_ARGS
   GSR_LAUNCHED();
   return (int)cudaGetLastError();
 }

@@ -5,9 +5,12 @@
 // preprocess_bwd.cu / adam.cu / knn.cu on the caller's stream.
 //
 // Forward pipeline (reference: Rasterizer::forward, rasterizer_impl.cu:366-538):
-//   memset(counters) -> preprocess (geometry, SH colours, EXACT per-tile splat counts) -> tile_meta
-//   (scan of the T counts: tile ranges, R, launch order) -> emit (every duplicate dropped into its
-//   tile's range) -> tile_sort_pack (per-tile depth sort + packed records) -> blend_fwd.
+//   memset(counters) -> precull (conservative cull -> candidates; skipped while most of the map is rendered) ->
+//   preprocess (geometry, SH colours, EXACT per-tile splat counts) [-> count_large] -> tile_meta (scan of the T
+//   counts: tile ranges, R, launch order) -> emit (every duplicate dropped into its tile's range) ->
+//   tile_sort_pack (per-tile depth sort + packed records; of lists of 512+ entries only the nearest < 512 are
+//   selected, sorted and packed) -> blend_fwd [-> full sort + second blend of the tiles whose pixels were not
+//   saturated at the end of that prefix; a context that meets such tiles orders its long lists in full].
 //   No global sort, no scan over Gaussians, no mid-pipeline host synchronisation: the per-duplicate
 //   buffer is sized optimistically from the previous call of the same context and R (24 bytes, read
 //   back asynchronously) is only checked once everything has been enqueued (the reference has two
@@ -53,6 +56,11 @@ struct gsr_context {
   int hint_mid = -1, hint_long = -1;
   // the previous call rendered more than half of the map: the conservative cull has nothing to remove, skip it
   int hint_dense = 0;
+  // Prefix sort of the lists of 512+ entries (binning.cu: tile_select_kernel): pays off where pixels saturate
+  // within the prefix (dense views); where many tiles end up in the full sort anyway it is switched off for
+  // partial_off calls.  The count of redone tiles of call k is read back asynchronously and looked at in call k + 1.
+  int partial_off = 0;
+  bool redo_pending = false;
 };
 
 namespace gsr {
@@ -192,7 +200,7 @@ int gsr_forward(const gsr_forward_args* a) {
   ImageView im = image_view(img_base, N, T);
 
   GSR_CUDA(cudaMemsetAsync(g.hdr, 0, sizeof(GeomHeader), s));
-  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));  // tile_count | tile_fill
+  GSR_CUDA(cudaMemsetAsync(im.tile_count, 0, im.zero_bytes, s));  // tile_count | tile_fill | redo_flag | redo_count
 
   uint32_t* host_R = ctx->pinned;
   cudaEvent_t ev_R = ctx->ev;
@@ -213,6 +221,8 @@ int gsr_forward(const gsr_forward_args* a) {
     cap_hint = 0;
     hint_mid = hint_long = -1;
     ctx->hint_dense = 0;
+    ctx->partial_off = 0;
+    ctx->redo_pending = false;
   }
   ctx->hint_P = P; ctx->hint_W = W; ctx->hint_H = H;
   uint32_t cap = cap_hint;
@@ -265,13 +275,18 @@ int gsr_forward(const gsr_forward_args* a) {
     do_long = host_R[5] > 0;
   }
   BinView b;
+  bool redo_issued = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
+    const bool longer = do_mid || do_long;          // lists of 512+ entries exist (or are expected)
+    const bool partial = ctx->partial_off <= 0;     // ... and only their depth-sorted PREFIX is packed
     char* bin_base = a->binning_resize(a->binning_user, bin_bytes((size_t)cap));
     if (!bin_base) return GSR_ERR_ALLOC;
     b = bin_view(bin_base, (size_t)cap);
     if (attempt > 0) {
       // max_contrib may hold values of the aborted attempt (blend_fwd only ever raises it)
-      GSR_CUDA(cudaMemsetAsync(im.tile_fill, 0, (size_t)T * sizeof(uint32_t), s));
+      // tile_fill | redo_flag | redo_count (contiguous, behind tile_count)
+      GSR_CUDA(cudaMemsetAsync(im.tile_fill, 0, im.zero_bytes - (size_t)(reinterpret_cast<char*>(im.tile_fill) -
+                                                                      reinterpret_cast<char*>(im.tile_count)), s));
       GSR_CUDA(cudaMemsetAsync(im.max_contrib, 0, (size_t)T * sizeof(uint32_t), s));
       GSR_CUDA(cudaMemsetAsync(&g.hdr->num_large, 0, sizeof(uint32_t), s));
     }
@@ -280,10 +295,26 @@ int gsr_forward(const gsr_forward_args* a) {
                                    g.conic_opacity, a->radii, gx, gy, im.ranges, im.tile_fill, b.items, cap,
                                    &g.hdr->num_large, g.large_list, s));
       GSR_PROF("tile_sort_pack", launch_tile_sort_pack(P, T, im.ranges, im.tile_order, g.hdr, b.hdr, cap, b.items, b.scratch,
-                                                       g.splat_rec, b.rec, do_mid, do_long, s));
+                                                       g.splat_rec, b.rec, do_mid && partial, do_long && partial,
+                                                       im.sorted_len, im.redo_flag, im.redo_list, im.redo_count, s));
+      if (longer && !partial)   // the prefix sort is switched off for this context: every long list in full
+        GSR_PROF("tile_sort_full", launch_tile_sort_full(P, T, im.ranges, im.tile_order, g.hdr, cap, b.items, b.scratch,
+                                                         g.splat_rec, b.rec, do_mid, do_long, nullptr, nullptr, s));
     }
     GSR_PROF("blend_fwd", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
-                            im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, nullptr, s));
+                            im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, nullptr,
+                            (longer && partial) ? im.sorted_len : nullptr, im.redo_flag, im.redo_list, im.redo_count,
+                            false, s));
+    if (longer && partial && (!have_R || R > 0)) {
+      // the tiles whose pixels were not saturated at the end of their prefix: full sort, blended again
+      GSR_PROF("tile_sort_redo", launch_tile_sort_full(P, T, im.ranges, im.tile_order, g.hdr, cap, b.items, b.scratch,
+                                                       g.splat_rec, b.rec, do_mid, do_long, im.redo_list, im.redo_count, s));
+      GSR_PROF("blend_fwd_redo", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
+                              im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, nullptr, nullptr, im.redo_flag,
+                              im.redo_list, im.redo_count, true, s));
+      GSR_CUDA(cudaMemcpyAsync(&host_R[8], im.redo_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      redo_issued = true;
+    }
     if (!have_R) {
       GSR_CUDA(cudaEventSynchronize(ev_R));  // completed long ago: the GPU is several kernels further
       R = host_R[0];
@@ -303,6 +334,12 @@ int gsr_forward(const gsr_forward_args* a) {
     cap_hint = want > decayed ? want : decayed;
   }
   ctx->hint_dense = host_R[2] > (uint32_t)P / 2 ? 1 : 0;   // header word 2: rendered Gaussians
+  // the previous call's count of redone tiles has arrived (its copy precedes this call's tile_meta in stream order)
+  // (ANY redone tile switches it off: its CTA walks a whole long list alone, after everybody else — ~90 us at
+  // cfg5 for a handful of tiles; views whose pixels saturate, cfg1 / cfg4, never redo one)
+  if (ctx->redo_pending && host_R[8] > 0u) ctx->partial_off = kHintFrames;
+  else if (ctx->partial_off > 0) ctx->partial_off -= 1;
+  ctx->redo_pending = redo_issued;
   hint_mid = host_R[4] > host_R[5] ? kHintFrames : (hint_mid > 0 ? hint_mid - 1 : 0);
   hint_long = host_R[5] > 0 ? kHintFrames : (hint_long > 0 ? hint_long - 1 : 0);
   *a->num_rendered = (int)R;
@@ -414,9 +451,8 @@ int gsr_adam_step_rows(const gsr_adam_group* groups, int n_groups, double beta1,
 
 int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
                        int P, int R, int W, int H, uint64_t* keys_sorted, uint32_t* point_list, void* stream) {
-  (void)P; (void)geom_buffer;
   if (R <= 0) return GSR_OK;
-  if (!binning_buffer || !image_buffer) return GSR_ERR_BAD_ARG;
+  if (!binning_buffer || !image_buffer || !geom_buffer || P <= 0) return GSR_ERR_BAD_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t N = (size_t)W * H;
   const uint32_t T = (uint32_t)(((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y));
@@ -427,6 +463,12 @@ int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, cons
   GSR_CUDA(cudaStreamSynchronize(s));
   if (cap < (uint64_t)R) return GSR_ERR_BAD_ARG;
   BinView b = bin_view(const_cast<char*>(binning_buffer), (size_t)cap);
+  // The forward pass orders only a prefix of the lists of 512+ entries (the part the blend kernels read): the
+  // export completes the job — the full sort of every such list, from the list as emitted (re-sorting the few
+  // lists the forward pass had to sort fully is harmless; the packed records keep the same prefix).
+  GeomView g = geom_view(const_cast<char*>(geom_buffer), (size_t)P);
+  GSR_RC(launch_tile_sort_full(P, T, im.ranges, im.tile_order, g.hdr, (uint32_t)cap, b.items, b.scratch, g.splat_rec,
+                               b.rec, true, true, nullptr, nullptr, s));
   return launch_export_binning(T, im.ranges, b.items, keys_sorted, point_list, s);
 }
 
@@ -458,7 +500,8 @@ int gsr_export_pair_counts(const char* binning_buffer, char* image_buffer, int R
   ImageView im = image_view(image_buffer, N, T);
   BinView b = bin_view(const_cast<char*>(binning_buffer), (size_t)R);  // rec does not depend on the capacity
   return launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, background, scratch_color, im.final_T, im.n_contrib,
-                          im.accum_c, im.max_contrib, 0xffffffffu, reinterpret_cast<unsigned long long*>(counts_out), s);
+                          im.accum_c, im.max_contrib, 0xffffffffu, reinterpret_cast<unsigned long long*>(counts_out),
+                          im.sorted_len, im.redo_flag, im.redo_list, im.redo_count, false, s);
 }
 
 int gsr_export_geometry(const char* geom_buffer, int P, float* depths, float* means2D,

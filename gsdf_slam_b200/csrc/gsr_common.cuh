@@ -59,13 +59,17 @@ struct ImageView {
   // tile_count | tile_fill are contiguous and zeroed by one memset before preprocess
   uint32_t* tile_count;      // [T] exact number of splats per tile (accumulated by preprocess)
   uint32_t* tile_fill;       // [T] slots handed out so far by the emit stage
-  size_t zero_bytes;         // bytes to clear starting at tile_count
+  uint32_t* redo_flag;       // [T] != 0: the tile's sorted prefix was too short (or could not be selected): full sort + re-blend
+  uint32_t* redo_count;      // [4] length of redo_list (word 0)
+  size_t zero_bytes;         // bytes to clear starting at tile_count (the four arrays above)
   float* final_T;            // [N]
   uint32_t* n_contrib;       // [N]
   float* accum_c;            // [3N] blended colour WITHOUT background (planar)
   uint2* ranges;             // [T]
   uint32_t* max_contrib;     // [T]
   uint32_t* tile_order;      // [T] tiles sorted by list length, longest first (CTA launch order)
+  uint32_t* sorted_len;      // [T] lists of kSortSmallCap+ entries: length of the depth-sorted, packed PREFIX (binning.cu)
+  uint32_t* redo_list;       // [T] tiles flagged for the full sort
 };
 
 // per-tile sort (binning.cu): lists shorter than kSortSmallCap are sorted in registers by one
@@ -126,6 +130,8 @@ inline ImageView image_view(char* base, size_t N, size_t T) {
   char* p = base;
   v.tile_count = carve<uint32_t>(p, T);
   v.tile_fill = carve<uint32_t>(p, T);
+  v.redo_flag = carve<uint32_t>(p, T);
+  v.redo_count = carve<uint32_t>(p, 4);
   v.zero_bytes = (size_t)(p - reinterpret_cast<char*>(v.tile_count));
   v.final_T = carve<float>(p, N);
   v.n_contrib = carve<uint32_t>(p, N);
@@ -133,11 +139,13 @@ inline ImageView image_view(char* base, size_t N, size_t T) {
   v.ranges = carve<uint2>(p, T);
   v.max_contrib = carve<uint32_t>(p, T);
   v.tile_order = carve<uint32_t>(p, T);
+  v.sorted_len = carve<uint32_t>(p, T);
+  v.redo_list = carve<uint32_t>(p, T);
   return v;
 }
 inline size_t image_bytes(size_t N, size_t T) {
   ImageView v = image_view(nullptr, N, T);
-  return reinterpret_cast<size_t>(v.tile_order) + T * 4 + 128;
+  return reinterpret_cast<size_t>(v.redo_list) + T * 4 + 128;
 }
 
 inline BinView bin_view(char* base, size_t cap) {

@@ -94,13 +94,22 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
                 cudaStream_t s);
 int launch_tile_sort_pack(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
                           BinHeader* bin_hdr, uint32_t capacity, uint64_t* items, uint64_t* scratch,
-                          const float4* splat_rec, float4* rec, bool do_mid, bool do_long, cudaStream_t s);
+                          const float4* splat_rec, float4* rec, bool do_mid, bool do_long, uint32_t* sorted_len,
+                          uint32_t* redo_flag, uint32_t* redo_list, uint32_t* redo_count, cudaStream_t s);
+int launch_tile_sort_full(int P, uint32_t T, const uint2* ranges, const uint32_t* order, const GeomHeader* hdr,
+                          uint32_t capacity, uint64_t* items, uint64_t* scratch, const float4* splat_rec, float4* rec,
+                          bool do_mid, bool do_long, const uint32_t* redo_list, const uint32_t* redo_count,
+                          cudaStream_t s);
 int launch_export_binning(uint32_t T, const uint2* ranges, const uint64_t* items, uint64_t* keys,
                           uint32_t* point_list, cudaStream_t s);
+// sorted_len != nullptr: lists of kSortSmallCap+ entries are only sorted / packed up to sorted_len[tile]; a tile whose
+// pixels are not saturated there is flagged (redo_flag / redo_list / redo_count).  redo: blend the flagged tiles
+// (fully sorted by launch_tile_sort_full) instead of all tiles.
 int launch_blend_fwd(int W, int H, const uint2* ranges, const uint32_t* tile_order, const float4* rec,
                      const float* bg, float* out_color, float* final_T,
                      uint32_t* n_contrib, float* accum_c, uint32_t* max_contrib, uint32_t capacity,
-                     unsigned long long* pair_counts, cudaStream_t s);
+                     unsigned long long* pair_counts, const uint32_t* sorted_len, uint32_t* redo_flag,
+                     uint32_t* redo_list, uint32_t* redo_count, bool redo, cudaStream_t s);
 int launch_blend_bwd(int W, int H, const uint2* ranges, const uint32_t* tile_order,
                      const uint32_t* max_contrib, const float4* rec, const float* bg,
                      const float* final_T, const uint32_t* n_contrib, const float* accum_c,
