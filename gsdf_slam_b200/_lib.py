@@ -129,7 +129,7 @@ class DensifyArgs(C.Structure):
 # every symbol include/gsr_capi.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = [
     "gsr_forward", "gsr_backward", "gsr_mark_visible", "gsr_knn_mean_dist2", "gsr_adam_step", "gsr_adam_step_rows", "gsr_adam_step_peer", "gsr_peer_union_mask", "gsr_peer_rank_mask_u8",
-    "gsr_peer_local_stats", "gsr_peer_stats_exchange",
+    "gsr_peer_local_stats", "gsr_peer_stats_exchange", "gsr_export_redo_count",
     "gsr_l1_ssim_loss", "gsr_l1_ssim_workspace_bytes",
     "gsr_store_workspace_bytes", "gsr_prune_points", "gsr_densify_and_prune", "gsr_densification_postfix",
     "gsr_add_densification_stats", "gsr_reset_opacity", "gsr_voxel_dedup_workspace_bytes", "gsr_voxel_dedup",
@@ -259,6 +259,8 @@ def lib() -> C.CDLL:
     L.gsr_export_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_export_image.restype = C.c_int
+    L.gsr_export_redo_count.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
+    L.gsr_export_redo_count.restype = C.c_int
     L.gsr_export_geometry.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsr_export_geometry.restype = C.c_int

@@ -472,6 +472,17 @@ int gsr_export_binning(const char* geom_buffer, const char* binning_buffer, cons
   return launch_export_binning(T, im.ranges, b.items, keys_sorted, point_list, s);
 }
 
+int gsr_export_redo_count(const char* image_buffer, int W, int H, uint32_t* count_host, void* stream) {
+  if (!image_buffer || !count_host || W <= 0 || H <= 0) return GSR_ERR_BAD_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t N = (size_t)W * H;
+  const size_t T = (size_t)((W + GSR_TILE_X - 1) / GSR_TILE_X) * ((H + GSR_TILE_Y - 1) / GSR_TILE_Y);
+  ImageView im = image_view(const_cast<char*>(image_buffer), N, T);
+  GSR_CUDA(cudaMemcpyAsync(count_host, im.redo_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  GSR_CUDA(cudaStreamSynchronize(s));
+  return GSR_OK;
+}
+
 int gsr_export_image(const char* image_buffer, int W, int H, float* final_T, uint32_t* n_contrib,
                      uint32_t* ranges, uint32_t* max_contrib, void* stream) {
   if (!image_buffer) return GSR_ERR_BAD_ARG;

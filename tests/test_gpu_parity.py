@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import (product_exports, rel_l2, run_product_backward, run_product_forward,
+from util import (_lib, product_exports, rel_l2, run_product_backward, run_product_forward,
                   run_reference, scenes, to_dev, valid_prefix)
 
 pytestmark = pytest.mark.gpu
@@ -256,6 +256,51 @@ def test_repeated_calls_skip_the_cull_when_most_of_the_map_is_rendered():
             first = (fwd[0], fwd[2].clone(), fwd[3].clone())
         else:
             assert fwd[0] == first[0] and torch.equal(fwd[2], first[1]) and torch.equal(fwd[3], first[2])
+
+
+def _redo_count(scene, fwd):
+    import ctypes as C
+    n = C.c_uint32(0)
+    _lib.check(_lib.lib().gsr_export_redo_count(C.c_void_p(fwd[6].data_ptr()), scene.cam.W, scene.cam.H, C.byref(n), None),
+               "gsr_export_redo_count")
+    return int(n.value)
+
+
+def _pile(P, opacity, seed, log_scale):
+    """Every Gaussian projects onto the same few tiles: per-tile lists of thousands of entries."""
+    s = scenes.frustum_scene(P, 96, 64, 90.0, 90.0, seed=seed, degree=0, sh_coeffs=0, zmin=1.0, zmax=4.0,
+                             log_scale=log_scale, behind_frac=0.0, name=f"pile_{opacity}")
+    s.means3D[:, :2] *= 0.3
+    s.opacity[:] = opacity
+    return s
+
+
+def test_prefix_sort_of_long_lists_and_its_fallback():
+    """Lists of 512+ entries are ordered and packed only as far as the blend is expected to read (binning.cu:
+    tile_select_kernel).  Opaque pile: the pixels saturate inside the prefix, (almost) no tile is redone.  Nearly transparent
+    pile (alpha just above 1/255: a pixel needs ~2300 splats to saturate): the prefix does not suffice, the tiles take
+    the full sort and are blended again — and the context then orders its long lists in full (the count of redone
+    tiles of call k is read back asynchronously and acted upon from call k + 2).  Every call must pass the bit-exact
+    gates (sorted keys / ids of the WHOLE lists through the export, n_contrib, max_contrib)."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not built")
+    # big opaque splats (every pixel saturates after a few) / small, nearly transparent ones; different P: the context
+    # starts afresh
+    opaque, clear = _pile(12_000, 0.9, 41, 0.3), _pile(12_001, 0.0042, 42, 0.02)
+    for sc, want_redo in ((opaque, None), (clear, True), (clear, True), (clear, False)):
+        t = to_dev(sc)
+        ref = run_reference(sc, t)
+        lens = ref["ranges"][:, 1] - ref["ranges"][:, 0]
+        assert int(lens.max()) >= 2000
+        fwd = run_product_forward(sc, t)
+        torch.cuda.synchronize()
+        redone = _redo_count(sc, fwd)
+        if want_redo is None:   # opaque: the prefix serves most long lists (fringe tiles of the pile may not saturate)
+            assert redone < int((lens >= 512).sum()) // 2, (sc.name, redone)
+        else:
+            assert (redone > 0) == want_redo, (sc.name, redone)
+        _compare_forward(sc, t, fwd, ref)
+        _compare_grads(run_product_backward(sc, t, fwd), ref["grads"])
 
 
 def test_grad_rows_mask_skips_the_rows_no_pixel_blended():

@@ -7,7 +7,7 @@ python bench.py --impl reference > $O/bench_ref.json 2> $O/bench_ref.err; echo "
 python bench.py > $O/bench1.json 2> $O/bench1.err; echo "bench rc=$?"
 for cfg in cfg1 cfg4; do python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-cfg5 --no-shim --config $cfg > $O/bench_$cfg.json 2> $O/bench_$cfg.err; echo "$cfg rc=$?"; done
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-cfg5 --no-shim"
-KRE='regex:precull_kernel|preprocess_kernel|count_large_kernel|tile_meta_kernel|emit_kernel|emit_large_kernel|tile_sort_pack|blend_fwd_kernel|blend_bwd_kernel|select_grad_rows_kernel|preprocess_bwd_kernel|adam_rows_all_kernel'
+KRE='regex:precull_kernel|preprocess_kernel|count_large_kernel|tile_meta_kernel|emit_kernel|emit_large_kernel|tile_sort_pack|tile_select_kernel|blend_fwd_kernel|blend_bwd_kernel|select_grad_rows_kernel|preprocess_bwd_kernel|adam_rows_all_kernel'
 $CMD > $O/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $O/launches.csv $CMD > $O/ncu_launches.log 2>&1
 echo "launches rc=$?"
