@@ -297,6 +297,7 @@ def timed_loop(fn, steps, warmup, world, dev, L):
     for _ in range(steps):
         fn()
     b.record()
+    timed_loop.host_ms_per_step = (time.time() - t0) * 1e3 / max(1, steps)   # host time to ENQUEUE a step
     barrier()
     t1 = time.time()
     ms = a.elapsed_time(b)
@@ -589,7 +590,9 @@ def run_product(args, rank, world, dev):
 
     kf_dev = make_kf(t(cam.viewmatrix), t(cam.projmatrix), t(cam.campos), big_dev)
     counts = workload_counts(scene, cam, params, dev)
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)    # device -> host (rendered image)
+    h2d_stream = torch.cuda.Stream(device=dev)     # host -> device: its own stream, PCIe is full duplex and the
+                                                   # upload of step k + 1 must not queue behind the read-back of step k
 
     def step_resident():
         mapper.step([kf_dev])
@@ -609,6 +612,7 @@ def run_product(args, rank, world, dev):
         ev.record(torch.cuda.current_stream(dev))
     dl_stage = [stage["dL_dout"], torch.empty_like(stage["dL_dout"])]
     counter = [0]
+    wait_s = [0.0]      # host time spent waiting for the image of step k-2 (the rest of the loop is enqueue work)
 
     def step_e2e():
         main = torch.cuda.current_stream(dev)
@@ -616,16 +620,18 @@ def run_product(args, rank, world, dev):
         counter[0] += 1
         # the result of step k-2 (the rendered image in img_host[slot]) must have reached the host before its
         # buffer is reused; the host never blocks on the step it has just enqueued
+        tw = time.time()
         ev_img[slot].synchronize()
+        wait_s[0] += time.time() - tw
         # camera + background first (tiny), the image-sized gradient on the copy stream so it
         # overlaps the forward (a real mapper uploads the ground-truth image the same way)
         cam_dev.copy_(cam_host, non_blocking=True)
         # the image-sized upload is double-buffered: it may start while the previous step's
         # backward pass still reads the other buffer (two steps back is finished: ev_step[slot])
-        copy_stream.wait_event(ev_step[slot])
-        with torch.cuda.stream(copy_stream):
+        h2d_stream.wait_event(ev_step[slot])
+        with torch.cuda.stream(h2d_stream):
             dl_stage[slot].copy_(hk["dL_dout"], non_blocking=True)
-            ev_h2d.record(copy_stream)
+            ev_h2d.record(h2d_stream)
         mapper.bg = stage["bg"]
         kf = make_kf(stage["viewmatrix"], stage["projmatrix"], stage["campos"], dl_stage[slot])
 
@@ -649,7 +655,12 @@ def run_product(args, rank, world, dev):
         time.sleep(0.3)
     ms, launches, (t0, t1) = timed_loop(step_resident, args.steps, args.warmup, world, dev, L)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    e2e_ms, _, _ = timed_loop(step_e2e, args.steps, max(3, args.warmup // 2), world, dev, L)
+    for _ in range(3):
+        step_e2e()
+    wait_s[0] = 0.0
+    e2e_ms, _, _ = timed_loop(step_e2e, args.steps, max(0, args.warmup // 2), world, dev, L)
+    e2e_host_ms = timed_loop.host_ms_per_step
+    e2e_wait_ms = wait_s[0] * 1e3 / max(1, args.steps + max(0, args.warmup // 2))
     for ev in ev_img:
         ev.synchronize()
 
@@ -773,7 +784,8 @@ def run_product(args, rank, world, dev):
         "counts": counts,
         "e2e": {"value": round(world * 1000.0 / e2e_step, 2), "unit": UNIT, "ms_per_step": round(e2e_step, 4),
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "pipelining": "copies double-buffered on a copy stream; the image of step k is awaited before step k+2"},
+                "host_loop_ms_per_step": round(e2e_host_ms, 4), "host_wait_ms_per_step": round(e2e_wait_ms, 4),
+                "pipelining": "uploads and read-backs double-buffered on two copy streams; the image of step k is awaited before step k+2"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -868,7 +880,8 @@ def run_reference(args, rank, world, dev):
     from oracle.loss_ref import reference_mapping_loss
     opt = LibtorchAdam(p, PARAM_NAMES)
 
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream = torch.cuda.Stream(device=dev)    # device -> host
+    h2d_stream = torch.cuda.Stream(device=dev)     # host -> device (as in the product arm)
     ev_h2d, ev_fwd = torch.cuda.Event(), torch.cuda.Event()
     ev_step = [torch.cuda.Event(), torch.cuda.Event()]
     ev_img = [torch.cuda.Event(), torch.cuda.Event()]
@@ -879,7 +892,7 @@ def run_reference(args, rank, world, dev):
 
     def step(debug=False, host_io=True, adam=True):
         # host I/O exactly like the product's e2e step: camera block on the compute stream, the
-        # image-sized gradient up and the rendered image down on a copy stream, double-buffered, the image of
+        # image-sized gradient up and the rendered image down on two copy streams, double-buffered, the image of
         # step k awaited before step k+2
         src = stage
         main = torch.cuda.current_stream(dev)
@@ -891,10 +904,10 @@ def run_reference(args, rank, world, dev):
             ev_img[slot].synchronize()
             cam_dev.copy_(cam_host, non_blocking=True)
             dl = dl_stage[slot]
-            copy_stream.wait_event(ev_step[slot])
-            with torch.cuda.stream(copy_stream):
+            h2d_stream.wait_event(ev_step[slot])
+            with torch.cuda.stream(h2d_stream):
                 dl.copy_(hk["dL_dout"], non_blocking=True)
-                ev_h2d.record(copy_stream)
+                ev_h2d.record(h2d_stream)
         # allocations exactly like the reference shim (src/rasterize_points.cu:74-76, 157-166)
         R, B, color, radii = rr.forward(src["bg"], p["means3D"], e, p["opacity"], p["scales"], p["rotations"],
                                         1.0, e, src["viewmatrix"], src["projmatrix"], cam.tanfovx,
