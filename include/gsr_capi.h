@@ -469,7 +469,11 @@ int gsr_colorize_points(const float* points, int64_t n, const float* lidar_pose,
                         void* stream);
 
 /* ---- test / debug exports (device -> device copies out of the opaque buffers) ---- */
-/* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits). */
+/* Any output pointer may be NULL.  keys are reconstructed 64-bit (tile<<32 | depth bits).
+ * gsr_export_binning returns the COMPLETE depth-sorted per-tile lists (what the reference's radix sort produces):
+ * gsr_forward itself orders and packs, of a list of 512 or more entries, only the prefix the blend kernels read
+ * (see gsr_export_redo_count), so the export first finishes the sort of those lists on `stream` (the packed
+ * records keep their prefix; the geometry buffer is needed for that). */
 int gsr_export_binning(const char* geom_buffer, const char* binning_buffer,
                        const char* image_buffer, int P, int R, int W, int H,
                        uint64_t* keys_sorted, uint32_t* point_list, void* stream);
