@@ -13,8 +13,8 @@ iterations / s over all ranks.  dL/d(image) is a seeded tensor (--with-loss puts
 `value`  : inputs resident in HBM, K steps timed with CUDA events between barriers.
 `e2e`    : the same step through the public API with HOST buffers: every step copies the keyframe inputs
            (camera block, dL/d(image)) from pinned host memory and reads the rendered image back into pinned
-           host memory; the copies run on a copy stream, double-buffered — the image of step k is waited for
-           before step k+2 is enqueued, so one rank's PCIe stall is not broadcast through the barriers.
+           host memory; uploads and read-backs run on two copy streams, double-buffered — the image of step k is
+           waited for before step k+2 is enqueued, so one rank's PCIe stall is not broadcast through the barriers.
 Further blocks of the same JSON line:
 `rasterizer_only` (N = 1): the metric's literal quantity — RasterizeGaussiansCUDA + RasterizeGaussiansBackwardCUDA
            through the C++ drop-in shim (dense gradients, the reference's allocation pattern), it/s.
@@ -452,7 +452,7 @@ def run_cfg5(args, rank, world, dev, L, scene5, params5, kfs):
            "value": round(1000.0 / ms_step, 2), "unit": "mapping it/s (optimiser steps of 8 keyframes)",
            "keyframes_per_s": round(1000.0 * len(kfs) / ms_step, 1), "gpu_launches": int(launches),
            "exchange": ("none (single rank): masked Adam over the rows some keyframe rendered" if world == 1 else
-                        "fused peer-memory kernel (gsr_adam_step_peer) + gsr_peer_stats_exchange"
+                        "fused peer-memory kernel (gsr_adam_step_peer: gradients, Adam, parameters, densification statistics)"
                         if mapper.peer is not None else "NCCL all-reduce fallback")}
     n1 = os.path.join(ROOT, "profiles", "mapping_cfg5_n1.json")
     if world > 1 and os.path.exists(n1) and not (args.small_cfg5 or args.config == "small"):

@@ -11,14 +11,16 @@ src/gaussian_mapper.cpp:443-447, src/gaussian_model.cpp:667-681) of all K views.
 
 Exchange, N > 1 ranks on one NVLink node (default): ONE fused kernel over peer memory
 (gsr_adam_step_peer): every rank owns an interleaved 1/N shard of the flat arena, sums the gradient
-arenas of the ranks that rendered each row (per-row rank bitmask), runs Adam on shard-local moments and
-stores the new parameters into all N replicas (one multicast store through the NVSwitch when the
-symmetric allocation has a multicast address, else N unicast stores).  A second small kernel
-(gsr_peer_stats_exchange) builds the rank bitmask and combines the densification statistics.
+arenas of the ranks that hold a valid gradient row (per-row rank bitmasks from one flag byte per rank and row:
+rendered | gradient valid; gsr_peer_rank_mask_u8), runs Adam on shard-local moments and stores the new
+parameters into all N replicas (one multicast store through the NVSwitch when the symmetric allocation has a
+multicast address, else N unicast stores).  The densification statistics ride through the same kernel as three
+one-float segments in the tail of the arenas (sum / sum / max over the ranks that rendered the row).
 Fallback (no symmetric memory, or GSR_PEER_EXCHANGE=0): NCCL all-reduce of the arena (chunked, pipelined
 with the fused Adam) and all-reduce sum / max of the statistics; every rank then applies the identical
-full-size update.  Single rank: the K backward passes write / add only the rows they render
-(gsr_backward_args.accumulate_rows) and ONE masked Adam pass reads the gradient only for those rows.
+full-size update.  Single rank: the K backward passes write / add only the rows that received a gradient
+(gsr_backward_args.grad_rows, a row mask the kernel keeps) and ONE masked Adam pass reads the gradient only for
+those rows.
 
 Gradient arena layout (fp32, each segment 16-byte aligned and itself a valid contiguous gradient
 tensor): [xyz 3P | f_dc 3P | opacity P | scaling 3P | rotation 4P | f_rest 3MP].
