@@ -459,8 +459,10 @@ tile_sort_pack_small_kernel(const uint2* __restrict__ ranges, const uint32_t* __
 // again (rare: 1 tile in 3000 at cfg5, none at cfg1 / cfg4).
 constexpr int kSelThreadsSort = 512;
 constexpr uint32_t kSelMinPrefix = 256;   // fewer selectable entries: take the full sort straight away
+// redo_flag bits: 1 / 2 = the upper / lower half tile continues behind its prefix in the second blend pass
+// (set by blend_fwd), 4 = the tile is in redo_list
 __device__ __forceinline__ void flag_redo(uint32_t tile, uint32_t* redo_flag, uint32_t* redo_list, uint32_t* redo_count) {
-  if (atomicExch(&redo_flag[tile], 1u) == 0u) redo_list[atomicAdd(redo_count, 1u)] = tile;
+  if (!(atomicOr(&redo_flag[tile], 4u) & 4u)) redo_list[atomicAdd(redo_count, 1u)] = tile;
 }
 __global__ void __launch_bounds__(kSelThreadsSort)
 tile_select_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ order, const GeomHeader* __restrict__ hdr,

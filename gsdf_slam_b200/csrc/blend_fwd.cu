@@ -44,6 +44,8 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   // 1-D grid in longest-list-first order (binning.cu: tile_order_kernel); two CTAs per tile
   const uint32_t tile_id = kRedo ? redo_list[blockIdx.x >> 1] : tile_order[blockIdx.x >> 1];
   const int warp = blockIdx.x & 1;  // upper / lower half of the tile
+  // second pass: only the half tiles that stopped at the end of their sorted prefix continue (bit 0 / 1 of the flag)
+  if (kRedo && !(redo_flag[tile_id] & (1u << warp))) return;
   const uint32_t grid_x = (uint32_t)(W + GSR_TILE_X - 1) / GSR_TILE_X;
   const uint32_t tile_x = tile_id % grid_x, tile_y = tile_id / grid_x;
 
@@ -66,9 +68,19 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   const int full = range.y <= capacity ? (int)(range.y - range.x) : 0;
   // lists of kSortSmallCap+ entries are sorted and packed only up to sorted_len[tile] (binning.cu: tile_select_kernel)
   // unless the tile has been through the full sort (kRedo; the instrumented replay: flagged tiles)
-  int total = full;
-  if (!kRedo && sorted_len != nullptr && full >= kSortSmallCap && !(kCount && redo_flag[tile_id] != 0))
-    total = min(full, (int)sorted_len[tile_id]);
+  // unless the tile has been through the full sort (the instrumented replay: flagged tiles).  The second pass
+  // (kRedo, after that full sort) CONTINUES behind the prefix: list positions first .. full - 1, with the pixel states
+  // the first pass left in final_T / accum_c / n_contrib (bit 31 of n_contrib: the pixel was saturated).
+  int first = 0, total = full;
+  if (sorted_len != nullptr && full >= kSortSmallCap) {
+    const int prefix = min(full, (int)sorted_len[tile_id]);
+    if (kRedo) {
+      first = prefix;
+      total = full - prefix;
+    } else if (!(kCount && redo_flag[tile_id] != 0)) {
+      total = prefix;
+    }
+  }
   const int rounds = (total + kBlendBatch - 1) / kBlendBatch;
 
   if (lane == 0) {
@@ -80,7 +92,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
   auto issue = [&](int round) {
     const int buf = round & 1;
-    const int start = range.x + round * kBlendBatch;
+    const int start = range.x + first + round * kBlendBatch;
     const int cnt = min(kBlendBatch, total - round * kBlendBatch);
     const uint32_t bytes = (uint32_t)cnt * 48u;
     mbar_expect_tx(&s_full[buf], bytes);
@@ -92,12 +104,22 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
   float T[kSlots];
   uint32_t last_contributor[kSlots];
   float C[kSlots][3];
+  const size_t N = (size_t)W * H;
 #pragma unroll
   for (int q = 0; q < kSlots; ++q) {
     done[q] = !inside[q];
     T[q] = 1.0f;
     last_contributor[q] = 0;
     C[q][0] = C[q][1] = C[q][2] = 0.f;
+    if (kRedo && inside[q]) {
+      const uint32_t nc = n_contrib[pix_id[q]];
+      done[q] = (nc >> 31) != 0;
+      last_contributor[q] = nc & 0x7fffffffu;
+      T[q] = final_T[pix_id[q]];
+      C[q][0] = accum_c[0 * N + pix_id[q]];
+      C[q][1] = accum_c[1 * N + pix_id[q]];
+      C[q][2] = accum_c[2 * N + pix_id[q]];
+    }
   }
 
   unsigned long long n_visit = 0, n_gate = 0, n_blend = 0;  // kCount only
@@ -112,7 +134,7 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     if (lane == 0 && i + 1 < rounds) issue(i + 1);
 
     const int cnt = min(kBlendBatch, total - i * kBlendBatch);
-    const uint32_t pos0 = (uint32_t)i * kBlendBatch;
+    const uint32_t pos0 = (uint32_t)first + (uint32_t)i * kBlendBatch;
     for (int j = 0; !all_done && j < cnt; j++) {
       const float4 A = sR[buf][3 * j];
       const float4 B = sR[buf][3 * j + 1];
@@ -166,24 +188,28 @@ blend_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     }
   }
 
+  bool to_be_continued = false;
   if (!kRedo && !kCount && total < full) {
-    // the sorted prefix ended before every pixel was saturated: the tile takes the full sort and is blended again
+    // the sorted prefix ended before every pixel was saturated: the tile takes the full sort and this half tile
+    // continues from here in the second pass; its pixel states are parked in the outputs
     bool all_done = true;
 #pragma unroll
     for (int q = 0; q < kSlots; ++q) all_done = all_done && done[q];
     if (!__all_sync(0xffffffffu, all_done)) {
-      if (lane == 0 && atomicExch(&redo_flag[tile_id], 1u) == 0u) redo_list[atomicAdd(redo_count, 1u)] = tile_id;
-      return;   // (the outputs of this half tile are written by the second pass)
+      to_be_continued = true;
+      if (lane == 0) {
+        const uint32_t old = atomicOr(&redo_flag[tile_id], (1u << warp) | 4u);   // bit 2: the tile is listed
+        if (!(old & 4u)) redo_list[atomicAdd(redo_count, 1u)] = tile_id;
+      }
     }
   }
 
-  const size_t N = (size_t)W * H;
   uint32_t my_max = 0;
 #pragma unroll
   for (int q = 0; q < kSlots; ++q) {
     if (inside[q]) {
       final_T[pix_id[q]] = T[q];
-      n_contrib[pix_id[q]] = last_contributor[q];
+      n_contrib[pix_id[q]] = last_contributor[q] | ((to_be_continued && done[q]) ? 0x80000000u : 0u);
       out_color[0 * N + pix_id[q]] = C[q][0] + T[q] * bg[0];
       out_color[1 * N + pix_id[q]] = C[q][1] + T[q] * bg[1];
       out_color[2 * N + pix_id[q]] = C[q][2] + T[q] * bg[2];

@@ -44,6 +44,10 @@ namespace gsr {
 
 // Host-side state of gsr_forward: everything that used to be implicit per-thread state.  Bound to the
 // device that was current when it was created.
+// the prefix sort is switched off when more than 1 / GSR_PARTIAL_REDO_DIV of the long lists needed the second pass
+#ifndef GSR_PARTIAL_REDO_DIV
+#define GSR_PARTIAL_REDO_DIV 16
+#endif
 struct gsr_context {
   int device = -1;
   uint32_t* pinned = nullptr;     // 64 bytes of pinned host memory: R and the list-length class counts
@@ -61,6 +65,7 @@ struct gsr_context {
   // partial_off calls.  The count of redone tiles of call k is read back asynchronously and looked at in call k + 1.
   int partial_off = 0;
   bool redo_pending = false;
+  uint32_t redo_long_tiles = 0;
 };
 
 namespace gsr {
@@ -306,12 +311,13 @@ int gsr_forward(const gsr_forward_args* a) {
                             (longer && partial) ? im.sorted_len : nullptr, im.redo_flag, im.redo_list, im.redo_count,
                             false, s));
     if (longer && partial && (!have_R || R > 0)) {
-      // the tiles whose pixels were not saturated at the end of their prefix: full sort, blended again
+      // the tiles whose pixels were not saturated at the end of their prefix: full sort, and their half tiles
+      // continue behind the prefix
       GSR_PROF("tile_sort_redo", launch_tile_sort_full(P, T, im.ranges, im.tile_order, g.hdr, cap, b.items, b.scratch,
                                                        g.splat_rec, b.rec, do_mid, do_long, im.redo_list, im.redo_count, s));
       GSR_PROF("blend_fwd_redo", launch_blend_fwd(W, H, im.ranges, im.tile_order, b.rec, a->background, a->out_color,
-                              im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, nullptr, nullptr, im.redo_flag,
-                              im.redo_list, im.redo_count, true, s));
+                              im.final_T, im.n_contrib, im.accum_c, im.max_contrib, cap, nullptr, im.sorted_len,
+                              im.redo_flag, im.redo_list, im.redo_count, true, s));
       GSR_CUDA(cudaMemcpyAsync(&host_R[8], im.redo_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
       redo_issued = true;
     }
@@ -335,11 +341,12 @@ int gsr_forward(const gsr_forward_args* a) {
   }
   ctx->hint_dense = host_R[2] > (uint32_t)P / 2 ? 1 : 0;   // header word 2: rendered Gaussians
   // the previous call's count of redone tiles has arrived (its copy precedes this call's tile_meta in stream order)
-  // (ANY redone tile switches it off: its CTA walks a whole long list alone, after everybody else — ~90 us at
-  // cfg5 for a handful of tiles; views whose pixels saturate, cfg1 / cfg4, never redo one)
-  if (ctx->redo_pending && host_R[8] > 0u) ctx->partial_off = kHintFrames;
+  // (the second pass is a serial tail — a flagged tile's CTA walks the rest of a long list alone, after everybody
+  // else — so it pays only while few tiles need it; views whose pixels saturate, cfg1 / cfg4, flag none)
+  if (ctx->redo_pending && (uint64_t)host_R[8] * GSR_PARTIAL_REDO_DIV > ctx->redo_long_tiles) ctx->partial_off = kHintFrames;
   else if (ctx->partial_off > 0) ctx->partial_off -= 1;
   ctx->redo_pending = redo_issued;
+  ctx->redo_long_tiles = host_R[4];
   hint_mid = host_R[4] > host_R[5] ? kHintFrames : (hint_mid > 0 ? hint_mid - 1 : 0);
   hint_long = host_R[5] > 0 ? kHintFrames : (hint_long > 0 ? hint_long - 1 : 0);
   *a->num_rendered = (int)R;

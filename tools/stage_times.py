@@ -42,5 +42,9 @@ st = {}
 for line in buf.value.decode().splitlines():
     n, c, tot = line.split()
     st[n] = round(1000.0 * float(tot) / max(1, int(c)), 2)
+redo = C.c_uint32(0)
+if hasattr(L, "gsr_export_redo_count"):
+    L.gsr_export_redo_count(C.c_void_p(fwd[6].data_ptr()), scene.cam.W, scene.cam.H, C.byref(redo), None)
+st["redo_tiles"] = int(redo.value)
 print(json.dumps({"tag": a.tag, "cfg": a.cfg, "lib": os.path.basename(_lib.LIB_PATH), "fwd_bwd_ms": round(total, 4),
                   "R": int(fwd[0]), "stages_us": st}))
