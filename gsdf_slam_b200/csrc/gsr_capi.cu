@@ -9,8 +9,9 @@
 //   preprocess (geometry, SH colours, EXACT per-tile splat counts) [-> count_large] -> tile_meta (scan of the T
 //   counts: tile ranges, R, launch order) -> emit (every duplicate dropped into its tile's range) ->
 //   tile_sort_pack (per-tile depth sort + packed records; of lists of 512+ entries only the nearest < 512 are
-//   selected, sorted and packed) -> blend_fwd [-> full sort + second blend of the tiles whose pixels were not
-//   saturated at the end of that prefix; a context that meets such tiles orders its long lists in full].
+//   selected, sorted and packed) -> blend_fwd [-> full sort of the tiles whose pixels were not saturated at the end
+//   of that prefix + a second blend_fwd launch that continues their half tiles behind it; a context in which more
+//   than 1/16 of the long lists need that orders its long lists in full].
 //   No global sort, no scan over Gaussians, no mid-pipeline host synchronisation: the per-duplicate
 //   buffer is sized optimistically from the previous call of the same context and R (24 bytes, read
 //   back asynchronously) is only checked once everything has been enqueued (the reference has two

@@ -477,9 +477,10 @@ int gsr_colorize_points(const float* points, int64_t n, const float* lidar_pose,
 int gsr_export_binning(const char* geom_buffer, const char* binning_buffer,
                        const char* image_buffer, int P, int R, int W, int H,
                        uint64_t* keys_sorted, uint32_t* point_list, void* stream);
-/* How many tiles of the last gsr_forward took the full sort + second blend because the depth-sorted PREFIX of their
- * list (lists of 512+ entries are ordered only as far as the blend is expected to read) did not saturate their pixels;
- * host value, synchronises the stream.  0 also when the context had the prefix sort switched off. */
+/* How many tiles of the last gsr_forward took the full sort + the second blend launch (which continues their half
+ * tiles) because the depth-sorted PREFIX of their list (lists of 512+ entries are ordered only as far as the blend is
+ * expected to read) did not saturate their pixels; host value, synchronises the stream.  0 also when the context
+ * had the prefix sort switched off. */
 int gsr_export_redo_count(const char* image_buffer, int W, int H, uint32_t* count_host, void* stream);
 int gsr_export_image(const char* image_buffer, int W, int H, float* final_T,
                      uint32_t* n_contrib, uint32_t* ranges /*[T,2]*/,
