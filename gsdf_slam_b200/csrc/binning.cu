@@ -252,12 +252,17 @@ emit_large_kernel(const uint32_t* __restrict__ large_count, const uint32_t* __re
     const int per_chunk = (area + (int)queue_chunks((uint32_t)area) - 1) / (int)queue_chunks((uint32_t)area);
     const int t_begin = (int)chunk * per_chunk;
     const int t_end = min(area, t_begin + per_chunk);
+    // per-rectangle constants out of the tile loop: the two reciprocals of the tile test (same operations on the
+    // same inputs as tile_min_power) and t / w by multiplication (gsr_common.cuh)
+    const float rcp_x = __frcp_rn(15 * 15 * co.x), rcp_z = __frcp_rn(15 * 15 * co.z);
+    const uint32_t w_magic = w > 1 ? 0xffffffffu / (uint32_t)w + 1u : 0u;
     for (int t0 = t_begin; t0 < t_end; t0 += 32) {
       const int t = t0 + lane;
       if (t < t_end) {
-        const int y = (int)rect_min.y + t / w;
-        const int x = (int)rect_min.x + t - (t / w) * w;
-        if (tile_min_power(co, xy, x, y) <= thr) {
+        const int q = w > 1 ? (int)__umulhi((uint32_t)t, w_magic) : t;
+        const int y = (int)rect_min.y + q;
+        const int x = (int)rect_min.x + t - q * w;
+        if (tile_min_power_pre(co, xy, x, y, rcp_x, rcp_z) <= thr) {
           const uint32_t tile = (uint32_t)(y * grid_x + x);
           const uint2 rg = ranges[tile];
           const uint32_t pos = rg.x + atomicAdd(&tile_fill[tile], 1u);
@@ -282,8 +287,8 @@ int launch_emit(int P, const uint64_t* vis_items, const uint32_t* num_visible,
                                               conic_opacity, radii, grid_x, grid_y, ranges, tile_fill,
                                               items, capacity, large_count, large_list, large_capacity);
   GSR_LAUNCHED();
-  // 148 SMs x 2 CTAs x 8 warps walk the queued large rectangles
-  emit_large_kernel<<<148 * 2, 256, 0, s>>>(large_count, large_list, vis_items, means2D, conic_opacity,
+  // 148 SMs x 4 CTAs x 8 warps walk the queued large rectangles
+  emit_large_kernel<<<148 * 4, 256, 0, s>>>(large_count, large_list, vis_items, means2D, conic_opacity,
                                             radii, grid_x, grid_y, ranges, tile_fill, items, capacity,
                                             large_capacity);
   GSR_LAUNCHED();
